@@ -1,0 +1,214 @@
+"""TEST INFRASTRUCTURE ONLY — generates tests/golden/*.pt by executing the UNMODIFIED reference
+(/root/reference, imported read-only through oracle/ref_loader.py) on seeded synthetic inputs.
+
+Run in the build container (CPU):  python oracle/make_golden.py
+The fixtures travel to the GPU box, where /root/reference does not exist.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_loader as rl  # noqa: E402
+import synth  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+warnings.filterwarnings("ignore")
+
+
+def golden_msda(ref):
+    """ops/test.py protocol (shapes :27-31, seed :34, inputs :39-42) on the reference's production
+    arithmetic (ms_deform_attn_core_pytorch), plus a D=32/M=8/L=3 case with autograd gradients."""
+    core = ref.ops_func.ms_deform_attn_core_pytorch
+    g = {}
+    N, M, D = 1, 2, 2
+    Lq, L, P = 2, 2, 2
+    shapes = [(6, 4), (3, 2)]
+    S = sum(h * w for h, w in shapes)
+    torch.manual_seed(3)
+    for tag in ("double", "float"):
+        value = torch.rand(N, S, M, D) * 0.01
+        loc = torch.rand(N, Lq, M, L, P, 2)
+        aw = torch.rand(N, Lq, M, L, P) + 1e-5
+        aw /= aw.sum(-1, keepdim=True).sum(-2, keepdim=True)
+        if tag == "double":
+            out = core(value.double(), torch.as_tensor(shapes), loc.double(), aw.double())
+        else:
+            out = core(value, torch.as_tensor(shapes), loc, aw)
+        g[f"kat_{tag}"] = dict(shapes=shapes, value=value, loc=loc, attn=aw, out=out)
+    # gradient cases: channels per head as in ops/test.py:91 (small ones) through autograd
+    for D in (30, 32, 64, 71):
+        value = (torch.rand(N, S, M, D) * 0.01).double().requires_grad_()
+        loc = torch.rand(N, Lq, M, L, P, 2).double().requires_grad_()
+        aw = torch.rand(N, Lq, M, L, P) + 1e-5
+        aw = (aw / aw.sum(-1, keepdim=True).sum(-2, keepdim=True)).double().requires_grad_()
+        out = core(value, torch.as_tensor(shapes), loc, aw)
+        go = torch.rand(out.shape, dtype=torch.float64)
+        gv, gl, ga = torch.autograd.grad(out, (value, loc, aw), go)
+        g[f"grad_D{D}"] = dict(shapes=shapes, value=value.detach(), loc=loc.detach(), attn=aw.detach(),
+                               grad_out=go, out=out.detach(), grad_value=gv, grad_loc=gl, grad_attn=ga)
+    # config-like: M=8, D=32, P=4, 3 levels, encoder-style (Lq == S), offsets a few px around centres
+    # plus out-of-range locations to exercise the zero padding.
+    shapes = [(4, 4), (8, 8), (16, 16)]
+    S = sum(h * w for h, w in shapes)
+    N, M, D, L, P = 2, 8, 32, 3, 4
+    gen = torch.Generator().manual_seed(11)
+    value = torch.randn(N, S, M, D, generator=gen).requires_grad_()
+    loc = (torch.rand(N, S, M, L, P, 2, generator=gen) * 1.3 - 0.15).requires_grad_()
+    aw = torch.softmax(torch.randn(N, S, M, L * P, generator=gen), -1).view(N, S, M, L, P).requires_grad_()
+    out = core(value, torch.as_tensor(shapes), loc, aw)
+    go = torch.randn(out.shape, generator=gen)
+    gv, gl, ga = torch.autograd.grad(out, (value, loc, aw), go)
+    g["cfg_like"] = dict(shapes=shapes, value=value.detach(), loc=loc.detach(), attn=aw.detach(), grad_out=go,
+                         out=out.detach(), grad_value=gv, grad_loc=gl, grad_attn=ga)
+    torch.save(g, os.path.join(OUT, "msda.pt"))
+    print("msda.pt", {k: tuple(v["out"].shape) for k, v in g.items()})
+
+
+HEAD_CASES = {
+    # name: (meta_arch, Q, dec_layers, points, importance_ratio, K, B, H, W)
+    "proposal_micro": ("ProposalModel", 10, 4, 256, 0.75, 3, 2, 128, 128),
+    "proposal_micro_uniform": ("ProposalModel", 12, 3, 192, 0.0, 4, 2, 128, 160),
+    "pd_micro": ("PartDistillationModel", 10, 4, 256, 0.75, 3, 2, 128, 128),
+}
+MICRO_CHANNELS = [32, 64, 128, 256]
+
+
+def golden_head(ref, name):
+    arch, Q, DL, PTS, ratio, K, B, H, W = HEAD_CASES[name]
+    pd = arch == "PartDistillationModel"
+    cfg = rl.make_cfg(arch, "swin_micro", num_queries=Q, dec_layers=DL, num_points=PTS,
+                      importance_sample_ratio=ratio, num_object_classes=50, num_part_classes=8)
+    model = rl.build_model(cfg, "/tmp/pd_oracle_work")
+    head_sd = {k: v for k, v in model.state_dict().items() if not k.startswith("backbone.")}
+    table = synth.table_of(head_sd)
+    new_sd = synth.synth_state_dict(table, seed=1)
+    missing = model.load_state_dict(new_sd, strict=False)
+    assert all(k.startswith("backbone.") or "empty_weight" in k for k in missing.missing_keys), missing
+    model.train()
+    feats = synth.synth_features(B, H, W, MICRO_CHANNELS, seed=5)
+    batch = synth.synth_batch(B, H, W, K, pd, 50, seed=9)
+    from detectron2.structures import ImageList, Instances, BitMasks
+    bi = []
+    for d in batch:
+        inst = Instances((H, W))
+        inst.gt_masks = BitMasks(d["gt_masks"])
+        inst.gt_classes = d["gt_classes"]
+        e = {"image": d["image"], "instances": inst, "height": H, "width": W}
+        if pd:
+            e["gt_object_class"] = d["gt_object_class"]
+        bi.append(e)
+    il = ImageList(torch.zeros(B, 3, H, W), [(H, W)] * B)
+    targets = model.prepare_targets(bi, il)
+
+    attn_masks = []
+    pred = model.sem_seg_head.predictor
+    orig_fph = pred.forward_prediction_heads
+
+    def fph(*a, **k):
+        r = orig_fph(*a, **k)
+        attn_masks.append(r[2].clone())
+        return r
+    pred.forward_prediction_heads = fph
+    lsap_calls = []
+    orig_lsap = ref.matcher.linear_sum_assignment
+
+    def lsap(C):
+        r = orig_lsap(C)
+        lsap_calls.append((C.clone(), np.asarray(r[0]).copy(), np.asarray(r[1]).copy()))
+        return r
+    ref.matcher.linear_sum_assignment = lsap
+    matcher_out = []
+    orig_mf = model.criterion.matcher.forward
+
+    try:
+        with synth.RecordRand() as rr:
+            mf, _, ms = model.sem_seg_head.pixel_decoder.forward_features(feats)
+            outputs = model.sem_seg_head(feats, mask=targets) if pd else model.sem_seg_head(feats)
+            n_head_draws = len(rr.draws)
+            indices_all = []
+            m = model.criterion.matcher
+
+            class _M(torch.nn.Module):
+                def forward(self, o, t):
+                    r = m(o, t)
+                    indices_all.append([(a.clone(), b.clone()) for a, b in r])
+                    return r
+            model.criterion.matcher = _M()
+            losses = model.criterion(outputs, targets)
+            model.criterion.matcher = m
+            draws = rr.draws[n_head_draws:]
+    finally:
+        ref.matcher.linear_sum_assignment = orig_lsap
+        pred.forward_prediction_heads = orig_fph
+    losses = {k: v * model.criterion.weight_dict[k] for k, v in losses.items()}
+    total = sum(losses.values())
+    total.backward()
+    grads = {n: p.grad for n, p in model.named_parameters() if p.grad is not None and not n.startswith("backbone.")}
+    keep = ["sem_seg_head.predictor.query_feat.weight", "sem_seg_head.predictor.mask_embed.layers.2.bias",
+            "sem_seg_head.predictor.decoder_norm.weight", "sem_seg_head.pixel_decoder.transformer.level_embed",
+            "sem_seg_head.pixel_decoder.input_proj.0.0.bias", "sem_seg_head.pixel_decoder.mask_features.bias",
+            "sem_seg_head.pixel_decoder.transformer.encoder.layers.0.self_attn.sampling_offsets.bias",
+            "sem_seg_head.pixel_decoder.transformer.encoder.layers.5.self_attn.attention_weights.bias",
+            "sem_seg_head.predictor.transformer_cross_attention_layers.0.multihead_attn.in_proj_bias",
+            "sem_seg_head.predictor.class_embed.bias"]
+    g = dict(
+        case=dict(arch=arch, Q=Q, dec_layers=DL, points=PTS, importance_ratio=ratio, K=K, B=B, H=H, W=W,
+                  channels=MICRO_CHANNELS, weight_seed=1, feature_seed=5, batch_seed=9,
+                  num_object_classes=50, num_part_classes=8),
+        table=table,
+        rand_draws=draws,
+        mask_features=mf.detach()[:, ::16, ::2, ::2].clone(),
+        mask_features_absmean=mf.detach().abs().mean(),
+        multi_scale=[x.detach()[:, ::32].clone() for x in ms],
+        pred_logits=[o["pred_logits"].detach() for o in outputs["aux_outputs"]] + [outputs["pred_logits"].detach()],
+        pred_masks=[o["pred_masks"].detach() for o in outputs["aux_outputs"]] + [outputs["pred_masks"].detach()],
+        decoder_output=outputs["decoder_output"].detach(),
+        attn_mask_bits=[np.packbits(a[::8].numpy(), axis=-1) for a in attn_masks],   # heads are replicas
+        attn_mask_shapes=[tuple(a.shape) for a in attn_masks],
+        lsap=[(c, r, cc) for c, r, cc in lsap_calls],
+        indices=indices_all,
+        losses={k: v.detach() for k, v in losses.items()},
+        grads={k: grads[k] for k in keep if k in grads},
+        grad_norms={k: v.double().norm().item() for k, v in grads.items()},
+    )
+    torch.save(g, os.path.join(OUT, f"head_{name}.pt"))
+    sz = os.path.getsize(os.path.join(OUT, f"head_{name}.pt")) / 1e6
+    print(f"head_{name}.pt {sz:.2f} MB  total loss {float(total):.6f}  #lsap {len(lsap_calls)}")
+
+
+def golden_swin(ref):
+    cfg = rl.make_cfg("ProposalModel", "swin_micro", num_queries=10, dec_layers=4, num_points=256)
+    model = rl.build_model(cfg, "/tmp/pd_oracle_work")
+    bb = model.backbone
+    table = synth.table_of(bb.state_dict())
+    bb.load_state_dict(synth.synth_state_dict(table, seed=2), strict=False)
+    bb.eval()
+    gen = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 3, 96, 128, generator=gen)       # 24x32 tokens: exercises window padding (ws=4 ok) + odd merges
+    with torch.no_grad():
+        out = bb(x)
+    sw = cfg.MODEL.SWIN
+    g = dict(table=table, weight_seed=2, x=x, out={k: v for k, v in out.items()},
+             cfg=dict(embed_dim=sw.EMBED_DIM, depths=list(sw.DEPTHS), num_heads=list(sw.NUM_HEADS),
+                      window_size=sw.WINDOW_SIZE))
+    torch.save(g, os.path.join(OUT, "swin_micro.pt"))
+    print("swin_micro.pt", {k: tuple(v.shape) for k, v in out.items()})
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = rl.load()
+    golden_msda(ref)
+    golden_swin(ref)
+    for name in HEAD_CASES:
+        torch.manual_seed(1234)
+        golden_head(ref, name)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,4 @@
+# TEST INFRASTRUCTURE ONLY (oracle shim). Minimal stand-in for the third-party
+# symbols the reference hot path touches; it exists so
+# /root/reference can be imported read-only in the build container to generate
+# golden vectors.  Never imported by the product package.

@@ -1,0 +1,28 @@
+# TEST INFRASTRUCTURE ONLY (oracle shim). Minimal stand-in for the third-party
+# symbols the reference hot path touches; it exists so
+# /root/reference can be imported read-only in the build container to generate
+# golden vectors.  Never imported by the product package.
+
+from torch import nn
+from detectron2.utils.registry import Registry
+from detectron2.layers import ShapeSpec
+
+META_ARCH_REGISTRY = Registry("META_ARCH")
+SEM_SEG_HEADS_REGISTRY = Registry("SEM_SEG_HEADS")
+BACKBONE_REGISTRY = Registry("BACKBONE")
+
+class Backbone(nn.Module):
+    @property
+    def size_divisibility(self):
+        return 0
+
+def build_backbone(cfg, input_shape=None):
+    if input_shape is None:
+        input_shape = ShapeSpec(channels=len(cfg.MODEL.PIXEL_MEAN))
+    return BACKBONE_REGISTRY.get(cfg.MODEL.BACKBONE.NAME)(cfg, input_shape)
+
+def build_sem_seg_head(cfg, input_shape):
+    return SEM_SEG_HEADS_REGISTRY.get(cfg.MODEL.SEM_SEG_HEAD.NAME)(cfg, input_shape)
+
+def build_model(cfg):
+    return META_ARCH_REGISTRY.get(cfg.MODEL.META_ARCHITECTURE)(cfg)
