@@ -1,0 +1,190 @@
+/*
+ * pdb200.h — C ABI of libpdb200.so: the sm_100a kernels behind PartDistillation's Mask2Former
+ * training hot path.  Citations (file:line) are into the reference checkout
+ * (facebookresearch/PartDistillation, part_distillation/...), naming the interface each entry
+ * point replaces.
+ *
+ * Conventions (all entry points):
+ *   - every tensor argument is a raw DEVICE pointer to a contiguous buffer of the documented
+ *     shape; small shape tables (spatial shapes, level starts, per-image offsets) are HOST arrays;
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous on that stream; the
+ *     library never synchronises, never allocates and never touches the default stream;
+ *   - return value 0 = launched; negative = rejected (nothing launched), the message is available
+ *     from pdb_last_error() (thread-local).  Kernel launch failures are returned, not printed
+ *     (the reference only printf()s them: ops/src/cuda/ms_deform_im2col_cuda.cuh:953-957);
+ *   - there is no CPU implementation (as in the reference: ops/src/ms_deform_attn.h:44).
+ */
+#ifndef PDB200_H_
+#define PDB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PDB_API __attribute__((visibility("default")))
+#else
+#define PDB_API
+#endif
+
+#define PDB_OK 0
+#define PDB_ERR_INVALID (-1)
+#define PDB_ERR_LAUNCH (-2)
+#define PDB_ERR_UNSUPPORTED (-3)
+
+#define PDB_F32 0
+#define PDB_F64 1
+
+/* ABI version of this header; bumped whenever a signature changes. */
+PDB_API int pdb_abi_version(void);
+/* Message of the last failing call on this thread ("" if none). */
+PDB_API const char* pdb_last_error(void);
+/* Number of kernel launches issued through this library by this process (bench.py's gpu_launches). */
+PDB_API int64_t pdb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * MSDeformAttn — replaces MSDA.ms_deform_attn_forward / ms_deform_attn_backward
+ * (ops/src/vision.cpp:19-22, ops/src/ms_deform_attn.h:27-67, ops/src/cuda/ms_deform_attn_cuda.cu:26-159)
+ * and the production arithmetic ms_deform_attn_core_pytorch (ops/functions/ms_deform_attn_func.py:55-75).
+ *   value  (N, S, M, D)        loc  (N, Lq, M, L, P, 2) in [0,1] as (x, y)
+ *   attn   (N, Lq, M, L, P)    out  (N, Lq, M*D)
+ *   shapes_hw: HOST int64[L*2] (H_l, W_l); level_start: HOST int64[L]
+ * dtype PDB_F32 (any D; D==32 takes the vectorised path) or PDB_F64 (generic path).
+ * backward ZERO-FILLS grad_value itself (the reference callee allocates zeros: .cu:127-129), then
+ * accumulates into it; grad_loc / grad_attn are fully overwritten.
+ * ---------------------------------------------------------------------------------------------- */
+PDB_API int pdb_msda_forward(const void* value, const int64_t* shapes_hw, const int64_t* level_start,
+                     const void* loc, const void* attn, void* out,
+                     int N, int S, int M, int D, int Lq, int L, int P, int dtype, void* stream);
+PDB_API int pdb_msda_backward(const void* value, const int64_t* shapes_hw, const int64_t* level_start,
+                      const void* loc, const void* attn, const void* grad_out,
+                      void* grad_value, void* grad_loc, void* grad_attn,
+                      int N, int S, int M, int D, int Lq, int L, int P, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Mask head einsum — replaces torch.einsum("bqc,bchw->bqhw")
+ * (mask2former_transformer_decoder.py:449, part_distillation_transformer_decoder.py:244).
+ *   embed (B, Q, C) f32;  feat (B, C, HW) f32;  out (B, Q, HW) f32.
+ * backward:  grad_embed (B,Q,C) = grad_out x feat^T (overwritten);
+ *            grad_feat  (B,C,HW) (+)= embed^T x grad_out  (accumulate != 0 adds into grad_feat).
+ * Either grad pointer may be NULL to skip it.
+ * ---------------------------------------------------------------------------------------------- */
+PDB_API int pdb_mask_einsum_forward(const float* embed, const float* feat, float* out,
+                            int B, int Q, int C, int64_t HW, void* stream);
+PDB_API int pdb_mask_einsum_backward(const float* embed, const float* feat, const float* grad_out,
+                             float* grad_embed, float* grad_feat, int accumulate,
+                             int B, int Q, int C, int64_t HW, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention-mask build — replaces F.interpolate(bilinear, align_corners=False) -> sigmoid() < 0.5
+ * -> repeat over heads (mask2former_transformer_decoder.py:453-457) and the all-masked-row reset
+ * of the next layer (:405).
+ *   logits (B, Q, H, W) f32  ->  mask (B, Q, h*w) uint8, 1 = key NOT attended.  The mask is the same
+ *   for every head, so it is stored once per (b, q) instead of B*heads times.
+ *   row_any (B*Q) int32 workspace: pass zero-filled; after the call row_any[r] != 0 iff row r
+ *   has at least one attended key.  Rows with no attended key are treated as "attend everywhere"
+ *   by pdb_masked_xattn_* (that is the reference's reset at :405); pdb_attn_mask_reset_rows applies
+ *   the same reset to the stored mask for callers that want the reference's tensor.
+ * ---------------------------------------------------------------------------------------------- */
+PDB_API int pdb_attn_mask_build(const float* logits, uint8_t* mask, int32_t* row_any,
+                        int B, int Q, int H, int W, int h, int w, void* stream);
+PDB_API int pdb_attn_mask_reset_rows(uint8_t* mask, const int32_t* row_any, int rows, int64_t hw, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Masked cross-attention core — replaces the scaled-dot-product inside nn.MultiheadAttention as used by
+ * CrossAttentionLayer (mask2former_transformer_decoder.py:84,102-114): softmax(q k^T + mask) v per head.
+ *   q (B, Q, heads*d) f32, already multiplied by 1/sqrt(d);  k, v (B, Lk, heads*d) f32;
+ *   mask (B, Q, Lk) uint8 (1 = masked) or NULL;  row_any (B*Q) int32 or NULL (see above);
+ *   out (B, Q, heads*d);  lse (B, heads, Q) f32 log-sum-exp saved for backward.
+ *   workspace: pdb_masked_xattn_workspace_bytes(...) bytes.
+ * backward overwrites grad_q, grad_k, grad_v.  d must be 32.
+ * ---------------------------------------------------------------------------------------------- */
+PDB_API int64_t pdb_masked_xattn_workspace_bytes(int B, int heads, int Q, int Lk, int d);
+PDB_API int pdb_masked_xattn_forward(const float* q, const float* k, const float* v, const uint8_t* mask,
+                             const int32_t* row_any, float* out, float* lse, void* workspace,
+                             int B, int heads, int Q, int Lk, int d, void* stream);
+PDB_API int pdb_masked_xattn_backward(const float* q, const float* k, const float* v, const uint8_t* mask,
+                              const int32_t* row_any, const float* out, const float* lse,
+                              const float* grad_out, float* grad_q, float* grad_k, float* grad_v,
+                              int B, int heads, int Q, int Lk, int d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Point sampling — replaces detectron2 point_sample == F.grid_sample(input, 2*coords-1,
+ * bilinear, zeros, align_corners=False) at its call sites criterion.py:178-196, matcher.py:130-140.
+ *   src: R_src maps of (H, W), f32 (src_dtype 0) or uint8 0/1 (src_dtype 1);
+ *   map_index (R) int32 or NULL (identity): which map row r samples from;
+ *   coords (Rc, P, 2) f32 (x, y) in [0,1]; coord_index (R) int32 or NULL (identity; a constant 0
+ *   table shares one point set across rows as matcher.py:128 does);
+ *   out (R, P) f32.
+ * backward (f32 maps only): grad_src (R_src, H, W) must be zero-filled by the caller; accumulated.
+ * ---------------------------------------------------------------------------------------------- */
+PDB_API int pdb_point_sample_forward(const void* src, int src_dtype, const int32_t* map_index,
+                             const float* coords, const int32_t* coord_index, float* out,
+                             int R, int P, int H, int W, void* stream);
+PDB_API int pdb_point_sample_backward(const float* grad_out, const int32_t* map_index, const float* coords,
+                              const int32_t* coord_index, float* grad_src,
+                              int R, int P, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Matcher cost — replaces batch_sigmoid_ce_loss / batch_dice_loss and the weighted sum
+ * (matcher.py:19-66,108-158) for every image of the batch in one launch.
+ *   pred_pts (B*Q, P) f32 sampled logits; tgt_pts (Ktot, P) f32 sampled gt (0..1);
+ *   cls_prob (B*Q, Kc) f32 class probabilities (softmax / sigmoid already applied);
+ *   tgt_label (Ktot) int32; tgt_offset: HOST int32[B+1] prefix offsets of each image's targets;
+ *   cost (sum_b Q*K_b) f32, image b's (Q, K_b) row-major block starting at Q*tgt_offset[b].
+ * ---------------------------------------------------------------------------------------------- */
+PDB_API int pdb_matcher_cost(const float* pred_pts, const float* tgt_pts, const float* cls_prob,
+                     const int32_t* tgt_label, const int32_t* tgt_offset, float* cost,
+                     int B, int Q, int Kc, int P, float w_class, float w_mask, float w_dice, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched rectangular linear sum assignment — replaces C.cpu() + scipy linear_sum_assignment +
+ * the ascending-cost re-ordering (matcher.py:159-163).  One warp per image; float64 arithmetic
+ * and tie-breaking follow SciPy's shortest-augmenting-path solver.
+ *   cost as produced by pdb_matcher_cost; tgt_offset HOST int32[B+1];
+ *   pred_idx / tgt_idx (Ktot) int64: image b's min(Q, K_b) matches at [tgt_offset[b], ...),
+ *   ordered by ascending matched cost; when K_b > Q the tail of the block is filled with -1.
+ * Limits: Q <= 1024, K_b <= 1024.
+ * ---------------------------------------------------------------------------------------------- */
+PDB_API int pdb_lsap_batched(const float* cost, const int32_t* tgt_offset, int64_t* pred_idx, int64_t* tgt_idx,
+                     int B, int Q, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Point-sampled mask loss — replaces point_sample x2 + sigmoid_ce_loss + dice_loss
+ * (criterion.py:25-69,188-206) fused over all matched pairs.
+ *   pred (Rp, H, W) f32 mask logits; pred_index (Nm) int64 (-1 entries are skipped);
+ *   gt (Rg, Hg, Wg) uint8; gt_index (Nm) int64; coords (Nm, P, 2) f32;
+ *   sums (Nm, 4) f32 out: [sum BCE, sum s*t, sum s, sum t] per pair (loss assembly is host-side:
+ *   loss_mask = sum_i BCE_i/P / num_masks, loss_dice = sum_i (1-(2 st+1)/(s+t+1)) / num_masks).
+ * backward: g_bce, g_dice (Nm) f32 = d loss / d (BCE_i/P), d loss / d dice_i; grad_pred (Rp, H, W)
+ * must be zero-filled by the caller; accumulated.
+ * ---------------------------------------------------------------------------------------------- */
+PDB_API int pdb_point_loss_forward(const float* pred, const int64_t* pred_index, const uint8_t* gt,
+                           const int64_t* gt_index, const float* coords, float* sums,
+                           int Nm, int P, int H, int W, int Hg, int Wg, void* stream);
+PDB_API int pdb_point_loss_backward(const float* pred, const int64_t* pred_index, const uint8_t* gt,
+                            const int64_t* gt_index, const float* coords, const float* sums,
+                            const float* g_bce, const float* g_dice, float* grad_pred,
+                            int Nm, int P, int H, int W, int Hg, int Wg, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * PartDistillation classifier rows — replaces the float64 Linear(256, P*O+1) followed by
+ * apply_gradient_mask (part_distillation_transformer_decoder.py:107,215-230,237-238): only the
+ * P columns of each image's object class plus the last (no-object) column are ever used.
+ *   x (B, Q, C) f32 (promoted to f64 inside); weight (Ncls, C) f64; bias (Ncls) f64;
+ *   obj (B) int32 object class per image; out (B, Q, Pn+1) f64.
+ * backward: grad_x (B,Q,C) f32 overwritten; grad_weight (Ncls, C) / grad_bias (Ncls) f64 must be
+ * zero-filled by the caller (dense zero rows keep AdamW parity); rows are accumulated atomically.
+ * ---------------------------------------------------------------------------------------------- */
+PDB_API int pdb_class_rows_forward(const float* x, const double* weight, const double* bias, const int32_t* obj,
+                           double* out, int B, int Q, int C, int Pn, int64_t Ncls, void* stream);
+PDB_API int pdb_class_rows_backward(const float* x, const double* weight, const int32_t* obj, const double* grad_out,
+                            float* grad_x, double* grad_weight, double* grad_bias,
+                            int B, int Q, int C, int Pn, int64_t Ncls, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDB200_H_ */

@@ -2,3 +2,4 @@
 # symbols the reference hot path touches; it exists so
 # /root/reference can be imported read-only in the build container to generate
 # golden vectors.  Never imported by the product package.
+__pdb_oracle_shim__ = True

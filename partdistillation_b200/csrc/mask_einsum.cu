@@ -1,0 +1,166 @@
+// Mask-head einsum  out[b,q,hw] = sum_c embed[b,q,c] * feat[b,c,hw]  and its two gradients.
+// Reference: torch.einsum("bqc,bchw->bqhw") at mask2former_transformer_decoder.py:449 and
+// part_distillation_transformer_decoder.py:244 (autograd supplies the backward there).
+//
+// Per image this is a (Q x C) x (C x HW) product with Q ~ 100, C = 256, HW = 65 536: the feature
+// map is streamed once from HBM (134 MB at B=2) and the (Q x HW) logits are written once (52 MB).
+//
+// Round-1 kernel: a shared-memory tiled fp32 FFMA GEMM (128x128x16 tiles, 8x8 register micro-tiles)
+// shared by the forward and both backward products through layout flags.  fp32 FFMA arithmetic keeps
+// the logits within ~1e-6 of the reference; see DESIGN.md for the roofline (FFMA-bound) and the
+// planned tcgen05 3xTF32 replacement.
+#include "common.cuh"
+
+namespace pdb {
+
+constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8, GEMM_THREADS = 256;
+
+enum { STORE = 0, ACCUM = 1, ATOMIC = 2 };
+
+// C[m][n] (+)= sum_k A(m,k) * B(k,n) for one batch item (blockIdx.z / ksplit) and one K slice.
+//   A(m,k) at A[m*lda + k] if A_KC (k contiguous) else A[k*lda + m]
+//   B(k,n) at B[k*ldb + n] if B_NC (n contiguous) else B[n*ldb + k]
+template <bool A_KC, bool B_NC, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS)
+tile_gemm(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ C, int M, int N, int64_t K,
+          int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB, int64_t strideC, int ksplit,
+          int64_t kchunk) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int b = blockIdx.z / ksplit;
+    const int ks = blockIdx.z - b * ksplit;
+    const int64_t k_begin = (int64_t)ks * kchunk;
+    const int64_t k_end = min(K, k_begin + kchunk);
+    A += (int64_t)b * strideA;
+    Bm += (int64_t)b * strideB;
+    C += (int64_t)b * strideC;
+    const int m0 = blockIdx.y * BM;
+    const int64_t n0 = (int64_t)blockIdx.x * BN;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;     // tx -> columns, ty -> rows
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int jn = 0; jn < TN; ++jn) acc[i][jn] = 0.f;
+
+    for (int64_t k0 = k_begin; k0 < k_end; k0 += BK) {
+        // ---- A tile (BM x BK) -> As[k][m]
+        if (A_KC) {
+#pragma unroll
+            for (int it = 0; it < (BM * BK) / GEMM_THREADS; ++it) {
+                int e = it * GEMM_THREADS + tid;
+                int kk = e & (BK - 1), mm = e >> 4;
+                int gm = m0 + mm;
+                int64_t gk = k0 + kk;
+                As[kk][mm] = (gm < M && gk < k_end) ? __ldg(A + (int64_t)gm * lda + gk) : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < (BM * BK) / GEMM_THREADS; ++it) {
+                int e = it * GEMM_THREADS + tid;
+                int mm = e & (BM - 1), kk = e >> 7;
+                int gm = m0 + mm;
+                int64_t gk = k0 + kk;
+                As[kk][mm] = (gm < M && gk < k_end) ? __ldg(A + gk * lda + gm) : 0.f;
+            }
+        }
+        // ---- B tile (BK x BN) -> Bs[k][n]
+        if (B_NC) {
+#pragma unroll
+            for (int it = 0; it < (BN * BK) / GEMM_THREADS; ++it) {
+                int e = it * GEMM_THREADS + tid;
+                int nn = e & (BN - 1), kk = e >> 7;
+                int64_t gn = n0 + nn, gk = k0 + kk;
+                Bs[kk][nn] = (gn < N && gk < k_end) ? __ldg(Bm + gk * ldb + gn) : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < (BN * BK) / GEMM_THREADS; ++it) {
+                int e = it * GEMM_THREADS + tid;
+                int kk = e & (BK - 1), nn = e >> 4;
+                int64_t gn = n0 + nn, gk = k0 + kk;
+                Bs[kk][nn] = (gn < N && gk < k_end) ? __ldg(Bm + gn * ldb + gk) : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[TM], bv[TN];
+            float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+            float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int jn = 0; jn < TN; ++jn) acc[i][jn] = fmaf(a[i], bv[jn], acc[i][jn]);
+        }
+        __syncthreads();
+    }
+    // rows: ty*4+{0..3} and 64+ty*4+{0..3}; cols: tx*4+{0..3} and 64+tx*4+{0..3}
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (gm >= M) continue;
+#pragma unroll
+        for (int jn = 0; jn < TN; ++jn) {
+            int64_t gn = n0 + (jn < 4 ? tx * 4 + jn : 64 + tx * 4 + (jn - 4));
+            if (gn >= N) continue;
+            float* p = C + (int64_t)gm * ldc + gn;
+            if (MODE == STORE) *p = acc[i][jn];
+            else if (MODE == ACCUM) *p += acc[i][jn];
+            else atomicAdd(p, acc[i][jn]);
+        }
+    }
+}
+
+}  // namespace pdb
+
+using namespace pdb;
+
+extern "C" int pdb_mask_einsum_forward(const float* embed, const float* feat, float* out, int B, int Q, int C,
+                                       int64_t HW, void* stream) {
+    PDB_REQUIRE(embed && feat && out, "mask_einsum_forward: null pointer");
+    PDB_REQUIRE(B > 0 && Q > 0 && C > 0 && HW > 0, "mask_einsum_forward: non-positive dimension");
+    dim3 grid((unsigned)((HW + BN - 1) / BN), (unsigned)((Q + BM - 1) / BM), (unsigned)B);
+    tile_gemm<true, true, STORE><<<grid, GEMM_THREADS, 0, as_stream(stream)>>>(
+        embed, feat, out, Q, (int)HW, C, C, HW, HW, (int64_t)Q * C, (int64_t)C * HW, (int64_t)Q * HW, 1, C);
+    return launched("mask_einsum_forward");
+}
+
+extern "C" int pdb_mask_einsum_backward(const float* embed, const float* feat, const float* grad_out,
+                                        float* grad_embed, float* grad_feat, int accumulate, int B, int Q, int C,
+                                        int64_t HW, void* stream) {
+    PDB_REQUIRE(embed && feat && grad_out, "mask_einsum_backward: null pointer");
+    PDB_REQUIRE(B > 0 && Q > 0 && C > 0 && HW > 0, "mask_einsum_backward: non-positive dimension");
+    cudaStream_t st = as_stream(stream);
+    if (grad_feat) {
+        // grad_feat[b] (C x HW) (+)= embed[b]^T (C x Q) * grad_out[b] (Q x HW)
+        dim3 grid((unsigned)((HW + BN - 1) / BN), (unsigned)((C + BM - 1) / BM), (unsigned)B);
+        if (accumulate)
+            tile_gemm<false, true, ACCUM><<<grid, GEMM_THREADS, 0, st>>>(
+                embed, grad_out, grad_feat, C, (int)HW, Q, C, HW, HW, (int64_t)Q * C, (int64_t)Q * HW,
+                (int64_t)C * HW, 1, Q);
+        else
+            tile_gemm<false, true, STORE><<<grid, GEMM_THREADS, 0, st>>>(
+                embed, grad_out, grad_feat, C, (int)HW, Q, C, HW, HW, (int64_t)Q * C, (int64_t)Q * HW,
+                (int64_t)C * HW, 1, Q);
+        PDB_TRY(launched("mask_einsum_backward(grad_feat)"));
+    }
+    if (grad_embed) {
+        // grad_embed[b] (Q x C) = grad_out[b] (Q x HW) * feat[b]^T (HW x C); split-K over HW
+        cudaMemsetAsync(grad_embed, 0, sizeof(float) * (size_t)B * Q * C, st);
+        int64_t kchunk = 1024;
+        int ksplit = (int)((HW + kchunk - 1) / kchunk);
+        dim3 grid((unsigned)((C + BN - 1) / BN), (unsigned)((Q + BM - 1) / BM), (unsigned)(B * ksplit));
+        tile_gemm<true, false, ATOMIC><<<grid, GEMM_THREADS, 0, st>>>(
+            grad_out, feat, grad_embed, Q, C, HW, HW, HW, C, (int64_t)Q * HW, (int64_t)C * HW, (int64_t)Q * C, ksplit,
+            kchunk);
+        PDB_TRY(launched("mask_einsum_backward(grad_embed)"));
+    }
+    return PDB_OK;
+}

@@ -1,0 +1,398 @@
+// Multi-scale deformable attention: bilinear gather (forward) and scatter (backward).
+//
+// Semantics follow the reference's production arithmetic, ms_deform_attn_core_pytorch
+// (ops/functions/ms_deform_attn_func.py:55-75): per level F.grid_sample(value_l, 2*loc-1, bilinear,
+// zeros, align_corners=False), times the attention weight, summed over levels and points.  The
+// reference's own (unused) CUDA kernel is ops/src/cuda/ms_deform_im2col_cuda.cuh:242-304 (forward)
+// and :306-408 (backward, D=32 variant).
+//
+// Layout in HBM (unchanged from the reference operator boundary):
+//   value (N, S, M, D): one (pixel, head) = D contiguous floats = one 128-byte line for D=32.
+//   loc (N, Lq, M, L, P, 2), attn (N, Lq, M, L, P), out (N, Lq, M*D).
+//
+// Fast path (f32, D == 32): a "slot" is one (n, q, m).  8 lanes share a slot, each lane owns 4
+// channels and issues LDG.128, so a warp instruction moves 4 slots x 128 B: the L1 data path
+// (128 B/clk/SM), not the LSU issue rate, is the limiter.  Sampling locations and weights of the
+// 32 slots of a CTA are staged through shared memory with coalesced loads and read back as
+// broadcasts.
+#include "common.cuh"
+
+namespace pdb {
+
+// ------------------------------------------------------------------------------------------------
+// generic path: one thread per (slot, channel); float or double; any D
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void msda_fwd_generic(const T* __restrict__ value, const __grid_constant__ LevelTable lt, const T* __restrict__ loc,
+                                 const T* __restrict__ attn, T* __restrict__ out, int64_t total, int S, int M,
+                                 int D, int Lq, int L, int P) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int d = (int)(idx % D);
+    int64_t g = idx / D;           // slot = (n*Lq + q)*M + m
+    int m = (int)(g % M);
+    int64_t n = g / M / Lq;
+    const T* lp = loc + g * L * P * 2;
+    const T* ap = attn + g * L * P;
+    T acc = 0;
+    for (int l = 0; l < L; ++l) {
+        const int H = lt.h[l], W = lt.w[l];
+        const T* vb = value + ((n * S + lt.start[l]) * M + m) * (int64_t)D + d;
+        for (int p = 0; p < P; ++p) {
+            T gx = T(2) * lp[(l * P + p) * 2] - T(1);
+            T gy = T(2) * lp[(l * P + p) * 2 + 1] - T(1);
+            T x = ((gx + T(1)) * T(W) - T(1)) * T(0.5);
+            T y = ((gy + T(1)) * T(H) - T(1)) * T(0.5);
+            T x0f = floor(x), y0f = floor(y);
+            T wx1 = x - x0f, wy1 = y - y0f, wx0 = T(1) - wx1, wy0 = T(1) - wy1;
+            int x0 = (int)x0f, y0 = (int)y0f;
+            T s = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                int xi = x0 + (c & 1), yi = y0 + (c >> 1);
+                if (xi >= 0 && xi < W && yi >= 0 && yi < H) {
+                    T w = ((c & 1) ? wx1 : wx0) * ((c >> 1) ? wy1 : wy0);
+                    s += w * vb[((int64_t)yi * W + xi) * M * D];
+                }
+            }
+            acc += ap[l * P + p] * s;
+        }
+    }
+    out[idx] = acc;
+}
+
+template <typename T>
+__global__ void msda_bwd_generic(const T* __restrict__ value, const __grid_constant__ LevelTable lt, const T* __restrict__ loc,
+                                 const T* __restrict__ attn, const T* __restrict__ grad_out,
+                                 T* __restrict__ grad_value, T* __restrict__ grad_loc, T* __restrict__ grad_attn,
+                                 int64_t total, int S, int M, int D, int Lq, int L, int P) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int d = (int)(idx % D);
+    int64_t g = idx / D;
+    int m = (int)(g % M);
+    int64_t n = g / M / Lq;
+    const T* lp = loc + g * L * P * 2;
+    const T* ap = attn + g * L * P;
+    const T go = grad_out[idx];
+    for (int l = 0; l < L; ++l) {
+        const int H = lt.h[l], W = lt.w[l];
+        const int64_t base = ((n * S + lt.start[l]) * M + m) * (int64_t)D + d;
+        for (int p = 0; p < P; ++p) {
+            T gx = T(2) * lp[(l * P + p) * 2] - T(1);
+            T gy = T(2) * lp[(l * P + p) * 2 + 1] - T(1);
+            T x = ((gx + T(1)) * T(W) - T(1)) * T(0.5);
+            T y = ((gy + T(1)) * T(H) - T(1)) * T(0.5);
+            T x0f = floor(x), y0f = floor(y);
+            T wx1 = x - x0f, wy1 = y - y0f, wx0 = T(1) - wx1, wy0 = T(1) - wy1;
+            int x0 = (int)x0f, y0 = (int)y0f;
+            T a = ap[l * P + p];
+            T v[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                int xi = x0 + (c & 1), yi = y0 + (c >> 1);
+                v[c] = 0;
+                if (xi >= 0 && xi < W && yi >= 0 && yi < H) {
+                    int64_t off = base + ((int64_t)yi * W + xi) * M * D;
+                    v[c] = value[off];
+                    T w = ((c & 1) ? wx1 : wx0) * ((c >> 1) ? wy1 : wy0);
+                    atomicAdd(grad_value + off, w * a * go);
+                }
+            }
+            T ga = (wy0 * (wx0 * v[0] + wx1 * v[1]) + wy1 * (wx0 * v[2] + wx1 * v[3])) * go;
+            T gxl = (wy0 * (v[1] - v[0]) + wy1 * (v[3] - v[2])) * go * a * T(W);
+            T gyl = (wx0 * (v[2] - v[0]) + wx1 * (v[3] - v[1])) * go * a * T(H);
+            atomicAdd(grad_attn + g * L * P + l * P + p, ga);
+            atomicAdd(grad_loc + (g * L * P + l * P + p) * 2, gxl);
+            atomicAdd(grad_loc + (g * L * P + l * P + p) * 2 + 1, gyl);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast path: f32, D == 32, 8 lanes per slot, 32 slots per 256-thread CTA
+// ------------------------------------------------------------------------------------------------
+constexpr int kSlotsPerCta = 32;
+constexpr int kFastThreads = 256;
+
+struct Tap {
+    float w[4];      // bilinear weight x attention weight per corner (0 when the corner is outside)
+    int off[4];      // float offset of the corner inside the level (clamped when outside)
+};
+
+__device__ __forceinline__ void tap_setup(float lx, float ly, int H, int W, int rowstride,
+                                          float& wx0, float& wx1, float& wy0, float& wy1, int off[4], bool ok[4]) {
+    // grid_sample(align_corners=False) un-normalisation of g = 2*loc - 1, evaluated without FMA
+    // contraction so that it follows the fp32 reference step by step.
+    float gx = __fsub_rn(__fmul_rn(2.f, lx), 1.f);
+    float gy = __fsub_rn(__fmul_rn(2.f, ly), 1.f);
+    float x = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)W), 1.f), 0.5f);
+    float y = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)H), 1.f), 0.5f);
+    // keep the float->int conversion defined for wild (learned) offsets
+    x = fminf(fmaxf(x, -2.f), (float)W + 1.f);
+    y = fminf(fmaxf(y, -2.f), (float)H + 1.f);
+    float x0f = floorf(x), y0f = floorf(y);
+    wx1 = x - x0f; wy1 = y - y0f; wx0 = 1.f - wx1; wy0 = 1.f - wy1;
+    int x0 = (int)x0f, y0 = (int)y0f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        int xi = x0 + (c & 1), yi = y0 + (c >> 1);
+        ok[c] = (xi >= 0) && (xi < W) && (yi >= 0) && (yi < H);
+        int xc = min(max(xi, 0), W - 1), yc = min(max(yi, 0), H - 1);
+        off[c] = (yc * W + xc) * rowstride;
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(kFastThreads)
+msda_fwd_d32(const float* __restrict__ value, const __grid_constant__ LevelTable lt, const float* __restrict__ loc,
+             const float* __restrict__ attn, float* __restrict__ out, int64_t slots, int S, int M, int Lq, int L) {
+    extern __shared__ float smem[];
+    const int LP = L * P;
+    const int loc_stride = LP * 2 + 2;
+    const int attn_stride = LP + 1;
+    float* s_loc = smem;
+    float* s_attn = smem + kSlotsPerCta * loc_stride;
+
+    const int64_t slot0 = (int64_t)blockIdx.x * kSlotsPerCta;
+    const int nslots = (int)min((int64_t)kSlotsPerCta, slots - slot0);
+    // coalesced staging of the CTA's sampling locations and weights
+    {
+        const float* gl = loc + slot0 * LP * 2;
+        for (int i = threadIdx.x; i < nslots * LP * 2; i += kFastThreads) {
+            int s = i / (LP * 2), r = i - s * (LP * 2);
+            s_loc[s * loc_stride + r] = __ldg(gl + i);
+        }
+        const float* ga = attn + slot0 * LP;
+        for (int i = threadIdx.x; i < nslots * LP; i += kFastThreads) {
+            int s = i / LP, r = i - s * LP;
+            s_attn[s * attn_stride + r] = __ldg(ga + i);
+        }
+    }
+    __syncthreads();
+    const int sl = threadIdx.x >> 3;     // slot within CTA
+    const int j = threadIdx.x & 7;       // 4-channel group
+    if (sl >= nslots) return;
+    const int64_t g = slot0 + sl;
+    const int m = (int)(g % M);
+    const int64_t n = g / M / Lq;
+    const int rowstride = M * 32;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* myloc = s_loc + sl * loc_stride;
+    const float* myattn = s_attn + sl * attn_stride;
+#pragma unroll 1
+    for (int l = 0; l < L; ++l) {
+        const int H = lt.h[l], W = lt.w[l];
+        const float* vb = value + ((n * S + lt.start[l]) * M + m) * 32 + j * 4;
+        float w[P][4];
+        int off[P][4];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            float2 lxy = *reinterpret_cast<const float2*>(myloc + (l * P + p) * 2);
+            float a = myattn[l * P + p];
+            float wx0, wx1, wy0, wy1;
+            bool ok[4];
+            tap_setup(lxy.x, lxy.y, H, W, rowstride, wx0, wx1, wy0, wy1, off[p], ok);
+            w[p][0] = ok[0] ? a * (wy0 * wx0) : 0.f;
+            w[p][1] = ok[1] ? a * (wy0 * wx1) : 0.f;
+            w[p][2] = ok[2] ? a * (wy1 * wx0) : 0.f;
+            w[p][3] = ok[3] ? a * (wy1 * wx1) : 0.f;
+        }
+        float4 v[P][4];
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[p][c] = __ldg(reinterpret_cast<const float4*>(vb + off[p][c]));
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                acc.x = fmaf(w[p][c], v[p][c].x, acc.x);
+                acc.y = fmaf(w[p][c], v[p][c].y, acc.y);
+                acc.z = fmaf(w[p][c], v[p][c].z, acc.z);
+                acc.w = fmaf(w[p][c], v[p][c].w, acc.w);
+            }
+    }
+    *reinterpret_cast<float4*>(out + g * 32 + j * 4) = acc;
+}
+
+template <int P>
+__global__ void __launch_bounds__(kFastThreads)
+msda_bwd_d32(const float* __restrict__ value, const __grid_constant__ LevelTable lt, const float* __restrict__ loc,
+             const float* __restrict__ attn, const float* __restrict__ grad_out, float* __restrict__ grad_value,
+             float* __restrict__ grad_loc, float* __restrict__ grad_attn, int64_t slots, int S, int M, int Lq, int L) {
+    extern __shared__ float smem[];
+    const int LP = L * P;
+    const int loc_stride = LP * 2 + 2;
+    const int attn_stride = LP + 1;
+    float* s_loc = smem;
+    float* s_attn = s_loc + kSlotsPerCta * loc_stride;
+    float* s_gloc = s_attn + kSlotsPerCta * attn_stride;     // dense (slot, LP*2)
+    float* s_gattn = s_gloc + kSlotsPerCta * LP * 2;         // dense (slot, LP)
+
+    const int64_t slot0 = (int64_t)blockIdx.x * kSlotsPerCta;
+    const int nslots = (int)min((int64_t)kSlotsPerCta, slots - slot0);
+    {
+        const float* gl = loc + slot0 * LP * 2;
+        for (int i = threadIdx.x; i < nslots * LP * 2; i += kFastThreads) {
+            int s = i / (LP * 2), r = i - s * (LP * 2);
+            s_loc[s * loc_stride + r] = __ldg(gl + i);
+        }
+        const float* ga = attn + slot0 * LP;
+        for (int i = threadIdx.x; i < nslots * LP; i += kFastThreads) {
+            int s = i / LP, r = i - s * LP;
+            s_attn[s * attn_stride + r] = __ldg(ga + i);
+        }
+    }
+    __syncthreads();
+    const int sl = threadIdx.x >> 3;
+    const int j = threadIdx.x & 7;
+    if (sl < nslots) {
+        const int64_t g = slot0 + sl;
+        const int m = (int)(g % M);
+        const int64_t n = g / M / Lq;
+        const int rowstride = M * 32;
+        const float4 go = __ldg(reinterpret_cast<const float4*>(grad_out + g * 32 + j * 4));
+        const float* myloc = s_loc + sl * loc_stride;
+        const float* myattn = s_attn + sl * attn_stride;
+#pragma unroll 1
+        for (int l = 0; l < L; ++l) {
+            const int H = lt.h[l], W = lt.w[l];
+            const int64_t lbase = ((n * S + lt.start[l]) * M + m) * 32 + j * 4;
+            const float* vb = value + lbase;
+            float* gvb = grad_value + lbase;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                float2 lxy = *reinterpret_cast<const float2*>(myloc + (l * P + p) * 2);
+                float a = myattn[l * P + p];
+                float wx0, wx1, wy0, wy1;
+                bool ok[4];
+                int off[4];
+                tap_setup(lxy.x, lxy.y, H, W, rowstride, wx0, wx1, wy0, wy1, off, ok);
+                float dot[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    dot[c] = 0.f;
+                    if (ok[c]) {
+                        float4 v = __ldg(reinterpret_cast<const float4*>(vb + off[c]));
+                        dot[c] = v.x * go.x + v.y * go.y + v.z * go.z + v.w * go.w;
+                        float wc = a * (((c >> 1) ? wy1 : wy0) * ((c & 1) ? wx1 : wx0));
+                        red_add_v4(gvb + off[c], wc * go.x, wc * go.y, wc * go.z, wc * go.w);
+                    }
+                }
+                float ga = wy0 * (wx0 * dot[0] + wx1 * dot[1]) + wy1 * (wx0 * dot[2] + wx1 * dot[3]);
+                float gx = (wy0 * (dot[1] - dot[0]) + wy1 * (dot[3] - dot[2])) * a * (float)W;
+                float gy = (wx0 * (dot[2] - dot[0]) + wx1 * (dot[3] - dot[1])) * a * (float)H;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) {
+                    ga += __shfl_xor_sync(0xffffffffu, ga, o);
+                    gx += __shfl_xor_sync(0xffffffffu, gx, o);
+                    gy += __shfl_xor_sync(0xffffffffu, gy, o);
+                }
+                if (j == 0) {
+                    s_gattn[sl * LP + l * P + p] = ga;
+                    s_gloc[(sl * LP + l * P + p) * 2] = gx;
+                    s_gloc[(sl * LP + l * P + p) * 2 + 1] = gy;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    float* ol = grad_loc + slot0 * LP * 2;
+    for (int i = threadIdx.x; i < nslots * LP * 2; i += kFastThreads) ol[i] = s_gloc[i];
+    float* oa = grad_attn + slot0 * LP;
+    for (int i = threadIdx.x; i < nslots * LP; i += kFastThreads) oa[i] = s_gattn[i];
+}
+
+static int make_levels(const int64_t* shapes_hw, const int64_t* level_start, int L, int S, LevelTable& lt) {
+    PDB_REQUIRE(L >= 1 && L <= kMaxLevels, "msda: L=%d outside [1,%d]", L, kMaxLevels);
+    for (int l = 0; l < L; ++l) {
+        int64_t h = shapes_hw[2 * l], w = shapes_hw[2 * l + 1], st = level_start[l];
+        PDB_REQUIRE(h > 0 && w > 0 && st >= 0 && st + h * w <= S, "msda: level %d (%lld x %lld @ %lld) exceeds S=%d",
+                    l, (long long)h, (long long)w, (long long)st, S);
+        lt.h[l] = (int)h; lt.w[l] = (int)w; lt.start[l] = (int)st;
+    }
+    return PDB_OK;
+}
+
+template <typename T>
+static int fwd_generic(const void* value, const LevelTable& lt, const void* loc, const void* attn, void* out,
+                       int N, int S, int M, int D, int Lq, int L, int P, cudaStream_t st) {
+    int64_t total = (int64_t)N * Lq * M * D;
+    int threads = 256;
+    int64_t blocks = (total + threads - 1) / threads;
+    msda_fwd_generic<T><<<(unsigned)blocks, threads, 0, st>>>((const T*)value, lt, (const T*)loc, (const T*)attn,
+                                                               (T*)out, total, S, M, D, Lq, L, P);
+    return launched("msda_fwd_generic");
+}
+
+template <typename T>
+static int bwd_generic(const void* value, const LevelTable& lt, const void* loc, const void* attn, const void* go,
+                       void* gv, void* gl, void* ga, int N, int S, int M, int D, int Lq, int L, int P,
+                       cudaStream_t st) {
+    int64_t total = (int64_t)N * Lq * M * D;
+    cudaMemsetAsync(gl, 0, sizeof(T) * (size_t)N * Lq * M * L * P * 2, st);
+    cudaMemsetAsync(ga, 0, sizeof(T) * (size_t)N * Lq * M * L * P, st);
+    int threads = 256;
+    int64_t blocks = (total + threads - 1) / threads;
+    msda_bwd_generic<T><<<(unsigned)blocks, threads, 0, st>>>((const T*)value, lt, (const T*)loc, (const T*)attn,
+                                                               (const T*)go, (T*)gv, (T*)gl, (T*)ga, total, S, M, D,
+                                                               Lq, L, P);
+    return launched("msda_bwd_generic");
+}
+
+}  // namespace pdb
+
+using namespace pdb;
+
+extern "C" int pdb_msda_forward(const void* value, const int64_t* shapes_hw, const int64_t* level_start,
+                                const void* loc, const void* attn, void* out, int N, int S, int M, int D, int Lq,
+                                int L, int P, int dtype, void* stream) {
+    PDB_REQUIRE(value && loc && attn && out && shapes_hw && level_start, "msda_forward: null pointer");
+    PDB_REQUIRE(N > 0 && S > 0 && M > 0 && D > 0 && Lq > 0 && P > 0, "msda_forward: non-positive dimension");
+    LevelTable lt;
+    PDB_TRY(make_levels(shapes_hw, level_start, L, S, lt));
+    cudaStream_t st = as_stream(stream);
+    if (dtype == PDB_F64) return fwd_generic<double>(value, lt, loc, attn, out, N, S, M, D, Lq, L, P, st);
+    PDB_REQUIRE(dtype == PDB_F32, "msda_forward: dtype %d (only f32/f64, as ms_deform_attn_cuda.cu:70)", dtype);
+    if (D == 32 && P == 4 && (int64_t)S * M * 32 < (1ll << 31)) {
+        int64_t slots = (int64_t)N * Lq * M;
+        int64_t blocks = (slots + kSlotsPerCta - 1) / kSlotsPerCta;
+        size_t smem = sizeof(float) * kSlotsPerCta * ((L * P * 2 + 2) + (L * P + 1));
+        msda_fwd_d32<4><<<(unsigned)blocks, kFastThreads, smem, st>>>((const float*)value, lt, (const float*)loc,
+                                                                       (const float*)attn, (float*)out, slots, S, M,
+                                                                       Lq, L);
+        return launched("msda_fwd_d32");
+    }
+    return fwd_generic<float>(value, lt, loc, attn, out, N, S, M, D, Lq, L, P, st);
+}
+
+extern "C" int pdb_msda_backward(const void* value, const int64_t* shapes_hw, const int64_t* level_start,
+                                 const void* loc, const void* attn, const void* grad_out, void* grad_value,
+                                 void* grad_loc, void* grad_attn, int N, int S, int M, int D, int Lq, int L, int P,
+                                 int dtype, void* stream) {
+    PDB_REQUIRE(value && loc && attn && grad_out && grad_value && grad_loc && grad_attn && shapes_hw && level_start,
+                "msda_backward: null pointer");
+    PDB_REQUIRE(N > 0 && S > 0 && M > 0 && D > 0 && Lq > 0 && P > 0, "msda_backward: non-positive dimension");
+    LevelTable lt;
+    PDB_TRY(make_levels(shapes_hw, level_start, L, S, lt));
+    cudaStream_t st = as_stream(stream);
+    size_t esz = dtype == PDB_F64 ? 8 : 4;
+    PDB_REQUIRE(dtype == PDB_F32 || dtype == PDB_F64, "msda_backward: dtype %d", dtype);
+    cudaMemsetAsync(grad_value, 0, esz * (size_t)N * S * M * D, st);
+    if (dtype == PDB_F64)
+        return bwd_generic<double>(value, lt, loc, attn, grad_out, grad_value, grad_loc, grad_attn, N, S, M, D, Lq, L,
+                                   P, st);
+    if (D == 32 && P == 4 && (int64_t)S * M * 32 < (1ll << 31)) {
+        int64_t slots = (int64_t)N * Lq * M;
+        int64_t blocks = (slots + kSlotsPerCta - 1) / kSlotsPerCta;
+        int LP = L * P;
+        size_t smem = sizeof(float) * kSlotsPerCta * ((LP * 2 + 2) + (LP + 1) + LP * 2 + LP);
+        msda_bwd_d32<4><<<(unsigned)blocks, kFastThreads, smem, st>>>(
+            (const float*)value, lt, (const float*)loc, (const float*)attn, (const float*)grad_out,
+            (float*)grad_value, (float*)grad_loc, (float*)grad_attn, slots, S, M, Lq, L);
+        return launched("msda_bwd_d32");
+    }
+    return bwd_generic<float>(value, lt, loc, attn, grad_out, grad_value, grad_loc, grad_attn, N, S, M, D, Lq, L, P,
+                              st);
+}

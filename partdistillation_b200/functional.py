@@ -1,0 +1,397 @@
+"""Host-side operators: torch.autograd Functions over the C ABI of libpdb200.so.
+
+Every function here requires CUDA tensors and the compiled library; nothing falls back to PyTorch
+or to the CPU (the reference's native op is CUDA-only as well: ops/src/ms_deform_attn.h:44).
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+_DT = {torch.float32: 0, torch.float64: 1}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("partdistillation_b200 operators are CUDA-only (no CPU implementation)")
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# MSDeformAttn  (ops/functions/ms_deform_attn_func.py:35-52 — same call signature)
+# --------------------------------------------------------------------------------------------------
+_shape_cache = {}
+
+
+def _host_levels(spatial_shapes, level_start_index):
+    """Accepts python sequences or the reference's int64 device tensors; the tensor form costs one
+    device->host sync per distinct tensor (cached), so callers on the hot path pass sequences."""
+    if isinstance(spatial_shapes, torch.Tensor):
+        key = (spatial_shapes.data_ptr(), spatial_shapes._version, tuple(spatial_shapes.shape),
+               level_start_index.data_ptr() if isinstance(level_start_index, torch.Tensor) else None)
+        hit = _shape_cache.get(key)
+        if hit is None:
+            shapes = [tuple(int(v) for v in r) for r in spatial_shapes.tolist()]
+            starts = ([int(v) for v in level_start_index.tolist()] if isinstance(level_start_index, torch.Tensor)
+                      else [int(v) for v in level_start_index])
+            if len(_shape_cache) > 64:
+                _shape_cache.clear()
+            hit = _shape_cache[key] = (shapes, starts)
+        return hit
+    shapes = [(int(h), int(w)) for h, w in spatial_shapes]
+    if level_start_index is None:
+        starts, s = [], 0
+        for h, w in shapes:
+            starts.append(s)
+            s += h * w
+    elif isinstance(level_start_index, torch.Tensor):
+        starts = [int(v) for v in level_start_index.tolist()]
+    else:
+        starts = [int(v) for v in level_start_index]
+    return shapes, starts
+
+
+class MSDeformAttnFunction(Function):
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                attention_weights, im2col_step=128):
+        _need_cuda(value, sampling_locations, attention_weights)
+        # the reference op hard-asserts contiguity (ms_deform_attn_cuda.cu:34-44)
+        for name, t in (("value", value), ("sampling_loc", sampling_locations), ("attn_weight", attention_weights)):
+            if not t.is_contiguous():
+                raise RuntimeError(f"{name} tensor has to be contiguous")
+        if value.dtype not in _DT or sampling_locations.dtype != value.dtype or attention_weights.dtype != value.dtype:
+            raise RuntimeError("ms_deform_attn: value / sampling_loc / attn_weight must share dtype float32 or float64")
+        N, S, M, D = value.shape
+        _, Lq, _, L, P, _ = sampling_locations.shape
+        step = min(N, int(im2col_step))
+        if N % step != 0:
+            raise RuntimeError(f"batch({N}) must divide im2col_step({step})")
+        shapes, starts = _host_levels(value_spatial_shapes, value_level_start_index)
+        if len(shapes) != L:
+            raise RuntimeError(f"ms_deform_attn: {len(shapes)} spatial shapes for L={L}")
+        out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+        hs = _lib.host_i64([v for hw in shapes for v in hw])
+        st = _lib.host_i64(starts)
+        rc = _lib.load().pdb_msda_forward(value.data_ptr(), hs, st, sampling_locations.data_ptr(),
+                                          attention_weights.data_ptr(), out.data_ptr(), N, S, M, D, Lq, L, P,
+                                          _DT[value.dtype], _stream())
+        _lib.check(rc, "pdb_msda_forward")
+        ctx.save_for_backward(value, sampling_locations, attention_weights)
+        ctx.levels = (shapes, starts)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, loc, attn = ctx.saved_tensors
+        shapes, starts = ctx.levels
+        N, S, M, D = value.shape
+        _, Lq, _, L, P, _ = loc.shape
+        grad_output = _c(grad_output)
+        gv = torch.empty_like(value)
+        gl = torch.empty_like(loc)
+        ga = torch.empty_like(attn)
+        rc = _lib.load().pdb_msda_backward(value.data_ptr(), _lib.host_i64([v for hw in shapes for v in hw]),
+                                           _lib.host_i64(starts), loc.data_ptr(), attn.data_ptr(),
+                                           grad_output.data_ptr(), gv.data_ptr(), gl.data_ptr(), ga.data_ptr(),
+                                           N, S, M, D, Lq, L, P, _DT[value.dtype], _stream())
+        _lib.check(rc, "pdb_msda_backward")
+        return gv, None, None, gl, ga, None
+
+
+def ms_deform_attn(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, im2col_step=128):
+    return MSDeformAttnFunction.apply(value, spatial_shapes, level_start_index, sampling_locations,
+                                      attention_weights, im2col_step)
+
+
+# --------------------------------------------------------------------------------------------------
+# mask-head einsum  bqc,bchw->bqhw  (mask2former_transformer_decoder.py:449)
+# --------------------------------------------------------------------------------------------------
+class MaskEinsumFunction(Function):
+    @staticmethod
+    def forward(ctx, mask_embed, mask_features):
+        _need_cuda(mask_embed, mask_features)
+        if mask_embed.dtype != torch.float32 or mask_features.dtype != torch.float32:
+            raise RuntimeError("mask_einsum: float32 only")
+        mask_embed, mask_features = _c(mask_embed), _c(mask_features)
+        B, Q, C = mask_embed.shape
+        Bf, Cf, H, W = mask_features.shape
+        if B != Bf or C != Cf:
+            raise RuntimeError(f"mask_einsum: shapes {tuple(mask_embed.shape)} x {tuple(mask_features.shape)}")
+        out = torch.empty((B, Q, H, W), dtype=torch.float32, device=mask_embed.device)
+        rc = _lib.load().pdb_mask_einsum_forward(mask_embed.data_ptr(), mask_features.data_ptr(), out.data_ptr(),
+                                                 B, Q, C, H * W, _stream())
+        _lib.check(rc, "pdb_mask_einsum_forward")
+        ctx.save_for_backward(mask_embed, mask_features)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        mask_embed, mask_features = ctx.saved_tensors
+        B, Q, C = mask_embed.shape
+        H, W = mask_features.shape[-2:]
+        grad_out = _c(grad_out)
+        ge = torch.empty_like(mask_embed) if ctx.needs_input_grad[0] else None
+        gf = torch.empty_like(mask_features) if ctx.needs_input_grad[1] else None
+        rc = _lib.load().pdb_mask_einsum_backward(mask_embed.data_ptr(), mask_features.data_ptr(), grad_out.data_ptr(),
+                                                  ge.data_ptr() if ge is not None else None,
+                                                  gf.data_ptr() if gf is not None else None, 0,
+                                                  B, Q, C, H * W, _stream())
+        _lib.check(rc, "pdb_mask_einsum_backward")
+        return ge, gf
+
+
+def mask_einsum(mask_embed, mask_features):
+    return MaskEinsumFunction.apply(mask_embed, mask_features)
+
+
+# --------------------------------------------------------------------------------------------------
+# attention mask  (mask2former_transformer_decoder.py:453-457 and the reset at :405)
+# --------------------------------------------------------------------------------------------------
+def build_attention_mask(pred_masks, size):
+    """pred_masks (B, Q, H, W) f32 logits -> (mask uint8 (B, Q, h*w) with 1 = masked, row_any int32 (B*Q,)).
+    Not differentiable (the reference detaches it)."""
+    _need_cuda(pred_masks)
+    pm = _c(pred_masks.detach())
+    if pm.dtype != torch.float32:
+        pm = pm.float()
+    B, Q, H, W = pm.shape
+    h, w = int(size[0]), int(size[1])
+    mask = torch.empty((B, Q, h * w), dtype=torch.uint8, device=pm.device)
+    row_any = torch.zeros((B * Q,), dtype=torch.int32, device=pm.device)
+    rc = _lib.load().pdb_attn_mask_build(pm.data_ptr(), mask.data_ptr(), row_any.data_ptr(), B, Q, H, W, h, w,
+                                         _stream())
+    _lib.check(rc, "pdb_attn_mask_build")
+    return mask, row_any
+
+
+def reset_fully_masked_rows(mask, row_any):
+    """In-place ``attn_mask[rows that are all True] = False`` on the compact mask."""
+    B, Q, hw = mask.shape
+    rc = _lib.load().pdb_attn_mask_reset_rows(mask.data_ptr(), row_any.data_ptr(), B * Q, hw, _stream())
+    _lib.check(rc, "pdb_attn_mask_reset_rows")
+    return mask
+
+
+# --------------------------------------------------------------------------------------------------
+# masked cross-attention core  (nn.MultiheadAttention inside CrossAttentionLayer, :84,102-114)
+# --------------------------------------------------------------------------------------------------
+class MaskedCrossAttentionFunction(Function):
+    @staticmethod
+    def forward(ctx, q, k, v, mask, row_any, heads):
+        _need_cuda(q, k, v, mask, row_any)
+        q, k, v = _c(q), _c(k), _c(v)
+        if q.dtype != torch.float32 or k.dtype != torch.float32 or v.dtype != torch.float32:
+            raise RuntimeError("masked_cross_attention: float32 only")
+        B, Q, E = q.shape
+        Lk = k.shape[1]
+        d = E // heads
+        if mask is not None:
+            mask = _c(mask)
+            if mask.dtype != torch.uint8 or tuple(mask.shape) != (B, Q, Lk):
+                raise RuntimeError("masked_cross_attention: mask must be uint8 (B, Q, Lk)")
+        lib = _lib.load()
+        ws_bytes = lib.pdb_masked_xattn_workspace_bytes(B, heads, Q, Lk, d)
+        if ws_bytes < 0:
+            raise RuntimeError(f"masked_cross_attention: unsupported shape B={B} heads={heads} Q={Q} Lk={Lk} d={d}")
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=q.device)
+        out = torch.empty_like(q)
+        lse = torch.empty((B, heads, Q), dtype=torch.float32, device=q.device)
+        rc = lib.pdb_masked_xattn_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                          mask.data_ptr() if mask is not None else None,
+                                          row_any.data_ptr() if row_any is not None else None,
+                                          out.data_ptr(), lse.data_ptr(), ws.data_ptr(), B, heads, Q, Lk, d, _stream())
+        _lib.check(rc, "pdb_masked_xattn_forward")
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.mask, ctx.row_any, ctx.heads = mask, row_any, heads
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        q, k, v, out, lse = ctx.saved_tensors
+        mask, row_any, heads = ctx.mask, ctx.row_any, ctx.heads
+        B, Q, E = q.shape
+        Lk = k.shape[1]
+        grad_out = _c(grad_out)
+        gq, gk, gv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        rc = _lib.load().pdb_masked_xattn_backward(
+            q.data_ptr(), k.data_ptr(), v.data_ptr(), mask.data_ptr() if mask is not None else None,
+            row_any.data_ptr() if row_any is not None else None, out.data_ptr(), lse.data_ptr(), grad_out.data_ptr(),
+            gq.data_ptr(), gk.data_ptr(), gv.data_ptr(), B, heads, Q, Lk, E // heads, _stream())
+        _lib.check(rc, "pdb_masked_xattn_backward")
+        return gq, gk, gv, None, None, None
+
+
+def masked_cross_attention(q, k, v, mask, row_any, heads):
+    """q (B, Q, E) pre-scaled, k/v (B, Lk, E), mask uint8 (B, Q, Lk) or None -> (B, Q, E)."""
+    return MaskedCrossAttentionFunction.apply(q, k, v, mask, row_any, heads)
+
+
+# --------------------------------------------------------------------------------------------------
+# point sampling / matcher / point loss  (matcher.py:100-168, criterion.py:147-207)
+# --------------------------------------------------------------------------------------------------
+class PointSampleFunction(Function):
+    @staticmethod
+    def forward(ctx, src, coords, map_index, coord_index):
+        _need_cuda(src, coords)
+        src, coords = _c(src), _c(coords)
+        R_src, H, W = src.shape
+        P = coords.shape[1]
+        R = map_index.shape[0] if map_index is not None else (coord_index.shape[0] if coord_index is not None else R_src)
+        if src.dtype == torch.float32:
+            sd = 0
+        elif src.dtype in (torch.uint8, torch.bool):
+            sd = 1
+        else:
+            raise RuntimeError("point_sample: maps must be float32 or uint8/bool")
+        out = torch.empty((R, P), dtype=torch.float32, device=src.device)
+        rc = _lib.load().pdb_point_sample_forward(src.data_ptr(), sd, map_index.data_ptr() if map_index is not None else None,
+                                                  coords.data_ptr(), coord_index.data_ptr() if coord_index is not None else None,
+                                                  out.data_ptr(), R, P, H, W, _stream())
+        _lib.check(rc, "pdb_point_sample_forward")
+        ctx.save_for_backward(coords)
+        ctx.meta = (map_index, coord_index, tuple(src.shape), sd)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        (coords,) = ctx.saved_tensors
+        map_index, coord_index, shape, sd = ctx.meta
+        if sd != 0 or not ctx.needs_input_grad[0]:
+            return None, None, None, None
+        grad_out = _c(grad_out)
+        R, P = grad_out.shape
+        gs = torch.zeros(shape, dtype=torch.float32, device=grad_out.device)
+        rc = _lib.load().pdb_point_sample_backward(grad_out.data_ptr(), map_index.data_ptr() if map_index is not None else None,
+                                                   coords.data_ptr(), coord_index.data_ptr() if coord_index is not None else None,
+                                                   gs.data_ptr(), R, P, shape[1], shape[2], _stream())
+        _lib.check(rc, "pdb_point_sample_backward")
+        return gs, None, None, None
+
+
+def point_sample(src, coords, map_index=None, coord_index=None):
+    """src (R_src, H, W) f32 / uint8, coords (Rc, P, 2) in [0,1] (x, y) -> (R, P) f32.
+    ``map_index`` / ``coord_index`` (int32) select the map / point set of each output row."""
+    return PointSampleFunction.apply(src, coords, map_index, coord_index)
+
+
+def matcher_cost(pred_pts, tgt_pts, cls_prob, tgt_label, tgt_offset, Q, w_class, w_mask, w_dice):
+    """Cost matrices of every image in one launch; returns the flat f32 buffer (sum_b Q*K_b)."""
+    _need_cuda(pred_pts, tgt_pts, cls_prob, tgt_label)
+    pred_pts, tgt_pts, cls_prob = _c(pred_pts), _c(tgt_pts), _c(cls_prob)
+    B = len(tgt_offset) - 1
+    P = pred_pts.shape[1]
+    Kc = cls_prob.shape[-1]
+    cost = torch.empty((Q * int(tgt_offset[-1]),), dtype=torch.float32, device=pred_pts.device)
+    rc = _lib.load().pdb_matcher_cost(pred_pts.data_ptr(), tgt_pts.data_ptr(), cls_prob.data_ptr(), tgt_label.data_ptr(),
+                                      _lib.host_i32(tgt_offset), cost.data_ptr(), B, Q, Kc, P,
+                                      float(w_class), float(w_mask), float(w_dice), _stream())
+    _lib.check(rc, "pdb_matcher_cost")
+    return cost
+
+
+def lsap_batched(cost, tgt_offset, Q):
+    """Returns (pred_idx, tgt_idx) int64 (Ktot,), per image ordered by ascending matched cost."""
+    _need_cuda(cost)
+    B = len(tgt_offset) - 1
+    Kt = int(tgt_offset[-1])
+    pred_idx = torch.empty((Kt,), dtype=torch.int64, device=cost.device)
+    tgt_idx = torch.empty((Kt,), dtype=torch.int64, device=cost.device)
+    rc = _lib.load().pdb_lsap_batched(cost.data_ptr(), _lib.host_i32(tgt_offset), pred_idx.data_ptr(), tgt_idx.data_ptr(),
+                                      B, Q, _stream())
+    _lib.check(rc, "pdb_lsap_batched")
+    return pred_idx, tgt_idx
+
+
+class PointLossFunction(Function):
+    @staticmethod
+    def forward(ctx, pred, pred_index, gt, gt_index, coords):
+        _need_cuda(pred, pred_index, gt, gt_index, coords)
+        pred, gt, coords = _c(pred), _c(gt), _c(coords)
+        if pred.dtype != torch.float32 or gt.dtype not in (torch.uint8, torch.bool):
+            raise RuntimeError("point_loss: pred float32, gt uint8/bool")
+        Rp, H, W = pred.shape
+        _, Hg, Wg = gt.shape
+        Nm, P = coords.shape[0], coords.shape[1]
+        sums = torch.empty((Nm, 4), dtype=torch.float32, device=pred.device)
+        rc = _lib.load().pdb_point_loss_forward(pred.data_ptr(), pred_index.data_ptr(), gt.data_ptr(), gt_index.data_ptr(),
+                                                coords.data_ptr(), sums.data_ptr(), Nm, P, H, W, Hg, Wg, _stream())
+        _lib.check(rc, "pdb_point_loss_forward")
+        ctx.save_for_backward(pred, pred_index, gt, gt_index, coords, sums)
+        bce = sums[:, 0] / P
+        dice = 1 - (2 * sums[:, 1] + 1) / (sums[:, 2] + sums[:, 3] + 1)
+        return bce, dice
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_bce, g_dice):
+        pred, pred_index, gt, gt_index, coords, sums = ctx.saved_tensors
+        Rp, H, W = pred.shape
+        _, Hg, Wg = gt.shape
+        Nm, P = coords.shape[0], coords.shape[1]
+        g_bce, g_dice = _c(g_bce.float()), _c(g_dice.float())
+        gp = torch.zeros_like(pred)
+        rc = _lib.load().pdb_point_loss_backward(pred.data_ptr(), pred_index.data_ptr(), gt.data_ptr(), gt_index.data_ptr(),
+                                                 coords.data_ptr(), sums.data_ptr(), g_bce.data_ptr(), g_dice.data_ptr(),
+                                                 gp.data_ptr(), Nm, P, H, W, Hg, Wg, _stream())
+        _lib.check(rc, "pdb_point_loss_backward")
+        return gp, None, None, None, None
+
+
+def point_loss(pred, pred_index, gt, gt_index, coords):
+    """Per matched pair: (mean BCE over the points, dice loss).  pred (Rp,H,W) f32, gt (Rg,Hg,Wg) uint8."""
+    return PointLossFunction.apply(pred, pred_index, gt, gt_index, coords)
+
+
+# --------------------------------------------------------------------------------------------------
+# PartDistillation fp64 classifier rows  (part_distillation_transformer_decoder.py:107,215-238)
+# --------------------------------------------------------------------------------------------------
+class ClassRowsFunction(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, obj, num_parts):
+        _need_cuda(x, weight, bias, obj)
+        x = _c(x.float())
+        if weight.dtype != torch.float64 or bias.dtype != torch.float64:
+            raise RuntimeError("class_rows: weight/bias must be float64 (the reference's class_embed is .double())")
+        B, Q, C = x.shape
+        Ncls = weight.shape[0]
+        out = torch.empty((B, Q, num_parts + 1), dtype=torch.float64, device=x.device)
+        rc = _lib.load().pdb_class_rows_forward(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), obj.data_ptr(),
+                                                out.data_ptr(), B, Q, C, num_parts, Ncls, _stream())
+        _lib.check(rc, "pdb_class_rows_forward")
+        ctx.save_for_backward(x, weight, obj)
+        ctx.num_parts = num_parts
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        x, weight, obj = ctx.saved_tensors
+        B, Q, C = x.shape
+        Ncls = weight.shape[0]
+        grad_out = _c(grad_out.double())
+        gx = torch.empty_like(x)
+        gw = torch.zeros_like(weight)                     # dense zero rows: AdamW parity with the reference
+        gb = torch.zeros((Ncls,), dtype=torch.float64, device=x.device)
+        rc = _lib.load().pdb_class_rows_backward(x.data_ptr(), weight.data_ptr(), obj.data_ptr(), grad_out.data_ptr(),
+                                                 gx.data_ptr(), gw.data_ptr(), gb.data_ptr(), B, Q, C, ctx.num_parts, Ncls,
+                                                 _stream())
+        _lib.check(rc, "pdb_class_rows_backward")
+        return gx, gw, gb, None, None
+
+
+def class_rows(x, weight, bias, obj, num_parts):
+    return ClassRowsFunction.apply(x, weight, bias, obj, num_parts)

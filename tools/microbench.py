@@ -1,0 +1,94 @@
+"""Kernel microbenchmarks (C5 shapes of SURVEY.md §8d): CUDA-event timing, L2 flushed between iterations."""
+import json
+import sys
+import os
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from partdistillation_b200 import functional as fn  # noqa: E402
+
+
+def timeit(f, iters=20, warmup=3, flush=None):
+    for _ in range(warmup):
+        f()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+        s.record(); f(); e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2] * 1e-3
+
+
+def msda_case(N, shapes, spread, rand_loc=False):
+    g = torch.Generator().manual_seed(0)
+    S = sum(h * w for h, w in shapes); L = len(shapes); M, D, P = 8, 32, 4
+    value = torch.randn(N, S, M, D, generator=g).cuda().requires_grad_()
+    refs = []
+    for (H, W) in shapes:
+        ys, xs = torch.meshgrid((torch.arange(H) + 0.5) / H, (torch.arange(W) + 0.5) / W, indexing="ij")
+        refs.append(torch.stack((xs.reshape(-1), ys.reshape(-1)), -1))
+    ref = torch.cat(refs)[None, :, None, None, None, :]
+    norm = torch.tensor([[w, h] for h, w in shapes], dtype=torch.float32)[None, None, None, :, None, :]
+    if rand_loc:
+        loc = torch.rand(N, S, M, L, P, 2, generator=g)
+    else:
+        loc = ref + (torch.rand(N, S, M, L, P, 2, generator=g) * 2 - 1) * spread / norm
+    loc = loc.contiguous().cuda().requires_grad_()
+    attn = torch.softmax(torch.randn(N, S, M, L * P, generator=g), -1).view(N, S, M, L, P).contiguous().cuda().requires_grad_()
+    fwd_bytes = 4 * (N * S * M * D + N * S * M * L * P * 3 + N * S * M * D)
+    bwd_bytes = 2 * fwd_bytes - 4 * N * S * M * D
+    return value, loc, attn, shapes, fwd_bytes, bwd_bytes
+
+
+def main():
+    peak = 6546.9
+    try:
+        peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    res = {}
+    for name, N, shapes, rnd in (("msda_C5i_4lvl_N1", 1, [(256, 256), (128, 128), (64, 64), (32, 32)], False),
+                                 ("msda_C5i_randloc", 1, [(256, 256), (128, 128), (64, 64), (32, 32)], True),
+                                 ("msda_C2_3lvl_N2", 2, [(32, 32), (64, 64), (128, 128)], False)):
+        value, loc, attn, shapes, fb, bb = msda_case(N, shapes, 4.0, rnd)
+        with torch.no_grad():
+            t = timeit(lambda: fn.ms_deform_attn(value, shapes, None, loc, attn), flush=flush)
+        out = fn.ms_deform_attn(value, shapes, None, loc, attn)
+        go = torch.randn_like(out)
+        tb = timeit(lambda: torch.autograd.grad(out, (value, loc, attn), go, retain_graph=True), flush=flush)
+        res[name] = dict(fwd_us=t * 1e6, fwd_gbs=fb / t / 1e9, fwd_frac=fb / t / 1e9 / peak,
+                         bwd_us=tb * 1e6, bwd_gbs=bb / tb / 1e9, bwd_frac=bb / tb / 1e9 / peak)
+    B, Q, C, H, W = 2, 100, 256, 256, 256
+    e = torch.randn(B, Q, C, device="cuda").requires_grad_(); f = torch.randn(B, C, H, W, device="cuda").requires_grad_()
+    eb = 4 * (B * Q * C + B * C * H * W + B * Q * H * W)
+    with torch.no_grad():
+        t = timeit(lambda: fn.mask_einsum(e, f), flush=flush)
+        tt = timeit(lambda: torch.einsum("bqc,bchw->bqhw", e, f), flush=flush)
+    out = fn.mask_einsum(e, f); go = torch.randn_like(out)
+    tb = timeit(lambda: torch.autograd.grad(out, (e, f), go, retain_graph=True), flush=flush)
+    res["mask_einsum"] = dict(fwd_us=t * 1e6, fwd_gbs=eb / t / 1e9, fwd_frac=eb / t / 1e9 / peak, torch_einsum_us=tt * 1e6,
+                              bwd_us=tb * 1e6)
+    # masked cross-attention at the three decoder levels
+    for Lk in (1024, 4096, 16384):
+        q = torch.randn(2, 100, 256, device="cuda").requires_grad_(); k = torch.randn(2, Lk, 256, device="cuda").requires_grad_()
+        v = torch.randn(2, Lk, 256, device="cuda").requires_grad_()
+        mask = (torch.rand(2, 100, Lk, device="cuda") < 0.8).to(torch.uint8)
+        ra = torch.ones(200, dtype=torch.int32, device="cuda")
+        with torch.no_grad():
+            t = timeit(lambda: fn.masked_cross_attention(q, k, v, mask, ra, 8), flush=flush)
+        out = fn.masked_cross_attention(q, k, v, mask, ra, 8); go = torch.randn_like(out)
+        tb = timeit(lambda: torch.autograd.grad(out, (q, k, v), go, retain_graph=True), flush=flush)
+        res[f"xattn_Lk{Lk}"] = dict(fwd_us=t * 1e6, bwd_us=tb * 1e6)
+    print(json.dumps(res, indent=1))
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(res, open("gpurun_out/microbench.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
