@@ -1,0 +1,140 @@
+"""Set criterion (reference: modeling/criterion.py:94-286): Hungarian matching per decoder output,
+weighted cross-entropy on the classes, point-sampled BCE + dice on the masks.
+
+Same constructor, ``forward(outputs, targets) -> dict`` keys and arithmetic.  Structural changes:
+targets are packed once per step (targets.py), matching stays on the device (no ``.cpu()``, no SciPy),
+``num_masks`` stays a device scalar (no ``.item()``), and the two point_sample calls + BCE + dice of
+``loss_masks`` are one fused kernel pair.  ``torch.rand`` is called with the reference's shapes in
+the reference's order (detectron2 get_uncertain_point_coords_with_randomness: two draws).
+"""
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+from torch import nn
+
+from .. import functional as PF
+from .targets import pack_targets
+
+
+def calculate_uncertainty(logits):
+    """-(|logit|) of the foreground class (criterion.py:77-91)."""
+    assert logits.shape[1] == 1
+    return -(torch.abs(logits.clone()))
+
+
+class SetCriterion(nn.Module):
+    def __init__(self, num_classes, matcher, weight_dict, eos_coef, losses, num_points, oversample_ratio,
+                 importance_sample_ratio):
+        super().__init__()
+        self.num_classes = num_classes
+        self.matcher = matcher
+        self.weight_dict = weight_dict
+        self.eos_coef = eos_coef
+        self.losses = losses
+        empty_weight = torch.ones(self.num_classes + 1)
+        empty_weight[-1] = self.eos_coef
+        self.register_buffer("empty_weight", empty_weight)
+        self.num_points = num_points
+        self.oversample_ratio = oversample_ratio
+        self.importance_sample_ratio = importance_sample_ratio
+        self.rand = torch.rand
+
+    # ------------------------------------------------------------------------------------------
+    def _flat_indices(self, targets, match, B, Q):
+        """Flat (b*Q + q) prediction index and (offset_b + k) target index of every VALID pair, in
+        (image, ascending cost) order — the order the reference concatenates them in (:209-225)."""
+        pi, ti = match
+        offs = targets.offsets
+        dev = pi.device
+        cache = getattr(targets, "_crit_cache", None)
+        if cache is None or cache["Q"] != Q:
+            base_p, base_t, keep = [], [], []
+            need_filter = False
+            for b in range(B):
+                k = offs[b + 1] - offs[b]
+                n = min(Q, k)
+                need_filter |= n < k
+                base_p += [b * Q] * k
+                base_t += [offs[b]] * k
+                keep += list(range(offs[b], offs[b] + n))
+            cache = dict(Q=Q, base_p=torch.tensor(base_p, dtype=torch.int64, device=dev),
+                         base_t=torch.tensor(base_t, dtype=torch.int64, device=dev),
+                         keep=torch.tensor(keep, dtype=torch.int64, device=dev) if need_filter else None)
+            targets._crit_cache = cache
+        src = pi + cache["base_p"]
+        tgt = ti + cache["base_t"]
+        if cache["keep"] is not None:
+            src, tgt = src[cache["keep"]], tgt[cache["keep"]]
+        return src, tgt
+
+    def loss_labels(self, outputs, targets, match, num_masks):
+        """Weighted cross-entropy; unmatched queries are the no-object class (:126-145)."""
+        logits = outputs["pred_logits"].float()
+        B, Q, _ = logits.shape
+        src, tgt = self._flat_indices(targets, match, B, Q)
+        target_classes = torch.full((B * Q,), self.num_classes, dtype=torch.int64, device=logits.device)
+        target_classes[src] = targets.packed_labels[tgt].long()
+        loss_ce = F.cross_entropy(logits.view(B * Q, -1), target_classes, self.empty_weight)
+        return {"loss_ce": loss_ce}
+
+    def loss_masks(self, outputs, targets, match, num_masks):
+        """Point-sampled sigmoid-CE + dice on the matched masks (:147-207)."""
+        pred = outputs["pred_masks"]
+        B, Q, H, W = pred.shape
+        src, tgt = self._flat_indices(targets, match, B, Q)
+        Nm = src.shape[0]
+        flat = pred.float().flatten(0, 1)
+        with torch.no_grad():
+            coords = self._uncertain_point_coords(flat, src, Nm)
+        bce, dice = PF.point_loss(flat, src, targets.packed_masks, tgt, coords)
+        return {"loss_mask": bce.sum() / num_masks, "loss_dice": dice.sum() / num_masks}
+
+    def _uncertain_point_coords(self, flat, src, Nm):
+        """detectron2 get_uncertain_point_coords_with_randomness with uncertainty = -|logit|."""
+        dev = flat.device
+        n_over = int(self.num_points * self.oversample_ratio)
+        n_unc = int(self.importance_sample_ratio * self.num_points)
+        n_rand = self.num_points - n_unc
+        over = self.rand(Nm, n_over, 2, device=dev, dtype=flat.dtype)
+        if n_unc > 0:
+            unc = -PF.point_sample(flat.detach(), over, src.to(torch.int32), None).abs()
+            idx = torch.topk(unc, k=n_unc, dim=1)[1]
+            coords = torch.gather(over, 1, idx[:, :, None].expand(-1, -1, 2))
+        else:
+            coords = over[:, :0]
+        if n_rand > 0:
+            coords = torch.cat([coords, self.rand(Nm, n_rand, 2, device=dev)], dim=1)
+        return coords.contiguous()
+
+    def get_loss(self, loss, outputs, targets, indices, num_masks):
+        loss_map = {"labels": self.loss_labels, "masks": self.loss_masks}
+        assert loss in loss_map, f"do you really want to compute {loss} loss?"
+        return loss_map[loss](outputs, targets, indices, num_masks)
+
+    def forward(self, outputs, targets):
+        targets = pack_targets(targets)
+        dev = outputs["pred_masks"].device
+        # average number of target masks across ranks, >= 1 (:248-254) — kept on the device
+        num_masks = torch.as_tensor([float(targets.total)], dtype=torch.float, device=dev)
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(num_masks)
+            num_masks = num_masks / dist.get_world_size()
+        num_masks = torch.clamp(num_masks, min=1)[0]
+
+        losses = {}
+        main = {k: v for k, v in outputs.items() if k != "aux_outputs"}
+        match = self.matcher.match_packed(main, targets)
+        for loss in self.losses:
+            losses.update(self.get_loss(loss, main, targets, match, num_masks))
+        for i, aux in enumerate(outputs.get("aux_outputs", [])):
+            match = self.matcher.match_packed(aux, targets)
+            for loss in self.losses:
+                losses.update({f"{k}_{i}": v for k, v in self.get_loss(loss, aux, targets, match, num_masks).items()})
+        return losses
+
+    def __repr__(self):
+        body = [f"matcher: {self.matcher.__repr__(_repr_indent=8)}", f"losses: {self.losses}",
+                f"weight_dict: {self.weight_dict}", f"num_classes: {self.num_classes}", f"eos_coef: {self.eos_coef}",
+                f"num_points: {self.num_points}", f"oversample_ratio: {self.oversample_ratio}",
+                f"importance_sample_ratio: {self.importance_sample_ratio}"]
+        return "\n".join(["Criterion " + self.__class__.__name__] + [" " * 4 + line for line in body])

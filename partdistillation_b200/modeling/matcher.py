@@ -1,0 +1,74 @@
+"""Hungarian matcher (reference: modeling/matcher.py:74-201).
+
+Same constructor and ``forward(outputs, targets) -> [(index_i, index_j)]`` (int64, ordered by ascending
+matched cost — the PartDistillation-specific re-ordering of matcher.py:162-163).  Internally the
+B per-image Python iterations, host syncs and SciPy calls of the reference collapse into four
+launches per decoder layer: point-sample predictions, point-sample targets, cost matrices, batched LSAP.
+The random point sets are still drawn with one ``torch.rand(1, P, 2)`` per image, in the reference's
+order, so the CUDA RNG stream is the same as the reference PyTorch path's.
+"""
+import torch
+from torch import nn
+
+from .. import functional as PF
+from .targets import pack_targets
+
+
+class HungarianMatcher(nn.Module):
+    def __init__(self, cost_class: float = 1, cost_mask: float = 1, cost_dice: float = 1, num_points: int = 0):
+        super().__init__()
+        self.cost_class = cost_class
+        self.cost_mask = cost_mask
+        self.cost_dice = cost_dice
+        assert cost_class != 0 or cost_mask != 0 or cost_dice != 0, "all costs cant be 0"
+        self.num_points = num_points
+        self.rand = torch.rand           # injectable point-coordinate provider (tests replay recorded draws)
+
+    @torch.no_grad()
+    def match_packed(self, outputs, targets):
+        """-> (pred_idx, tgt_idx) int64 (Ktot,): image b's matches at targets.offsets[b]:..., in ascending
+        cost order; pred_idx is the query index inside the image, tgt_idx the target index inside the image."""
+        targets = pack_targets(targets)
+        logits = outputs["pred_logits"]
+        masks = outputs["pred_masks"]
+        B, Q = logits.shape[:2]
+        dev = masks.device
+        if targets.total == 0:
+            e = torch.zeros((0,), dtype=torch.int64, device=dev)
+            return e, e
+        coords = torch.cat([self.rand(1, self.num_points, 2, device=dev) for _ in range(B)], 0)
+        cache = _index_cache(targets, B, Q, dev)
+        prob = logits.float().sigmoid() if logits.shape[-1] == 1 else logits.float().softmax(-1)
+        pred_pts = PF.point_sample(masks.detach().float().flatten(0, 1), coords, None, cache["img_of_query"])
+        tgt_pts = PF.point_sample(targets.packed_masks, coords, None, cache["img_of_target"])
+        cost = PF.matcher_cost(pred_pts, tgt_pts, prob.reshape(B * Q, -1), targets.packed_labels, targets.offsets, Q,
+                               self.cost_class, self.cost_mask, self.cost_dice)
+        return PF.lsap_batched(cost, targets.offsets, Q)
+
+    @torch.no_grad()
+    def forward(self, outputs, targets):
+        targets = pack_targets(targets)
+        pi, ti = self.match_packed(outputs, targets)
+        Q = outputs["pred_logits"].shape[1]
+        out = []
+        for b in range(len(targets)):
+            n = min(Q, targets.offsets[b + 1] - targets.offsets[b])
+            s = targets.offsets[b]
+            out.append((pi[s:s + n], ti[s:s + n]))
+        return out
+
+    def __repr__(self, _repr_indent=4):
+        body = [f"cost_class: {self.cost_class}", f"cost_mask: {self.cost_mask}", f"cost_dice: {self.cost_dice}"]
+        return "\n".join(["Matcher " + self.__class__.__name__] + [" " * _repr_indent + line for line in body])
+
+
+def _index_cache(targets, B, Q, dev):
+    """int32 helper tables that depend only on the target counts (built once per step)."""
+    c = getattr(targets, "_cache", None)
+    if c is None or c["Q"] != Q:
+        counts = torch.tensor([targets.offsets[b + 1] - targets.offsets[b] for b in range(B)])
+        c = dict(Q=Q,
+                 img_of_query=torch.arange(B, dtype=torch.int32).repeat_interleave(Q).to(dev),
+                 img_of_target=torch.arange(B, dtype=torch.int32).repeat_interleave(counts).to(dev))
+        targets._cache = c
+    return c

@@ -1,0 +1,150 @@
+"""GPU: the whole hot path (pixel decoder -> masked-attention decoder -> criterion, forward + backward)
+of the product modules against golden tensors produced by the UNMODIFIED reference
+(oracle/make_golden.py) on identical weights, features, targets and random point draws.
+
+Bars (north_star): mask logits and losses <= 1e-3 relative; Hungarian indices exact; attention-mask
+bits exact stage-wise (tests/test_ops_gpu.py) and here identical to the reference's bits except where the
+interpolated logit is within fp32 noise of the threshold."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(g, device="cuda"):
+    from partdistillation_b200 import compat, presets
+    c = g["case"]
+    cfg = presets.make_cfg(c["arch"], "swin_micro", num_queries=c["Q"], dec_layers=c["dec_layers"],
+                           num_points=c["points"], importance_sample_ratio=c["importance_ratio"],
+                           num_object_classes=c["num_object_classes"], num_part_classes=c["num_part_classes"],
+                           device=device)
+    model = compat.build_model(cfg)
+    sd = synth.synth_state_dict(g["table"], seed=c["weight_seed"])
+    missing = model.load_state_dict(sd, strict=False)
+    assert all(k.startswith("backbone.") or "empty_weight" in k for k in missing.missing_keys), missing
+    assert not missing.unexpected_keys
+    model.train()
+    return model, c
+
+
+def _inputs(model, c):
+    from partdistillation_b200.compat import BitMasks, ImageList, Instances
+    pd = c["arch"] == "PartDistillationModel"
+    feats = {k: v.cuda() for k, v in synth.synth_features(c["B"], c["H"], c["W"], c["channels"], seed=c["feature_seed"]).items()}
+    batch = synth.synth_batch(c["B"], c["H"], c["W"], c["K"], pd, c["num_object_classes"], seed=c["batch_seed"])
+    bi = []
+    for d in batch:
+        inst = Instances((c["H"], c["W"]))
+        inst.gt_masks = BitMasks(d["gt_masks"])
+        inst.gt_classes = d["gt_classes"]
+        e = {"image": d["image"], "instances": inst, "height": c["H"], "width": c["W"]}
+        if pd:
+            e["gt_object_class"] = d["gt_object_class"]
+        bi.append(e)
+    il = ImageList(torch.zeros(c["B"], 3, c["H"], c["W"], device="cuda"), [(c["H"], c["W"])] * c["B"])
+    return feats, model.prepare_targets(bi, il)
+
+
+@pytest.mark.parametrize("name", ["proposal_micro", "proposal_micro_uniform", "pd_micro"])
+def test_head_and_loss_vs_reference_golden(golden_dir, name):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    g = torch.load(os.path.join(golden_dir, f"head_{name}.pt"), weights_only=False)
+    model, c = _build(g)
+    feats, targets = _inputs(model, c)
+    replay = synth.ReplayRand(g["rand_draws"], device="cuda")
+    model.criterion.rand = replay
+    model.criterion.matcher.rand = replay
+
+    pred = model.sem_seg_head.predictor
+    masks_rec = []
+    orig = pred.forward_prediction_heads
+
+    def fph(*a, **k):
+        r = orig(*a, **k)
+        masks_rec.append(r[2])
+        return r
+    pred.forward_prediction_heads = fph
+    matches = []
+    mp = model.criterion.matcher.match_packed
+
+    def rec_match(o, t):
+        r = mp(o, t)
+        matches.append(r)
+        return r
+    model.criterion.matcher.match_packed = rec_match
+
+    outputs = model.run_head(feats, targets)
+    losses = model.criterion(outputs, targets)
+    losses = {k: v * model.criterion.weight_dict[k] for k, v in losses.items()}
+    assert replay.i == len(g["rand_draws"])                       # same number / order / shapes of RNG draws
+
+    # ---- mask logits and class logits of every decoder output
+    pm = [o["pred_masks"] for o in outputs["aux_outputs"]] + [outputs["pred_masks"]]
+    for a, b in zip(pm, g["pred_masks"]):
+        assert float((a.cpu() - b).abs().max() / b.abs().max()) < 1e-3
+    pl = [o["pred_logits"] for o in outputs["aux_outputs"]] + [outputs["pred_logits"]]
+    for a, b in zip(pl, g["pred_logits"]):
+        assert a.dtype == b.dtype
+        assert torch.allclose(a.cpu(), b, rtol=1e-3, atol=1e-4)
+    assert torch.allclose(outputs["decoder_output"].cpu(), g["decoder_output"], rtol=1e-3, atol=1e-4)
+
+    # ---- attention-mask bits (heads are replicas in the reference tensor)
+    nflip = ntot = 0
+    for am, bits, shp, ref_masks in zip(masks_rec, g["attn_mask_bits"], g["attn_mask_shapes"], g["pred_masks"]):
+        mine = am.mask.bool().cpu()
+        assert (mine.shape[0] * model.sem_seg_head.predictor.num_heads, mine.shape[1], mine.shape[2]) == shp
+        ref = torch.from_numpy(np.unpackbits(bits, axis=-1)[..., :mine.shape[-1]]).bool()
+        flips = mine != ref
+        if flips.any():
+            hw = mine.shape[-1]
+            for size in [(h, hw // h) for h in range(1, hw + 1) if hw % h == 0]:
+                if size[0] * ref_masks.shape[-1] == size[1] * ref_masks.shape[-2]:
+                    interp = F.interpolate(ref_masks, size=size, mode="bilinear", align_corners=False).flatten(2)
+                    assert not (flips & (interp.abs() > 1e-4)).any()
+                    break
+        nflip += int(flips.sum()); ntot += flips.numel()
+    assert nflip <= 1e-4 * ntot
+
+    # ---- Hungarian indices: exact, in the reference's (ascending cost) order
+    assert len(matches) == len(g["indices"])
+    for (pi, ti), ref in zip(matches, g["indices"]):
+        for b, (ri, rj) in enumerate(ref):
+            s = targets.offsets[b]
+            assert torch.equal(pi[s:s + len(ri)].cpu(), ri) and torch.equal(ti[s:s + len(rj)].cpu(), rj)
+
+    # ---- losses
+    assert set(losses) == set(g["losses"])
+    for k, v in g["losses"].items():
+        assert abs(float(losses[k]) - float(v)) <= 1e-3 * max(1.0, abs(float(v))), (k, float(losses[k]), float(v))
+
+    # ---- gradients through the whole path
+    sum(losses.values()).backward()
+    named = dict(model.named_parameters())
+    for k, v in g["grads"].items():
+        assert float((named[k].grad.cpu() - v).abs().max()) <= 5e-3 * float(v.abs().max()), k
+    for k, n in g["grad_norms"].items():
+        mine = named[k].grad.double().norm().item()
+        assert abs(mine - n) <= 5e-3 * max(n, 1e-6), k
+
+
+def test_matcher_public_api(golden_dir):
+    """HungarianMatcher.forward keeps the reference's return type: list of (int64, int64) per image."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    g = torch.load(os.path.join(golden_dir, "head_proposal_micro.pt"), weights_only=False)
+    model, c = _build(g)
+    feats, targets = _inputs(model, c)
+    model.criterion.matcher.rand = synth.ReplayRand(g["rand_draws"][:c["B"]], device="cuda")
+    with torch.no_grad():
+        outputs = model.run_head(feats, targets)
+        plain = [dict(t) for t in targets]                      # reference-format list of dicts
+        idx = model.criterion.matcher({k: v for k, v in outputs.items() if k != "aux_outputs"}, plain)
+    for (i, j), (ri, rj) in zip(idx, g["indices"][0]):
+        assert i.dtype == torch.int64 and torch.equal(i.cpu(), ri) and torch.equal(j.cpu(), rj)
