@@ -66,9 +66,11 @@ PDB_API int pdb_msda_backward(const void* value, const int64_t* shapes_hw, const
 /* ------------------------------------------------------------------------------------------------
  * Mask head einsum — replaces torch.einsum("bqc,bchw->bqhw")
  * (mask2former_transformer_decoder.py:449, part_distillation_transformer_decoder.py:244).
- *   embed (B, Q, C) f32;  feat (B, C, HW) f32;  out (B, Q, HW) f32.
- * backward:  grad_embed (B,Q,C) = grad_out x feat^T (overwritten);
- *            grad_feat  (B,C,HW) (+)= embed^T x grad_out  (accumulate != 0 adds into grad_feat).
+ *   embed (B, Q, C) f32;  feat (B, HW, C) f32 PIXEL-MAJOR (the NCHW mask_features tensor in
+ *   channels_last memory format);  out (B, Q, HW) f32.  C % 4 == 0, 16-byte aligned bases.
+ *   forward: tcgen05 kind::tf32 with a 3-term hi/lo split of both operands (fp32-accurate logits).
+ * backward:  grad_embed (B,Q,C) = grad_out x feat (overwritten);
+ *            grad_feat  (B,HW,C) (+)= grad_out^T x embed  (accumulate != 0 adds into grad_feat).
  * Either grad pointer may be NULL to skip it.
  * ---------------------------------------------------------------------------------------------- */
 PDB_API int pdb_mask_einsum_forward(const float* embed, const float* feat, float* out,

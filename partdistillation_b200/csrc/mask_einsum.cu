@@ -1,14 +1,13 @@
-// Mask-head einsum  out[b,q,hw] = sum_c embed[b,q,c] * feat[b,c,hw]  and its two gradients.
-// Reference: torch.einsum("bqc,bchw->bqhw") at mask2former_transformer_decoder.py:449 and
-// part_distillation_transformer_decoder.py:244 (autograd supplies the backward there).
+// Mask-head einsum  out[b,q,p] = sum_c embed[b,q,c] * feat[b,p,c]  — C-ABI entry points and the two
+// gradient products.  Reference: torch.einsum("bqc,bchw->bqhw") at mask2former_transformer_decoder.py:449
+// and part_distillation_transformer_decoder.py:244 (autograd supplies the backward there).
 //
-// Per image this is a (Q x C) x (C x HW) product with Q ~ 100, C = 256, HW = 65 536: the feature
-// map is streamed once from HBM (134 MB at B=2) and the (Q x HW) logits are written once (52 MB).
-//
-// Round-1 kernel: a shared-memory tiled fp32 FFMA GEMM (128x128x16 tiles, 8x8 register micro-tiles)
-// shared by the forward and both backward products through layout flags.  fp32 FFMA arithmetic keeps
-// the logits within ~1e-6 of the reference; see DESIGN.md for the roofline (FFMA-bound) and the
-// planned tcgen05 3xTF32 replacement.
+// The feature map is pixel-major (B, HW, C) ("channels last"): the 1x1 mask_features convolution that
+// produces it is a GEMM over pixels, so this layout is free, and it makes both einsum operands K-major.
+// Forward: tcgen05 3xTF32 kernel in mask_einsum_tc.cu.  Backward (this file): shared-memory tiled
+// fp32 FFMA GEMM (128x128x16 tiles, 8x8 register micro-tiles) used through layout flags for
+//   grad_feat (HW x C) = grad_out^T (HW x Q) x embed (Q x C)     and
+//   grad_embed (Q x C) = grad_out (Q x HW) x feat (HW x C)        (split-K over HW, atomics).
 #include "common.cuh"
 
 namespace pdb {
@@ -120,16 +119,22 @@ tile_gemm(const float* __restrict__ A, const float* __restrict__ Bm, float* __re
 
 }  // namespace pdb
 
+namespace pdb {
+int mask_einsum_forward_tc(const float* embed, const float* feat_pm, float* out, int B, int Q, int C, int64_t HW,
+                           cudaStream_t st);
+}
+
 using namespace pdb;
 
 extern "C" int pdb_mask_einsum_forward(const float* embed, const float* feat, float* out, int B, int Q, int C,
                                        int64_t HW, void* stream) {
     PDB_REQUIRE(embed && feat && out, "mask_einsum_forward: null pointer");
     PDB_REQUIRE(B > 0 && Q > 0 && C > 0 && HW > 0, "mask_einsum_forward: non-positive dimension");
-    dim3 grid((unsigned)((HW + BN - 1) / BN), (unsigned)((Q + BM - 1) / BM), (unsigned)B);
-    tile_gemm<true, true, STORE><<<grid, GEMM_THREADS, 0, as_stream(stream)>>>(
-        embed, feat, out, Q, (int)HW, C, C, HW, HW, (int64_t)Q * C, (int64_t)C * HW, (int64_t)Q * HW, 1, C);
-    return launched("mask_einsum_forward");
+    PDB_REQUIRE(C % 4 == 0, "mask_einsum_forward: C=%d must be a multiple of 4 (16-byte TMA rows)", C);
+    PDB_REQUIRE((reinterpret_cast<uintptr_t>(embed) & 15) == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0,
+                "mask_einsum_forward: embed / feat must be 16-byte aligned");
+    PDB_REQUIRE((int64_t)B * HW < (1ll << 31) && (int64_t)B * Q < (1ll << 31), "mask_einsum_forward: too many rows");
+    return mask_einsum_forward_tc(embed, feat, out, B, Q, C, HW, as_stream(stream));
 }
 
 extern "C" int pdb_mask_einsum_backward(const float* embed, const float* feat, const float* grad_out,
@@ -139,26 +144,26 @@ extern "C" int pdb_mask_einsum_backward(const float* embed, const float* feat, c
     PDB_REQUIRE(B > 0 && Q > 0 && C > 0 && HW > 0, "mask_einsum_backward: non-positive dimension");
     cudaStream_t st = as_stream(stream);
     if (grad_feat) {
-        // grad_feat[b] (C x HW) (+)= embed[b]^T (C x Q) * grad_out[b] (Q x HW)
-        dim3 grid((unsigned)((HW + BN - 1) / BN), (unsigned)((C + BM - 1) / BM), (unsigned)B);
+        // grad_feat[b] (HW x C) (+)= grad_out[b]^T (HW x Q) * embed[b] (Q x C)
+        dim3 grid((unsigned)((C + BN - 1) / BN), (unsigned)((HW + BM - 1) / BM), (unsigned)B);
         if (accumulate)
             tile_gemm<false, true, ACCUM><<<grid, GEMM_THREADS, 0, st>>>(
-                embed, grad_out, grad_feat, C, (int)HW, Q, C, HW, HW, (int64_t)Q * C, (int64_t)Q * HW,
+                grad_out, embed, grad_feat, (int)HW, C, Q, HW, C, C, (int64_t)Q * HW, (int64_t)Q * C,
                 (int64_t)C * HW, 1, Q);
         else
             tile_gemm<false, true, STORE><<<grid, GEMM_THREADS, 0, st>>>(
-                embed, grad_out, grad_feat, C, (int)HW, Q, C, HW, HW, (int64_t)Q * C, (int64_t)Q * HW,
+                grad_out, embed, grad_feat, (int)HW, C, Q, HW, C, C, (int64_t)Q * HW, (int64_t)Q * C,
                 (int64_t)C * HW, 1, Q);
         PDB_TRY(launched("mask_einsum_backward(grad_feat)"));
     }
     if (grad_embed) {
-        // grad_embed[b] (Q x C) = grad_out[b] (Q x HW) * feat[b]^T (HW x C); split-K over HW
+        // grad_embed[b] (Q x C) = grad_out[b] (Q x HW) * feat[b] (HW x C); split-K over HW
         cudaMemsetAsync(grad_embed, 0, sizeof(float) * (size_t)B * Q * C, st);
         int64_t kchunk = 1024;
         int ksplit = (int)((HW + kchunk - 1) / kchunk);
         dim3 grid((unsigned)((C + BN - 1) / BN), (unsigned)((Q + BM - 1) / BM), (unsigned)(B * ksplit));
-        tile_gemm<true, false, ATOMIC><<<grid, GEMM_THREADS, 0, st>>>(
-            grad_out, feat, grad_embed, Q, C, HW, HW, HW, C, (int64_t)Q * HW, (int64_t)C * HW, (int64_t)Q * C, ksplit,
+        tile_gemm<true, true, ATOMIC><<<grid, GEMM_THREADS, 0, st>>>(
+            grad_out, feat, grad_embed, Q, C, HW, HW, C, C, (int64_t)Q * HW, (int64_t)C * HW, (int64_t)Q * C, ksplit,
             kchunk);
         PDB_TRY(launched("mask_einsum_backward(grad_embed)"));
     }

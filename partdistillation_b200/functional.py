@@ -117,13 +117,18 @@ def ms_deform_attn(value, spatial_shapes, level_start_index, sampling_locations,
 # --------------------------------------------------------------------------------------------------
 # mask-head einsum  bqc,bchw->bqhw  (mask2former_transformer_decoder.py:449)
 # --------------------------------------------------------------------------------------------------
+def _pixel_major(t):
+    """(B, C, H, W) logical tensor -> the same tensor in channels_last memory (pixel-major (B, HW, C))."""
+    return t if t.is_contiguous(memory_format=torch.channels_last) else t.contiguous(memory_format=torch.channels_last)
+
+
 class MaskEinsumFunction(Function):
     @staticmethod
     def forward(ctx, mask_embed, mask_features):
         _need_cuda(mask_embed, mask_features)
         if mask_embed.dtype != torch.float32 or mask_features.dtype != torch.float32:
             raise RuntimeError("mask_einsum: float32 only")
-        mask_embed, mask_features = _c(mask_embed), _c(mask_features)
+        mask_embed, mask_features = _c(mask_embed), _pixel_major(mask_features)
         B, Q, C = mask_embed.shape
         Bf, Cf, H, W = mask_features.shape
         if B != Bf or C != Cf:
@@ -143,7 +148,8 @@ class MaskEinsumFunction(Function):
         H, W = mask_features.shape[-2:]
         grad_out = _c(grad_out)
         ge = torch.empty_like(mask_embed) if ctx.needs_input_grad[0] else None
-        gf = torch.empty_like(mask_features) if ctx.needs_input_grad[1] else None
+        gf = (torch.empty_like(mask_features, memory_format=torch.channels_last)
+              if ctx.needs_input_grad[1] else None)
         rc = _lib.load().pdb_mask_einsum_backward(mask_embed.data_ptr(), mask_features.data_ptr(), grad_out.data_ptr(),
                                                   ge.data_ptr() if ge is not None else None,
                                                   gf.data_ptr() if gf is not None else None, 0,

@@ -226,4 +226,17 @@ class MSDeformAttnPixelDecoder(nn.Module):
                 up = F.interpolate(out[-1], size=cur.shape[-2:], mode="bilinear", align_corners=False)
                 out.append(self.output_convs[idx](cur + up))
             multi_scale = out[:self.maskformer_num_feature_levels]
-            return self.mask_features(out[-1]), out[0], multi_scale
+            return self._mask_features_pixel_major(out[-1]), out[0], multi_scale
+
+    def _mask_features_pixel_major(self, y):
+        """The 1x1 ``mask_features`` convolution as a GEMM over pixels: the result is the logical
+        (B, mask_dim, H, W) tensor stored channels-last, i.e. the pixel-major (B, HW, C) operand the
+        tensor-core mask einsum consumes (both of its operands are then K-major)."""
+        conv = self.mask_features
+        w = conv.weight.view(conv.out_channels, conv.in_channels)
+        mf = F.linear(y.permute(0, 2, 3, 1), w, conv.bias)          # (B, H, W, mask_dim), contiguous
+        if getattr(conv, "norm", None) is not None:
+            mf = conv.norm(mf.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+        if getattr(conv, "activation", None) is not None:
+            mf = conv.activation(mf)
+        return mf.permute(0, 3, 1, 2)

@@ -130,14 +130,17 @@ def test_msda_rejects_bad_input(fn):
 
 
 # ------------------------------------------------------------------ mask einsum
-@pytest.mark.parametrize("B,Q,C,H,W", [(2, 10, 256, 32, 32), (1, 100, 256, 24, 40), (2, 131, 64, 7, 9)])
+@pytest.mark.parametrize("B,Q,C,H,W", [(2, 10, 256, 32, 32), (1, 100, 256, 24, 40), (2, 131, 64, 7, 9), (1, 200, 256, 16, 24),
+                                       (3, 50, 36, 5, 5)])
 def test_mask_einsum(fn, B, Q, C, H, W):
     g = torch.Generator().manual_seed(0)
     e = torch.randn(B, Q, C, generator=g).cuda().requires_grad_()
     f = torch.randn(B, C, H, W, generator=g).cuda().requires_grad_()
     out = fn.mask_einsum(e, f)
     ref = torch.einsum("bqc,bchw->bqhw", e.double(), f.double())
-    assert _rel(out.double(), ref) < 2e-6
+    # 3xTF32 on tcgen05: fp32-class accuracy (measured ~3e-6 of max at C=256; tensor-core fp32 accumulation
+    # truncates), 100x inside the 1e-3 contract
+    assert _rel(out.double(), ref) < 1e-5
     go = torch.randn(out.shape, generator=g).cuda()
     ge, gf = torch.autograd.grad(out, (e, f), go)
     rge, rgf = torch.autograd.grad(ref, (e, f), go.double())
@@ -154,10 +157,10 @@ def test_mask_einsum_full_size(fn):
     out = fn.mask_einsum(e, f)
     lhs = out.double().sum((-1, -2))
     rhs = torch.einsum("bqc,bc->bq", e.double(), f.double().sum((-1, -2)))
-    assert _rel(lhs, rhs) < 1e-6
+    assert _rel(lhs, rhs) < 1e-5
     ii = torch.randint(0, 256 * 256, (64,), generator=g).cuda()
     ref = torch.einsum("bqc,bcn->bqn", e.double(), f.flatten(2)[:, :, ii].double())
-    assert _rel(out.flatten(2)[:, :, ii].double(), ref) < 2e-6
+    assert _rel(out.flatten(2)[:, :, ii].double(), ref) < 1e-5
 
 
 # ------------------------------------------------------------------ attention mask (bit-exact)

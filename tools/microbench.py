@@ -65,11 +65,12 @@ def main():
         res[name] = dict(fwd_us=t * 1e6, fwd_gbs=fb / t / 1e9, fwd_frac=fb / t / 1e9 / peak,
                          bwd_us=tb * 1e6, bwd_gbs=bb / tb / 1e9, bwd_frac=bb / tb / 1e9 / peak)
     B, Q, C, H, W = 2, 100, 256, 256, 256
-    e = torch.randn(B, Q, C, device="cuda").requires_grad_(); f = torch.randn(B, C, H, W, device="cuda").requires_grad_()
+    e = torch.randn(B, Q, C, device="cuda").requires_grad_(); f = torch.randn(B, C, H, W, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_()
     eb = 4 * (B * Q * C + B * C * H * W + B * Q * H * W)
     with torch.no_grad():
         t = timeit(lambda: fn.mask_einsum(e, f), flush=flush)
-        tt = timeit(lambda: torch.einsum("bqc,bchw->bqhw", e, f), flush=flush)
+        fn_nchw = f.detach().contiguous()
+        tt = timeit(lambda: torch.einsum("bqc,bchw->bqhw", e, fn_nchw), flush=flush)
     out = fn.mask_einsum(e, f); go = torch.randn_like(out)
     tb = timeit(lambda: torch.autograd.grad(out, (e, f), go, retain_graph=True), flush=flush)
     res["mask_einsum"] = dict(fwd_us=t * 1e6, fwd_gbs=eb / t / 1e9, fwd_frac=eb / t / 1e9 / peak, torch_einsum_us=tt * 1e6,
