@@ -1,0 +1,61 @@
+"""Where one training step spends its time: wall clock vs summed kernel time (torch.profiler / CUPTI, warm
+caches, real overlap) and the top kernels.  Answers "is the step launch-bound or GPU-bound?".
+Usage: python tools/step_profile.py [out.txt]"""
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main(out_path):
+    from partdistillation_b200 import compat, presets
+    from partdistillation_b200.engine import DataParallelTrainer
+    device = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    cfg = presets.make_cfg("ProposalModel", "swin_b", bench.QUERIES, 10, bench.POINTS, 0.0, device=str(device))
+    torch.manual_seed(0)
+    model = compat.build_model(cfg)
+    model.train()
+    trainer = DataParallelTrainer(model, freeze_keys=("backbone", "encoder"))
+    batch = bench.make_batch(0, bench.PER_GPU_BATCH, device=device)
+    for _ in range(3):
+        trainer.step(batch)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n = 5
+    for _ in range(n):
+        trainer.step(batch)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / n * 1e3
+    # stage split with events
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        for _ in range(2):
+            trainer.step(batch)
+        torch.cuda.synchronize()
+    ev = prof.key_averages()
+    rows = []
+    total = 0.0
+    for e in ev:
+        t = getattr(e, "self_device_time_total", 0.0) or 0.0
+        if t > 0 and e.device_type == torch.autograd.DeviceType.CUDA:
+            rows.append((t / 2, e.count // 2, e.key))
+            total += t / 2
+    rows.sort(reverse=True)
+    with open(out_path, "w") as w:
+        w.write(f"# one training step (Swin-B 1024^2, bs=2, 100q): wall {wall:.2f} ms/step; summed kernel time "
+                f"{total / 1e3:.2f} ms/step over {sum(r[1] for r in rows)} launches (torch.profiler, warm)\n")
+        w.write(f"{'us/step':>10} {'share':>7} {'count':>6}  kernel\n")
+        for t, c, k in rows[:70]:
+            w.write(f"{t:10.1f} {100 * t / total:6.1f}% {c:6d}  {k[:110]}\n")
+    print(open(out_path).read()[:6000])
+
+
+if __name__ == "__main__":
+    os.makedirs("gpurun_out", exist_ok=True)
+    main(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/step_profile.txt")
