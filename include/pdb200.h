@@ -80,6 +80,25 @@ PDB_API int pdb_mask_einsum_backward(const float* embed, const float* feat, cons
                              int B, int Q, int C, int64_t HW, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Dense fp32 contraction on the tcgen05 tensor cores (3xTF32: fp32-accurate, fp32 TMEM accumulation) —
+ * replaces the cuBLAS sgemm behind nn.Linear forward / backward of the encoder and decoder layers
+ * (msdeformattn.py:120-135, ops/modules/ms_deform_attn.py:102-130,
+ * mask2former_transformer_decoder.py:148-208) and behind autograd of the mask-head einsum (:449).
+ * For each batch item b:   C_b[m][n] (+)= sum_k A_b(m,k) * B_b(n,k)  (+ bias[n]) (ReLU)
+ *   a_mn = 0: A_b(m,k) = A[b*sa + m*lda + k]   (K-major)      a_mn = 1: A[b*sa + k*lda + m]   (MN-major)
+ *   b_mn = 0: B_b(n,k) = B[b*sb + n*ldb + k]                  b_mn = 1: B[b*sb + k*ldb + n]
+ *   c_trans = 0: C[b*sc + m*ldc + n]                          c_trans = 1: C[b*sc + n*ldc + m]
+ *   accumulate != 0: C += (red.add; C must be initialised); ksplit > 1 (split-K) requires accumulate.
+ * A, B 16-byte aligned; lda, ldb, sa, sb multiples of 4 floats.  bias may be NULL.
+ * nn.Linear:  y = x W^T + b      -> A = x (K-major), B = W (K-major), bias, relu optional
+ *             dx = dy W          -> A = dy (K-major), B = W (MN-major)
+ *             dW = dy^T x        -> A = dy (MN-major), B = x (MN-major), split-K over the rows, accumulate
+ * ---------------------------------------------------------------------------------------------- */
+PDB_API int pdb_gemm_tf32x3(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int batch,
+                    int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc, int a_mn, int b_mn,
+                    int c_trans, int relu, int accumulate, int ksplit, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Attention-mask build — replaces F.interpolate(bilinear, align_corners=False) -> sigmoid() < 0.5
  * -> repeat over heads (mask2former_transformer_decoder.py:453-457) and the all-masked-row reset
  * of the next layer (:405).
