@@ -7,8 +7,11 @@
 // (mask2former_transformer_decoder.py:449), all of which cuBLAS runs as SIMT sgemm when TF32 is off.
 //
 // fp32 accuracy on TF32 tensor cores: every operand x is split into hi = x with the low 13 mantissa
-// bits cleared (exact in tf32) and lo = x - hi (exact in fp32); D += lo*hi + hi*lo + hi*hi accumulates in
-// fp32 TMEM (the dropped lo*lo term is ~2^-22 relative).
+// bits cleared (exact in tf32) and lo = x - hi (exact in fp32).  hi*hi accumulates in one fp32 TMEM
+// accumulator and the correction lo*hi + hi*lo in a second one; the epilogue adds them (the dropped lo*lo
+// term is ~2^-22 relative).  Two accumulators because the tensor core truncates when it aligns addends to the
+// accumulator: adding the 2^-11-sized corrections into the main sum would cost one truncation each, tripling
+// the (biased) rounding error; measured error vs fp64 ~1e-6 of max at K=256.
 //
 // Operand layouts are described to TMA / UMMA instead of being materialised:
 //   K-major  operand (k contiguous):  3-D tensor map (k, mn, batch), one box (32, rows, 1) per k-block,
@@ -49,7 +52,7 @@ struct GemmSmem {
     static constexpr int B_BYTES = BN * G_BK * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr int TMEM_COLS = 2 * BN;              // main (hi*hi) + correction (lo*hi + hi*lo) accumulators
 };
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
@@ -181,9 +184,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                         dbh = tc::umma_desc_k_sw128(b_hi(s), k * 32);
                         dbl = tc::umma_desc_k_sw128(b_lo(s), k * 32);
                     }
-                    tc::mma_tf32(tmem_d, dal, dbh, idesc, (kb | k) != 0);      // small terms first
-                    tc::mma_tf32(tmem_d, dah, dbl, idesc, 1);
-                    tc::mma_tf32(tmem_d, dah, dbh, idesc, 1);
+                    tc::mma_tf32(tmem_d + BN, dal, dbh, idesc, (kb | k) != 0);    // correction accumulator
+                    tc::mma_tf32(tmem_d + BN, dah, dbl, idesc, 1);
+                    tc::mma_tf32(tmem_d, dah, dbh, idesc, (kb | k) != 0);          // main accumulator
                 }
                 tc::tc_commit(&empty[s]);          // frees the stage once these MMAs have read it
             }
@@ -218,8 +221,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             const int m = m0 + quarter * 32 + lane;
 #pragma unroll 1
             for (int c0 = 0; c0 < bn_eff; c0 += 16) {
-                float v[16];
+                float v[16], w[16];
                 tc::tmem_ld16(tbase + c0, v);
+                tc::tmem_ld16(tbase + BN + c0, w);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += w[i];
                 if (m < p.M) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -241,11 +247,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             const int mrow0 = m0 + quarter * 32;
 #pragma unroll 1
             for (int c0 = 0; c0 < bn_eff; c0 += 32) {
-                float v[32];
+                float v[32], w[32];
                 tc::tmem_ld16(tbase + c0, v);
                 tc::tmem_ld16(tbase + c0 + 16, v + 16);      // columns beyond bn_eff hold stale TMEM: never stored
+                tc::tmem_ld16(tbase + BN + c0, w);
+                tc::tmem_ld16(tbase + BN + c0 + 16, w + 16);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = v[i];
+                for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = v[i] + w[i];
                 __syncwarp();
                 const int n = n0 + c0 + lane;
                 const bool n_ok = n < p.N;

@@ -4,10 +4,14 @@
 //
 // The feature map is pixel-major (B, HW, C) ("channels last"): the 1x1 mask_features convolution that
 // produces it is a GEMM over pixels, so this layout is free, and it makes both einsum operands K-major.
-// Forward: tcgen05 3xTF32 kernel in mask_einsum_tc.cu.  Backward (this file): shared-memory tiled
-// fp32 FFMA GEMM (128x128x16 tiles, 8x8 register micro-tiles) used through layout flags for
-//   grad_feat (HW x C) = grad_out^T (HW x Q) x embed (Q x C)     and
-//   grad_embed (Q x C) = grad_out (Q x HW) x feat (HW x C)        (split-K over HW, atomics).
+// Forward and both gradient products run on the tcgen05 3xTF32 GEMM of gemm_tc.cu (operand layouts are
+// described to TMA / UMMA in place, nothing is transposed in memory):
+//   out (Q x HW)^T      : A = feat (pixels x C, K-major),  B = embed (Q x C, K-major), transposed store
+//   grad_feat (HW x C)  = grad_out^T (HW x Q) x embed (Q x C)     A, B MN-major
+//   grad_embed (Q x C)  = grad_out (Q x HW) x feat (HW x C)        B MN-major, split-K over HW, red.add
+// The shared-memory tiled fp32 FFMA GEMM below (128x128x16 tiles, 8x8 register micro-tiles) only serves
+// shapes whose rows are not 16-byte multiples (C or HW not divisible by 4).
+#include <algorithm>
 #include "common.cuh"
 
 namespace pdb {
@@ -120,8 +124,9 @@ tile_gemm(const float* __restrict__ A, const float* __restrict__ Bm, float* __re
 }  // namespace pdb
 
 namespace pdb {
-int mask_einsum_forward_tc(const float* embed, const float* feat_pm, float* out, int B, int Q, int C, int64_t HW,
-                           cudaStream_t st);
+int gemm_tf32x3(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int batch,
+                int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc, int a_mn, int b_mn,
+                int c_trans, int relu, int accumulate, int ksplit, cudaStream_t st);
 }
 
 using namespace pdb;
@@ -133,8 +138,11 @@ extern "C" int pdb_mask_einsum_forward(const float* embed, const float* feat, fl
     PDB_REQUIRE(C % 4 == 0, "mask_einsum_forward: C=%d must be a multiple of 4 (16-byte TMA rows)", C);
     PDB_REQUIRE((reinterpret_cast<uintptr_t>(embed) & 15) == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0,
                 "mask_einsum_forward: embed / feat must be 16-byte aligned");
-    PDB_REQUIRE((int64_t)B * HW < (1ll << 31) && (int64_t)B * Q < (1ll << 31), "mask_einsum_forward: too many rows");
-    return mask_einsum_forward_tc(embed, feat, out, B, Q, C, HW, as_stream(stream));
+    PDB_REQUIRE(HW < (1ll << 31), "mask_einsum_forward: too many pixels");
+    // out[b][q][p] = sum_c feat[b][p][c] * embed[b][q][c]: M = pixels (TMEM lanes), N = queries, both operands
+    // K-major, transposed store (32 consecutive pixels per warp store)
+    return gemm_tf32x3(feat, embed, out, nullptr, (int)HW, Q, C, B, C, C, HW, (int64_t)HW * C, (int64_t)Q * C,
+                       (int64_t)Q * HW, 0, 0, 1, 0, 0, 1, as_stream(stream));
 }
 
 extern "C" int pdb_mask_einsum_backward(const float* embed, const float* feat, const float* grad_out,
@@ -143,6 +151,26 @@ extern "C" int pdb_mask_einsum_backward(const float* embed, const float* feat, c
     PDB_REQUIRE(embed && feat && grad_out, "mask_einsum_backward: null pointer");
     PDB_REQUIRE(B > 0 && Q > 0 && C > 0 && HW > 0, "mask_einsum_backward: non-positive dimension");
     cudaStream_t st = as_stream(stream);
+    // tensor-core path (tcgen05 3xTF32, operands described in place as MN-major): needs 16-byte rows
+    const bool tc_ok = C % 4 == 0 && HW % 4 == 0 && HW < (1ll << 31) &&
+                       ((reinterpret_cast<uintptr_t>(embed) | reinterpret_cast<uintptr_t>(feat) |
+                         reinterpret_cast<uintptr_t>(grad_out)) & 15) == 0;
+    if (tc_ok) {
+        if (grad_feat) {
+            // grad_feat[b][p][c] (+)= sum_q grad_out[b][q][p] * embed[b][q][c]: A(m=p,k=q) and B(n=c,k=q) are MN-major
+            PDB_TRY(gemm_tf32x3(grad_out, embed, grad_feat, nullptr, (int)HW, C, Q, B, HW, C, C, (int64_t)Q * HW,
+                                (int64_t)Q * C, (int64_t)C * HW, 1, 1, 0, 0, accumulate ? 1 : 0, 1, st));
+        }
+        if (grad_embed) {
+            // grad_embed[b][q][c] = sum_p grad_out[b][q][p] * feat[b][p][c]: A K-major, B(n=c,k=p) MN-major, split-K over HW
+            cudaMemsetAsync(grad_embed, 0, sizeof(float) * (size_t)B * Q * C, st);
+            int tiles = B * ((Q + 127) / 128) * ((C + 127) / 128);
+            int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>((HW + 1023) / 1024, (2 * kNumSMs + tiles - 1) / tiles));
+            PDB_TRY(gemm_tf32x3(grad_out, feat, grad_embed, nullptr, Q, C, (int)HW, B, HW, C, C, (int64_t)Q * HW,
+                                (int64_t)C * HW, (int64_t)Q * C, 0, 1, 0, 0, 1, ksplit, st));
+        }
+        return PDB_OK;
+    }
     if (grad_feat) {
         // grad_feat[b] (HW x C) (+)= grad_out[b]^T (HW x Q) * embed[b] (Q x C)
         dim3 grid((unsigned)((C + BN - 1) / BN), (unsigned)((HW + BM - 1) / BM), (unsigned)B);

@@ -106,8 +106,4 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
 
 }  // namespace tc
 
-// host: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
-int make_tensor_map_2d_f32(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
-                           uint32_t box_inner, uint32_t box_outer);
-
 }  // namespace pdb

@@ -401,3 +401,83 @@ class ClassRowsFunction(Function):
 
 def class_rows(x, weight, bias, obj, num_parts):
     return ClassRowsFunction.apply(x, weight, bias, obj, num_parts)
+
+
+# --------------------------------------------------------------------------------------------------
+# dense contractions on the tcgen05 tensor cores (3xTF32, fp32-accurate)  — csrc/gemm_tc.cu
+# --------------------------------------------------------------------------------------------------
+def gemm_tf32x3(A, B, C, M, N, K, *, batch=1, lda, ldb, ldc, sa=0, sb=0, sc=0, a_mn=False, b_mn=False, c_trans=False,
+                bias=None, relu=False, accumulate=False, ksplit=1):
+    """Raw entry point: C_b[m][n] (+)= sum_k A_b(m,k) B_b(n,k) (+bias[n]) (ReLU); see include/pdb200.h."""
+    rc = _lib.load().pdb_gemm_tf32x3(A.data_ptr(), B.data_ptr(), C.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                     M, N, K, batch, lda, ldb, ldc, sa, sb, sc, int(a_mn), int(b_mn), int(c_trans),
+                                     int(relu), int(accumulate), int(ksplit), _stream())
+    _lib.check(rc, "pdb_gemm_tf32x3")
+    return C
+
+
+def _split_k(M, N, K):
+    """K slices so that a weight-gradient / reduction-shaped GEMM fills the 148 SMs."""
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    return max(1, min((K + 31) // 32, (2 * 148 + tiles - 1) // tiles))
+
+
+def linear_supported(x, weight):
+    return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32
+            and weight.shape[0] % 4 == 0 and weight.shape[1] % 4 == 0 and weight.is_contiguous())
+
+
+class LinearFunction(Function):
+    """y = x W^T + b (optionally ReLU) with forward, input-gradient and weight-gradient GEMMs on tcgen05."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        _need_cuda(x, weight, bias)
+        N, K = weight.shape
+        x2 = _c(x).view(-1, K)
+        if x2.data_ptr() % 16:
+            x2 = x2.clone()
+        M = x2.shape[0]
+        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        if M > 0:
+            gemm_tf32x3(x2, weight, out, M, N, K, lda=K, ldb=K, ldc=N, bias=bias, relu=relu)
+        ctx.relu = relu
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x2, weight, out if relu else None)
+        return out.view(*x.shape[:-1], N)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x2, weight, out = ctx.saved_tensors
+        N, K = weight.shape
+        M = x2.shape[0]
+        gy2 = _c(gy).view(M, N)
+        if ctx.relu:
+            gy2 = gy2 * (out > 0)
+        if gy2.data_ptr() % 16:
+            gy2 = gy2.clone()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty((M, K), dtype=torch.float32, device=gy.device)
+            # dx[m,i] = sum_o gy[m,o] W[o,i]:  A = gy (K-major), B(n=i,k=o) = W[o*K+i] (MN-major)
+            gemm_tf32x3(gy2, weight, gx, M, K, N, lda=N, ldb=K, ldc=K, b_mn=True)
+            gx = gx.view(*gy.shape[:-1], K)
+        if ctx.needs_input_grad[1]:
+            gw = torch.zeros((N, K), dtype=torch.float32, device=gy.device)
+            # dW[o,i] = sum_m gy[m,o] x[m,i]:  A(m'=o,k=m) = gy[m*N+o], B(n'=i,k=m) = x[m*K+i]  (both MN-major)
+            gemm_tf32x3(gy2, x2, gw, N, K, M, lda=N, ldb=K, ldc=K, a_mn=True, b_mn=True, accumulate=True,
+                        ksplit=_split_k(N, K, M))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy2.sum(0)
+        return gx, gw, gb, None
+
+
+def linear(x, weight, bias=None, relu=False):
+    """nn.Linear (optionally fused ReLU) on the tensor cores for fp32 CUDA tensors whose feature sizes are
+    multiples of 4; other dtypes (autocast halves, the fp64 classifier) and tiny ragged heads go through
+    the library GEMM."""
+    if linear_supported(x, weight):
+        return LinearFunction.apply(x, weight, bias, relu)
+    y = torch.nn.functional.linear(x, weight.to(x.dtype), None if bias is None else bias.to(x.dtype))
+    return torch.relu(y) if relu else y

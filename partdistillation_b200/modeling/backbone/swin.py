@@ -8,6 +8,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from ... import functional as PF
 from ...compat import BACKBONE_REGISTRY, Backbone, ShapeSpec
 
 
@@ -39,7 +40,8 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
-        return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+        h = self.act(PF.linear(x, self.fc1.weight, self.fc1.bias))
+        return self.drop(PF.linear(self.drop(h), self.fc2.weight, self.fc2.bias))
 
 
 def window_partition(x, ws):
@@ -73,7 +75,7 @@ class WindowAttention(nn.Module):
     def forward(self, x, mask=None):
         """x (nW*B, N, C); mask (nW, N, N) additive (0 / -100) or None."""
         Bw, N, C = x.shape
-        qkv = self.qkv(x).reshape(Bw, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+        qkv = PF.linear(x, self.qkv.weight, self.qkv.bias).reshape(Bw, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
         bias = self.relative_position_bias_table[self.relative_position_index.view(-1)].view(N, N, -1)
         bias = bias.permute(2, 0, 1).unsqueeze(0)                               # (1, heads, N, N)
         if mask is not None:
@@ -81,7 +83,7 @@ class WindowAttention(nn.Module):
             bias = (bias + mask[:, None]).repeat(Bw // nW, 1, 1, 1)              # (Bw, heads, N, N)
         o = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], attn_mask=bias.to(qkv.dtype),
                                            dropout_p=self.attn_drop.p if self.training else 0.0, scale=self.scale)
-        return self.proj_drop(self.proj(o.transpose(1, 2).reshape(Bw, N, C)))
+        return self.proj_drop(PF.linear(o.transpose(1, 2).reshape(Bw, N, C), self.proj.weight, self.proj.bias))
 
 
 class SwinTransformerBlock(nn.Module):
@@ -127,7 +129,7 @@ class PatchMerging(nn.Module):
         if H % 2 or W % 2:
             x = F.pad(x, (0, 0, 0, W % 2, 0, H % 2))
         x = torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1)
-        return self.reduction(self.norm(x.view(B, -1, 4 * C)))
+        return PF.linear(self.norm(x.view(B, -1, 4 * C)), self.reduction.weight, None)
 
 
 class BasicLayer(nn.Module):

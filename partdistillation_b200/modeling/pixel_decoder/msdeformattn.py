@@ -13,6 +13,7 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
+from ... import functional as PF
 from ...compat import SEM_SEG_HEADS_REGISTRY, Conv2d, ShapeSpec, c2_xavier_fill, configurable, get_norm
 from ..transformer_decoder.position_encoding import PositionEmbeddingSine
 from .ops.modules import MSDeformAttn
@@ -50,7 +51,11 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         src2 = self.self_attn(q, reference_points, src, spatial_shapes, level_start_index, padding_mask,
                               offset_normalizer=offset_normalizer)
         src = self.norm1(src + self.dropout1(src2))
-        src2 = self.linear2(self.dropout2(self.activation(self.linear1(src))))
+        if self.activation is F.relu:
+            hidden = PF.linear(src, self.linear1.weight, self.linear1.bias, relu=True)
+        else:
+            hidden = self.activation(PF.linear(src, self.linear1.weight, self.linear1.bias))
+        src2 = PF.linear(self.dropout2(hidden), self.linear2.weight, self.linear2.bias)
         return self.norm2(src + self.dropout3(src2))
 
 
@@ -234,7 +239,7 @@ class MSDeformAttnPixelDecoder(nn.Module):
         tensor-core mask einsum consumes (both of its operands are then K-major)."""
         conv = self.mask_features
         w = conv.weight.view(conv.out_channels, conv.in_channels)
-        mf = F.linear(y.permute(0, 2, 3, 1), w, conv.bias)          # (B, H, W, mask_dim), contiguous
+        mf = PF.linear(y.permute(0, 2, 3, 1).contiguous(), w, conv.bias)   # (B, H, W, mask_dim), contiguous
         if getattr(conv, "norm", None) is not None:
             mf = conv.norm(mf.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
         if getattr(conv, "activation", None) is not None:

@@ -48,12 +48,12 @@ class MSDeformAttn(nn.Module):
         N, Lq, _ = query.shape
         S = input_flatten.shape[1]
         M, L, P = self.n_heads, self.n_levels, self.n_points
-        value = self.value_proj(input_flatten)
+        value = PF.linear(input_flatten, self.value_proj.weight, self.value_proj.bias)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], 0.0)
         value = value.view(N, S, M, self.d_model // M)
-        offsets = self.sampling_offsets(query).view(N, Lq, M, L, P, 2)
-        weights = F.softmax(self.attention_weights(query).view(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
+        offsets = PF.linear(query, self.sampling_offsets.weight, self.sampling_offsets.bias).view(N, Lq, M, L, P, 2)
+        weights = F.softmax(PF.linear(query, self.attention_weights.weight, self.attention_weights.bias).view(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
         if reference_points.shape[-1] == 2:
             if offset_normalizer is None:
                 if isinstance(input_spatial_shapes, torch.Tensor):
@@ -69,4 +69,4 @@ class MSDeformAttn(nn.Module):
             raise ValueError(f"Last dim of reference_points must be 2 or 4, but get {reference_points.shape[-1]} instead.")
         out = PF.ms_deform_attn(value, input_spatial_shapes, input_level_start_index, loc.contiguous(),
                                 weights, self.im2col_step)
-        return self.output_proj(out)
+        return PF.linear(out, self.output_proj.weight, self.output_proj.bias)

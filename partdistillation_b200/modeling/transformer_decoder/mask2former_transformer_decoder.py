@@ -45,7 +45,7 @@ class _AttentionParams(nn.Module):
 
     def project(self, x, lo, hi):
         E = self.embed_dim
-        return F.linear(x, self.in_proj_weight[lo * E:hi * E], self.in_proj_bias[lo * E:hi * E])
+        return PF.linear(x, self.in_proj_weight[lo * E:hi * E], self.in_proj_bias[lo * E:hi * E])
 
 
 def _xavier(module):
@@ -70,7 +70,7 @@ class SelfAttentionLayer(nn.Module):
         qk = a.project(qk_in, 0, 2).view(B, Q, 2, a.num_heads, a.head_dim)
         v = a.project(x, 2, 3).view(B, Q, a.num_heads, a.head_dim)
         o = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2), v.transpose(1, 2))
-        o = a.out_proj(o.transpose(1, 2).reshape(B, Q, E))
+        o = PF.linear(o.transpose(1, 2).reshape(B, Q, E), a.out_proj.weight, a.out_proj.bias)
         return tgt + o if self.normalize_before else self.norm(tgt + o)
 
 
@@ -95,7 +95,7 @@ class CrossAttentionLayer(nn.Module):
         v = a.project(memory, 2, 3)
         mask, row_any = (memory_mask.mask, memory_mask.row_any) if memory_mask is not None else (None, None)
         o = PF.masked_cross_attention(q.float(), k.float(), v.float(), mask, row_any, a.num_heads)
-        o = a.out_proj(o.to(x.dtype))
+        o = PF.linear(o.to(x.dtype), a.out_proj.weight, a.out_proj.bias)
         return tgt + o if self.normalize_before else self.norm(tgt + o)
 
 
@@ -110,7 +110,7 @@ class FFNLayer(nn.Module):
 
     def forward(self, tgt):
         x = self.norm(tgt) if self.normalize_before else tgt
-        y = self.linear2(F.relu(self.linear1(x)))
+        y = PF.linear(PF.linear(x, self.linear1.weight, self.linear1.bias, relu=True), self.linear2.weight, self.linear2.bias)
         return tgt + y if self.normalize_before else self.norm(tgt + y)
 
 
@@ -123,9 +123,7 @@ class MLP(nn.Module):
 
     def forward(self, x):
         for i, layer in enumerate(self.layers):
-            x = layer(x)
-            if i < self.num_layers - 1:
-                x = F.relu(x)
+            x = PF.linear(x, layer.weight, layer.bias, relu=i < self.num_layers - 1)
         return x
 
 

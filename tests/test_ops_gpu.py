@@ -144,8 +144,8 @@ def test_mask_einsum(fn, B, Q, C, H, W):
     go = torch.randn(out.shape, generator=g).cuda()
     ge, gf = torch.autograd.grad(out, (e, f), go)
     rge, rgf = torch.autograd.grad(ref, (e, f), go.double())
-    assert _rel(ge.double(), rge.double()) < 2e-6
-    assert _rel(gf.double(), rgf.double()) < 2e-6
+    assert _rel(ge.double(), rge.double()) < 1e-5
+    assert _rel(gf.double(), rgf.double()) < 1e-5
 
 
 def test_mask_einsum_full_size(fn):
@@ -161,6 +161,54 @@ def test_mask_einsum_full_size(fn):
     ii = torch.randint(0, 256 * 256, (64,), generator=g).cuda()
     ref = torch.einsum("bqc,bcn->bqn", e.double(), f.flatten(2)[:, :, ii].double())
     assert _rel(out.flatten(2)[:, :, ii].double(), ref) < 1e-5
+
+
+# ------------------------------------------------------------------ tcgen05 3xTF32 GEMM / nn.Linear
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,batch,c_trans,ksplit", [
+    (256, 128, 64, 0, 0, 1, 0, 1), (300, 200, 100, 0, 0, 1, 0, 1), (1024, 100, 256, 0, 0, 2, 1, 1),
+    (300, 256, 200, 0, 1, 1, 0, 1), (256, 256, 4000, 1, 1, 1, 0, 8), (384, 96, 128, 1, 0, 1, 0, 1),
+    (4096, 256, 100, 1, 1, 2, 0, 1), (100, 256, 4096, 0, 1, 2, 0, 4), (1, 4, 4, 0, 0, 1, 0, 1)])
+def test_gemm_tf32x3_layouts(fn, M, N, K, a_mn, b_mn, batch, c_trans, ksplit):
+    """Every operand layout of pdb_gemm_tf32x3 (K-major / MN-major, batch, split-K, transposed store, ragged
+    M/N/K) against a float64 product."""
+    g = torch.Generator().manual_seed(1)
+    A = torch.randn((batch, K, M) if a_mn else (batch, M, K), generator=g).cuda()
+    B = torch.randn((batch, K, N) if b_mn else (batch, N, K), generator=g).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    acc = ksplit > 1
+    out = (torch.zeros if acc else torch.empty)((batch, N, M) if c_trans else (batch, M, N), device="cuda")
+    fn.gemm_tf32x3(A, B, out, M, N, K, batch=batch, lda=A.stride(1), ldb=B.stride(1), ldc=out.stride(1),
+                   sa=A.stride(0), sb=B.stride(0), sc=out.stride(0), a_mn=a_mn, b_mn=b_mn, c_trans=c_trans,
+                   bias=None if acc else bias, relu=not acc, accumulate=acc, ksplit=ksplit)
+    Am = A.double().transpose(1, 2) if a_mn else A.double()
+    Bm = B.double().transpose(1, 2) if b_mn else B.double()
+    ref = Am @ Bm.transpose(1, 2)
+    if not acc:
+        ref = (ref + bias.double()).clamp_min(0)
+    if c_trans:
+        ref = ref.transpose(1, 2)
+    assert _rel(out.double(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("rows,K,N,relu", [((2, 300), 256, 1024, True), ((43008,), 256, 288, False), ((200,), 2048, 256, False),
+                                           ((3, 7, 5), 64, 36, True)])
+def test_linear_forward_backward(fn, rows, K, N, relu):
+    """functional.linear (forward, input-gradient and split-K weight-gradient GEMMs) against float64 nn.Linear."""
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(*rows, K, generator=g).cuda().requires_grad_()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().requires_grad_()
+    b = torch.randn(N, generator=g).cuda().requires_grad_()
+    y = fn.linear(x, w, b, relu=relu)
+    ref = F.linear(x.double(), w.double(), b.double())
+    if relu:
+        ref = ref.relu()
+    assert _rel(y.double(), ref) < 1e-5
+    go = torch.randn(y.shape, generator=g).cuda()
+    gx, gw, gb = torch.autograd.grad(y, (x, w, b), go)
+    rx, rw, rb = torch.autograd.grad(ref, (x, w, b), go.double())
+    assert _rel(gx.double(), rx.double()) < 1e-5
+    assert _rel(gw.double(), rw.double()) < 1e-5
+    assert _rel(gb.double(), rb.double()) < 1e-5
 
 
 # ------------------------------------------------------------------ attention mask (bit-exact)
