@@ -3,7 +3,7 @@
 //     C_b[m][n] (+)= sum_k A_b(m,k) * B_b(n,k)  (+ bias[n]) (ReLU)
 // It serves nn.Linear forward / input-gradient / weight-gradient of the encoder and decoder layers
 // (reference: msdeformattn.py:120-135, ops/modules/ms_deform_attn.py:102-130,
-// mask2former_transformer_decoder.py:148-208) and the two gradient products of the mask-head einsum
+// mask2former_transformer_decoder.py:148-208) and the mask-head einsum with its two gradient products
 // (mask2former_transformer_decoder.py:449), all of which cuBLAS runs as SIMT sgemm when TF32 is off.
 //
 // fp32 accuracy on TF32 tensor cores: every operand x is split into hi = x with the low 13 mantissa
@@ -22,11 +22,17 @@
 //                                     (UMMA layout SWIZZLE_128B_BASE32B, instruction-descriptor a_major/b_major = 1)
 // TMA zero-fills out-of-range rows / k, so ragged M, N, K (and per-batch K ranges) need no masking.
 //
-// One CTA computes a 128 x BN tile of one batch item and one K slice:
-//   warp 0      TMA producer            warp 1   TMEM allocator + tcgen05.mma issuer (one elected lane)
-//   warps 2..5  hi/lo split of every landed stage in shared memory (element-wise, hence layout-agnostic),
-//               then the epilogue: tcgen05.ld -> (+bias, ReLU) -> coalesced store / red.add
-// Pipeline per stage: full (TMA bytes landed) -> split (hi/lo ready) -> tcgen05.commit -> empty.
+// Persistent kernel, one CTA per SM, 14 warps; a CTA walks 128 x BN output tiles (n fastest, so the CTAs that
+// run together share their A rows in L2):
+//   warp 0      TMA producer: raw fp32 A / B k-blocks into a 3-deep ring
+//   warps 2..9  split every landed k-block: the raw tile is the hi operand (tf32 ignores the low 13 bits), lo =
+//               x - trunc(x) is written next to it: B_lo right behind B_hi (so one N = 2*BN MMA yields
+//               hi*hi and hi*lo side by side in TMEM), A_lo into its own 2-deep ring
+//   warp 1      TMEM allocator + tcgen05.mma issuer (one elected lane): per 8-wide k step
+//               [main | corr] += A_hi x [B_hi ; B_lo]^T   and   corr += A_lo x B_hi^T
+//   warps 10..13 epilogue: tcgen05.ld (main + corr) -> (+bias, ReLU) -> coalesced store / red.add, overlapped
+//               with the next tile's main loop through a double-buffered TMEM accumulator
+#include <algorithm>
 #include "common.cuh"
 #include "tc_gemm.cuh"
 
@@ -34,7 +40,11 @@ namespace pdb {
 
 constexpr int G_BM = 128;
 constexpr int G_BK = 32;              // fp32 per 128-byte swizzled row
-constexpr int G_THREADS = 192;
+constexpr int G_SPLIT_THREADS = 256;  // warps 2..9
+constexpr int G_EPI_WARP0 = 2 + G_SPLIT_THREADS / 32;
+constexpr int G_THREADS = (G_EPI_WARP0 + 4) * 32;     // 448
+constexpr int G_RS = 3;               // raw ring depth
+constexpr int G_LS = 2;               // A_lo ring depth
 
 struct GemmParams {
     float* C;
@@ -43,16 +53,22 @@ struct GemmParams {
     int64_t ldc, sc;
     int batch, ksplit, kchunk;        // kchunk: multiple of G_BK
     int c_trans, relu, atomic;
+    int mt, nt, total_tiles;
+    long long* trace;                 // debug timeline of CTA 0 (pdb_debug_set_trace), normally NULL
 };
 
 template <int BN>
 struct GemmSmem {
-    static constexpr int STAGES = BN <= 128 ? 3 : 2;
     static constexpr int A_BYTES = G_BM * G_BK * 4;       // 16 KB
     static constexpr int B_BYTES = BN * G_BK * 4;
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int TMEM_COLS = 2 * BN;              // main (hi*hi) + correction (lo*hi + hi*lo) accumulators
+    static constexpr int RAW_STAGE = A_BYTES + 2 * B_BYTES;            // A raw/hi | B raw/hi | B lo
+    static constexpr int RAW_TOTAL = G_RS * RAW_STAGE;
+    static constexpr int ALO_TOTAL = G_LS * A_BYTES;
+    static constexpr int STAGING = 4 * 32 * 36 * 4;                    // epilogue transpose tiles (row stride 36 floats)
+    static constexpr int BAR_OFF = RAW_TOTAL + ALO_TOTAL + STAGING;
+    static constexpr int TOTAL = BAR_OFF + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int ACC_COLS = 2 * BN;               // main (hi*hi) | correction (lo*hi + hi*lo)
+    static constexpr int TMEM_COLS = 2 * ACC_COLS;        // double buffered
 };
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
@@ -73,208 +89,352 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(const void* smem_tile, ui
     return d;
 }
 
-__device__ __forceinline__ void split_f4(float4* hi_ptr, float4* lo_ptr) {
-    float4 x = *hi_ptr;
-    float4 h, l;
+template <bool MN>
+__device__ __forceinline__ uint64_t operand_desc(const void* tile, int k8) {
+    return MN ? umma_desc_mn_sw128(tile, k8 * 1024, 4096u, 512u) : tc::umma_desc_k_sw128(tile, k8 * 32);
+}
+
+__device__ __forceinline__ void split4(const float4 x, float4& h, float4& l) {
     h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
     h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
     h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
     h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
-    *hi_ptr = h;
-    *lo_ptr = l;
 }
 
-__device__ int g_desc_mode = 0;     // debug hook (pdb_debug_set_desc_mode): 1 swaps LBO / SBO of MN-major descriptors
+__device__ __forceinline__ void trace_evt(const GemmParams& p, int role, int idx, int slot) {
+    if (p.trace && blockIdx.x == 0 && idx < 256) p.trace[(role * 256 + idx) * 4 + slot] = clock64();
+}
+
+// Writes lo = x - trunc_tf32(x) for NV float4 per thread of a tile.  The raw tile itself serves as the hi operand:
+// kind::tf32 reads the top 19 bits of each 32-bit container and ignores the low 13 mantissa bits, i.e. the
+// tensor core sees exactly trunc_tf32(x) (verified on B200: bit-identical results with and without masking).
+template <int NV>
+__device__ __forceinline__ void split_tile(const float4* raw, float4* lo, int t) {
+    float4 x[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) x[i] = raw[i * G_SPLIT_THREADS + t];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float4 h, l;
+        split4(x[i], h, l);
+        lo[i * G_SPLIT_THREADS + t] = l;
+    }
+}
+
+struct TileCoord {
+    int m0, n0, b, k_begin, num_kb, bn_eff;
+};
+
+template <int BN>
+__device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int tile) {
+    TileCoord c;
+    const int ni = tile % p.nt;
+    int r = tile / p.nt;
+    const int mi = r % p.mt;
+    r /= p.mt;
+    const int ks = r % p.ksplit;
+    c.b = r / p.ksplit;
+    c.m0 = mi * G_BM;
+    c.n0 = ni * BN;
+    c.k_begin = ks * p.kchunk;
+    const int k_end = min(p.K, c.k_begin + p.kchunk);
+    c.num_kb = (k_end - c.k_begin + G_BK - 1) / G_BK;
+    c.bn_eff = min(BN, ((p.N - c.n0 + 15) >> 4) << 4);     // MMA N actually needed: ragged N costs no tensor time
+    return c;
+}
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const GemmParams p) {
     using S = GemmSmem<BN>;
-    constexpr int STAGES = S::STAGES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
-    uint64_t* full = bars;
-    uint64_t* split = bars + STAGES;
-    uint64_t* empty = bars + 2 * STAGES;
-    uint64_t* accum = bars + 3 * STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+    // 1 KB alignment by pointer arithmetic (no integer round trip), so the compiler keeps the shared state space
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* alo_ring = smem + S::RAW_TOTAL;
+    float* staging = reinterpret_cast<float*>(smem + S::RAW_TOTAL + S::ALO_TOTAL);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* raw_full = bars;                      // TMA bytes landed
+    uint64_t* raw_empty = bars + G_RS;              // MMAs reading the stage completed
+    uint64_t* split_done = bars + 2 * G_RS;         // hi / lo of the stage ready (128 arrivals)
+    uint64_t* alo_empty = bars + 3 * G_RS;          // [G_LS]
+    uint64_t* acc_full = alo_empty + G_LS;          // [2]
+    uint64_t* acc_empty = acc_full + 2;             // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * G_BM;
-    const int n0 = blockIdx.y * BN;
-    const int b = blockIdx.z / p.ksplit;
-    const int ks = blockIdx.z - b * p.ksplit;
-    const int k_begin = ks * p.kchunk;
-    const int k_end = min(p.K, k_begin + p.kchunk);
-    const int num_kb = (k_end - k_begin + G_BK - 1) / G_BK;
-    // MMA N actually needed by this tile (multiple of 16): ragged N costs no tensor time
-    const int bn_eff = min(BN, ((p.N - n0 + 15) >> 4) << 4);
 
-    auto a_hi = [&](int s) { return smem + s * S::STAGE_BYTES; };
-    auto a_lo = [&](int s) { return smem + s * S::STAGE_BYTES + S::A_BYTES; };
-    auto b_hi = [&](int s) { return smem + s * S::STAGE_BYTES + 2 * S::A_BYTES; };
-    auto b_lo = [&](int s) { return smem + s * S::STAGE_BYTES + 2 * S::A_BYTES + S::B_BYTES; };
+    auto a_raw = [&](int s) { return smem + s * S::RAW_STAGE; };
+    auto b_raw = [&](int s) { return smem + s * S::RAW_STAGE + S::A_BYTES; };
+    auto a_lo = [&](int s) { return alo_ring + s * S::A_BYTES; };
 
     if (threadIdx.x == 0) {
         tc::prefetch_tensormap(&tm_a);
         tc::prefetch_tensormap(&tm_b);
-        for (int s = 0; s < STAGES; ++s) {
-            tc::mbar_init(&full[s], 1);
-            tc::mbar_init(&split[s], 128);
-            tc::mbar_init(&empty[s], 1);
+        for (int s = 0; s < G_RS; ++s) {
+            tc::mbar_init(&raw_full[s], 1);
+            tc::mbar_init(&raw_empty[s], 1);
+            tc::mbar_init(&split_done[s], G_SPLIT_THREADS);
         }
-        tc::mbar_init(accum, 1);
+        for (int s = 0; s < G_LS; ++s) tc::mbar_init(&alo_empty[s], 1);
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&acc_full[s], 1);
+            tc::mbar_init(&acc_empty[s], 128);
+        }
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc<S::TMEM_COLS>(tmem_slot);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                const int k0 = k_begin + kb * G_BK;
-                tc::mbar_wait(&empty[s], ph ^ 1);
-                tc::mbar_expect_tx(&full[s], S::A_BYTES + S::B_BYTES);
-                if (A_MN) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord c = tile_coord<BN>(p, tile);
+                for (int kb = 0; kb < c.num_kb; ++kb, ++it) {
+                    const int s = it % G_RS;
+                    const uint32_t ph = (it / G_RS) & 1;
+                    const int k0 = c.k_begin + kb * G_BK;
+                    tc::mbar_wait(&raw_empty[s], ph ^ 1);
+                    trace_evt(p, 0, it, 0);
+                    tc::mbar_expect_tx(&raw_full[s], S::A_BYTES + S::B_BYTES);
+                    if (A_MN) {
 #pragma unroll
-                    for (int i = 0; i < G_BM / 32; ++i) tma_load_3d(a_hi(s) + i * 4096, &tm_a, &full[s], m0 + 32 * i, k0, b);
-                } else {
-                    tma_load_3d(a_hi(s), &tm_a, &full[s], k0, m0, b);
-                }
-                if (B_MN) {
+                        for (int i = 0; i < G_BM / 32; ++i) tma_load_3d(a_raw(s) + i * 4096, &tm_a, &raw_full[s], c.m0 + 32 * i, k0, c.b);
+                    } else {
+                        tma_load_3d(a_raw(s), &tm_a, &raw_full[s], k0, c.m0, c.b);
+                    }
+                    if (B_MN) {
 #pragma unroll
-                    for (int i = 0; i < BN / 32; ++i) tma_load_3d(b_hi(s) + i * 4096, &tm_b, &full[s], n0 + 32 * i, k0, b);
-                } else {
-                    tma_load_3d(b_hi(s), &tm_b, &full[s], k0, n0, b);
+                        for (int i = 0; i < BN / 32; ++i) tma_load_3d(b_raw(s) + i * 4096, &tm_b, &raw_full[s], c.n0 + 32 * i, k0, c.b);
+                    } else {
+                        tma_load_3d(b_raw(s), &tm_b, &raw_full[s], k0, c.n0, c.b);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = tc::umma_idesc_tf32(G_BM, bn_eff) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
-            const uint32_t lbo = g_desc_mode ? 512u : 4096u, sbo = g_desc_mode ? 4096u : 512u;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                tc::mbar_wait(&full[s], ph);
-                tc::mbar_wait(&split[s], ph);
+            uint32_t it = 0, t = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+                const TileCoord c = tile_coord<BN>(p, tile);
+                const uint32_t ab = t & 1;
+                const uint32_t tmem_main = tmem_base + ab * S::ACC_COLS;
+                const uint32_t tmem_corr = tmem_main + c.bn_eff;
+                // B_lo sits bn_eff rows behind B_hi; a single N = 2*bn_eff MMA needs that to be a whole number of
+                // 32-column blocks for MN-major B
+                const bool stacked = !B_MN || (c.bn_eff % 32 == 0);
+                const uint32_t major = (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+                const uint32_t idesc1 = tc::umma_idesc_tf32(G_BM, c.bn_eff) | major;
+                const uint32_t idesc2 = tc::umma_idesc_tf32(G_BM, 2 * c.bn_eff) | major;
+                trace_evt(p, 1, it, 3);
+                tc::mbar_wait(&acc_empty[ab], ((t >> 1) & 1) ^ 1);
                 tc::tc_fence_after();
+                for (int kb = 0; kb < c.num_kb; ++kb, ++it) {
+                    const int s = it % G_RS;
+                    const int ls = it % G_LS;
+                    tc::mbar_wait(&raw_full[s], (it / G_RS) & 1);
+                    trace_evt(p, 1, it, 0);
+                    tc::mbar_wait(&split_done[s], (it / G_RS) & 1);
+                    tc::tc_fence_after();
+                    trace_evt(p, 1, it, 1);
+                    const uint8_t* blo = b_raw(s) + (B_MN ? ((c.bn_eff + 31) / 32) * 4096 : c.bn_eff * 128);
 #pragma unroll
-                for (int k = 0; k < G_BK / 8; ++k) {
-                    uint64_t dah, dal, dbh, dbl;
-                    if (A_MN) {
-                        dah = umma_desc_mn_sw128(a_hi(s), k * 1024, lbo, sbo);
-                        dal = umma_desc_mn_sw128(a_lo(s), k * 1024, lbo, sbo);
-                    } else {
-                        dah = tc::umma_desc_k_sw128(a_hi(s), k * 32);
-                        dal = tc::umma_desc_k_sw128(a_lo(s), k * 32);
+                    for (int k = 0; k < G_BK / 8; ++k) {
+                        const uint64_t dah = operand_desc<A_MN>(a_raw(s), k);
+                        const uint64_t dal = operand_desc<A_MN>(a_lo(ls), k);
+                        const uint64_t dbh = operand_desc<B_MN>(b_raw(s), k);
+                        const uint32_t acc = (kb | k) != 0;
+                        if (stacked) {
+                            tc::mma_tf32(tmem_main, dah, dbh, idesc2, acc);      // [main | corr] += A_hi x [B_hi ; B_lo]^T
+                            tc::mma_tf32(tmem_corr, dal, dbh, idesc1, 1);        // corr += A_lo x B_hi^T
+                        } else {
+                            const uint64_t dbl = operand_desc<B_MN>(blo, k);
+                            tc::mma_tf32(tmem_corr, dal, dbh, idesc1, acc);
+                            tc::mma_tf32(tmem_corr, dah, dbl, idesc1, 1);
+                            tc::mma_tf32(tmem_main, dah, dbh, idesc1, acc);
+                        }
                     }
-                    if (B_MN) {
-                        dbh = umma_desc_mn_sw128(b_hi(s), k * 1024, lbo, sbo);
-                        dbl = umma_desc_mn_sw128(b_lo(s), k * 1024, lbo, sbo);
-                    } else {
-                        dbh = tc::umma_desc_k_sw128(b_hi(s), k * 32);
-                        dbl = tc::umma_desc_k_sw128(b_lo(s), k * 32);
-                    }
-                    tc::mma_tf32(tmem_d + BN, dal, dbh, idesc, (kb | k) != 0);    // correction accumulator
-                    tc::mma_tf32(tmem_d + BN, dah, dbl, idesc, 1);
-                    tc::mma_tf32(tmem_d, dah, dbh, idesc, (kb | k) != 0);          // main accumulator
+                    tc::tc_commit(&raw_empty[s]);          // both arrive once the MMAs above have read their operands
+                    tc::tc_commit(&alo_empty[ls]);
+                    trace_evt(p, 1, it, 2);
                 }
-                tc::tc_commit(&empty[s]);          // frees the stage once these MMAs have read it
+                tc::tc_commit(&acc_full[ab]);
             }
-            tc::tc_commit(accum);
         }
-    } else {
-        // ---- hi/lo split of every landed stage (warps 2..5 = 128 threads)
-        const int t = threadIdx.x - 64;
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            tc::mbar_wait(&full[s], ph);
-            float4* ah = reinterpret_cast<float4*>(a_hi(s));
-            float4* al = reinterpret_cast<float4*>(a_lo(s));
+    } else if (warp < G_EPI_WARP0) {
+        // ------------------------------------------------------------------ hi / lo split (warps 2..9)
+        const int tid = threadIdx.x - 64;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const TileCoord c = tile_coord<BN>(p, tile);
+            const int blo_off = B_MN ? ((c.bn_eff + 31) / 32) * 4096 : c.bn_eff * 128;
+            for (int kb = 0; kb < c.num_kb; ++kb, ++it) {
+                const int s = it % G_RS;
+                const int ls = it % G_LS;
+                if (tid == 0) trace_evt(p, 2, it, 0);
+                tc::mbar_wait(&raw_full[s], (it / G_RS) & 1);
+                if (tid == 0) trace_evt(p, 2, it, 1);
+                tc::mbar_wait(&alo_empty[ls], ((it / G_LS) & 1) ^ 1);
+                if (tid == 0) trace_evt(p, 2, it, 2);
+                split_tile<S::A_BYTES / 16 / G_SPLIT_THREADS>(reinterpret_cast<float4*>(a_raw(s)), reinterpret_cast<float4*>(a_lo(ls)), tid);
+                float4* braw = reinterpret_cast<float4*>(b_raw(s));
+                float4* blo = reinterpret_cast<float4*>(b_raw(s) + blo_off);
+                if (c.bn_eff == BN) {
+                    split_tile<S::B_BYTES / 16 / G_SPLIT_THREADS>(braw, blo, tid);
+                } else {
+                    // ragged N tile: only the first bn_eff rows (K-major) / 32-column blocks (MN-major) matter; B_lo
+                    // starts right behind them, over the unused (zero-filled) tail of the raw tile, so the ranges
+                    // read (index < nvec) and written as lo (index >= nvec) are disjoint
+                    const int nvec = B_MN ? ((c.bn_eff + 31) / 32) * 256 : c.bn_eff * 8;
+                    constexpr int NVB = S::B_BYTES / 16 / G_SPLIT_THREADS;
+                    float4 x[NVB];
 #pragma unroll
-            for (int i = 0; i < S::A_BYTES / 16 / 128; ++i) split_f4(ah + i * 128 + t, al + i * 128 + t);
-            float4* bh = reinterpret_cast<float4*>(b_hi(s));
-            float4* bl = reinterpret_cast<float4*>(b_lo(s));
+                    for (int i = 0; i < NVB; ++i) x[i] = (i * G_SPLIT_THREADS + tid < nvec) ? braw[i * G_SPLIT_THREADS + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < S::B_BYTES / 16 / 128; ++i) split_f4(bh + i * 128 + t, bl + i * 128 + t);
-            tc::fence_proxy_async();
-            tc::mbar_arrive(&split[s]);
-        }
-        // ---- epilogue
-        tc::mbar_wait(accum, 0);
-        tc::tc_fence_after();
-        const int quarter = warp & 3;                          // TMEM lanes this warp may access
-        const uint32_t tbase = tmem_d + ((uint32_t)(quarter * 32) << 16);
-        float* Cb = p.C + (int64_t)b * p.sc;
-        if (p.c_trans) {
-            // C[n][m]: lane = m, so for a fixed n the warp stores 32 consecutive floats
-            const int m = m0 + quarter * 32 + lane;
-#pragma unroll 1
-            for (int c0 = 0; c0 < bn_eff; c0 += 16) {
-                float v[16], w[16];
-                tc::tmem_ld16(tbase + c0, v);
-                tc::tmem_ld16(tbase + BN + c0, w);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] += w[i];
-                if (m < p.M) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int n = n0 + c0 + i;
-                        if (n < p.N) {
-                            float x = v[i];
-                            if (p.bias) x += __ldg(p.bias + n);
-                            if (p.relu) x = fmaxf(x, 0.f);
-                            float* dst = Cb + (int64_t)n * p.ldc + m;
-                            if (p.atomic) atomicAdd(dst, x); else *dst = x;
+                    for (int i = 0; i < NVB; ++i) {
+                        if (i * G_SPLIT_THREADS + tid < nvec) {
+                            float4 h, l;
+                            split4(x[i], h, l);
+                            blo[i * G_SPLIT_THREADS + tid] = l;
                         }
                     }
                 }
-            }
-        } else {
-            // C[m][n]: transpose 32x32 blocks through shared memory so that each store instruction
-            // writes 32 consecutive floats of one row
-            float* tile = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
-            const int mrow0 = m0 + quarter * 32;
-#pragma unroll 1
-            for (int c0 = 0; c0 < bn_eff; c0 += 32) {
-                float v[32], w[32];
-                tc::tmem_ld16(tbase + c0, v);
-                tc::tmem_ld16(tbase + c0 + 16, v + 16);      // columns beyond bn_eff hold stale TMEM: never stored
-                tc::tmem_ld16(tbase + BN + c0, w);
-                tc::tmem_ld16(tbase + BN + c0 + 16, w + 16);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = v[i] + w[i];
-                __syncwarp();
-                const int n = n0 + c0 + lane;
-                const bool n_ok = n < p.N;
-                const float bv = (p.bias && n_ok) ? __ldg(p.bias + n) : 0.f;
-#pragma unroll 4
-                for (int r = 0; r < 32; ++r) {
-                    const int m = mrow0 + r;
-                    if (m < p.M && n_ok) {
-                        float x = tile[r * 33 + lane] + bv;
-                        if (p.relu) x = fmaxf(x, 0.f);
-                        float* dst = Cb + (int64_t)m * p.ldc + n;
-                        if (p.atomic) atomicAdd(dst, x); else *dst = x;
-                    }
-                }
-                __syncwarp();
+                tc::fence_proxy_async();
+                tc::mbar_arrive(&split_done[s]);
+                if (tid == 0) trace_evt(p, 2, it, 3);
             }
         }
-        tc::tc_fence_before();
+    } else {
+        // ------------------------------------------------------------------ epilogue (last 4 warps)
+        const int quarter = warp & 3;                          // TMEM lanes this warp may access
+        float* tile_s = staging + (warp - G_EPI_WARP0) * (32 * 36);
+        const bool trace_thread = threadIdx.x == G_EPI_WARP0 * 32;
+        // 16-byte row stores need aligned rows
+        const bool vec_ok = !p.c_trans && (p.N % 4 == 0) && (p.ldc % 4 == 0) && (p.sc % 4 == 0) &&
+                            ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+        uint32_t t = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+            const TileCoord c = tile_coord<BN>(p, tile);
+            const uint32_t ab = t & 1;
+            const uint32_t tbase = tmem_base + ab * S::ACC_COLS + ((uint32_t)(quarter * 32) << 16);
+            if (trace_thread) trace_evt(p, 3, t, 0);
+            tc::mbar_wait(&acc_full[ab], (t >> 1) & 1);
+            tc::tc_fence_after();
+            if (trace_thread) trace_evt(p, 3, t, 1);
+            float* Cb = p.C + (int64_t)c.b * p.sc;
+            if (p.c_trans) {
+                // C[n][m]: lane = m, so for a fixed n the warp stores 32 consecutive floats
+                const int m = c.m0 + quarter * 32 + lane;
+                const bool m_ok = m < p.M;
+                float* col = Cb + (int64_t)c.n0 * p.ldc + m;
+                const int nvalid = min(c.bn_eff, p.N - c.n0);
+#pragma unroll 1
+                for (int c0 = 0; c0 < c.bn_eff; c0 += 16) {
+                    float v[16], w[16];
+                    tc::tmem_ld16(tbase + c0, v);
+                    tc::tmem_ld16(tbase + c.bn_eff + c0, w);
+                    if (c0 + 16 >= c.bn_eff) {                 // last read of this accumulator: hand it back to the MMA warp
+                        tc::tc_fence_before();
+                        tc::mbar_arrive(&acc_empty[ab]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float x = v[i] + w[i];
+                        if (p.bias) x += __ldg(p.bias + min(c.n0 + c0 + i, p.N - 1));
+                        if (p.relu) x = fmaxf(x, 0.f);
+                        v[i] = x;
+                    }
+                    if (m_ok) {
+                        const int lim = nvalid - c0;           // columns of this group that exist
+                        if (p.atomic) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (i < lim) atomicAdd(col + (int64_t)i * p.ldc, v[i]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (i < lim) col[(int64_t)i * p.ldc] = v[i];
+                        }
+                    }
+                    col += 16 * p.ldc;
+                }
+            } else {
+                // C[m][n]: transpose 32 x 32 blocks through shared memory so that a warp store instruction writes
+                // four 128-byte row segments (float4 per lane)
+                const int mrow0 = c.m0 + quarter * 32;
+                const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+#pragma unroll 1
+                for (int c0 = 0; c0 < c.bn_eff; c0 += 32) {
+                    const bool two = c0 + 16 < c.bn_eff;       // bn_eff is a multiple of 16, not of 32
+                    float v[16], w[16];
+                    tc::tmem_ld16(tbase + c0, v);
+                    tc::tmem_ld16(tbase + c.bn_eff + c0, w);
+                    float4* srow = reinterpret_cast<float4*>(tile_s + lane * 36);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        srow[i] = make_float4(v[4 * i] + w[4 * i], v[4 * i + 1] + w[4 * i + 1], v[4 * i + 2] + w[4 * i + 2], v[4 * i + 3] + w[4 * i + 3]);
+                    if (two) {
+                        tc::tmem_ld16(tbase + c0 + 16, v);
+                        tc::tmem_ld16(tbase + c.bn_eff + c0 + 16, w);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            srow[4 + i] = make_float4(v[4 * i] + w[4 * i], v[4 * i + 1] + w[4 * i + 1], v[4 * i + 2] + w[4 * i + 2], v[4 * i + 3] + w[4 * i + 3]);
+                    }
+                    if (c0 + 32 >= c.bn_eff) {
+                        tc::tc_fence_before();
+                        tc::mbar_arrive(&acc_empty[ab]);
+                    }
+                    __syncwarp();
+                    const int ncols = min(two ? 32 : 16, p.N - c.n0 - c0);       // valid columns of this block
+                    if (vec_ok) {
+                        const int n = c.n0 + c0 + sub_c;
+                        const bool n_ok = sub_c < ncols;                            // N % 4 == 0: whole float4 valid
+                        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias && n_ok) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                        float* dst = Cb + (int64_t)(mrow0 + sub_r) * p.ldc + n;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = i * 4 + sub_r;
+                            float4 x = *reinterpret_cast<const float4*>(tile_s + r * 36 + sub_c);
+                            x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+                            if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                            if (n_ok && mrow0 + r < p.M) {
+                                if (p.atomic) red_add_v4(dst, x.x, x.y, x.z, x.w);
+                                else *reinterpret_cast<float4*>(dst) = x;
+                            }
+                            dst += 4 * p.ldc;
+                        }
+                    } else {
+                        const int n = c.n0 + c0 + lane;
+                        const bool n_ok = lane < ncols;
+                        const float bv = (p.bias && n_ok) ? __ldg(p.bias + n) : 0.f;
+                        float* dst = Cb + (int64_t)mrow0 * p.ldc + n;
+#pragma unroll 4
+                        for (int r = 0; r < 32; ++r) {
+                            if (mrow0 + r < p.M && n_ok) {
+                                float x = tile_s[r * 36 + lane] + bv;
+                                if (p.relu) x = fmaxf(x, 0.f);
+                                if (p.atomic) atomicAdd(dst, x); else *dst = x;
+                            }
+                            dst += p.ldc;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            if (trace_thread) trace_evt(p, 3, t, 2);
+        }
     }
+    tc::tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc<S::TMEM_COLS>(tmem_d);
+    if (warp == 1) tc::tmem_dealloc<S::TMEM_COLS>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -319,6 +479,8 @@ static int make_operand_map(CUtensorMap* map, const float* base, bool mn_major, 
                                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+static long long* g_trace_ptr = nullptr;
+
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
     using S = GemmSmem<BN>;
@@ -328,8 +490,13 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
         if (e != cudaSuccess) return fail(PDB_ERR_LAUNCH, "gemm_tf32x3: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    dim3 grid((unsigned)((p.M + G_BM - 1) / G_BM), (unsigned)((p.N + BN - 1) / BN), (unsigned)(p.batch * p.ksplit));
-    gemm_tf32x3_kernel<BN, A_MN, B_MN><<<grid, G_THREADS, S::TOTAL, st>>>(ta, tb, p);
+    GemmParams q = p;
+    q.trace = g_trace_ptr;
+    q.mt = (p.M + G_BM - 1) / G_BM;
+    q.nt = (p.N + BN - 1) / BN;
+    q.total_tiles = q.mt * q.nt * p.batch * p.ksplit;
+    const unsigned grid = (unsigned)std::min(q.total_tiles, kNumSMs);        // persistent: one CTA per SM
+    gemm_tf32x3_kernel<BN, A_MN, B_MN><<<grid, G_THREADS, S::TOTAL, st>>>(ta, tb, q);
     return launched("gemm_tf32x3");
 }
 
@@ -378,7 +545,7 @@ extern "C" int pdb_gemm_tf32x3(const float* A, const float* B, float* C, const f
                        ksplit, as_stream(stream));
 }
 
-extern "C" PDB_API int pdb_debug_set_desc_mode(int mode) {
-    cudaError_t e = cudaMemcpyToSymbol(g_desc_mode, &mode, sizeof(int));
-    return e == cudaSuccess ? PDB_OK : fail(PDB_ERR_LAUNCH, "set_desc_mode: %s", cudaGetErrorString(e));
+extern "C" PDB_API int pdb_debug_set_trace(long long* buf) {
+    g_trace_ptr = buf;
+    return PDB_OK;
 }
