@@ -162,42 +162,89 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
-def kernel_roofline(device):
-    """Dominant custom kernel of the step: the MSDeformAttn gather at the C2 encoder shape
-    (N=2, levels 32^2/64^2/128^2, S=Lq=21504, M=8, D=32, P=4): 137.6 MB algorithmic per launch."""
+def _time_kernel(f, flush, iters=20, warmup=3):
+    """Average launch duration in seconds: CUDA events on the launching (current) stream, L2 flushed before each."""
+    ts = []
+    for i in range(warmup + iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+        s.record()
+        f()
+        e.record()
+        torch.cuda.synchronize()
+        if i >= warmup:
+            ts.append(s.elapsed_time(e) * 1e-3)
+    return sum(ts) / len(ts)
+
+
+def kernel_rooflines(device):
+    """Live rooflines of the hot kernels at the C2 shapes of one step (N = 2 images per GPU):
+      * mask einsum forward  B=2, Q=100, C=256, 256x256      186.9 MB algorithmic
+      * MSDeformAttn gather  N=2, levels 32^2/64^2/128^2, S=Lq=21504, M=8, D=32, P=4     137.6 MB
+      * MSDeformAttn scatter (backward)                                                    231.2 MB
+      * encoder FFN linear 43008 x 256 -> 1024 on the tcgen05 3xTF32 GEMM                  22.5 GFLOP (tensor bound)
+    """
     from partdistillation_b200 import functional as fn
     g = torch.Generator().manual_seed(0)
-    shapes = [(32, 32), (64, 64), (128, 128)]
+    peak, how = measured_peak()
+    try:
+        tf_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        tf_peak = 1590.0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    out = []
+
+    def hbm_entry(name, alg_bytes, t):
+        ach = alg_bytes / t / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "peak_source": how, "unit": "GB/s",
+                "frac": round(ach / peak, 4), "traffic": None, "algorithmic_bytes": alg_bytes,
+                "avg_launch_us": round(t * 1e6, 2)}
+
+    # ---- mask einsum (bqc,bchw->bqhw)
+    B, Q, C, HH, WW = PER_GPU_BATCH, QUERIES, 256, H // 4, W // 4
+    e = torch.randn(B, Q, C, generator=g).to(device)
+    f = torch.randn(B, C, HH, WW, generator=g).to(device).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        t = _time_kernel(lambda: fn.mask_einsum(e, f), flush)
+    out.append(hbm_entry("gemm_tf32x3_kernel (mask einsum fwd)", 4 * (B * Q * C + B * C * HH * WW + B * Q * HH * WW), t))
+    out[-1]["traffic"] = 191.2e6          # dram read+write per launch from profiles/r01_ncu_einsum_fwd.txt (ncu --set full)
+
+    # ---- MSDeformAttn gather / scatter at the encoder shape
+    shapes = [(H // 32, W // 32), (H // 16, W // 16), (H // 8, W // 8)]
     N, M, D, P, L = PER_GPU_BATCH, 8, 32, 4, 3
     S = sum(h * w for h, w in shapes)
-    value = torch.randn(N, S, M, D, generator=g).to(device)
+    value = torch.randn(N, S, M, D, generator=g).to(device).requires_grad_()
     refs = []
     for (hh, ww) in shapes:
         ys, xs = torch.meshgrid((torch.arange(hh) + 0.5) / hh, (torch.arange(ww) + 0.5) / ww, indexing="ij")
         refs.append(torch.stack((xs.reshape(-1), ys.reshape(-1)), -1))
     ref = torch.cat(refs)[None, :, None, None, None, :]
     norm = torch.tensor([[w_, h_] for h_, w_ in shapes], dtype=torch.float32)[None, None, None, :, None, :]
-    loc = (ref + (torch.rand(N, S, M, L, P, 2, generator=g) * 2 - 1) * 4.0 / norm).contiguous().to(device)
-    attn = torch.softmax(torch.randn(N, S, M, L * P, generator=g), -1).view(N, S, M, L, P).contiguous().to(device)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    alg_bytes = 4 * (N * S * M * D + N * S * M * L * P * 3 + N * S * M * D)
-    times = []
+    loc = (ref + (torch.rand(N, S, M, L, P, 2, generator=g) * 2 - 1) * 4.0 / norm).contiguous().to(device).requires_grad_()
+    attn = torch.softmax(torch.randn(N, S, M, L * P, generator=g), -1).view(N, S, M, L, P).contiguous().to(device).requires_grad_()
+    fwd_bytes = 4 * (N * S * M * D + N * S * M * L * P * 3 + N * S * M * D)
     with torch.no_grad():
-        for i in range(3 + 20):
-            flush.zero_()
-            s, e = torch.cuda.Event(True), torch.cuda.Event(True)
-            s.record()
-            fn.ms_deform_attn(value, shapes, None, loc, attn)
-            e.record()
-            torch.cuda.synchronize()
-            if i >= 3:
-                times.append(s.elapsed_time(e) * 1e-3)
-    t = sum(times) / len(times)
-    peak, how = measured_peak()
-    ach = alg_bytes / t / 1e9
-    return {"kernel": "msda_fwd_d32", "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "peak_source": how,
-            "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None, "algorithmic_bytes": alg_bytes,
-            "avg_launch_us": round(t * 1e6, 2)}
+        t = _time_kernel(lambda: fn.ms_deform_attn(value, shapes, None, loc, attn), flush)
+    out.append(hbm_entry("msda_fwd_tiled", fwd_bytes, t))
+    o = fn.ms_deform_attn(value, shapes, None, loc, attn)
+    go = torch.randn_like(o)
+    t = _time_kernel(lambda: torch.autograd.grad(o, (value, loc, attn), go, retain_graph=True), flush)
+    out.append(hbm_entry("msda_bwd_tiled (+ grad_value zero fill)", 2 * fwd_bytes - 4 * N * S * M * D, t))
+
+    # ---- encoder FFN linear on the tensor cores (3 tf32 MMAs per fp32 product: ceiling = tf32 dense / 3 ~ bf16 peak / 6)
+    rows = N * S
+    x = torch.randn(rows, 256, generator=g).to(device)
+    w = torch.randn(1024, 256, generator=g).to(device)
+    bias = torch.randn(1024, generator=g).to(device)
+    with torch.no_grad():
+        t = _time_kernel(lambda: fn.linear(x, w, bias, relu=True), flush)
+    flops = 2.0 * rows * 1024 * 256
+    ach = flops / t / 1e12
+    out.append({"kernel": "gemm_tf32x3_kernel (encoder FFN linear1 43008x256->1024, fp32-equivalent flops)", "bound": "tensor",
+                "achieved": round(ach, 1), "peak": tf_peak, "peak_source": how + " bf16 burst", "unit": "TFLOP/s",
+                "frac": round(ach / tf_peak, 4), "frac_of_3xtf32_ceiling": round(ach / (tf_peak / 6), 4), "traffic": None,
+                "algorithmic_flops": flops, "avg_launch_us": round(t * 1e6, 2)})
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -301,7 +348,8 @@ def main():
     images = PER_GPU_BATCH * world * args.steps
     line = None
     if rank == 0:
-        roof = kernel_roofline(device)
+        roofs = kernel_rooflines(device)
+        roof = roofs[0]
         line = {"metric": METRIC, "value": round(images / (ms * 1e-3), 3), "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -317,7 +365,7 @@ def main():
                         "h2d_bytes_per_step": batch_bytes(host_batch), "d2h_bytes_per_step": 4,
                         "ms_per_step": round(e2e_ms / args.steps, 3), "last_loss": last_loss},
                 "gpu_launches": int(launches),
-                "roofline": roof}
+                "roofline": roof, "roofline_kernels": roofs}
     if world > 1:
         dist.barrier()
     if rank == 0:

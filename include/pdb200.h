@@ -205,6 +205,23 @@ PDB_API int pdb_class_rows_backward(const float* x, const double* weight, const 
                             float* grad_x, double* grad_weight, double* grad_bias,
                             int B, int Q, int C, int Pn, int64_t Ncls, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer step on the flat gradient buffer — replaces FullModelGradientClippingOptimizer
+ * (clip_grad_norm_ over all parameters, CLIP_VALUE 0.01) + torch.optim.AdamW with per-parameter lr / weight
+ * decay groups (base_trainer.py:65-147), which launch one kernel per parameter group.
+ *   pdb_grad_sumsq: out (device float64 scalar) = sum_i (grad_scale * grad[i])^2; n % 4 == 0.
+ *   pdb_adamw_flat: param / grad / exp_avg / exp_avg_sq are flat fp32 buffers of n elements (n % 4 == 0, 16-byte
+ *     aligned) in which every parameter occupies a 4-element-aligned segment; seg_start (DEVICE int64[num_segs],
+ *     ascending, seg_start[0] == 0), seg_lr / seg_wd (DEVICE float[num_segs]).  Gradients are multiplied by
+ *     grad_scale (1 / world size after the all-reduce) and by min(1, clip_norm / (sqrt(*sumsq) + 1e-6)) when
+ *     clip_norm > 0 and sumsq != NULL; `step` is the 1-based step count (bias corrections).
+ * ---------------------------------------------------------------------------------------------- */
+PDB_API int pdb_grad_sumsq(const float* grad, int64_t n, float grad_scale, double* out, void* stream);
+PDB_API int pdb_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   const int64_t* seg_start, const float* seg_lr, const float* seg_wd, int num_segs, float beta1,
+                   float beta2, float eps, int64_t step, float grad_scale, float clip_norm, const double* sumsq,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

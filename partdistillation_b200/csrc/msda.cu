@@ -304,6 +304,303 @@ msda_bwd_d32(const float* __restrict__ value, const __grid_constant__ LevelTable
     for (int i = threadIdx.x; i < nslots * LP; i += kFastThreads) oa[i] = s_gattn[i];
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// tiled fast path (f32, D == 32, P == 4, every level at least 2 x 2)
+//
+// What bounds the gather: one tap corner of one head is one 128-byte line = one L1 wavefront, so a (query, head)
+// slot moves LP*4*128 B through the L1 data pipe (128 B/clk/SM) against 448 B of compulsory HBM traffic; the kernel
+// can at best be L1-wavefront-bound (~30-36 % of the HBM roofline) and must (1) keep the instruction stream below
+// that bound and (2) make the wavefronts hit in L1 instead of L2.
+//  (1) The tap set-up (un-normalise, floor, border handling, 4 corner weights) is done ONCE per tap by one of the 8
+//      lanes of a slot (lane j sets up taps j and j+8) and handed to the others through shared memory as a 5-word
+//      record {w00, w01, w10, w11, offset}; every lane then only issues 2 LDS + 4 LDG.128 + 16 FFMA per tap.
+//      Border handling without branches: the 2x2 footprint is clamped into the map (xb in [0, W-2]) and each
+//      in-map position receives the weight of the original corner that falls on it (0 if none), so all four loads
+//      are always in bounds and relative to one base offset: {0, M*32, W*M*32, (W+1)*M*32} floats.
+//  (2) When the queries are the pixels of the value pyramid itself (Lq == S: the encoder), a CTA takes an 8 x 4
+//      patch of queries of one level and ONE head, so the 32 slots of a CTA read overlapping footprints of a single
+//      head's 128-byte lines and L1 serves the reuse; otherwise slots are taken in memory order.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPatchW = 8, kPatchH = 4;
+constexpr int kTileSlots = kPatchW * kPatchH;       // 32 slots x 8 lanes = 256 threads
+
+struct PatchTable {
+    int first[kMaxLevels + 1];      // first patch index of each level (prefix sums), [L] = patches per image
+    int px[kMaxLevels];             // patches per row of each level
+};
+
+struct TapRec {
+    float4 w;                       // weights of the 4 clamped positions, already multiplied by the attention weight
+};
+
+// one tap: clamped base offset (floats, relative to the image's head plane) and the 4 position weights
+__device__ __forceinline__ void tap_record(float lx, float ly, float a, int H, int W, int level_start, int rowstride,
+                                           float4& w, int& off) {
+    float gx = __fsub_rn(__fmul_rn(2.f, lx), 1.f);
+    float gy = __fsub_rn(__fmul_rn(2.f, ly), 1.f);
+    float x = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)W), 1.f), 0.5f);
+    float y = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)H), 1.f), 0.5f);
+    x = fminf(fmaxf(x, -2.f), (float)W + 1.f);      // keeps the float->int conversion defined for wild offsets
+    y = fminf(fmaxf(y, -2.f), (float)H + 1.f);
+    const float x0f = floorf(x), y0f = floorf(y);
+    const float wx1 = x - x0f, wy1 = y - y0f, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const int xb = min(max(x0, 0), W - 2), yb = min(max(y0, 0), H - 2);
+    // weight of clamped position xb / xb+1 = weight of the original corner (x0 or x0+1) lying on it, if any
+    const float wxa = (x0 == xb ? wx0 : 0.f) + (x0 + 1 == xb ? wx1 : 0.f);
+    const float wxb = (x0 == xb + 1 ? wx0 : 0.f) + (x0 == xb ? wx1 : 0.f);
+    const float wya = (y0 == yb ? wy0 : 0.f) + (y0 + 1 == yb ? wy1 : 0.f);
+    const float wyb = (y0 == yb + 1 ? wy0 : 0.f) + (y0 == yb ? wy1 : 0.f);
+    w = make_float4(a * (wya * wxa), a * (wya * wxb), a * (wyb * wxa), a * (wyb * wxb));
+    off = (level_start + yb * W + xb) * rowstride;
+}
+
+// slot -> (n, q, m); returns false for slots outside the problem
+__device__ __forceinline__ bool slot_coords(bool tiled, const LevelTable& lt, const PatchTable& pt, int L, int M, int Lq,
+                                            int64_t slots, int sl, int& n, int& q, int& m) {
+    if (tiled) {
+        const int per_image = pt.first[L] * M;
+        n = blockIdx.x / per_image;
+        int r = blockIdx.x - n * per_image;
+        const int patch = r / M;
+        m = r - patch * M;                                   // heads innermost: the 8 heads of a pixel share DRAM pages
+        int l = 0;
+        while (l + 1 < L && patch >= pt.first[l + 1]) ++l;
+        const int pl = patch - pt.first[l];
+        const int py = pl / pt.px[l], pxi = pl - py * pt.px[l];
+        const int x = pxi * kPatchW + (sl & (kPatchW - 1)), y = py * kPatchH + (sl / kPatchW);
+        q = lt.start[l] + y * lt.w[l] + x;
+        return x < lt.w[l] && y < lt.h[l];
+    }
+    const int64_t g = (int64_t)blockIdx.x * kTileSlots + sl;
+    m = (int)(g % M);
+    q = (int)((g / M) % Lq);
+    n = (int)(g / M / Lq);
+    return g < slots;
+}
+
+template <int P>
+__global__ void __launch_bounds__(kTileSlots * 8)
+msda_fwd_tiled(const float* __restrict__ value, const __grid_constant__ LevelTable lt, const __grid_constant__ PatchTable pt,
+               const float* __restrict__ loc, const float* __restrict__ attn, float* __restrict__ out, int64_t slots,
+               int S, int M, int Lq, int L, int tiled) {
+    extern __shared__ __align__(16) uint8_t smem_msda[];
+    const int LP = L * P;
+    const int LPS = LP + 1;              // padded per-slot stride: the 4 slots of a warp read distinct banks
+    float4* s_w = reinterpret_cast<float4*>(smem_msda);                        // [slot][LPS]
+    int* s_off = reinterpret_cast<int*>(smem_msda + sizeof(float4) * kTileSlots * LPS);   // [slot][LPS]
+
+    const int sl = threadIdx.x >> 3;     // slot within CTA (4 slots per warp: set-up and use stay inside the warp)
+    const int j = threadIdx.x & 7;       // 4-channel group, and the lane that sets up taps j, j + 8, ...
+    int n, q, m;
+    const bool ok = slot_coords(tiled != 0, lt, pt, L, M, Lq, slots, sl, n, q, m);
+    const int rowstride = M * 32;
+    const int64_t g = ((int64_t)n * Lq + q) * M + m;
+    if (ok) {
+        const float2* lp = reinterpret_cast<const float2*>(loc) + g * LP;
+        const float* ap = attn + g * LP;
+        for (int t = j; t < LP; t += 8) {
+            const int l = t / P;
+            const float2 lxy = __ldg(lp + t);
+            float4 w;
+            int off;
+            tap_record(lxy.x, lxy.y, __ldg(ap + t), lt.h[l], lt.w[l], lt.start[l], rowstride, w, off);
+            s_w[sl * LPS + t] = w;
+            s_off[sl * LPS + t] = off;
+        }
+    }
+    __syncwarp();
+    if (!ok) return;
+    const float* vb = value + ((int64_t)n * S * M + m) * 32 + j * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int l = 0; l < L; ++l) {
+        const int down = lt.w[l] * rowstride;
+        float4 w[P];
+        const float* p0[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            w[p] = s_w[sl * LPS + l * P + p];
+            p0[p] = vb + s_off[sl * LPS + l * P + p];
+        }
+        float4 v[P][4];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            v[p][0] = __ldg(reinterpret_cast<const float4*>(p0[p]));
+            v[p][1] = __ldg(reinterpret_cast<const float4*>(p0[p] + rowstride));
+            v[p][2] = __ldg(reinterpret_cast<const float4*>(p0[p] + down));
+            v[p][3] = __ldg(reinterpret_cast<const float4*>(p0[p] + down + rowstride));
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const float wc[4] = {w[p].x, w[p].y, w[p].z, w[p].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                acc.x = fmaf(wc[c], v[p][c].x, acc.x);
+                acc.y = fmaf(wc[c], v[p][c].y, acc.y);
+                acc.z = fmaf(wc[c], v[p][c].z, acc.z);
+                acc.w = fmaf(wc[c], v[p][c].w, acc.w);
+            }
+        }
+    }
+    *reinterpret_cast<float4*>(out + g * 32 + j * 4) = acc;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// tiled backward (same slot mapping and per-tap set-up distribution as msda_fwd_tiled)
+//
+// Per tap the set-up lane publishes, for each of the 4 clamped positions p, the value weight w_p (without the
+// attention weight) and the coefficients of d(out)/d(loc.x), d(out)/d(loc.y) in dot(value_p, grad_out):
+//     grad_attn = sum_p w_p   * dot_p        grad_loc.x = sum_p gxw_p * dot_p       grad_loc.y = sum_p gyw_p * dot_p
+//     grad_value[p] += (attn * w_p) * grad_out          (red.global.add.v4.f32, skipped when the weight is 0)
+// Each of the 8 lanes of a slot holds 4 channels: it forms its partial of the three sums (12 FFMA) and the three
+// values are butterfly-reduced over the 8 lanes; lane (tap % 8) keeps the totals and stores them at the end.
+// ------------------------------------------------------------------------------------------------
+struct BwdRec {
+    float4 w, gxw, gyw;
+    float a;
+    int off;
+    int pad0, pad1;
+};     // 64 bytes
+
+__device__ __forceinline__ void tap_record_bwd(float lx, float ly, float a, int H, int W, int level_start, int rowstride,
+                                               BwdRec& r) {
+    float gx = __fsub_rn(__fmul_rn(2.f, lx), 1.f);
+    float gy = __fsub_rn(__fmul_rn(2.f, ly), 1.f);
+    float x = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)W), 1.f), 0.5f);
+    float y = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)H), 1.f), 0.5f);
+    x = fminf(fmaxf(x, -2.f), (float)W + 1.f);
+    y = fminf(fmaxf(y, -2.f), (float)H + 1.f);
+    const float x0f = floorf(x), y0f = floorf(y);
+    const float wx1 = x - x0f, wy1 = y - y0f, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const int xb = min(max(x0, 0), W - 2), yb = min(max(y0, 0), H - 2);
+    // position xb (+0 / +1) carries original corner x0 (weight wx0, d/dx = -1) or x0 + 1 (weight wx1, d/dx = +1)
+    const float wxa = (x0 == xb ? wx0 : 0.f) + (x0 + 1 == xb ? wx1 : 0.f);
+    const float wxb = (x0 == xb + 1 ? wx0 : 0.f) + (x0 == xb ? wx1 : 0.f);
+    const float dxa = (x0 == xb ? -1.f : 0.f) + (x0 + 1 == xb ? 1.f : 0.f);
+    const float dxb = (x0 == xb + 1 ? -1.f : 0.f) + (x0 == xb ? 1.f : 0.f);
+    const float wya = (y0 == yb ? wy0 : 0.f) + (y0 + 1 == yb ? wy1 : 0.f);
+    const float wyb = (y0 == yb + 1 ? wy0 : 0.f) + (y0 == yb ? wy1 : 0.f);
+    const float dya = (y0 == yb ? -1.f : 0.f) + (y0 + 1 == yb ? 1.f : 0.f);
+    const float dyb = (y0 == yb + 1 ? -1.f : 0.f) + (y0 == yb ? 1.f : 0.f);
+    r.w = make_float4(wya * wxa, wya * wxb, wyb * wxa, wyb * wxb);
+    const float aw = a * (float)W, ah = a * (float)H;
+    r.gxw = make_float4(aw * (wya * dxa), aw * (wya * dxb), aw * (wyb * dxa), aw * (wyb * dxb));
+    r.gyw = make_float4(ah * (dya * wxa), ah * (dya * wxb), ah * (dyb * wxa), ah * (dyb * wxb));
+    r.a = a;
+    r.off = (level_start + yb * W + xb) * rowstride;
+    r.pad0 = r.pad1 = 0;
+}
+
+template <int P>
+__global__ void __launch_bounds__(kTileSlots * 8)
+msda_bwd_tiled(const float* __restrict__ value, const __grid_constant__ LevelTable lt, const __grid_constant__ PatchTable pt,
+               const float* __restrict__ loc, const float* __restrict__ attn, const float* __restrict__ grad_out,
+               float* __restrict__ grad_value, float* __restrict__ grad_loc, float* __restrict__ grad_attn, int64_t slots,
+               int S, int M, int Lq, int L, int tiled) {
+    extern __shared__ __align__(16) uint8_t smem_msda[];
+    const int LP = L * P;
+    const int LPS = LP * 4 + 1;          // float4 units per slot, padded (bank spread across the 4 slots of a warp)
+    float4* s_rec = reinterpret_cast<float4*>(smem_msda);
+
+    const int sl = threadIdx.x >> 3;
+    const int j = threadIdx.x & 7;
+    int n, q, m;
+    const bool ok = slot_coords(tiled != 0, lt, pt, L, M, Lq, slots, sl, n, q, m);
+    const int rowstride = M * 32;
+    const int64_t g = ((int64_t)n * Lq + q) * M + m;
+    if (ok) {
+        const float2* lp = reinterpret_cast<const float2*>(loc) + g * LP;
+        const float* ap = attn + g * LP;
+        for (int t = j; t < LP; t += 8) {
+            const int l = t / P;
+            const float2 lxy = __ldg(lp + t);
+            BwdRec r;
+            tap_record_bwd(lxy.x, lxy.y, __ldg(ap + t), lt.h[l], lt.w[l], lt.start[l], rowstride, r);
+            float4* dst = s_rec + sl * LPS + t * 4;
+            dst[0] = r.w;
+            dst[1] = r.gxw;
+            dst[2] = r.gyw;
+            dst[3] = make_float4(r.a, __int_as_float(r.off), 0.f, 0.f);
+        }
+    }
+    __syncwarp();
+    if (!ok) return;
+    const int64_t plane = ((int64_t)n * S * M + m) * 32 + j * 4;
+    const float* vb = value + plane;
+    float* gvb = grad_value + plane;
+    const float4 go = __ldg(reinterpret_cast<const float4*>(grad_out + g * 32 + j * 4));
+    float ka0 = 0.f, kx0 = 0.f, ky0 = 0.f, ka1 = 0.f, kx1 = 0.f, ky1 = 0.f;          // totals of taps j and j + 8 (LP <= 16)
+#pragma unroll 1
+    for (int l = 0; l < L; ++l) {
+        const int down = lt.w[l] * rowstride;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const int t = l * P + p;
+            const float4* rec = s_rec + sl * LPS + t * 4;
+            const float4 w = rec[0], gxw = rec[1], gyw = rec[2], ao = rec[3];
+            const int off = __float_as_int(ao.y);
+            const float* p0 = vb + off;
+            float4 v[4];
+            v[0] = __ldg(reinterpret_cast<const float4*>(p0));
+            v[1] = __ldg(reinterpret_cast<const float4*>(p0 + rowstride));
+            v[2] = __ldg(reinterpret_cast<const float4*>(p0 + down));
+            v[3] = __ldg(reinterpret_cast<const float4*>(p0 + down + rowstride));
+            const float wc[4] = {w.x, w.y, w.z, w.w};
+            const float xc[4] = {gxw.x, gxw.y, gxw.z, gxw.w};
+            const float yc[4] = {gyw.x, gyw.y, gyw.z, gyw.w};
+            const int poff[4] = {0, rowstride, down, down + rowstride};
+            float pa = 0.f, px = 0.f, py = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float d = v[c].x * go.x + v[c].y * go.y + v[c].z * go.z + v[c].w * go.w;
+                pa = fmaf(wc[c], d, pa);
+                px = fmaf(xc[c], d, px);
+                py = fmaf(yc[c], d, py);
+                const float cw = ao.x * wc[c];
+                if (cw != 0.f) red_add_v4(gvb + off + poff[c], cw * go.x, cw * go.y, cw * go.z, cw * go.w);
+            }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                pa += __shfl_xor_sync(0xffffffffu, pa, o);
+                px += __shfl_xor_sync(0xffffffffu, px, o);
+                py += __shfl_xor_sync(0xffffffffu, py, o);
+            }
+            if (t == j) { ka0 = pa; kx0 = px; ky0 = py; }
+            if (t == j + 8) { ka1 = pa; kx1 = px; ky1 = py; }
+        }
+    }
+    if (j < LP) {
+        grad_attn[g * LP + j] = ka0;
+        *reinterpret_cast<float2*>(grad_loc + (g * LP + j) * 2) = make_float2(kx0, ky0);
+    }
+    if (j + 8 < LP) {
+        grad_attn[g * LP + j + 8] = ka1;
+        *reinterpret_cast<float2*>(grad_loc + (g * LP + j + 8) * 2) = make_float2(kx1, ky1);
+    }
+}
+
+// host: patch grid of the tiled mapping; returns the number of CTAs
+static int64_t make_patches(const LevelTable& lt, int L, int N, int M, PatchTable& pt) {
+    int total = 0;
+    for (int l = 0; l < L; ++l) {
+        pt.first[l] = total;
+        pt.px[l] = (lt.w[l] + kPatchW - 1) / kPatchW;
+        total += pt.px[l] * ((lt.h[l] + kPatchH - 1) / kPatchH);
+    }
+    pt.first[L] = total;
+    return (int64_t)total * M * N;
+}
+
+static bool levels_at_least_2x2(const LevelTable& lt, int L) {
+    for (int l = 0; l < L; ++l)
+        if (lt.h[l] < 2 || lt.w[l] < 2) return false;
+    return true;
+}
+
 static int make_levels(const int64_t* shapes_hw, const int64_t* level_start, int L, int S, LevelTable& lt) {
     PDB_REQUIRE(L >= 1 && L <= kMaxLevels, "msda: L=%d outside [1,%d]", L, kMaxLevels);
     for (int l = 0; l < L; ++l) {
@@ -355,6 +652,19 @@ extern "C" int pdb_msda_forward(const void* value, const int64_t* shapes_hw, con
     cudaStream_t st = as_stream(stream);
     if (dtype == PDB_F64) return fwd_generic<double>(value, lt, loc, attn, out, N, S, M, D, Lq, L, P, st);
     PDB_REQUIRE(dtype == PDB_F32, "msda_forward: dtype %d (only f32/f64, as ms_deform_attn_cuda.cu:70)", dtype);
+    if (D == 32 && P == 4 && (int64_t)S * M * 32 < (1ll << 31) && levels_at_least_2x2(lt, L)) {
+        int64_t slots = (int64_t)N * Lq * M;
+        PatchTable pt;
+        const bool tiled = Lq == S;      // queries are the pyramid's own pixels (encoder self-attention): 2-D patches
+        int64_t blocks = make_patches(lt, L, N, M, pt);
+        if (!tiled) blocks = (slots + kTileSlots - 1) / kTileSlots;
+        PDB_REQUIRE(blocks < (1ll << 31), "msda_forward: too many CTAs");
+        size_t smem = (sizeof(float4) + sizeof(int)) * kTileSlots * (L * P + 1);
+        msda_fwd_tiled<4><<<(unsigned)blocks, kTileSlots * 8, smem, st>>>((const float*)value, lt, pt, (const float*)loc,
+                                                                         (const float*)attn, (float*)out, slots, S, M, Lq,
+                                                                         L, tiled ? 1 : 0);
+        return launched("msda_fwd_tiled");
+    }
     if (D == 32 && P == 4 && (int64_t)S * M * 32 < (1ll << 31)) {
         int64_t slots = (int64_t)N * Lq * M;
         int64_t blocks = (slots + kSlotsPerCta - 1) / kSlotsPerCta;
@@ -383,6 +693,19 @@ extern "C" int pdb_msda_backward(const void* value, const int64_t* shapes_hw, co
     if (dtype == PDB_F64)
         return bwd_generic<double>(value, lt, loc, attn, grad_out, grad_value, grad_loc, grad_attn, N, S, M, D, Lq, L,
                                    P, st);
+    if (D == 32 && P == 4 && L * P <= 16 && (int64_t)S * M * 32 < (1ll << 31) && levels_at_least_2x2(lt, L)) {
+        int64_t slots = (int64_t)N * Lq * M;
+        PatchTable pt;
+        const bool tiled = Lq == S;
+        int64_t blocks = make_patches(lt, L, N, M, pt);
+        if (!tiled) blocks = (slots + kTileSlots - 1) / kTileSlots;
+        PDB_REQUIRE(blocks < (1ll << 31), "msda_backward: too many CTAs");
+        size_t smem = sizeof(float4) * kTileSlots * (L * P * 4 + 1);
+        msda_bwd_tiled<4><<<(unsigned)blocks, kTileSlots * 8, smem, st>>>(
+            (const float*)value, lt, pt, (const float*)loc, (const float*)attn, (const float*)grad_out,
+            (float*)grad_value, (float*)grad_loc, (float*)grad_attn, slots, S, M, Lq, L, tiled ? 1 : 0);
+        return launched("msda_bwd_tiled");
+    }
     if (D == 32 && P == 4 && (int64_t)S * M * 32 < (1ll << 31)) {
         int64_t slots = (int64_t)N * Lq * M;
         int64_t blocks = (slots + kSlotsPerCta - 1) / kSlotsPerCta;

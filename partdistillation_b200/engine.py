@@ -3,10 +3,10 @@
 What the reference does with detectron2's DDP + AMPTrainer + BaseTrainer.build_optimizer
 (base_trainer.py:65-147): per-parameter AdamW groups (backbone LR x0.1, no weight decay on norm /
 embedding / relative-position parameters, ``FREEZE_KEYS``), full-model gradient-norm clipping
-(CLIP_VALUE 0.01), and a bucketed NCCL gradient all-reduce.  Here all trainable fp32 gradients live
-in ONE flat buffer (parameters' ``.grad`` are views into it): the step issues a single
-``all_reduce`` over that buffer (plus one for the fp64 classifier of PartDistillation when present),
-the clip norm is one reduction over the same buffer, and AdamW is PyTorch's fused multi-tensor kernel.
+(CLIP_VALUE 0.01), and a bucketed NCCL gradient all-reduce.  Here all trainable fp32 parameters, gradients and
+Adam moments live in flat buffers (``p.data`` / ``p.grad`` are views): the step issues a single ``all_reduce``
+over the gradient buffer (plus one for the fp64 classifier of PartDistillation when present), the clip norm is
+one reduction kernel over it and clip + AdamW one more (csrc/optim.cu).
 """
 import torch
 import torch.distributed as dist
@@ -43,27 +43,63 @@ def build_param_groups(model, base_lr=1e-4, weight_decay=0.05, weight_decay_norm
 
 
 class DataParallelTrainer:
-    """model(batched_inputs) -> loss dict; backward; ONE flat gradient all-reduce; clip; AdamW."""
+    """model(batched_inputs) -> loss dict; backward; ONE flat gradient all-reduce; clip; AdamW.
+
+    fp32 CUDA parameters live in flat buffers (parameter, gradient, exp_avg, exp_avg_sq; every parameter a
+    4-element-aligned segment, ``p.data`` / ``p.grad`` are views), so the step after backward is: one
+    ``all_reduce`` (world > 1), ``pdb_grad_sumsq`` and ``pdb_adamw_flat`` — two kernel launches instead of one
+    fused-AdamW launch per parameter group (the reference builds one group per parameter, base_trainer.py:76-116).
+    Parameters of other dtypes (PartDistillation's fp64 classifier) and CPU models (the gloo tests of the
+    sharding / all-reduce logic) are stepped by ``torch.optim.AdamW`` with the same clip coefficient."""
 
     def __init__(self, model, base_lr=1e-4, weight_decay=0.05, clip_norm=0.01, freeze_keys=("backbone", "encoder"),
-                 backbone_multiplier=0.1):
+                 backbone_multiplier=0.1, betas=(0.9, 0.999), eps=1e-8):
         self.model = model
         groups = build_param_groups(model, base_lr, weight_decay, freeze_keys=freeze_keys,
                                     backbone_multiplier=backbone_multiplier)
         self.params = [g["params"][0] for g in groups]
-        self.clip_norm = clip_norm
+        self.clip_norm = float(clip_norm or 0.0)
+        self.betas, self.eps = betas, eps
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        # flat gradient buffers, one per dtype (fp32; fp64 only for PartDistillation's class_embed)
-        self.flat = {}
-        for dt in sorted({p.dtype for p in self.params}, key=str):
-            ps = [p for p in self.params if p.dtype == dt]
+        self.step_count = 0
+        flat_groups = [g for g in groups if g["params"][0].dtype == torch.float32 and g["params"][0].is_cuda]
+        other_groups = [g for g in groups if not (g["params"][0].dtype == torch.float32 and g["params"][0].is_cuda)]
+        self.flat = {}                      # name -> flat gradient buffer (what the all-reduce moves)
+        self.flat_param = self.flat_m = self.flat_v = None
+        if flat_groups:
+            dev = flat_groups[0]["params"][0].device
+            starts, o = [], 0
+            for g in flat_groups:
+                starts.append(o)
+                o += (g["params"][0].numel() + 3) // 4 * 4
+            self.flat_param = torch.zeros(o, dtype=torch.float32, device=dev)
+            self.flat["f32"] = torch.zeros(o, dtype=torch.float32, device=dev)
+            self.flat_m = torch.zeros(o, dtype=torch.float32, device=dev)
+            self.flat_v = torch.zeros(o, dtype=torch.float32, device=dev)
+            for g, st in zip(flat_groups, starts):
+                p = g["params"][0]
+                n = p.numel()
+                self.flat_param[st:st + n].copy_(p.data.reshape(-1))
+                p.data = self.flat_param[st:st + n].view(p.shape)
+                p.grad = self.flat["f32"][st:st + n].view(p.shape)
+            self.seg_start = torch.tensor(starts, dtype=torch.int64, device=dev)
+            self.seg_lr = torch.tensor([g["lr"] for g in flat_groups], dtype=torch.float32, device=dev)
+            self.seg_wd = torch.tensor([g["weight_decay"] for g in flat_groups], dtype=torch.float32, device=dev)
+            self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        # everything else: flat gradient buffer per dtype + torch AdamW
+        self.other_params = [g["params"][0] for g in other_groups]
+        for dt in sorted({p.dtype for p in self.other_params}, key=str):
+            ps = [p for p in self.other_params if p.dtype == dt]
             buf = torch.zeros(sum(p.numel() for p in ps), dtype=dt, device=ps[0].device)
             o = 0
             for p in ps:
                 p.grad = buf[o:o + p.numel()].view_as(p)
                 o += p.numel()
-            self.flat[dt] = buf
-        self.optimizer = torch.optim.AdamW(groups, lr=base_lr, fused=True)
+            self.flat[str(dt)] = buf
+        self.optimizer = None
+        if other_groups:
+            fused = all(g["params"][0].is_cuda for g in other_groups)
+            self.optimizer = torch.optim.AdamW(other_groups, lr=base_lr, betas=betas, eps=eps, fused=fused)
         self.grad_bytes = sum(b.numel() * b.element_size() for b in self.flat.values())
 
     def zero_grad(self):
@@ -71,18 +107,43 @@ class DataParallelTrainer:
             b.zero_()
 
     def reduce_gradients(self):
+        """The one data-path collective of the step: SUM all-reduce of the flat gradient buffers (the 1 / world
+        scale is applied inside the optimizer kernels)."""
         if self.world > 1:
             for b in self.flat.values():
                 dist.all_reduce(b)
-                b.div_(self.world)
 
     def clip_and_step(self):
-        if self.clip_norm and self.clip_norm > 0:
-            sq = sum((b.double() if b.dtype != torch.float64 else b).pow(2).sum() for b in self.flat.values())
-            coef = torch.clamp(self.clip_norm / (sq.sqrt() + 1e-6), max=1.0)
-            for b in self.flat.values():
-                b.mul_(coef.to(b.dtype))
-        self.optimizer.step()
+        self.step_count += 1
+        scale = 1.0 / self.world
+        others = [b for k, b in self.flat.items() if k != "f32"]
+        if "f32" in self.flat:
+            from . import _lib
+            from .functional import _stream
+            lib = _lib.load()
+            g = self.flat["f32"]
+            _lib.check(lib.pdb_grad_sumsq(g.data_ptr(), g.numel(), scale, self.sumsq.data_ptr(), _stream()), "pdb_grad_sumsq")
+            total = self.sumsq
+            for b in others:
+                total = total + (b.double() * scale).pow(2).sum()
+            if others:
+                self.sumsq.copy_(total)
+            _lib.check(lib.pdb_adamw_flat(self.flat_param.data_ptr(), g.data_ptr(), self.flat_m.data_ptr(),
+                                          self.flat_v.data_ptr(), g.numel(), self.seg_start.data_ptr(),
+                                          self.seg_lr.data_ptr(), self.seg_wd.data_ptr(), self.seg_start.numel(),
+                                          self.betas[0], self.betas[1], self.eps, self.step_count, scale, self.clip_norm,
+                                          self.sumsq.data_ptr() if self.clip_norm > 0 else None, _stream()),
+                       "pdb_adamw_flat")
+            sq = self.sumsq[0]
+        else:
+            sq = sum((b.double() * scale).pow(2).sum() for b in others)
+        if others:
+            coef = scale
+            if self.clip_norm > 0:
+                coef = torch.clamp(self.clip_norm / (sq.sqrt() + 1e-6), max=1.0) * scale
+            for b in others:
+                b.mul_(coef.to(b.dtype) if torch.is_tensor(coef) else coef)
+            self.optimizer.step()
 
     def backward_and_step(self, losses):
         total = sum(losses.values())

@@ -96,6 +96,24 @@ def test_msda_fast_path_vs_oracle(fn):
         assert _rel(gl.cpu(), rgl) < 1e-4
 
 
+def test_msda_decoder_style_queries(fn):
+    """Lq != S (queries are not the pyramid's pixels): the kernel takes slots in memory order instead of 2-D
+    patches; also a 1-pixel-wide level, which falls back to the per-corner path."""
+    for shapes, Lq in (([(16, 16), (8, 8), (4, 4)], 100), ([(16, 1), (8, 8)], 37)):
+        value, loc, attn = _msda_inputs(2, shapes, Lq, seed=7, spread=5.0, encoder=False)
+        v, l, a = (t.clone().requires_grad_() for t in (value, loc, attn))
+        ref = O.ms_deform_attn_core(v, shapes, l, a)
+        go = torch.randn(ref.shape, generator=torch.Generator().manual_seed(6))
+        rgv, rgl, rga = torch.autograd.grad(ref, (v, l, a), go)
+        vc, lc, ac = (t.cuda().requires_grad_() for t in (value, loc, attn))
+        out = fn.ms_deform_attn(vc, shapes, None, lc, ac)
+        gv, gl, ga = torch.autograd.grad(out, (vc, lc, ac), go.cuda())
+        assert _rel(out.cpu(), ref.detach()) < 1e-5
+        assert _rel(gv.cpu(), rgv) < 1e-5
+        assert _rel(ga.cpu(), rga) < 1e-5
+        assert _rel(gl.cpu(), rgl) < 1e-4
+
+
 def test_msda_full_size_properties(fn):
     """C5(i): 4 levels 256^2..32^2, N=1, Lq=S=87040.  (1) constant value map + in-range locations ->
     output == constant (weights sum to 1); (2) linearity in value; (3) a strided subset of queries vs
