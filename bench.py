@@ -276,6 +276,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="run the step eagerly instead of replaying its CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -299,7 +300,7 @@ def main():
     model = compat.build_model(cfg)
     model.train()
     trainer = DataParallelTrainer(model, base_lr=1e-4, weight_decay=0.05, clip_norm=0.01,
-                                  freeze_keys=("backbone", "encoder"))
+                                  freeze_keys=("backbone", "encoder"), cuda_graph=not args.no_cuda_graph)
     cpu_sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()} if rank == 0 else None
 
     dev_batch = make_batch(rank, PER_GPU_BATCH, device=device)
@@ -319,7 +320,7 @@ def main():
         prof = os.environ.get("PDB_PROFILE") == "1" and not read_loss
         if prof:
             torch.cuda.profiler.start()        # ncu --profile-from-start off: only the timed steps
-        l0 = _lib.launch_count()
+        l0 = trainer.pdb_launches
         s, e = torch.cuda.Event(True), torch.cuda.Event(True)
         t0 = time.perf_counter()
         s.record()
@@ -337,7 +338,7 @@ def main():
         t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1]), _lib.launch_count() - l0, last
+        return float(t[0]), float(t[1]), trainer.pdb_launches - l0, last
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms, _, launches, _ = timed(dev_batch, args.steps, args.warmup, read_loss=False)
@@ -356,7 +357,7 @@ def main():
                 "config": {"workload": "proposal_learning Swin-B 100q 1024x1024 bs=2/GPU fwd+bwd (BASELINE configs[1])",
                            "global_batch": PER_GPU_BATCH * world, "queries": QUERIES, "dec_layers": 10,
                            "train_num_points": POINTS, "importance_sample_ratio": 0.0,
-                           "freeze_keys": ["backbone", "encoder"], "optimizer": "AdamW + full-model clip 0.01",
+                           "freeze_keys": ["backbone", "encoder"], "optimizer": "AdamW + full-model clip 0.01", "cuda_graph": not args.no_cuda_graph,
                            "parallelism": f"dp{world}", "grad_allreduce_bytes": trainer.grad_bytes,
                            "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; kernel roofline "
                                  "run flushes L2 between launches"},

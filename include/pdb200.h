@@ -214,12 +214,13 @@ PDB_API int pdb_class_rows_backward(const float* x, const double* weight, const 
  *     aligned) in which every parameter occupies a 4-element-aligned segment; seg_start (DEVICE int64[num_segs],
  *     ascending, seg_start[0] == 0), seg_lr / seg_wd (DEVICE float[num_segs]).  Gradients are multiplied by
  *     grad_scale (1 / world size after the all-reduce) and by min(1, clip_norm / (sqrt(*sumsq) + 1e-6)) when
- *     clip_norm > 0 and sumsq != NULL; `step` is the 1-based step count (bias corrections).
+ *     clip_norm > 0 and sumsq != NULL; `step` points to the 1-based step count in DEVICE memory (bias
+ *     corrections are computed on the device, so a captured CUDA graph of the step stays valid).
  * ---------------------------------------------------------------------------------------------- */
 PDB_API int pdb_grad_sumsq(const float* grad, int64_t n, float grad_scale, double* out, void* stream);
 PDB_API int pdb_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                    const int64_t* seg_start, const float* seg_lr, const float* seg_wd, int num_segs, float beta1,
-                   float beta2, float eps, int64_t step, float grad_scale, float clip_norm, const double* sumsq,
+                   float beta2, float eps, const int64_t* step, float grad_scale, float clip_norm, const double* sumsq,
                    void* stream);
 
 #ifdef __cplusplus

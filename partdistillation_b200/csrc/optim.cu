@@ -36,8 +36,12 @@ grad_sumsq_kernel(const float4* __restrict__ g, int64_t n4, float scale, double*
 __global__ void __launch_bounds__(256)
 adamw_flat_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
                   int64_t n4, const int64_t* __restrict__ seg_start, const float* __restrict__ seg_lr,
-                  const float* __restrict__ seg_wd, int num_segs, float beta1, float beta2, float eps, float bc1,
-                  float bc2_sqrt, float grad_scale, float clip_norm, const double* __restrict__ sumsq) {
+                  const float* __restrict__ seg_wd, int num_segs, float beta1, float beta2, float eps,
+                  const int64_t* __restrict__ step_ptr, float grad_scale, float clip_norm, const double* __restrict__ sumsq) {
+    // bias corrections from the device-side step counter (so a CUDA graph of the training step stays valid)
+    const double step = (double)*step_ptr;
+    const float bc1 = (float)(1.0 - pow((double)beta1, step));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, step));
     float coef = grad_scale;
     if (clip_norm > 0.f && sumsq) {
         float total = (float)sqrt(*sumsq);
@@ -85,19 +89,18 @@ extern "C" int pdb_grad_sumsq(const float* grad, int64_t n, float grad_scale, do
 
 extern "C" int pdb_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                               const int64_t* seg_start, const float* seg_lr, const float* seg_wd, int num_segs, float beta1,
-                              float beta2, float eps, int64_t step, float grad_scale, float clip_norm, const double* sumsq,
+                              float beta2, float eps, const int64_t* step, float grad_scale, float clip_norm, const double* sumsq,
                               void* stream) {
     PDB_REQUIRE(param && grad && exp_avg && exp_avg_sq && seg_start && seg_lr && seg_wd, "adamw_flat: null pointer");
-    PDB_REQUIRE(n > 0 && n % 4 == 0 && num_segs > 0 && step > 0, "adamw_flat: bad sizes (n %% 4 == 0, step >= 1)");
+    PDB_REQUIRE(step, "adamw_flat: null step pointer");
+    PDB_REQUIRE(n > 0 && n % 4 == 0 && num_segs > 0, "adamw_flat: bad sizes (n %% 4 == 0)");
     PDB_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
                   reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0, "adamw_flat: buffers must be 16-byte aligned");
-    const double bc1 = 1.0 - pow((double)beta1, (double)step);
-    const double bc2 = 1.0 - pow((double)beta2, (double)step);
     int64_t n4 = n / 4;
     int blocks = (int)std::min<int64_t>((n4 + 255) / 256, 8 * kNumSMs);
     adamw_flat_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
         reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad), reinterpret_cast<float4*>(exp_avg),
-        reinterpret_cast<float4*>(exp_avg_sq), n4, seg_start, seg_lr, seg_wd, num_segs, beta1, beta2, eps, (float)bc1,
-        (float)sqrt(bc2), grad_scale, clip_norm, sumsq);
+        reinterpret_cast<float4*>(exp_avg_sq), n4, seg_start, seg_lr, seg_wd, num_segs, beta1, beta2, eps, step,
+        grad_scale, clip_norm, sumsq);
     return launched("adamw_flat");
 }

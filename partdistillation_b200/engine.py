@@ -53,8 +53,12 @@ class DataParallelTrainer:
     sharding / all-reduce logic) are stepped by ``torch.optim.AdamW`` with the same clip coefficient."""
 
     def __init__(self, model, base_lr=1e-4, weight_decay=0.05, clip_norm=0.01, freeze_keys=("backbone", "encoder"),
-                 backbone_multiplier=0.1, betas=(0.9, 0.999), eps=1e-8):
+                 backbone_multiplier=0.1, betas=(0.9, 0.999), eps=1e-8, cuda_graph=False):
         self.model = model
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs = {}
+        self._side = None
+        self.pdb_launches = 0               # kernels launched through libpdb200.so, graph replays included
         groups = build_param_groups(model, base_lr, weight_decay, freeze_keys=freeze_keys,
                                     backbone_multiplier=backbone_multiplier)
         self.params = [g["params"][0] for g in groups]
@@ -86,6 +90,7 @@ class DataParallelTrainer:
             self.seg_lr = torch.tensor([g["lr"] for g in flat_groups], dtype=torch.float32, device=dev)
             self.seg_wd = torch.tensor([g["weight_decay"] for g in flat_groups], dtype=torch.float32, device=dev)
             self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+            self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         # everything else: flat gradient buffer per dtype + torch AdamW
         self.other_params = [g["params"][0] for g in other_groups]
         for dt in sorted({p.dtype for p in self.other_params}, key=str):
@@ -99,7 +104,8 @@ class DataParallelTrainer:
         self.optimizer = None
         if other_groups:
             fused = all(g["params"][0].is_cuda for g in other_groups)
-            self.optimizer = torch.optim.AdamW(other_groups, lr=base_lr, betas=betas, eps=eps, fused=fused)
+            self.optimizer = torch.optim.AdamW(other_groups, lr=base_lr, betas=betas, eps=eps, fused=fused,
+                                               capturable=fused and self.cuda_graph)
         self.grad_bytes = sum(b.numel() * b.element_size() for b in self.flat.values())
 
     def zero_grad(self):
@@ -122,6 +128,7 @@ class DataParallelTrainer:
             from .functional import _stream
             lib = _lib.load()
             g = self.flat["f32"]
+            self.step_dev.add_(1)
             _lib.check(lib.pdb_grad_sumsq(g.data_ptr(), g.numel(), scale, self.sumsq.data_ptr(), _stream()), "pdb_grad_sumsq")
             total = self.sumsq
             for b in others:
@@ -131,7 +138,7 @@ class DataParallelTrainer:
             _lib.check(lib.pdb_adamw_flat(self.flat_param.data_ptr(), g.data_ptr(), self.flat_m.data_ptr(),
                                           self.flat_v.data_ptr(), g.numel(), self.seg_start.data_ptr(),
                                           self.seg_lr.data_ptr(), self.seg_wd.data_ptr(), self.seg_start.numel(),
-                                          self.betas[0], self.betas[1], self.eps, self.step_count, scale, self.clip_norm,
+                                          self.betas[0], self.betas[1], self.eps, self.step_dev.data_ptr(), scale, self.clip_norm,
                                           self.sumsq.data_ptr() if self.clip_norm > 0 else None, _stream()),
                        "pdb_adamw_flat")
             sq = self.sumsq[0]
@@ -152,7 +159,71 @@ class DataParallelTrainer:
         self.clip_and_step()
         return total
 
-    def step(self, batched_inputs):
+    def _eager_step(self, batched_inputs):
         self.zero_grad()
         losses = self.model(batched_inputs)
         return self.backward_and_step(losses), losses
+
+    def step(self, batched_inputs):
+        """One training step -> (total loss, loss dict).  With ``cuda_graph=True`` the whole step (forward, loss,
+        backward, all-reduce, clip, AdamW) is captured once per batch signature (image shapes and per-image mask
+        counts) after two eager steps, and replayed afterwards: the inputs are copied into the graph's static
+        buffers, the returned tensors are the graph's static outputs."""
+        from . import _lib
+        if not self.cuda_graph:
+            n0 = _lib.launch_count()
+            out = self._eager_step(batched_inputs)
+            self.pdb_launches += _lib.launch_count() - n0
+            return out
+        sig = tuple((tuple(d["image"].shape), tuple(d["instances"].gt_masks.tensor.shape),
+                     d.get("gt_object_class")) for d in batched_inputs)
+        entry = self._graphs.setdefault(sig, {"warm": 0})
+        if "graph" not in entry:
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            if entry["warm"] < 2:                       # lets shape-keyed caches fill and cuDNN / NCCL initialise
+                # warm-up runs on the capture stream: autograd's AccumulateGrad nodes remember the stream they were
+                # created on, and a node living on the default stream would invalidate the capture
+                entry["warm"] += 1
+                n0 = _lib.launch_count()
+                cur = torch.cuda.current_stream()
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    out = self._eager_step(batched_inputs)
+                cur.wait_stream(self._side)
+                self.pdb_launches += _lib.launch_count() - n0
+                return out
+            static = _clone_batch(batched_inputs, next(self.model.parameters()).device)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(graph, stream=self._side):
+                total, losses = self._eager_step(static)
+            entry.update(graph=graph, static=static, total=total, losses=losses, launches=_lib.launch_count() - n0)
+        _copy_batch(entry["static"], batched_inputs)
+        entry["graph"].replay()
+        self.pdb_launches += entry["launches"]
+        return entry["total"], entry["losses"]
+
+
+def _clone_batch(batch, device):
+    """Device-resident copy of a batch (list of dicts with "image" and "instances") used as a graph's static input."""
+    out = []
+    for d in batch:
+        e = dict(d)
+        e["image"] = d["image"].to(device, copy=True)
+        src = d["instances"]
+        inst = type(src)(src.image_size)
+        inst.gt_masks = type(src.gt_masks)(src.gt_masks.tensor.to(device, copy=True))
+        inst.gt_classes = src.gt_classes.to(device, copy=True)
+        e["instances"] = inst
+        out.append(e)
+    return out
+
+
+def _copy_batch(static, batch):
+    for s, d in zip(static, batch):
+        if s["image"] is not d["image"]:
+            s["image"].copy_(d["image"], non_blocking=True)
+            s["instances"].gt_masks.tensor.copy_(d["instances"].gt_masks.tensor, non_blocking=True)
+            s["instances"].gt_classes.copy_(d["instances"].gt_classes, non_blocking=True)

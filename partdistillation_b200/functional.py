@@ -26,6 +26,22 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+_table_cache = {}
+
+
+def host_table(values, dtype, device):
+    """Small host-side index table (python ints / floats) as a device tensor.  Tables are cached by content: the
+    per-step tables of the criterion / matcher depend only on the per-image target counts, so steady-state
+    steps issue no host->device copy for them (and a CUDA-graph capture of the step contains none)."""
+    key = (tuple(values), dtype, str(device))
+    t = _table_cache.get(key)
+    if t is None:
+        if len(_table_cache) > 512:
+            _table_cache.clear()
+        t = _table_cache[key] = torch.tensor(list(values), dtype=dtype).to(device)
+    return t
+
+
 # --------------------------------------------------------------------------------------------------
 # MSDeformAttn  (ops/functions/ms_deform_attn_func.py:35-52 — same call signature)
 # --------------------------------------------------------------------------------------------------

@@ -7,6 +7,7 @@ import torch
 from torch import nn
 
 from .compat import ImageList
+from .functional import host_table
 from .modeling.targets import TargetList
 
 
@@ -89,7 +90,7 @@ class Mask2FormerTrainingArch(nn.Module):
         out.packed_masks = packed
         out.packed_labels = torch.cat(labels).to(torch.int32) if offs[-1] else torch.zeros((0,), dtype=torch.int32, device=dev)
         if self.part_distillation:
-            out.object_classes = torch.tensor([int(x["gt_object_class"]) for x in inputs], dtype=torch.int32, device=dev)
+            out.object_classes = host_table([int(x["gt_object_class"]) for x in inputs], torch.int32, dev)
         return out
 
     def run_head(self, features, targets):

@@ -57,9 +57,9 @@ class SetCriterion(nn.Module):
                 base_p += [b * Q] * k
                 base_t += [offs[b]] * k
                 keep += list(range(offs[b], offs[b] + n))
-            cache = dict(Q=Q, base_p=torch.tensor(base_p, dtype=torch.int64, device=dev),
-                         base_t=torch.tensor(base_t, dtype=torch.int64, device=dev),
-                         keep=torch.tensor(keep, dtype=torch.int64, device=dev) if need_filter else None)
+            cache = dict(Q=Q, base_p=PF.host_table(base_p, torch.int64, dev),
+                         base_t=PF.host_table(base_t, torch.int64, dev),
+                         keep=PF.host_table(keep, torch.int64, dev) if need_filter else None)
             targets._crit_cache = cache
         src = pi + cache["base_p"]
         tgt = ti + cache["base_t"]
@@ -115,7 +115,7 @@ class SetCriterion(nn.Module):
         targets = pack_targets(targets)
         dev = outputs["pred_masks"].device
         # average number of target masks across ranks, >= 1 (:248-254) — kept on the device
-        num_masks = torch.as_tensor([float(targets.total)], dtype=torch.float, device=dev)
+        num_masks = torch.full((1,), float(targets.total), dtype=torch.float, device=dev)
         if dist.is_available() and dist.is_initialized():
             dist.all_reduce(num_masks)
             num_masks = num_masks / dist.get_world_size()

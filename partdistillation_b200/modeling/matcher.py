@@ -66,9 +66,9 @@ def _index_cache(targets, B, Q, dev):
     """int32 helper tables that depend only on the target counts (built once per step)."""
     c = getattr(targets, "_cache", None)
     if c is None or c["Q"] != Q:
-        counts = torch.tensor([targets.offsets[b + 1] - targets.offsets[b] for b in range(B)])
+        counts = [targets.offsets[b + 1] - targets.offsets[b] for b in range(B)]
         c = dict(Q=Q,
-                 img_of_query=torch.arange(B, dtype=torch.int32).repeat_interleave(Q).to(dev),
-                 img_of_target=torch.arange(B, dtype=torch.int32).repeat_interleave(counts).to(dev))
+                 img_of_query=PF.host_table([b for b in range(B) for _ in range(Q)], torch.int32, dev),
+                 img_of_target=PF.host_table([b for b in range(B) for _ in range(counts[b])], torch.int32, dev))
         targets._cache = c
     return c

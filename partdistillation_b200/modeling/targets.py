@@ -7,6 +7,8 @@ made once per step: all masks as uint8 (Ktot, H, W), labels as int32, host-side 
 """
 import torch
 
+from ..functional import host_table
+
 
 class TargetList(list):
     """list of {"labels", "masks"[, "gt_object_class"]} dicts (reference format) + packed views."""
@@ -43,5 +45,5 @@ def pack_targets(targets):
     out.packed_labels = torch.cat([t["labels"] for t in targets]).to(torch.int32) if offs[-1] else \
         torch.zeros((0,), dtype=torch.int32, device=dev)
     if len(targets) and "gt_object_class" in targets[0]:
-        out.object_classes = torch.tensor([int(t["gt_object_class"]) for t in targets], dtype=torch.int32, device=dev)
+        out.object_classes = host_table([int(t["gt_object_class"]) for t in targets], torch.int32, dev)
     return out

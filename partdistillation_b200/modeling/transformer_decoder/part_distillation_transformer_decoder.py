@@ -42,8 +42,7 @@ class PartDistillationTransformerDecoder(MultiScaleMaskedTransformerDecoder):
     def _classify(self, decoder_output, targets):
         obj = getattr(targets, "object_classes", None)
         if obj is None:
-            obj = torch.tensor([int(t["gt_object_class"]) for t in targets], dtype=torch.int32,
-                               device=decoder_output.device)
+            obj = PF.host_table([int(t["gt_object_class"]) for t in targets], torch.int32, decoder_output.device)
         return PF.class_rows(decoder_output, self.class_embed.weight, self.class_embed.bias, obj,
                              self.num_part_classes)
 
