@@ -58,6 +58,7 @@ class DataParallelTrainer:
         self.cuda_graph = bool(cuda_graph)
         self._graphs = {}
         self._side = None
+        self._num_masks = None
         self.pdb_launches = 0               # kernels launched through libpdb200.so, graph replays included
         groups = build_param_groups(model, base_lr, weight_decay, freeze_keys=freeze_keys,
                                     backbone_multiplier=backbone_multiplier)
@@ -164,6 +165,28 @@ class DataParallelTrainer:
         losses = self.model(batched_inputs)
         return self.backward_and_step(losses), losses
 
+    def _forward_backward(self, batched_inputs):
+        self.zero_grad()
+        losses = self.model(batched_inputs)
+        total = sum(losses.values())
+        total.backward()
+        return total, losses
+
+    def _global_num_masks(self, batched_inputs):
+        """mean over ranks of the per-rank number of target masks, clamped to >= 1 (criterion.py:248-254), all-reduced
+        here, ahead of the step, so that the captured forward/backward holds no collective."""
+        crit = getattr(self.model, "criterion", None)
+        if crit is None or not hasattr(crit, "external_num_masks"):
+            return
+        total = sum(int(d["instances"].gt_masks.tensor.shape[0]) for d in batched_inputs)
+        if self._num_masks is None:
+            self._num_masks = torch.zeros(1, dtype=torch.float32, device=next(self.model.parameters()).device)
+            self._num_masks_tmp = torch.zeros_like(self._num_masks)
+        self._num_masks_tmp.fill_(float(total))
+        dist.all_reduce(self._num_masks_tmp)
+        torch.clamp(self._num_masks_tmp / self.world, min=1, out=self._num_masks)
+        crit.external_num_masks = self._num_masks
+
     def step(self, batched_inputs):
         """One training step -> (total loss, loss dict).  With ``cuda_graph=True`` the whole step (forward, loss,
         backward, all-reduce, clip, AdamW) is captured once per batch signature (image shapes and per-image mask
@@ -185,6 +208,8 @@ class DataParallelTrainer:
                 # warm-up runs on the capture stream: autograd's AccumulateGrad nodes remember the stream they were
                 # created on, and a node living on the default stream would invalidate the capture
                 entry["warm"] += 1
+                if self.world > 1:
+                    self._global_num_masks(batched_inputs)
                 n0 = _lib.launch_count()
                 cur = torch.cuda.current_stream()
                 self._side.wait_stream(cur)
@@ -198,11 +223,20 @@ class DataParallelTrainer:
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
             with torch.cuda.graph(graph, stream=self._side):
-                total, losses = self._eager_step(static)
+                # world 1: the whole step; world > 1: forward + backward only — the collectives (num_masks before,
+                # the flat-gradient all-reduce after) and the two optimizer kernels stay outside the graph
+                total, losses = self._eager_step(static) if self.world == 1 else self._forward_backward(static)
             entry.update(graph=graph, static=static, total=total, losses=losses, launches=_lib.launch_count() - n0)
         _copy_batch(entry["static"], batched_inputs)
+        if self.world > 1:
+            self._global_num_masks(batched_inputs)
         entry["graph"].replay()
         self.pdb_launches += entry["launches"]
+        if self.world > 1:
+            n0 = _lib.launch_count()
+            self.reduce_gradients()
+            self.clip_and_step()
+            self.pdb_launches += _lib.launch_count() - n0
         return entry["total"], entry["losses"]
 
 

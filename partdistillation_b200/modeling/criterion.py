@@ -38,6 +38,7 @@ class SetCriterion(nn.Module):
         self.oversample_ratio = oversample_ratio
         self.importance_sample_ratio = importance_sample_ratio
         self.rand = torch.rand
+        self.external_num_masks = None     # device float tensor set by the trainer (see forward)
 
     # ------------------------------------------------------------------------------------------
     def _flat_indices(self, targets, match, B, Q):
@@ -114,12 +115,17 @@ class SetCriterion(nn.Module):
     def forward(self, outputs, targets):
         targets = pack_targets(targets)
         dev = outputs["pred_masks"].device
-        # average number of target masks across ranks, >= 1 (:248-254) — kept on the device
-        num_masks = torch.full((1,), float(targets.total), dtype=torch.float, device=dev)
-        if dist.is_available() and dist.is_initialized():
-            dist.all_reduce(num_masks)
-            num_masks = num_masks / dist.get_world_size()
-        num_masks = torch.clamp(num_masks, min=1)[0]
+        # average number of target masks across ranks, >= 1 (:248-254) — kept on the device.  It depends only on the
+        # target counts, so a trainer may all-reduce it before the step and hand it over (external_num_masks): the
+        # forward/backward then contains no collective and can be replayed as a CUDA graph on every rank.
+        if self.external_num_masks is not None:
+            num_masks = self.external_num_masks.reshape(-1)[0]
+        else:
+            num_masks = torch.full((1,), float(targets.total), dtype=torch.float, device=dev)
+            if dist.is_available() and dist.is_initialized():
+                dist.all_reduce(num_masks)
+                num_masks = num_masks / dist.get_world_size()
+            num_masks = torch.clamp(num_masks, min=1)[0]
 
         losses = {}
         main = {k: v for k, v in outputs.items() if k != "aux_outputs"}
