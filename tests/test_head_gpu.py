@@ -153,3 +153,69 @@ def test_matcher_public_api(golden_dir):
         idx = model.criterion.matcher({k: v for k, v in outputs.items() if k != "aux_outputs"}, plain)
     for (i, j), (ri, rj) in zip(idx, g["indices"][0]):
         assert i.dtype == torch.int64 and torch.equal(i.cpu(), ri) and torch.equal(j.cpu(), rj)
+
+
+class _RecordRand:
+    """torch.rand on the device, keeping a CPU copy of every draw for the oracle to replay."""
+
+    def __init__(self):
+        self.draws = []
+
+    def __call__(self, *size, **kw):
+        t = torch.rand(*size, **kw)
+        self.draws.append(t.detach().cpu())
+        return t
+
+
+def test_full_size_config2_losses_vs_oracle():
+    """BASELINE configs[1] at full size (Swin-B, 1024x1024, 100 queries, 10 decoder outputs, 12544 points), one
+    image: every loss of the product path on the B200 against the CPU oracle on the same backbone features, weights,
+    targets and random point draws.  Bar: <= 1e-3 relative (north_star)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import bench
+    import m2f_oracle as O
+    from partdistillation_b200 import compat, presets
+    cfg = presets.make_cfg("ProposalModel", "swin_b", 100, 10, 12544, 0.0, device="cuda")
+    torch.manual_seed(0)
+    model = compat.build_model(cfg)
+    model.train()
+    batch = bench.make_batch(0, 1, device=torch.device("cuda"))
+    rec = _RecordRand()
+    model.criterion.rand = rec
+    model.criterion.matcher.rand = rec
+    with torch.no_grad():
+        images = model.preprocess_images(batch)
+        feats = model.backbone(images.tensor)
+        targets = model.prepare_targets(batch, images)
+        losses = model.losses_from_features(feats, targets)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    hp = dict(num_classes=1, dec_layers=10, num_points_match=12544, num_points_loss=12544, w_class=2.0, w_mask=5.0,
+              w_dice=5.0, eos_coef=0.1, oversample_ratio=3.0, importance_ratio=0.0)
+    tg = O.prepare_targets([{"gt_masks": batch[0]["instances"].gt_masks.tensor.cpu()}], bench.H, bench.W)
+    replay = synth.ReplayRand(rec.draws)
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        ref = O.head_and_loss(sd, {k: v.cpu() for k, v in feats.items()}, tg, hp, rand=replay)
+    assert replay.i == len(rec.draws)
+    assert set(ref) == set(losses)
+    for k, v in ref.items():
+        assert abs(float(losses[k]) - float(v)) <= 1e-3 * max(1.0, abs(float(v))), (k, float(losses[k]), float(v))
+
+
+def test_part_distillation_step_under_bf16_autocast(golden_dir):
+    """BASELINE configs[2] runs under bf16 autocast (the pixel decoder and the kernels stay fp32, the fp64 classifier
+    rows stay fp64): one forward + backward of PartDistillationModel gives finite losses and gradients."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    g = torch.load(os.path.join(golden_dir, "head_pd_micro.pt"), weights_only=False)
+    model, c = _build(g)
+    feats, targets = _inputs(model, c)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        losses = model.losses_from_features(feats, targets)
+    total = sum(losses.values())
+    assert torch.isfinite(total)
+    total.backward()
+    grads = [p.grad for p in model.sem_seg_head.parameters() if p.grad is not None]
+    assert grads and all(torch.isfinite(x).all() for x in grads)
+    assert set(losses) == set(g["losses"])
