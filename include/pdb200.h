@@ -68,12 +68,13 @@ PDB_API int pdb_msda_backward(const void* value, const int64_t* shapes_hw, const
  * (mask2former_transformer_decoder.py:449, part_distillation_transformer_decoder.py:244).
  *   embed (B, Q, C) f32;  feat (B, HW, C) f32 PIXEL-MAJOR (the NCHW mask_features tensor in
  *   channels_last memory format);  out (B, Q, HW) f32.  C % 4 == 0, 16-byte aligned bases.
- *   forward: tcgen05 kind::tf32 with a 3-term hi/lo split of both operands (fp32-accurate logits).
+ *   forward: tcgen05 kind::tf32 with a 3-term hi/lo split of both operands (fp32-accurate logits);
+ *   embed_lo (B, Q, C) = pdb_split_lo(embed) or NULL (then the kernel splits embed itself, once per pixel tile).
  * backward:  grad_embed (B,Q,C) = grad_out x feat (overwritten);
  *            grad_feat  (B,HW,C) (+)= grad_out^T x embed  (accumulate != 0 adds into grad_feat).
  * Either grad pointer may be NULL to skip it.
  * ---------------------------------------------------------------------------------------------- */
-PDB_API int pdb_mask_einsum_forward(const float* embed, const float* feat, float* out,
+PDB_API int pdb_mask_einsum_forward(const float* embed, const float* embed_lo, const float* feat, float* out,
                             int B, int Q, int C, int64_t HW, void* stream);
 PDB_API int pdb_mask_einsum_backward(const float* embed, const float* feat, const float* grad_out,
                              float* grad_embed, float* grad_feat, int accumulate,
@@ -90,13 +91,18 @@ PDB_API int pdb_mask_einsum_backward(const float* embed, const float* feat, cons
  *   c_trans = 0: C[b*sc + m*ldc + n]                          c_trans = 1: C[b*sc + n*ldc + m]
  *   accumulate != 0: C += (red.add; C must be initialised); ksplit > 1 (split-K) requires accumulate.
  * A, B 16-byte aligned; lda, ldb, sa, sb multiples of 4 floats.  bias may be NULL.
+ * B_lo: NULL, or the low parts of B (same layout as B) from pdb_split_lo — worthwhile when B is a weight matrix
+ * shared by many row tiles (every 128-row tile would otherwise re-split it).
  * nn.Linear:  y = x W^T + b      -> A = x (K-major), B = W (K-major), bias, relu optional
  *             dx = dy W          -> A = dy (K-major), B = W (MN-major)
  *             dW = dy^T x        -> A = dy (MN-major), B = x (MN-major), split-K over the rows, accumulate
  * ---------------------------------------------------------------------------------------------- */
-PDB_API int pdb_gemm_tf32x3(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int batch,
+PDB_API int pdb_gemm_tf32x3(const float* A, const float* B, const float* B_lo, float* C, const float* bias, int M, int N,
+                    int K, int batch,
                     int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc, int a_mn, int b_mn,
                     int c_trans, int relu, int accumulate, int ksplit, void* stream);
+/* lo[i] = x[i] - trunc_tf32(x[i]) (x with its low 13 mantissa bits cleared); n % 4 == 0, 16-byte aligned. */
+PDB_API int pdb_split_lo(const float* x, float* lo, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Attention-mask build — replaces F.interpolate(bilinear, align_corners=False) -> sigmoid() < 0.5

@@ -23,9 +23,10 @@ SIGNATURES = {
     "pdb_launch_count": (_l, []),
     "pdb_msda_forward": (_i, [_p, _hp64, _hp64, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "pdb_msda_backward": (_i, [_p, _hp64, _hp64, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
-    "pdb_mask_einsum_forward": (_i, [_p, _p, _p, _i, _i, _i, _l, _p]),
+    "pdb_mask_einsum_forward": (_i, [_p, _p, _p, _p, _i, _i, _i, _l, _p]),
     "pdb_mask_einsum_backward": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _l, _p]),
-    "pdb_gemm_tf32x3": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _l, _l, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _p]),
+    "pdb_gemm_tf32x3": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _l, _l, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _p]),
+    "pdb_split_lo": (_i, [_p, _p, _l, _p]),
     "pdb_attn_mask_build": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "pdb_attn_mask_reset_rows": (_i, [_p, _p, _i, _l, _p]),
     "pdb_masked_xattn_workspace_bytes": (_l, [_i, _i, _i, _i, _i]),

@@ -22,7 +22,7 @@
 //                                     (UMMA layout SWIZZLE_128B_BASE32B, instruction-descriptor a_major/b_major = 1)
 // TMA zero-fills out-of-range rows / k, so ragged M, N, K (and per-batch K ranges) need no masking.
 //
-// Persistent kernel, one CTA per SM, 14 warps; a CTA walks 128 x BN output tiles (n fastest, so the CTAs that
+// Persistent kernel, one CTA per SM, 18 warps; a CTA walks 128 x BN output tiles (n fastest, so the CTAs that
 // run together share their A rows in L2):
 //   warp 0      TMA producer: raw fp32 A / B k-blocks into a 3-deep ring
 //   warps 2..9  split every landed k-block: the raw tile is the hi operand (tf32 ignores the low 13 bits), lo =
@@ -30,7 +30,7 @@
 //               hi*hi and hi*lo side by side in TMEM), A_lo into its own 2-deep ring
 //   warp 1      TMEM allocator + tcgen05.mma issuer (one elected lane): per 8-wide k step
 //               [main | corr] += A_hi x [B_hi ; B_lo]^T   and   corr += A_lo x B_hi^T
-//   warps 10..13 epilogue: tcgen05.ld (main + corr) -> (+bias, ReLU) -> coalesced store / red.add, overlapped
+//   warps 10..17 epilogue (two per TMEM lane quarter): tcgen05.ld (main + corr) -> (+bias, ReLU) -> coalesced store / red.add, overlapped
 //               with the next tile's main loop through a double-buffered TMEM accumulator
 #include <algorithm>
 #include "common.cuh"
@@ -42,7 +42,8 @@ constexpr int G_BM = 128;
 constexpr int G_BK = 32;              // fp32 per 128-byte swizzled row
 constexpr int G_SPLIT_THREADS = 256;  // warps 2..9
 constexpr int G_EPI_WARP0 = 2 + G_SPLIT_THREADS / 32;
-constexpr int G_THREADS = (G_EPI_WARP0 + 4) * 32;     // 448
+constexpr int G_EPI_WARPS = 8;          // two warps per TMEM lane quarter, each takes every other column chunk
+constexpr int G_THREADS = (G_EPI_WARP0 + G_EPI_WARPS) * 32;     // 576
 constexpr int G_RS = 3;               // raw ring depth
 constexpr int G_LS = 2;               // A_lo ring depth
 
@@ -54,6 +55,8 @@ struct GemmParams {
     int batch, ksplit, kchunk;        // kchunk: multiple of G_BK
     int c_trans, relu, atomic;
     int mt, nt, total_tiles;
+    int presplit;                     // B_lo comes pre-computed from global memory (tm_blo) instead of being split here
+    int b_box_rows;                   // rows of the K-major B box (BN, or the 16-multiple covering N when N < BN)
     long long* trace;                 // debug timeline of CTA 0 (pdb_debug_set_trace), normally NULL
 };
 
@@ -64,7 +67,7 @@ struct GemmSmem {
     static constexpr int RAW_STAGE = A_BYTES + 2 * B_BYTES;            // A raw/hi | B raw/hi | B lo
     static constexpr int RAW_TOTAL = G_RS * RAW_STAGE;
     static constexpr int ALO_TOTAL = G_LS * A_BYTES;
-    static constexpr int STAGING = 4 * 32 * 36 * 4;                    // epilogue transpose tiles (row stride 36 floats)
+    static constexpr int STAGING = G_EPI_WARPS * 32 * 36 * 4;                    // epilogue transpose tiles (row stride 36 floats)
     static constexpr int BAR_OFF = RAW_TOTAL + ALO_TOTAL + STAGING;
     static constexpr int TOTAL = BAR_OFF + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int ACC_COLS = 2 * BN;               // main (hi*hi) | correction (lo*hi + hi*lo)
@@ -143,10 +146,28 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int tile) {
     return c;
 }
 
+// Where B_lo of a tile lives relative to B_hi, how many bytes TMA delivers for B_hi, and whether B_lo is directly
+// behind the bn_eff valid rows / blocks (so that one N = 2*bn_eff MMA covers [B_hi ; B_lo]).
+template <int BN, bool B_MN>
+__device__ __forceinline__ void b_layout(const GemmParams& p, int bn_eff, int& blo_off, int& hi_bytes, bool& stacked) {
+    const int adjacent = B_MN ? ((bn_eff + 31) / 32) * 4096 : bn_eff * 128;
+    if (!p.presplit) {                  // lo written by the split warps after the (full-box) TMA has landed
+        blo_off = adjacent;
+        hi_bytes = BN * G_BK * 4;
+    } else if (B_MN) {                  // only the needed 32-column blocks are loaded
+        blo_off = adjacent;
+        hi_bytes = adjacent;
+    } else {                            // K-major box rows are fixed by the tensor map
+        hi_bytes = p.b_box_rows * 128;
+        blo_off = (p.b_box_rows == bn_eff) ? adjacent : BN * G_BK * 4;
+    }
+    stacked = (blo_off == adjacent) && (!B_MN || bn_eff % 32 == 0);
+}
+
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                   const GemmParams p) {
+                   const __grid_constant__ CUtensorMap tm_blo, const GemmParams p) {
     using S = GemmSmem<BN>;
     extern __shared__ uint8_t smem_raw[];
     // 1 KB alignment by pointer arithmetic (no integer round trip), so the compiler keeps the shared state space
@@ -180,7 +201,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         for (int s = 0; s < G_LS; ++s) tc::mbar_init(&alo_empty[s], 1);
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&acc_full[s], 1);
-            tc::mbar_init(&acc_empty[s], 128);
+            tc::mbar_init(&acc_empty[s], G_EPI_WARPS * 32);
         }
         tc::fence_barrier_init();
     }
@@ -196,13 +217,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const TileCoord c = tile_coord<BN>(p, tile);
+                int blo_off, hi_bytes;
+                bool stacked;
+                b_layout<BN, B_MN>(p, c.bn_eff, blo_off, hi_bytes, stacked);
+                const int nblk = p.presplit ? (c.bn_eff + 31) / 32 : BN / 32;      // MN-major B: 32-column blocks to load
                 for (int kb = 0; kb < c.num_kb; ++kb, ++it) {
                     const int s = it % G_RS;
                     const uint32_t ph = (it / G_RS) & 1;
                     const int k0 = c.k_begin + kb * G_BK;
                     tc::mbar_wait(&raw_empty[s], ph ^ 1);
                     trace_evt(p, 0, it, 0);
-                    tc::mbar_expect_tx(&raw_full[s], S::A_BYTES + S::B_BYTES);
+                    tc::mbar_expect_tx(&raw_full[s], S::A_BYTES + hi_bytes * (p.presplit ? 2 : 1));
                     if (A_MN) {
 #pragma unroll
                         for (int i = 0; i < G_BM / 32; ++i) tma_load_3d(a_raw(s) + i * 4096, &tm_a, &raw_full[s], c.m0 + 32 * i, k0, c.b);
@@ -210,10 +235,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                         tma_load_3d(a_raw(s), &tm_a, &raw_full[s], k0, c.m0, c.b);
                     }
                     if (B_MN) {
-#pragma unroll
-                        for (int i = 0; i < BN / 32; ++i) tma_load_3d(b_raw(s) + i * 4096, &tm_b, &raw_full[s], c.n0 + 32 * i, k0, c.b);
+                        for (int i = 0; i < nblk; ++i) tma_load_3d(b_raw(s) + i * 4096, &tm_b, &raw_full[s], c.n0 + 32 * i, k0, c.b);
+                        if (p.presplit)
+                            for (int i = 0; i < nblk; ++i)
+                                tma_load_3d(b_raw(s) + blo_off + i * 4096, &tm_blo, &raw_full[s], c.n0 + 32 * i, k0, c.b);
                     } else {
                         tma_load_3d(b_raw(s), &tm_b, &raw_full[s], k0, c.n0, c.b);
+                        if (p.presplit) tma_load_3d(b_raw(s) + blo_off, &tm_blo, &raw_full[s], k0, c.n0, c.b);
                     }
                 }
             }
@@ -227,9 +255,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 const uint32_t ab = t & 1;
                 const uint32_t tmem_main = tmem_base + ab * S::ACC_COLS;
                 const uint32_t tmem_corr = tmem_main + c.bn_eff;
-                // B_lo sits bn_eff rows behind B_hi; a single N = 2*bn_eff MMA needs that to be a whole number of
-                // 32-column blocks for MN-major B
-                const bool stacked = !B_MN || (c.bn_eff % 32 == 0);
+                // one N = 2*bn_eff MMA when B_lo sits directly behind the bn_eff valid rows / blocks of B_hi
+                int blo_off, hi_bytes;
+                bool stacked;
+                b_layout<BN, B_MN>(p, c.bn_eff, blo_off, hi_bytes, stacked);
                 const uint32_t major = (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
                 const uint32_t idesc1 = tc::umma_idesc_tf32(G_BM, c.bn_eff) | major;
                 const uint32_t idesc2 = tc::umma_idesc_tf32(G_BM, 2 * c.bn_eff) | major;
@@ -244,7 +273,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                     tc::mbar_wait(&split_done[s], (it / G_RS) & 1);
                     tc::tc_fence_after();
                     trace_evt(p, 1, it, 1);
-                    const uint8_t* blo = b_raw(s) + (B_MN ? ((c.bn_eff + 31) / 32) * 4096 : c.bn_eff * 128);
+                    const uint8_t* blo = b_raw(s) + blo_off;
 #pragma unroll
                     for (int k = 0; k < G_BK / 8; ++k) {
                         const uint64_t dah = operand_desc<A_MN>(a_raw(s), k);
@@ -274,7 +303,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const TileCoord c = tile_coord<BN>(p, tile);
-            const int blo_off = B_MN ? ((c.bn_eff + 31) / 32) * 4096 : c.bn_eff * 128;
+            int blo_off, hi_bytes;
+            bool stacked;
+            b_layout<BN, B_MN>(p, c.bn_eff, blo_off, hi_bytes, stacked);
             for (int kb = 0; kb < c.num_kb; ++kb, ++it) {
                 const int s = it % G_RS;
                 const int ls = it % G_LS;
@@ -286,7 +317,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 split_tile<S::A_BYTES / 16 / G_SPLIT_THREADS>(reinterpret_cast<float4*>(a_raw(s)), reinterpret_cast<float4*>(a_lo(ls)), tid);
                 float4* braw = reinterpret_cast<float4*>(b_raw(s));
                 float4* blo = reinterpret_cast<float4*>(b_raw(s) + blo_off);
-                if (c.bn_eff == BN) {
+                if (p.presplit) {
+                    // B_lo arrived by TMA
+                } else if (c.bn_eff == BN) {
                     split_tile<S::B_BYTES / 16 / G_SPLIT_THREADS>(braw, blo, tid);
                 } else {
                     // ragged N tile: only the first bn_eff rows (K-major) / 32-column blocks (MN-major) matter; B_lo
@@ -314,6 +347,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     } else {
         // ------------------------------------------------------------------ epilogue (last 4 warps)
         const int quarter = warp & 3;                          // TMEM lanes this warp may access
+        const int half = (warp - G_EPI_WARP0) >> 2;            // which of the two warps of this quarter
         float* tile_s = staging + (warp - G_EPI_WARP0) * (32 * 36);
         const bool trace_thread = threadIdx.x == G_EPI_WARP0 * 32;
         // 16-byte row stores need aligned rows
@@ -335,18 +369,25 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 const bool m_ok = m < p.M;
                 float* col = Cb + (int64_t)c.n0 * p.ldc + m;
                 const int nvalid = min(c.bn_eff, p.N - c.n0);
+                col += (int64_t)(half * 16) * p.ldc;
+                if (half * 16 >= c.bn_eff) {                   // nothing to read for this warp: release at once
+                    tc::tc_fence_before();
+                    tc::mbar_arrive(&acc_empty[ab]);
+                }
 #pragma unroll 1
-                for (int c0 = 0; c0 < c.bn_eff; c0 += 16) {
-                    float v[16], w[16];
-                    tc::tmem_ld16(tbase + c0, v);
-                    tc::tmem_ld16(tbase + c.bn_eff + c0, w);
-                    if (c0 + 16 >= c.bn_eff) {                 // last read of this accumulator: hand it back to the MMA warp
+                for (int c0 = half * 16; c0 < c.bn_eff; c0 += 32) {
+                    uint32_t vr[16], wr[16];
+                    tc::tmem_ld16_nowait(tbase + c0, vr);
+                    tc::tmem_ld16_nowait(tbase + c.bn_eff + c0, wr);
+                    tc::tmem_ld_wait();
+                    if (c0 + 32 >= c.bn_eff) {                 // last read of this accumulator: hand it back to the MMA warp
                         tc::tc_fence_before();
                         tc::mbar_arrive(&acc_empty[ab]);
                     }
+                    float v[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        float x = v[i] + w[i];
+                        float x = __uint_as_float(vr[i]) + __uint_as_float(wr[i]);
                         if (p.bias) x += __ldg(p.bias + min(c.n0 + c0 + i, p.N - 1));
                         if (p.relu) x = fmaxf(x, 0.f);
                         v[i] = x;
@@ -363,33 +404,46 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                                 if (i < lim) col[(int64_t)i * p.ldc] = v[i];
                         }
                     }
-                    col += 16 * p.ldc;
+                    col += 32 * p.ldc;
                 }
             } else {
                 // C[m][n]: transpose 32 x 32 blocks through shared memory so that a warp store instruction writes
                 // four 128-byte row segments (float4 per lane)
                 const int mrow0 = c.m0 + quarter * 32;
                 const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+                if (half * 32 >= c.bn_eff) {
+                    tc::tc_fence_before();
+                    tc::mbar_arrive(&acc_empty[ab]);
+                }
 #pragma unroll 1
-                for (int c0 = 0; c0 < c.bn_eff; c0 += 32) {
+                for (int c0 = half * 32; c0 < c.bn_eff; c0 += 64) {
                     const bool two = c0 + 16 < c.bn_eff;       // bn_eff is a multiple of 16, not of 32
-                    float v[16], w[16];
-                    tc::tmem_ld16(tbase + c0, v);
-                    tc::tmem_ld16(tbase + c.bn_eff + c0, w);
+                    uint32_t v0[16], w0[16], v1[16], w1[16];
+                    tc::tmem_ld16_nowait(tbase + c0, v0);
+                    tc::tmem_ld16_nowait(tbase + c.bn_eff + c0, w0);
+                    if (two) {
+                        tc::tmem_ld16_nowait(tbase + c0 + 16, v1);
+                        tc::tmem_ld16_nowait(tbase + c.bn_eff + c0 + 16, w1);
+                    }
+                    tc::tmem_ld_wait();
+                    if (c0 + 64 >= c.bn_eff) {
+                        tc::tc_fence_before();
+                        tc::mbar_arrive(&acc_empty[ab]);
+                    }
                     float4* srow = reinterpret_cast<float4*>(tile_s + lane * 36);
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        srow[i] = make_float4(v[4 * i] + w[4 * i], v[4 * i + 1] + w[4 * i + 1], v[4 * i + 2] + w[4 * i + 2], v[4 * i + 3] + w[4 * i + 3]);
+                        srow[i] = make_float4(__uint_as_float(v0[4 * i]) + __uint_as_float(w0[4 * i]),
+                                              __uint_as_float(v0[4 * i + 1]) + __uint_as_float(w0[4 * i + 1]),
+                                              __uint_as_float(v0[4 * i + 2]) + __uint_as_float(w0[4 * i + 2]),
+                                              __uint_as_float(v0[4 * i + 3]) + __uint_as_float(w0[4 * i + 3]));
                     if (two) {
-                        tc::tmem_ld16(tbase + c0 + 16, v);
-                        tc::tmem_ld16(tbase + c.bn_eff + c0 + 16, w);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            srow[4 + i] = make_float4(v[4 * i] + w[4 * i], v[4 * i + 1] + w[4 * i + 1], v[4 * i + 2] + w[4 * i + 2], v[4 * i + 3] + w[4 * i + 3]);
-                    }
-                    if (c0 + 32 >= c.bn_eff) {
-                        tc::tc_fence_before();
-                        tc::mbar_arrive(&acc_empty[ab]);
+                            srow[4 + i] = make_float4(__uint_as_float(v1[4 * i]) + __uint_as_float(w1[4 * i]),
+                                                      __uint_as_float(v1[4 * i + 1]) + __uint_as_float(w1[4 * i + 1]),
+                                                      __uint_as_float(v1[4 * i + 2]) + __uint_as_float(w1[4 * i + 2]),
+                                                      __uint_as_float(v1[4 * i + 3]) + __uint_as_float(w1[4 * i + 3]));
                     }
                     __syncwarp();
                     const int ncols = min(two ? 32 : 16, p.N - c.n0 - c0);       // valid columns of this block
@@ -482,7 +536,7 @@ static int make_operand_map(CUtensorMap* map, const float* base, bool mn_major, 
 static long long* g_trace_ptr = nullptr;
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbl, const GemmParams& p, cudaStream_t st) {
     using S = GemmSmem<BN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -496,19 +550,19 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     q.nt = (p.N + BN - 1) / BN;
     q.total_tiles = q.mt * q.nt * p.batch * p.ksplit;
     const unsigned grid = (unsigned)std::min(q.total_tiles, kNumSMs);        // persistent: one CTA per SM
-    gemm_tf32x3_kernel<BN, A_MN, B_MN><<<grid, G_THREADS, S::TOTAL, st>>>(ta, tb, q);
+    gemm_tf32x3_kernel<BN, A_MN, B_MN><<<grid, G_THREADS, S::TOTAL, st>>>(ta, tb, tbl, q);
     return launched("gemm_tf32x3");
 }
 
 template <int BN>
-static int dispatch_layout(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, bool a_mn, bool b_mn, cudaStream_t st) {
-    if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(ta, tb, p, st);
-    if (!a_mn && b_mn) return launch_gemm<BN, false, true>(ta, tb, p, st);
-    if (a_mn && !b_mn) return launch_gemm<BN, true, false>(ta, tb, p, st);
-    return launch_gemm<BN, true, true>(ta, tb, p, st);
+static int dispatch_layout(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbl, const GemmParams& p, bool a_mn, bool b_mn, cudaStream_t st) {
+    if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(ta, tb, tbl, p, st);
+    if (!a_mn && b_mn) return launch_gemm<BN, false, true>(ta, tb, tbl, p, st);
+    if (a_mn && !b_mn) return launch_gemm<BN, true, false>(ta, tb, tbl, p, st);
+    return launch_gemm<BN, true, true>(ta, tb, tbl, p, st);
 }
 
-int gemm_tf32x3(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int batch,
+int gemm_tf32x3(const float* A, const float* B, const float* B_lo, float* C, const float* bias, int M, int N, int K, int batch,
                 int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc, int a_mn, int b_mn,
                 int c_trans, int relu, int accumulate, int ksplit, cudaStream_t st) {
     PDB_REQUIRE(A && B && C, "gemm_tf32x3: null pointer");
@@ -526,23 +580,49 @@ int gemm_tf32x3(const float* A, const float* B, float* C, const float* bias, int
     p.kchunk = ((kb_total + ksplit - 1) / ksplit) * G_BK;
     p.ksplit = (K + p.kchunk - 1) / p.kchunk;           // no empty slices
     p.c_trans = c_trans; p.relu = relu; p.atomic = accumulate;
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tbl;
     PDB_TRY(make_operand_map(&ta, A, a_mn != 0, M, K, batch, lda, sa, G_BM));
-    PDB_TRY(make_operand_map(&tb, B, b_mn != 0, N, K, batch, ldb, sb, BN));
-    if (BN == 32) return dispatch_layout<32>(ta, tb, p, a_mn != 0, b_mn != 0, st);
-    if (BN == 64) return dispatch_layout<64>(ta, tb, p, a_mn != 0, b_mn != 0, st);
-    return dispatch_layout<128>(ta, tb, p, a_mn != 0, b_mn != 0, st);
+    p.presplit = B_lo != nullptr;
+    // pre-split K-major B with a single n tile: the box covers exactly the rows the MMA needs, B_lo lands right behind
+    p.b_box_rows = (p.presplit && N < BN) ? ((N + 15) / 16) * 16 : BN;
+    PDB_REQUIRE(!B_lo || (reinterpret_cast<uintptr_t>(B_lo) & 15) == 0, "gemm_tf32x3: B_lo must be 16-byte aligned");
+    PDB_TRY(make_operand_map(&tb, B, b_mn != 0, N, K, batch, ldb, sb, p.b_box_rows));
+    tbl = tb;
+    if (B_lo) PDB_TRY(make_operand_map(&tbl, B_lo, b_mn != 0, N, K, batch, ldb, sb, p.b_box_rows));
+    if (BN == 32) return dispatch_layout<32>(ta, tb, tbl, p, a_mn != 0, b_mn != 0, st);
+    if (BN == 64) return dispatch_layout<64>(ta, tb, tbl, p, a_mn != 0, b_mn != 0, st);
+    return dispatch_layout<128>(ta, tb, tbl, p, a_mn != 0, b_mn != 0, st);
 }
 
 }  // namespace pdb
 
 using namespace pdb;
 
-extern "C" int pdb_gemm_tf32x3(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int batch,
+extern "C" int pdb_gemm_tf32x3(const float* A, const float* B, const float* B_lo, float* C, const float* bias, int M, int N, int K, int batch,
                                int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc, int a_mn,
                                int b_mn, int c_trans, int relu, int accumulate, int ksplit, void* stream) {
-    return gemm_tf32x3(A, B, C, bias, M, N, K, batch, lda, ldb, ldc, sa, sb, sc, a_mn, b_mn, c_trans, relu, accumulate,
+    return gemm_tf32x3(A, B, B_lo, C, bias, M, N, K, batch, lda, ldb, ldc, sa, sb, sc, a_mn, b_mn, c_trans, relu, accumulate,
                        ksplit, as_stream(stream));
+}
+
+namespace pdb {
+__global__ void __launch_bounds__(256) split_lo_kernel(const float4* __restrict__ x, float4* __restrict__ lo, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 h, l;
+        split4(__ldg(x + i), h, l);
+        lo[i] = l;
+    }
+}
+}  // namespace pdb
+
+extern "C" int pdb_split_lo(const float* x, float* lo, int64_t n, void* stream) {
+    PDB_REQUIRE(x && lo && n >= 0 && n % 4 == 0, "split_lo: null pointer or n not a multiple of 4");
+    PDB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0, "split_lo: 16-byte alignment");
+    if (n == 0) return PDB_OK;
+    int64_t n4 = n / 4;
+    int blocks = (int)std::min<int64_t>((n4 + 255) / 256, 8 * kNumSMs);
+    split_lo_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(lo), n4);
+    return launched("split_lo");
 }
 
 extern "C" PDB_API int pdb_debug_set_trace(long long* buf) {

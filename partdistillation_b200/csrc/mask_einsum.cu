@@ -124,15 +124,15 @@ tile_gemm(const float* __restrict__ A, const float* __restrict__ Bm, float* __re
 }  // namespace pdb
 
 namespace pdb {
-int gemm_tf32x3(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int batch,
+int gemm_tf32x3(const float* A, const float* B, const float* B_lo, float* C, const float* bias, int M, int N, int K, int batch,
                 int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc, int a_mn, int b_mn,
                 int c_trans, int relu, int accumulate, int ksplit, cudaStream_t st);
 }
 
 using namespace pdb;
 
-extern "C" int pdb_mask_einsum_forward(const float* embed, const float* feat, float* out, int B, int Q, int C,
-                                       int64_t HW, void* stream) {
+extern "C" int pdb_mask_einsum_forward(const float* embed, const float* embed_lo, const float* feat, float* out, int B,
+                                       int Q, int C, int64_t HW, void* stream) {
     PDB_REQUIRE(embed && feat && out, "mask_einsum_forward: null pointer");
     PDB_REQUIRE(B > 0 && Q > 0 && C > 0 && HW > 0, "mask_einsum_forward: non-positive dimension");
     PDB_REQUIRE(C % 4 == 0, "mask_einsum_forward: C=%d must be a multiple of 4 (16-byte TMA rows)", C);
@@ -141,7 +141,7 @@ extern "C" int pdb_mask_einsum_forward(const float* embed, const float* feat, fl
     PDB_REQUIRE(HW < (1ll << 31), "mask_einsum_forward: too many pixels");
     // out[b][q][p] = sum_c feat[b][p][c] * embed[b][q][c]: M = pixels (TMEM lanes), N = queries, both operands
     // K-major, transposed store (32 consecutive pixels per warp store)
-    return gemm_tf32x3(feat, embed, out, nullptr, (int)HW, Q, C, B, C, C, HW, (int64_t)HW * C, (int64_t)Q * C,
+    return gemm_tf32x3(feat, embed, embed_lo, out, nullptr, (int)HW, Q, C, B, C, C, HW, (int64_t)HW * C, (int64_t)Q * C,
                        (int64_t)Q * HW, 0, 0, 1, 0, 0, 1, as_stream(stream));
 }
 
@@ -158,7 +158,7 @@ extern "C" int pdb_mask_einsum_backward(const float* embed, const float* feat, c
     if (tc_ok) {
         if (grad_feat) {
             // grad_feat[b][p][c] (+)= sum_q grad_out[b][q][p] * embed[b][q][c]: A(m=p,k=q) and B(n=c,k=q) are MN-major
-            PDB_TRY(gemm_tf32x3(grad_out, embed, grad_feat, nullptr, (int)HW, C, Q, B, HW, C, C, (int64_t)Q * HW,
+            PDB_TRY(gemm_tf32x3(grad_out, embed, nullptr, grad_feat, nullptr, (int)HW, C, Q, B, HW, C, C, (int64_t)Q * HW,
                                 (int64_t)Q * C, (int64_t)C * HW, 1, 1, 0, 0, accumulate ? 1 : 0, 1, st));
         }
         if (grad_embed) {
@@ -166,7 +166,7 @@ extern "C" int pdb_mask_einsum_backward(const float* embed, const float* feat, c
             cudaMemsetAsync(grad_embed, 0, sizeof(float) * (size_t)B * Q * C, st);
             int tiles = B * ((Q + 127) / 128) * ((C + 127) / 128);
             int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>((HW + 1023) / 1024, (2 * kNumSMs + tiles - 1) / tiles));
-            PDB_TRY(gemm_tf32x3(grad_out, feat, grad_embed, nullptr, Q, C, (int)HW, B, HW, C, C, (int64_t)Q * HW,
+            PDB_TRY(gemm_tf32x3(grad_out, feat, nullptr, grad_embed, nullptr, Q, C, (int)HW, B, HW, C, C, (int64_t)Q * HW,
                                 (int64_t)C * HW, (int64_t)Q * C, 0, 1, 0, 0, 1, ksplit, st));
         }
         return PDB_OK;

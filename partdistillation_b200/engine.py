@@ -142,6 +142,8 @@ class DataParallelTrainer:
                                           self.betas[0], self.betas[1], self.eps, self.step_dev.data_ptr(), scale, self.clip_norm,
                                           self.sumsq.data_ptr() if self.clip_norm > 0 else None, _stream()),
                        "pdb_adamw_flat")
+            from . import functional as PF
+            PF.weights_epoch += 1          # trainable weights changed in place: their cached pre-split parts are stale
             sq = self.sumsq[0]
         else:
             sq = sum((b.double() * scale).pow(2).sum() for b in others)

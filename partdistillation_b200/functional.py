@@ -150,8 +150,9 @@ class MaskEinsumFunction(Function):
         if B != Bf or C != Cf:
             raise RuntimeError(f"mask_einsum: shapes {tuple(mask_embed.shape)} x {tuple(mask_features.shape)}")
         out = torch.empty((B, Q, H, W), dtype=torch.float32, device=mask_embed.device)
-        rc = _lib.load().pdb_mask_einsum_forward(mask_embed.data_ptr(), mask_features.data_ptr(), out.data_ptr(),
-                                                 B, Q, C, H * W, _stream())
+        embed_lo = None      # the (Q, C) operand is tiny: splitting it inside the kernel is cheaper than a second launch
+        rc = _lib.load().pdb_mask_einsum_forward(mask_embed.data_ptr(), embed_lo.data_ptr() if embed_lo is not None else None,
+                                                 mask_features.data_ptr(), out.data_ptr(), B, Q, C, H * W, _stream())
         _lib.check(rc, "pdb_mask_einsum_forward")
         ctx.save_for_backward(mask_embed, mask_features)
         return out
@@ -422,10 +423,37 @@ def class_rows(x, weight, bias, obj, num_parts):
 # --------------------------------------------------------------------------------------------------
 # dense contractions on the tcgen05 tensor cores (3xTF32, fp32-accurate)  — csrc/gemm_tc.cu
 # --------------------------------------------------------------------------------------------------
+def split_lo(x):
+    """lo = x - trunc_tf32(x) for a contiguous fp32 tensor whose numel is a multiple of 4 (the pre-split B operand)."""
+    lo = torch.empty_like(x)
+    _lib.check(_lib.load().pdb_split_lo(x.data_ptr(), lo.data_ptr(), x.numel(), _stream()), "pdb_split_lo")
+    return lo
+
+
+_weight_lo = {}          # frozen weights: (data_ptr, shape) -> lo tensor (computed once)
+weights_epoch = 0        # bumped by the trainer after every optimizer step (trainable weights change in place)
+
+
+def weight_lo(weight, rows):
+    """Pre-split low parts of a Linear weight for GEMMs with many row tiles (every 128-row tile would otherwise
+    re-split the same weight tile).  Frozen weights are split once; trainable ones once per optimizer step."""
+    if rows < 2048 or weight.numel() % 4 or weight.data_ptr() % 16 or not weight.is_contiguous():
+        return None
+    key = (weight.data_ptr(), tuple(weight.shape))
+    epoch = weights_epoch if weight.requires_grad or weight._base is not None and weight._base.requires_grad else -1
+    hit = _weight_lo.get(key)
+    if hit is None or hit[0] != epoch:
+        if len(_weight_lo) > 4096:
+            _weight_lo.clear()
+        hit = _weight_lo[key] = (epoch, split_lo(weight.detach()))
+    return hit[1]
+
+
 def gemm_tf32x3(A, B, C, M, N, K, *, batch=1, lda, ldb, ldc, sa=0, sb=0, sc=0, a_mn=False, b_mn=False, c_trans=False,
-                bias=None, relu=False, accumulate=False, ksplit=1):
+                bias=None, relu=False, accumulate=False, ksplit=1, B_lo=None):
     """Raw entry point: C_b[m][n] (+)= sum_k A_b(m,k) B_b(n,k) (+bias[n]) (ReLU); see include/pdb200.h."""
-    rc = _lib.load().pdb_gemm_tf32x3(A.data_ptr(), B.data_ptr(), C.data_ptr(), bias.data_ptr() if bias is not None else None,
+    rc = _lib.load().pdb_gemm_tf32x3(A.data_ptr(), B.data_ptr(), B_lo.data_ptr() if B_lo is not None else None,
+                                     C.data_ptr(), bias.data_ptr() if bias is not None else None,
                                      M, N, K, batch, lda, ldb, ldc, sa, sb, sc, int(a_mn), int(b_mn), int(c_trans),
                                      int(relu), int(accumulate), int(ksplit), _stream())
     _lib.check(rc, "pdb_gemm_tf32x3")
@@ -455,8 +483,10 @@ class LinearFunction(Function):
             x2 = x2.clone()
         M = x2.shape[0]
         out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        w_lo = weight_lo(weight, M)
         if M > 0:
-            gemm_tf32x3(x2, weight, out, M, N, K, lda=K, ldb=K, ldc=N, bias=bias, relu=relu)
+            gemm_tf32x3(x2, weight, out, M, N, K, lda=K, ldb=K, ldc=N, bias=bias, relu=relu, B_lo=w_lo)
+        ctx.w_lo = w_lo
         ctx.relu = relu
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x2, weight, out if relu else None)
@@ -477,7 +507,7 @@ class LinearFunction(Function):
         if ctx.needs_input_grad[0]:
             gx = torch.empty((M, K), dtype=torch.float32, device=gy.device)
             # dx[m,i] = sum_o gy[m,o] W[o,i]:  A = gy (K-major), B(n=i,k=o) = W[o*K+i] (MN-major)
-            gemm_tf32x3(gy2, weight, gx, M, K, N, lda=N, ldb=K, ldc=K, b_mn=True)
+            gemm_tf32x3(gy2, weight, gx, M, K, N, lda=N, ldb=K, ldc=K, b_mn=True, B_lo=ctx.w_lo)
             gx = gx.view(*gy.shape[:-1], K)
         if ctx.needs_input_grad[1]:
             gw = torch.zeros((N, K), dtype=torch.float32, device=gy.device)

@@ -186,7 +186,8 @@ def test_mask_einsum_full_size(fn):
     (256, 128, 64, 0, 0, 1, 0, 1), (300, 200, 100, 0, 0, 1, 0, 1), (1024, 100, 256, 0, 0, 2, 1, 1),
     (300, 256, 200, 0, 1, 1, 0, 1), (256, 256, 4000, 1, 1, 1, 0, 8), (384, 96, 128, 1, 0, 1, 0, 1),
     (4096, 256, 100, 1, 1, 2, 0, 1), (100, 256, 4096, 0, 1, 2, 0, 4), (1, 4, 4, 0, 0, 1, 0, 1)])
-def test_gemm_tf32x3_layouts(fn, M, N, K, a_mn, b_mn, batch, c_trans, ksplit):
+@pytest.mark.parametrize("presplit", [False, True])
+def test_gemm_tf32x3_layouts(fn, M, N, K, a_mn, b_mn, batch, c_trans, ksplit, presplit):
     """Every operand layout of pdb_gemm_tf32x3 (K-major / MN-major, batch, split-K, transposed store, ragged
     M/N/K) against a float64 product."""
     g = torch.Generator().manual_seed(1)
@@ -197,7 +198,8 @@ def test_gemm_tf32x3_layouts(fn, M, N, K, a_mn, b_mn, batch, c_trans, ksplit):
     out = (torch.zeros if acc else torch.empty)((batch, N, M) if c_trans else (batch, M, N), device="cuda")
     fn.gemm_tf32x3(A, B, out, M, N, K, batch=batch, lda=A.stride(1), ldb=B.stride(1), ldc=out.stride(1),
                    sa=A.stride(0), sb=B.stride(0), sc=out.stride(0), a_mn=a_mn, b_mn=b_mn, c_trans=c_trans,
-                   bias=None if acc else bias, relu=not acc, accumulate=acc, ksplit=ksplit)
+                   bias=None if acc else bias, relu=not acc, accumulate=acc, ksplit=ksplit,
+                   B_lo=fn.split_lo(B) if presplit else None)
     Am = A.double().transpose(1, 2) if a_mn else A.double()
     Bm = B.double().transpose(1, 2) if b_mn else B.double()
     ref = Am @ Bm.transpose(1, 2)

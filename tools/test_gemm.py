@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from partdistillation_b200 import _lib  # noqa: E402
 
 
-def gemm(A, B, M, N, K, batch=1, a_mn=0, b_mn=0, c_trans=0, bias=None, relu=0, accumulate=0, ksplit=1, out=None):
+def gemm(A, B, M, N, K, batch=1, a_mn=0, b_mn=0, c_trans=0, bias=None, relu=0, accumulate=0, ksplit=1, out=None, B_lo=None):
     lib = _lib.load()
     lda = A.stride(-2)
     ldb = B.stride(-2)
@@ -21,14 +21,21 @@ def gemm(A, B, M, N, K, batch=1, a_mn=0, b_mn=0, c_trans=0, bias=None, relu=0, a
         out = torch.zeros(shape, device="cuda") if accumulate else torch.empty(shape, device="cuda")
     ldc = out.stride(-2)
     sc = out.stride(0)
-    rc = lib.pdb_gemm_tf32x3(A.data_ptr(), B.data_ptr(), out.data_ptr(), bias.data_ptr() if bias is not None else None,
+    rc = lib.pdb_gemm_tf32x3(A.data_ptr(), B.data_ptr(), B_lo.data_ptr() if B_lo is not None else None, out.data_ptr(),
+                             bias.data_ptr() if bias is not None else None,
                              M, N, K, batch, lda, ldb, ldc, sa, sb, sc, a_mn, b_mn, c_trans, relu, accumulate, ksplit,
                              torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "pdb_gemm_tf32x3")
     return out
 
 
-def check(name, M, N, K, batch=1, a_mn=0, b_mn=0, c_trans=0, use_bias=False, relu=0, accumulate=0, ksplit=1):
+def split_lo(x):
+    lo = torch.empty_like(x)
+    _lib.check(_lib.load().pdb_split_lo(x.data_ptr(), lo.data_ptr(), x.numel(), torch.cuda.current_stream().cuda_stream), "split_lo")
+    return lo
+
+
+def check(name, M, N, K, batch=1, a_mn=0, b_mn=0, c_trans=0, use_bias=False, relu=0, accumulate=0, ksplit=1, presplit=False):
     g = torch.Generator(device="cuda").manual_seed(1)
     A = torch.randn((batch, K, M) if a_mn else (batch, M, K), device="cuda", generator=g)
     B = torch.randn((batch, K, N) if b_mn else (batch, N, K), device="cuda", generator=g)
@@ -42,7 +49,7 @@ def check(name, M, N, K, batch=1, a_mn=0, b_mn=0, c_trans=0, use_bias=False, rel
         ref = ref.clamp_min(0)
     if c_trans:
         ref = ref.transpose(1, 2)
-    out = gemm(A, B, M, N, K, batch, a_mn, b_mn, c_trans, bias, relu, accumulate, ksplit)
+    out = gemm(A, B, M, N, K, batch, a_mn, b_mn, c_trans, bias, relu, accumulate, ksplit, B_lo=split_lo(B) if presplit else None)
     torch.cuda.synchronize()
     err = float((out.double() - ref).abs().max() / ref.abs().max())
     print(f"{name:40s} M={M} N={N} K={K} b={batch} a_mn={a_mn} b_mn={b_mn} ct={c_trans} ks={ksplit}: rel err {err:.2e}",
@@ -78,6 +85,15 @@ def main():
     ok &= check("einsum grad_embed (B MN, split-K)", 100, 256, 4096, batch=2, b_mn=1, accumulate=1, ksplit=4)
     ok &= check("B MN ragged N=112-ish", 300, 100, 64, b_mn=1)
     ok &= check("many tiles persistent", 43008, 288, 256, use_bias=True, relu=1)
+    for ps in (True,):
+        ok &= check("presplit NT plain", 256, 128, 64, presplit=ps)
+        ok &= check("presplit NT ragged + bias + relu", 300, 200, 100, use_bias=True, relu=1, presplit=ps)
+        ok &= check("presplit einsum fwd", 1024, 100, 256, batch=2, c_trans=1, presplit=ps)
+        ok &= check("presplit N=24", 500, 24, 256, use_bias=True, presplit=ps)
+        ok &= check("presplit dgrad (B MN)", 300, 256, 200, b_mn=1, presplit=ps)
+        ok &= check("presplit B MN ragged", 300, 100, 64, b_mn=1, presplit=ps)
+        ok &= check("presplit B MN N=288", 4096, 288, 256, b_mn=1, presplit=ps)
+        ok &= check("presplit many tiles", 43008, 288, 256, use_bias=True, relu=1, presplit=ps)
     ok &= check("einsum fwd full", 65536, 100, 256, batch=2, c_trans=1)
     # timing at the encoder shapes (rows = 43008)
     M = 43008
@@ -88,15 +104,20 @@ def main():
         bias = torch.randn(N, device="cuda")
         out = torch.empty(1, M, N, device="cuda")
         t = timeit(lambda: gemm(xx, w, M, N, K, bias=bias, out=out))
+        wl = split_lo(w)
+        tp = timeit(lambda: gemm(xx, w, M, N, K, bias=bias, out=out, B_lo=wl))
         torch.backends.cuda.matmul.allow_tf32 = False
         t2 = timeit(lambda: torch.nn.functional.linear(xx[0], w[0], bias))
         fl = 2.0 * M * N * K
-        print(f"linear {M}x{K} -> {N}: tcgen05 3xTF32 {t * 1e6:.1f} us ({fl / t / 1e12:.1f} TFLOP/s fp32-equivalent), "
+        print(f"linear {M}x{K} -> {N}: tcgen05 3xTF32 {t * 1e6:.1f} us ({fl / t / 1e12:.1f} TFLOP/s fp32-equivalent), pre-split B {tp * 1e6:.1f} us, "
               f"cuBLAS fp32 {t2 * 1e6:.1f} us ({fl / t2 / 1e12:.1f} TFLOP/s)", flush=True)
     # mask einsum forward / backward shapes
     e = torch.randn(2, 100, 256, device="cuda"); f = torch.randn(2, 65536, 256, device="cuda"); o = torch.empty(2, 100, 65536, device="cuda")
     t = timeit(lambda: gemm(f, e, 65536, 100, 256, batch=2, c_trans=1, out=o))
     print(f"einsum fwd: {t * 1e6:.1f} us -> {186.9e6 / t / 1e9:.0f} GB/s algorithmic")
+    el = split_lo(e)
+    t = timeit(lambda: gemm(f, e, 65536, 100, 256, batch=2, c_trans=1, out=o, B_lo=el))
+    print(f"einsum fwd, pre-split embed: {t * 1e6:.1f} us -> {186.9e6 / t / 1e9:.0f} GB/s algorithmic")
     print("RESULT", "PASS" if ok else "FAIL")
 
 
