@@ -229,6 +229,18 @@ PDB_API int pdb_adamw_flat(float* param, const float* grad, float* exp_avg, floa
                    float beta2, float eps, const int64_t* step, float grad_scale, float clip_norm, const double* sumsq,
                    void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Pixel grouping affinity — replaces, inside PixelGroupingModel.generate_part_segments
+ * (pixel_grouping_model.py:139-144,197-211), the bilinear up-sampling of the backbone features to image size,
+ * the host copy of the masked pixels, measure_distance() and topk(1), and the label-map scatter.
+ *   feat (C, h, w) f32 backbone-resolution features; centroids (Kc, C) f32 (k-means centres, Kc <= 16);
+ *   mask (H, W) uint8 object mask at image size; labels (H, W) int32 out: 0 outside the mask, else
+ *   1 + argmax_k score_k with score = <f, c_k> (metric 0, "dot") or 2<f, c_k> - |c_k|^2 (metric 1, "l2"),
+ *   f = the feature bilinearly interpolated (align_corners=False) at that pixel.
+ * ---------------------------------------------------------------------------------------------- */
+PDB_API int pdb_group_affinity(const float* feat, const float* centroids, const uint8_t* mask, int32_t* labels,
+                       int C, int Kc, int h, int w, int H, int W, int metric, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -634,3 +634,29 @@ def head_and_loss(sd, features, targets, hp, rand=torch.rand, record=None, core=
                            hp["importance_ratio"], 1, rand, record)
     wd = {"loss_ce": hp["w_class"], "loss_mask": hp["w_mask"], "loss_dice": hp["w_dice"]}
     return {k: v * wd[k.split("_")[0] + "_" + k.split("_")[1]] for k, v in losses.items()}
+
+
+# --------------------------------------------------------------------------------------
+# a12  pixel grouping  (pixel_grouping_model.py:139-144 up-sampling, :197-201 measure_distance, :205-218 segments)
+# --------------------------------------------------------------------------------------
+
+
+def pixel_grouping_scores(feature, centroids, out_size, metric="dot"):
+    """(C, h, w) features -> (Kc, H, W) affinity of every image-resolution pixel to every centroid."""
+    up = F.interpolate(feature[None], size=out_size, mode="bilinear", align_corners=False)[0]     # (:139-144)
+    A = up.flatten(1).t()
+    B = centroids
+    if metric == "dot":
+        d = A @ B.t()                                                                                # (:198-199)
+    else:
+        d = 2 * A @ B.t() - (A * A).sum(dim=1)[:, None] - (B * B).sum(1, keepdim=True).t()          # (:200-201)
+    return d.t().reshape(centroids.shape[0], *out_size)
+
+
+def pixel_grouping_segments(feature, centroids, mask_resized, metric="dot"):
+    """generate_part_segments with given centroids (:205-218): -> (label map (H, W) int64, bool (P, H, W))."""
+    scores = pixel_grouping_scores(feature, centroids, tuple(mask_resized.shape), metric)
+    labels = torch.zeros(mask_resized.shape, dtype=torch.long)
+    labels[mask_resized] = scores[:, mask_resized].argmax(0) + 1
+    present = labels[mask_resized].unique()
+    return labels, torch.stack([labels == p for p in present]) if len(present) else labels.new_zeros((0, *labels.shape)).bool()

@@ -200,9 +200,42 @@ def golden_swin(ref):
     print("swin_micro.pt", {k: tuple(v.shape) for k, v in out.items()})
 
 
+def golden_pixel_grouping(ref):
+    """PixelGroupingModel._prepare_features + generate_part_segments of the UNMODIFIED reference
+    (pixel_grouping_model.py:114-125,205-218), with the k-means centroids fixed (get_pixel_grouping stubbed to return
+    them) so the fixture pins the up-sample + measure_distance + topk + segment arithmetic, for both metrics."""
+    import importlib
+    import types
+    pg = importlib.import_module("part_distillation.pixel_grouping_model").PixelGroupingModel
+    g = torch.Generator().manual_seed(11)
+    C3, C4, h, w, H, W, Kc = 16, 24, 12, 10, 48, 40, 4
+    feats = {"res3": torch.randn(1, C3, h, w, generator=g), "res4": torch.randn(1, C4, h // 2, w // 2, generator=g)}
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    mask_resized = ((yy - H / 2) ** 2 / (H * 0.4) ** 2 + (xx - W / 2) ** 2 / (W * 0.35) ** 2) < 1.0
+    out = {}
+    for metric in ("dot", "l2"):
+        self = types.SimpleNamespace(backbone_feature_key_list=["res3", "res4"], feature_normalize=False,
+                                     distance_metric=metric, num_superpixel_clusters=Kc)
+        feature = pg._prepare_features(self, feats)[0]                       # (C3 + C4, h, w)
+        centroids = torch.randn(Kc, feature.shape[0], generator=g)
+        self.get_pixel_grouping = lambda f, m: centroids
+        self.measure_distance = types.MethodType(pg.measure_distance, self)
+        resized = torch.nn.functional.interpolate(feature[None], size=(H, W), mode="bilinear", align_corners=False)[0]
+        mask_feat = torch.nn.functional.interpolate(mask_resized[None, None].float(), size=(h, w), mode="nearest")[0, 0].bool()
+        binary = pg.generate_part_segments(self, {}, feature, resized, mask_feat, mask_resized)
+        out[metric] = dict(feature=feature, centroids=centroids, binary_mask=binary)
+    out.update(feats=feats, mask_resized=mask_resized)
+    torch.save(out, os.path.join(OUT, "pixel_grouping.pt"))
+    print("pixel_grouping.pt", {m: tuple(out[m]["binary_mask"].shape) for m in ("dot", "l2")})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = rl.load()
+    if "--pixel-grouping-only" in sys.argv:
+        golden_pixel_grouping(ref)
+        return
+    golden_pixel_grouping(ref)
     golden_msda(ref)
     golden_swin(ref)
     for name in HEAD_CASES:

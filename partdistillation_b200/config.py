@@ -58,6 +58,12 @@ _PART_DISTILLATION = {
 }
 
 
+_PIXEL_GROUPING = {
+    "PIXEL_GROUPING": dict(NUM_SUPERPIXEL_CLUSTERS=4, DISTANCE_METRIC="l2", BACKBONE_FEATURE_KEY_LIST=["res4"],
+                           FEATURE_NORMALIZE=False, DEBUG=False),
+}
+
+
 def _install(node, table):
     for key, val in table.items():
         if isinstance(val, dict):
@@ -82,3 +88,7 @@ def add_proposal_learning_config(cfg):
 
 def add_part_distillation_config(cfg):
     _install(cfg, _PART_DISTILLATION)
+
+
+def add_pixel_grouping_confing(cfg):          # (sic) the reference's spelling, config.py:255
+    _install(cfg, _PIXEL_GROUPING)

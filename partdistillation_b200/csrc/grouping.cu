@@ -1,0 +1,95 @@
+// Pixel grouping: per-pixel part label = argmax over centroids of the affinity between the (bilinearly up-sampled)
+// backbone feature and the k-means centroids — replaces, for every pixel of the object mask,
+//   F.interpolate(features, image size, bilinear, align_corners=False)          pixel_grouping_model.py:139-144
+//   feature[:, mask].T.contiguous().cpu();  measure_distance(...).topk(1)        :197-208
+//   label map scatter                                                             :210-211
+// of PixelGroupingModel.generate_part_segments (the reference moves the full-resolution (C, H, W) feature map to the
+// host for this).  The feature map stays at backbone resolution in HBM/L2 (C*h*w*4 bytes instead of C*H*W*4) and is
+// interpolated on the fly, ATen's align_corners=False source-index rule (src = (dst + 0.5) * in/out - 0.5, clamped
+// at 0; second tap clamped to in - 1).
+//   dot:  score_k = <f, c_k>          l2:  score_k = 2 <f, c_k> - |c_k|^2   (the -|f|^2 term does not change argmax)
+// One thread per output pixel; the C x Kc centroid table sits in shared memory (broadcast reads); neighbouring
+// pixels share their 4 source texels, so the feature reads are L1 hits after the first touch.
+#include "common.cuh"
+
+namespace pdb {
+
+constexpr int kMaxCentroids = 16;
+
+__global__ void __launch_bounds__(256)
+group_affinity_kernel(const float* __restrict__ feat, const float* __restrict__ centroids, const uint8_t* __restrict__ mask,
+                      int32_t* __restrict__ labels, int C, int Kc, int h, int w, int H, int W, int l2) {
+    extern __shared__ float s_cent[];       // [C][Kc] + |c_k|^2 [Kc]
+    float* s_norm = s_cent + C * Kc;
+    for (int i = threadIdx.x; i < C * Kc; i += blockDim.x) {
+        const int c = i / Kc, k = i - c * Kc;
+        s_cent[i] = __ldg(centroids + k * C + c);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < Kc; k += blockDim.x) {
+        float s = 0.f;
+        for (int c = 0; c < C; ++c) s = fmaf(s_cent[c * Kc + k], s_cent[c * Kc + k], s);
+        s_norm[k] = s;
+    }
+    __syncthreads();
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const int64_t pix = (int64_t)y * W + x;
+    if (!mask[pix]) {
+        labels[pix] = 0;
+        return;
+    }
+    const float sy = fmaxf(((float)y + 0.5f) * ((float)h / (float)H) - 0.5f, 0.f);
+    const float sx = fmaxf(((float)x + 0.5f) * ((float)w / (float)W) - 0.5f, 0.f);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float ly1 = sy - (float)y0, lx1 = sx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const int o00 = y0 * w + x0, o01 = y0 * w + x1, o10 = y1 * w + x0, o11 = y1 * w + x1;
+    float score[kMaxCentroids];
+#pragma unroll
+    for (int k = 0; k < kMaxCentroids; ++k) score[k] = 0.f;
+    const int plane = h * w;
+    for (int c = 0; c < C; ++c) {
+        const float* fp = feat + (int64_t)c * plane;
+        // ATen's upsample_bilinear2d: h0lambda * (w0lambda * a + w1lambda * b) + h1lambda * (w0lambda * c + w1lambda * d)
+        const float v = ly0 * (lx0 * __ldg(fp + o00) + lx1 * __ldg(fp + o01)) + ly1 * (lx0 * __ldg(fp + o10) + lx1 * __ldg(fp + o11));
+        const float* cc = s_cent + c * Kc;
+#pragma unroll
+        for (int k = 0; k < kMaxCentroids; ++k)
+            if (k < Kc) score[k] = fmaf(v, cc[k], score[k]);
+    }
+    int best = 0;
+    float bv = l2 ? 2.f * score[0] - s_norm[0] : score[0];
+#pragma unroll
+    for (int k = 1; k < kMaxCentroids; ++k) {
+        if (k < Kc) {
+            const float s = l2 ? 2.f * score[k] - s_norm[k] : score[k];
+            if (s > bv) { bv = s; best = k; }
+        }
+    }
+    labels[pix] = best + 1;
+}
+
+}  // namespace pdb
+
+using namespace pdb;
+
+extern "C" int pdb_group_affinity(const float* feat, const float* centroids, const uint8_t* mask, int32_t* labels, int C,
+                                  int Kc, int h, int w, int H, int W, int metric, void* stream) {
+    PDB_REQUIRE(feat && centroids && mask && labels, "group_affinity: null pointer");
+    PDB_REQUIRE(C > 0 && Kc > 0 && Kc <= kMaxCentroids && h > 0 && w > 0 && H > 0 && W > 0,
+                "group_affinity: bad sizes (1 <= Kc <= %d)", kMaxCentroids);
+    PDB_REQUIRE(metric == 0 || metric == 1, "group_affinity: metric %d (0 = dot, 1 = l2)", metric);
+    size_t smem = sizeof(float) * ((size_t)C * Kc + Kc);
+    PDB_REQUIRE(smem <= 200 * 1024, "group_affinity: centroid table of %zu bytes does not fit shared memory", smem);
+    static size_t attr_smem = 0;
+    if (smem > 48 * 1024 && smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(group_affinity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(PDB_ERR_LAUNCH, "group_affinity: smem attribute: %s", cudaGetErrorString(e));
+        attr_smem = smem;
+    }
+    dim3 grid((unsigned)((W + 31) / 32), (unsigned)((H + 7) / 8));
+    group_affinity_kernel<<<grid, 256, smem, as_stream(stream)>>>(feat, centroids, mask, labels, C, Kc, h, w, H, W, metric);
+    return launched("group_affinity");
+}

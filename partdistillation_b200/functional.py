@@ -527,3 +527,24 @@ def linear(x, weight, bias=None, relu=False):
         return LinearFunction.apply(x, weight, bias, relu)
     y = torch.nn.functional.linear(x, weight.to(x.dtype), None if bias is None else bias.to(x.dtype))
     return torch.relu(y) if relu else y
+
+
+# --------------------------------------------------------------------------------------------------
+# pixel grouping affinity  (pixel_grouping_model.py:139-144,197-211)
+# --------------------------------------------------------------------------------------------------
+def group_affinity(feat, centroids, mask, metric="dot"):
+    """feat (C, h, w) f32, centroids (Kc, C) f32, mask (H, W) bool/uint8 -> labels (H, W) int32: 0 outside the mask,
+    1 + argmax_k affinity(bilinear(feat) at the pixel, centroid k) inside."""
+    _need_cuda(feat, centroids, mask)
+    if metric not in ("dot", "l2"):
+        raise ValueError(f"distance metric {metric!r} (dot / l2)")
+    feat, centroids = _c(feat.float()), _c(centroids.float())
+    mask = _c(mask).view(torch.uint8) if mask.dtype == torch.bool else _c(mask.to(torch.uint8))
+    C, h, w = feat.shape
+    Kc = centroids.shape[0]
+    H, W = mask.shape
+    labels = torch.empty((H, W), dtype=torch.int32, device=feat.device)
+    rc = _lib.load().pdb_group_affinity(feat.data_ptr(), centroids.data_ptr(), mask.data_ptr(), labels.data_ptr(), C, Kc, h, w,
+                                        H, W, 0 if metric == "dot" else 1, _stream())
+    _lib.check(rc, "pdb_group_affinity")
+    return labels

@@ -1,0 +1,111 @@
+"""``PixelGroupingModel`` — evaluation-only pixel grouping baseline (reference:
+part_distillation/pixel_grouping_model.py:28-218; BASELINE.json configs[3]).
+
+Same registry name, ``from_config`` keys and output format (list of {"proposals", "gt_masks"}).  The k-means step
+stays scikit-learn on the host, as in the reference (:183-193).  What changes is ``generate_part_segments``: the
+reference up-samples the (C, h, w) feature map to image size, copies the masked pixels to the host and runs
+``measure_distance`` + ``topk`` there (:205-218); here one sm_100a kernel interpolates the backbone-resolution
+features on the fly and writes the label map (``functional.group_affinity``), so the full-resolution feature map
+is never materialised and nothing but the k-means sample leaves the device."""
+from typing import List, Tuple
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import functional as PF
+from .compat import META_ARCH_REGISTRY, ImageList, Instances, build_backbone, configurable
+
+
+@META_ARCH_REGISTRY.register()
+class PixelGroupingModel(nn.Module):
+    @configurable
+    def __init__(self, backbone, size_divisibility: int, pixel_mean: Tuple[float], pixel_std: Tuple[float],
+                 distance_metric: str = "l2", backbone_feature_key_list: List[str] = ("res4",),
+                 num_superpixel_clusters: int = 4, feature_normalize: bool = False, debug: bool = False,
+                 object_mask_type: str = "detic_based", wandb_vis_period: int = 100):
+        super().__init__()
+        self.backbone = backbone
+        if size_divisibility < 0:
+            size_divisibility = self.backbone.size_divisibility
+        self.size_divisibility = size_divisibility
+        self.register_buffer("pixel_mean", torch.Tensor(pixel_mean).view(-1, 1, 1), False)
+        self.register_buffer("pixel_std", torch.Tensor(pixel_std).view(-1, 1, 1), False)
+        self.distance_metric = distance_metric
+        self.backbone_feature_key_list = list(backbone_feature_key_list)
+        self.num_superpixel_clusters = num_superpixel_clusters
+        self.feature_normalize = feature_normalize
+        self.wandb_vis_period = wandb_vis_period
+        self.num_test_iterations = 0
+        self._kmeans = None
+
+    @classmethod
+    def from_config(cls, cfg):
+        g = cfg.PIXEL_GROUPING
+        return dict(backbone=build_backbone(cfg), size_divisibility=cfg.MODEL.MASK_FORMER.SIZE_DIVISIBILITY,
+                    pixel_mean=cfg.MODEL.PIXEL_MEAN, pixel_std=cfg.MODEL.PIXEL_STD,
+                    distance_metric=g.DISTANCE_METRIC, backbone_feature_key_list=g.BACKBONE_FEATURE_KEY_LIST,
+                    num_superpixel_clusters=g.NUM_SUPERPIXEL_CLUSTERS, feature_normalize=g.FEATURE_NORMALIZE,
+                    wandb_vis_period=cfg.WANDB.VIS_PERIOD_TEST, debug=g.DEBUG)
+
+    @property
+    def device(self):
+        return self.pixel_mean.device
+
+    def _prepare_features(self, features):
+        """Listed backbone maps, bilinearly aligned to the first one and concatenated (:114-125)."""
+        maps = [features[k] for k in self.backbone_feature_key_list]
+        size = maps[0].shape[-2:]
+        out = torch.cat([F.interpolate(v, size=size, mode="bilinear", align_corners=False) for v in maps], 1)
+        return F.normalize(out, dim=1, p=2) if self.feature_normalize else out
+
+    def get_pixel_grouping(self, feature_per_image, pred_mask):
+        """k-means centroids of the object's backbone-resolution pixels (scikit-learn, host; :183-193)."""
+        data = feature_per_image[:, pred_mask].transpose(0, 1).contiguous().cpu()
+        if len(data) > self.num_superpixel_clusters:
+            if self._kmeans is None:
+                from sklearn.cluster import KMeans
+                self._kmeans = KMeans(n_clusters=self.num_superpixel_clusters, random_state=0)
+            return torch.tensor(self._kmeans.fit(data).cluster_centers_).float()
+        return data.new_zeros(1, feature_per_image.shape[0])
+
+    def generate_part_segments(self, feature_per_image, object_mask, object_mask_resized, centroids=None):
+        """feature (C, h, w); object mask at feature and at image resolution -> bool (P, H, W), one mask per
+        label present (ascending label order, as :213-216)."""
+        if centroids is None:
+            centroids = self.get_pixel_grouping(feature_per_image, object_mask)
+        labels = PF.group_affinity(feature_per_image, centroids.to(feature_per_image.device), object_mask_resized,
+                                   self.distance_metric)
+        present = torch.unique(labels[labels > 0])
+        return labels.unsqueeze(0) == present.view(-1, 1, 1)
+
+    def forward(self, batched_inputs):
+        assert not self.training, "pixel grouping is eval only."
+        with torch.no_grad():
+            images = [(x["image"].to(self.device) - self.pixel_mean) / self.pixel_std for x in batched_inputs]
+            images = ImageList.from_tensors(images, self.size_divisibility)
+            h_pad, w_pad = images.tensor.shape[-2:]
+            features = self._prepare_features(self.backbone(images.tensor))
+            out = []
+            for x, feat, image_size in zip(batched_inputs, features, images.image_sizes):
+                obj = x["instances"].gt_masks.tensor.to(self.device)
+                masks = torch.zeros((obj.shape[0], h_pad, w_pad), dtype=obj.dtype, device=self.device)
+                masks[:, :obj.shape[1], :obj.shape[2]] = obj
+                if (x.get("height", image_size[0]), x.get("width", image_size[1])) != tuple(image_size) or \
+                        tuple(image_size) != (h_pad, w_pad):
+                    raise NotImplementedError("pixel grouping kernel: output size must equal the padded image size")
+                mask_resized = masks[0].bool()
+                mask_feat = F.interpolate(masks[None].float(), size=feat.shape[-2:], mode="nearest")[0, 0].bool()
+                pseudo = self.generate_part_segments(feat, mask_feat, mask_resized)
+                inst = Instances(tuple(pseudo.shape[-2:]))
+                inst.pred_masks = pseudo
+                inst.scores = pseudo.new_ones(pseudo.shape[0])
+                res = {"proposals": inst}
+                if "part_instances" in x:
+                    gt = Instances(tuple(pseudo.shape[-2:]))
+                    gt.gt_masks = x["part_instances"].gt_masks.tensor.to(self.device).bool()
+                    gt.pred_masks = gt.gt_masks
+                    res["gt_masks"] = gt
+                out.append(res)
+            self.num_test_iterations += 1
+            return out

@@ -426,3 +426,65 @@ def test_class_rows(fn):
     assert torch.allclose(xc.grad.cpu(), xr.grad, rtol=1e-5, atol=1e-6)
     assert torch.allclose(wc.grad.cpu(), wr.grad, rtol=1e-12, atol=1e-12)
     assert torch.allclose(bc.grad.cpu(), br.grad, rtol=1e-12, atol=1e-12)
+
+
+# ------------------------------------------------------------------ pixel grouping affinity (a12, configs[3])
+def _grouping_check(fn, feature, centroids, mask, metric, golden_masks=None):
+    labels = fn.group_affinity(feature.cuda(), centroids.cuda(), mask.cuda(), metric).cpu().long()
+    ref_labels, ref_masks = O.pixel_grouping_segments(feature, centroids, mask, metric)
+    assert torch.equal(labels == 0, ~mask)                                  # 0 exactly outside the object mask
+    diff = labels != ref_labels
+    if diff.any():
+        # an argmax may only differ where the two best affinities are within fp32 summation noise of each other
+        scores = O.pixel_grouping_scores(feature, centroids, tuple(mask.shape), metric)
+        top2 = scores.topk(2, dim=0)[0]
+        gap = (top2[0] - top2[1])[diff]
+        assert float(gap.max()) < 1e-3 * float(scores.abs().max())
+        assert int(diff.sum()) <= max(1, int(1e-4 * mask.sum()))
+    elif golden_masks is not None:
+        present = torch.unique(labels[labels > 0])
+        assert torch.equal(labels.unsqueeze(0) == present.view(-1, 1, 1), golden_masks)
+    return int(diff.sum())
+
+
+@pytest.mark.parametrize("metric", ["dot", "l2"])
+def test_group_affinity_vs_reference_golden(fn, golden_dir, metric):
+    g = _load(golden_dir, "pixel_grouping.pt")
+    c = g[metric]
+    _grouping_check(fn, c["feature"], c["centroids"], g["mask_resized"], metric, c["binary_mask"])
+
+
+def test_group_affinity_full_size(fn):
+    """BASELINE configs[3]: Swin-B res3+res4 features (768 channels) of a 512x512 image at 64x64, 4 centroids, disc
+    object mask; labels against the oracle (up-sample -> matmul -> argmax on the host)."""
+    g = torch.Generator().manual_seed(4)
+    feature = torch.randn(768, 64, 64, generator=g)
+    centroids = torch.randn(4, 768, generator=g)
+    yy, xx = torch.meshgrid(torch.arange(512), torch.arange(512), indexing="ij")
+    mask = ((yy - 256) ** 2 + (xx - 256) ** 2) < 160 ** 2
+    for metric in ("dot", "l2"):
+        _grouping_check(fn, feature, centroids, mask, metric)
+
+
+def test_pixel_grouping_model_forward(fn):
+    """The registered PixelGroupingModel end to end on a micro Swin trunk: output format of the reference
+    (list of {"proposals": Instances(pred_masks bool (P, H, W), scores)}), masks partition the object mask."""
+    from partdistillation_b200 import compat, presets
+    from partdistillation_b200.config import add_pixel_grouping_confing
+    cfg = presets.make_cfg("PixelGroupingModel", "swin_micro", device="cuda")
+    add_pixel_grouping_confing(cfg)
+    cfg.PIXEL_GROUPING.DISTANCE_METRIC = "dot"
+    cfg.PIXEL_GROUPING.BACKBONE_FEATURE_KEY_LIST = ["res3", "res4"]
+    torch.manual_seed(0)
+    model = compat.build_model(cfg).eval()
+    H = W = 128
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    obj = (((yy - 64) ** 2 + (xx - 64) ** 2) < 40 ** 2)[None]
+    inst = compat.Instances((H, W))
+    inst.gt_masks = compat.BitMasks(obj)
+    inst.gt_classes = torch.zeros(1, dtype=torch.long)
+    img = torch.randint(0, 256, (3, H, W), generator=torch.Generator().manual_seed(1), dtype=torch.uint8)
+    out = model([{"image": img, "instances": inst, "height": H, "width": W}])
+    pm = out[0]["proposals"].pred_masks
+    assert pm.dtype == torch.bool and pm.shape[1:] == (H, W) and 1 <= pm.shape[0] <= 4
+    assert torch.equal(pm.any(0).cpu(), obj[0]) and int(pm.sum()) == int(obj.sum())      # disjoint cover of the object
