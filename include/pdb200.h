@@ -101,6 +101,15 @@ PDB_API int pdb_gemm_tf32x3(const float* A, const float* B, const float* B_lo, f
                     int K, int batch,
                     int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc, int a_mn, int b_mn,
                     int c_trans, int relu, int accumulate, int ksplit, void* stream);
+/* Convolution-shaped variant: K = taps * Ck, and the k range of tap t reads the A rows shifted by tap_off[t]:
+ *   C_b[m][n] = sum_t sum_c A_b[m + tap_off[t]][c] * B[n][t * Ck + c]  (+ bias[n]) (ReLU)
+ * A_b = A + b*sa is (a_rows x Ck), K-major, rows beyond a_rows read as 0; B is (N x taps*Ck), K-major, shared by all batch
+ * items; Ck % 32 == 0; tap_off: HOST int32[taps] >= 0.  With the zero-padded NHWC image as A, M = H * (W + 2) and
+ * tap_off[ky*3+kx] = ky * (W + 2) + kx this is the 3x3 convolution of the pixel decoder's output layer
+ * (msdeformattn.py:275-287, F.conv2d in detectron2's Conv2d) as ONE tensor-core GEMM over the padded-width pixel grid. */
+PDB_API int pdb_gemm_taps_tf32x3(const float* A, const float* B, const float* B_lo, float* C, const float* bias, int M, int N,
+                         int Ck, int batch, int a_rows, int64_t lda, int64_t ldc, int64_t sa, int64_t sc, int taps,
+                         const int32_t* tap_off, int relu, void* stream);
 /* lo[i] = x[i] - trunc_tf32(x[i]) (x with its low 13 mantissa bits cleared); n % 4 == 0, 16-byte aligned. */
 PDB_API int pdb_split_lo(const float* x, float* lo, int64_t n, void* stream);
 
@@ -240,6 +249,15 @@ PDB_API int pdb_adamw_flat(float* param, const float* grad, float* exp_avg, floa
  * ---------------------------------------------------------------------------------------------- */
 PDB_API int pdb_group_affinity(const float* feat, const float* centroids, const uint8_t* mask, int32_t* labels,
                        int C, int Kc, int h, int w, int H, int W, int metric, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Swin window attention, forward only (frozen backbone) — replaces q @ k^T * scale + relative-position bias
+ * (+ shift mask) -> softmax -> @ v -> head transpose inside WindowAttention.forward (modeling/backbone/swin.py:78-176).
+ *   qkv (Bw, N, 3, heads, 32) f32; bias (heads, N, N) f32; mask (nW, N, N) f32 additive or NULL (row bw uses window
+ *   bw % nW); out (Bw, N, heads*32) f32.  N <= 256, head dim 32.
+ * ---------------------------------------------------------------------------------------------- */
+PDB_API int pdb_window_attention_forward(const float* qkv, const float* bias, const float* mask, float* out, int Bw, int N,
+                                 int heads, int d, int nW, float scale, void* stream);
 
 #ifdef __cplusplus
 }

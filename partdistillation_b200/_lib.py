@@ -26,6 +26,7 @@ SIGNATURES = {
     "pdb_mask_einsum_forward": (_i, [_p, _p, _p, _p, _i, _i, _i, _l, _p]),
     "pdb_mask_einsum_backward": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _l, _p]),
     "pdb_gemm_tf32x3": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _l, _l, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _p]),
+    "pdb_gemm_taps_tf32x3": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _l, _l, _l, _l, _i, _hp32, _i, _p]),
     "pdb_split_lo": (_i, [_p, _p, _l, _p]),
     "pdb_attn_mask_build": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "pdb_attn_mask_reset_rows": (_i, [_p, _p, _i, _l, _p]),
@@ -39,6 +40,7 @@ SIGNATURES = {
     "pdb_point_loss_forward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "pdb_point_loss_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "pdb_class_rows_forward": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _l, _p]),
+    "pdb_window_attention_forward": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p]),
     "pdb_group_affinity": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "pdb_grad_sumsq": (_i, [_p, _l, _f, _p, _p]),
     "pdb_adamw_flat": (_i, [_p, _p, _p, _p, _l, _p, _p, _p, _i, _f, _f, _f, _p, _f, _f, _p, _p]),

@@ -55,6 +55,8 @@ struct GemmParams {
     int batch, ksplit, kchunk;        // kchunk: multiple of G_BK
     int c_trans, relu, atomic;
     int mt, nt, total_tiles;
+    int taps, kb_per_tap;             // A rows shifted per K segment (3x3 convolution as one GEMM): see gemm_tf32x3_taps
+    int tap_off[9];
     int presplit;                     // B_lo comes pre-computed from global memory (tm_blo) instead of being split here
     int b_box_rows;                   // rows of the K-major B box (BN, or the 16-multiple covering N when N < BN)
     long long* trace;                 // debug timeline of CTA 0 (pdb_debug_set_trace), normally NULL
@@ -231,6 +233,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                     if (A_MN) {
 #pragma unroll
                         for (int i = 0; i < G_BM / 32; ++i) tma_load_3d(a_raw(s) + i * 4096, &tm_a, &raw_full[s], c.m0 + 32 * i, k0, c.b);
+                    } else if (p.taps > 1) {
+                        // K = taps * C: k-block kbg of tap t reads channels of the A rows shifted by tap_off[t]
+                        const int kbg = k0 / G_BK;
+                        const int t = kbg / p.kb_per_tap;
+                        tma_load_3d(a_raw(s), &tm_a, &raw_full[s], (kbg - t * p.kb_per_tap) * G_BK, c.m0 + p.tap_off[t], c.b);
                     } else {
                         tma_load_3d(a_raw(s), &tm_a, &raw_full[s], k0, c.m0, c.b);
                     }
@@ -562,9 +569,10 @@ static int dispatch_layout(const CUtensorMap& ta, const CUtensorMap& tb, const C
     return launch_gemm<BN, true, true>(ta, tb, tbl, p, st);
 }
 
-int gemm_tf32x3(const float* A, const float* B, const float* B_lo, float* C, const float* bias, int M, int N, int K, int batch,
-                int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc, int a_mn, int b_mn,
-                int c_trans, int relu, int accumulate, int ksplit, cudaStream_t st) {
+static int gemm_impl(const float* A, const float* B, const float* B_lo, float* C, const float* bias, int M, int N, int K, int batch,
+                     int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc, int a_mn, int b_mn,
+                     int c_trans, int relu, int accumulate, int ksplit, int taps, const int32_t* tap_off, int a_rows,
+                     cudaStream_t st) {
     PDB_REQUIRE(A && B && C, "gemm_tf32x3: null pointer");
     PDB_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "gemm_tf32x3: non-positive dimension");
     PDB_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm_tf32x3: operands must be 16-byte aligned");
@@ -580,8 +588,13 @@ int gemm_tf32x3(const float* A, const float* B, const float* B_lo, float* C, con
     p.kchunk = ((kb_total + ksplit - 1) / ksplit) * G_BK;
     p.ksplit = (K + p.kchunk - 1) / p.kchunk;           // no empty slices
     p.c_trans = c_trans; p.relu = relu; p.atomic = accumulate;
+    p.taps = taps;
+    p.kb_per_tap = taps > 1 ? (K / taps) / G_BK : 0;
+    for (int t = 0; t < 9; ++t) p.tap_off[t] = (taps > 1 && t < taps) ? tap_off[t] : 0;
     CUtensorMap ta, tb, tbl;
-    PDB_TRY(make_operand_map(&ta, A, a_mn != 0, M, K, batch, lda, sa, G_BM));
+    // with taps the A operand is (a_rows x K / taps) per batch item, read at shifted rows
+    if (taps > 1) PDB_TRY(make_operand_map(&ta, A, false, a_rows, K / taps, batch, lda, sa, G_BM));
+    else PDB_TRY(make_operand_map(&ta, A, a_mn != 0, M, K, batch, lda, sa, G_BM));
     p.presplit = B_lo != nullptr;
     // pre-split K-major B with a single n tile: the box covers exactly the rows the MMA needs, B_lo lands right behind
     p.b_box_rows = (p.presplit && N < BN) ? ((N + 15) / 16) * 16 : BN;
@@ -594,9 +607,26 @@ int gemm_tf32x3(const float* A, const float* B, const float* B_lo, float* C, con
     return dispatch_layout<128>(ta, tb, tbl, p, a_mn != 0, b_mn != 0, st);
 }
 
+int gemm_tf32x3(const float* A, const float* B, const float* B_lo, float* C, const float* bias, int M, int N, int K, int batch,
+                int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc, int a_mn, int b_mn,
+                int c_trans, int relu, int accumulate, int ksplit, cudaStream_t st) {
+    return gemm_impl(A, B, B_lo, C, bias, M, N, K, batch, lda, ldb, ldc, sa, sb, sc, a_mn, b_mn, c_trans, relu, accumulate,
+                     ksplit, 1, nullptr, 0, st);
+}
+
 }  // namespace pdb
 
 using namespace pdb;
+
+extern "C" int pdb_gemm_taps_tf32x3(const float* A, const float* B, const float* B_lo, float* C, const float* bias, int M,
+                                    int N, int Ck, int batch, int a_rows, int64_t lda, int64_t ldc, int64_t sa, int64_t sc,
+                                    int taps, const int32_t* tap_off, int relu, void* stream) {
+    PDB_REQUIRE(taps >= 1 && taps <= 9 && tap_off, "gemm_taps: 1 <= taps <= 9");
+    PDB_REQUIRE(Ck > 0 && Ck % G_BK == 0, "gemm_taps: channels per tap (%d) must be a multiple of %d", Ck, G_BK);
+    for (int t = 0; t < taps; ++t) PDB_REQUIRE(tap_off[t] >= 0, "gemm_taps: negative row offset");
+    return gemm_impl(A, B, B_lo, C, bias, M, N, taps * Ck, batch, lda, (int64_t)taps * Ck, ldc, sa, 0, sc, 0, 0, 0, relu, 0, 1,
+                     taps, tap_off, a_rows, as_stream(stream));
+}
 
 extern "C" int pdb_gemm_tf32x3(const float* A, const float* B, const float* B_lo, float* C, const float* bias, int M, int N, int K, int batch,
                                int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc, int a_mn,

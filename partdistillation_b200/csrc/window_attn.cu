@@ -1,0 +1,106 @@
+// Swin window attention, forward (frozen backbone: SURVEY.md section 8 f2) — replaces, inside WindowAttention.forward
+// (modeling/backbone/swin.py:78-176 of the reference), q @ k^T * scale + relative-position bias (+ shift mask) ->
+// softmax -> @ v and the head transpose, which the reference runs as separate matmul / add / softmax / matmul kernels
+// on (B*nW, heads, N, N) score tensors.
+//   qkv  (Bw, N, 3, heads, 32) f32 (output of the qkv Linear)       bias (heads, N, N) f32
+//   mask (nW, N, N) f32 additive or NULL (window of row bw is bw % nW)      out (Bw, N, heads*32) f32
+// One CTA per (window, head); thread i owns query row i: q_i and the 32-wide output accumulator live in registers,
+// K and V of the window (N x 32 each) in shared memory and are read as broadcasts; the softmax is computed online
+// (running max / sum, flash-attention style) so the N x N scores are never stored.
+#include "common.cuh"
+
+namespace pdb {
+
+constexpr int kWinD = 32;
+
+__global__ void __launch_bounds__(256)
+window_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ bias, const float* __restrict__ mask,
+                        float* __restrict__ out, int N, int heads, int nW, float scale) {
+    extern __shared__ __align__(16) float s_kv[];      // K [N][32] | V [N][32]
+    float* s_k = s_kv;
+    float* s_v = s_kv + N * kWinD;
+    const int bw = blockIdx.x / heads;
+    const int h = blockIdx.x - bw * heads;
+    const int C3 = 3 * heads * kWinD;
+    const float* base = qkv + (int64_t)bw * N * C3 + h * kWinD;
+    for (int i = threadIdx.x; i < N * (kWinD / 4); i += blockDim.x) {
+        const int row = i >> 3, c4 = (i & 7) * 4;
+        const float* src = base + (int64_t)row * C3 + c4;
+        *reinterpret_cast<float4*>(s_k + row * kWinD + c4) = __ldg(reinterpret_cast<const float4*>(src + heads * kWinD));
+        *reinterpret_cast<float4*>(s_v + row * kWinD + c4) = __ldg(reinterpret_cast<const float4*>(src + 2 * heads * kWinD));
+    }
+    __syncthreads();
+    const int i = threadIdx.x;
+    if (i >= N) return;
+    float q[kWinD], acc[kWinD];
+    {
+        const float4* qp = reinterpret_cast<const float4*>(base + (int64_t)i * C3);
+#pragma unroll
+        for (int c = 0; c < kWinD / 4; ++c) {
+            const float4 v = __ldg(qp + c);
+            q[4 * c] = v.x * scale; q[4 * c + 1] = v.y * scale; q[4 * c + 2] = v.z * scale; q[4 * c + 3] = v.w * scale;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < kWinD; ++c) acc[c] = 0.f;
+    const float* brow = bias + ((int64_t)h * N + i) * N;
+    const float* mrow = mask ? mask + ((int64_t)(bw % nW) * N + i) * N : nullptr;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < N; ++j) {
+        const float4* kp = reinterpret_cast<const float4*>(s_k + j * kWinD);
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < kWinD / 4; ++c) {
+            const float4 kv = kp[c];
+            s = fmaf(q[4 * c], kv.x, s); s = fmaf(q[4 * c + 1], kv.y, s);
+            s = fmaf(q[4 * c + 2], kv.z, s); s = fmaf(q[4 * c + 3], kv.w, s);
+        }
+        s += __ldg(brow + j);
+        if (mrow) s += __ldg(mrow + j);
+        if (s > m) {                        // new running maximum: rescale what has been accumulated
+            const float r = expf(m - s);    // expf(-inf) = 0 on the first key
+            l *= r;
+#pragma unroll
+            for (int c = 0; c < kWinD; ++c) acc[c] *= r;
+            m = s;
+        }
+        const float p = expf(s - m);
+        l += p;
+        const float4* vp = reinterpret_cast<const float4*>(s_v + j * kWinD);
+#pragma unroll
+        for (int c = 0; c < kWinD / 4; ++c) {
+            const float4 vv = vp[c];
+            acc[4 * c] = fmaf(p, vv.x, acc[4 * c]); acc[4 * c + 1] = fmaf(p, vv.y, acc[4 * c + 1]);
+            acc[4 * c + 2] = fmaf(p, vv.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(p, vv.w, acc[4 * c + 3]);
+        }
+    }
+    const float inv = 1.f / l;
+    float4* op = reinterpret_cast<float4*>(out + ((int64_t)bw * N + i) * heads * kWinD + h * kWinD);
+#pragma unroll
+    for (int c = 0; c < kWinD / 4; ++c)
+        op[c] = make_float4(acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv, acc[4 * c + 3] * inv);
+}
+
+}  // namespace pdb
+
+using namespace pdb;
+
+extern "C" int pdb_window_attention_forward(const float* qkv, const float* bias, const float* mask, float* out, int Bw, int N,
+                                            int heads, int d, int nW, float scale, void* stream) {
+    PDB_REQUIRE(qkv && bias && out, "window_attention: null pointer");
+    PDB_REQUIRE(d == kWinD, "window_attention: head dim %d (only 32, Swin's C / heads)", d);
+    PDB_REQUIRE(Bw > 0 && heads > 0 && N > 0 && N <= 256, "window_attention: bad sizes (N <= 256)");
+    PDB_REQUIRE(!mask || (nW > 0 && Bw % nW == 0), "window_attention: Bw must be a multiple of the mask's window count");
+    PDB_REQUIRE(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "window_attention: alignment");
+    PDB_REQUIRE((int64_t)Bw * heads < (1ll << 31), "window_attention: too many (window, head) pairs");
+    const int threads = ((N + 31) / 32) * 32;
+    const size_t smem = sizeof(float) * 2 * N * kWinD;
+    static bool attr = false;
+    if (!attr && smem > 48 * 1024) {
+        cudaFuncSetAttribute(window_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr = true;
+    }
+    window_attention_kernel<<<(unsigned)(Bw * heads), threads, smem, as_stream(stream)>>>(qkv, bias, mask, out, N, heads,
+                                                                                       mask ? nW : 1, scale);
+    return launched("window_attention");
+}

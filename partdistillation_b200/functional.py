@@ -519,6 +519,152 @@ class LinearFunction(Function):
         return gx, gw, gb, None
 
 
+class Conv1x1Function(Function):
+    """1x1 convolution as a GEMM over pixels.  An NCHW-contiguous input is read in place as an MN-major operand
+    (pixels contiguous), a channels-last one as a K-major operand; the result is the logical (B, O, H, W) tensor in
+    channels-last memory (pixel-major (B, HW, O)), which is what the deformable encoder flattens to anyway."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _need_cuda(x, weight, bias)
+        B, C, H, W = x.shape
+        O = weight.shape[0]
+        w2 = weight.view(O, C)
+        HW = H * W
+        cl = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
+        if not cl:
+            x = _c(x)
+        out = torch.empty((B, HW, O), dtype=torch.float32, device=x.device)
+        w_lo = weight_lo(w2, B * HW)
+        if cl:      # (B*HW, C) rows
+            gemm_tf32x3(x, w2, out, B * HW, O, C, lda=C, ldb=C, ldc=O, bias=bias, B_lo=w_lo)
+        else:       # A_b(m = pixel, k = channel) = x[b, k, m]
+            gemm_tf32x3(x, w2, out, HW, O, C, batch=B, lda=HW, ldb=C, ldc=O, sa=C * HW, sb=0, sc=HW * O, a_mn=True,
+                        bias=bias, B_lo=w_lo)
+        ctx.save_for_backward(x, weight)
+        ctx.cl, ctx.has_bias, ctx.w_lo = cl, bias is not None, w_lo
+        return out.view(B, H, W, O).permute(0, 3, 1, 2)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        B, C, H, W = x.shape
+        O = weight.shape[0]
+        HW = H * W
+        w2 = weight.view(O, C)
+        gy_pm = _c(gy.permute(0, 2, 3, 1)).view(B, HW, O)           # no copy when gy is channels-last
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gxp = torch.empty((B * HW, C), dtype=torch.float32, device=gy.device)
+            gemm_tf32x3(gy_pm, w2, gxp, B * HW, C, O, lda=O, ldb=C, ldc=C, b_mn=True, B_lo=ctx.w_lo)
+            gx = gxp.view(B, H, W, C).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            gw = torch.zeros((O, C), dtype=torch.float32, device=gy.device)
+            ks = _split_k(O, C, HW)
+            if ctx.cl:      # B_b(n = channel, k = pixel) = x[b, k, n]  (MN-major)
+                gemm_tf32x3(gy_pm, x, gw, O, C, HW, batch=B, lda=O, ldb=C, ldc=C, sa=HW * O, sb=HW * C, sc=0,
+                            a_mn=True, b_mn=True, accumulate=True, ksplit=ks)
+            else:           # x NCHW: B_b(n = channel, k = pixel) = x[b, n, k]  (K-major)
+                gemm_tf32x3(gy_pm, x, gw, O, C, HW, batch=B, lda=O, ldb=HW, ldc=C, sa=HW * O, sb=C * HW, sc=0,
+                            a_mn=True, accumulate=True, ksplit=ks)
+            gw = gw.view_as(weight)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy_pm.sum((0, 1))
+        return gx, gw, gb
+
+
+def conv1x1(x, weight, bias=None):
+    """F.conv2d with a 1x1 kernel on the tensor cores (fp32 CUDA, channel counts / pixel count multiples of 4);
+    returns the logical NCHW result in channels-last memory."""
+    B, C, H, W = x.shape
+    ok = (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and tuple(weight.shape[2:]) == (1, 1)
+          and C % 4 == 0 and weight.shape[0] % 4 == 0 and (H * W) % 4 == 0 and weight.is_contiguous())
+    if not ok:
+        return torch.nn.functional.conv2d(x, weight, bias)
+    return Conv1x1Function.apply(x, weight, bias)
+
+
+def _gemm_taps(A, Bw, C, M, N, Ck, batch, a_rows, tap_off, bias=None, relu=False, B_lo=None):
+    rc = _lib.load().pdb_gemm_taps_tf32x3(A.data_ptr(), Bw.data_ptr(), B_lo.data_ptr() if B_lo is not None else None,
+                                          C.data_ptr(), bias.data_ptr() if bias is not None else None, M, N, Ck, batch, a_rows,
+                                          Ck, N, a_rows * Ck, M * N, len(tap_off), _lib.host_i32(tap_off), int(relu), _stream())
+    _lib.check(rc, "pdb_gemm_taps_tf32x3")
+    return C
+
+
+def _pad_nhwc(x_nhwc):
+    """(B, H, W, C) -> zero-padded (B, H + 3, W + 2, C): one row above, one column left / right, two rows below (the
+    second one only keeps the shifted reads of the padded-width grid inside the image's own buffer)."""
+    B, H, W, C = x_nhwc.shape
+    xp = x_nhwc.new_zeros((B, H + 3, W + 2, C))
+    xp[:, 1:H + 1, 1:W + 1] = x_nhwc
+    return xp
+
+
+class Conv3x3Function(Function):
+    """3x3 / stride 1 / pad 1 convolution as ONE tensor-core GEMM: the zero-padded NHWC image is the A operand, the
+    9 taps are 9 K segments whose rows are shifted by ky * (W + 2) + kx (pdb_gemm_taps_tf32x3); outputs are computed
+    on the padded-width pixel grid and the two garbage columns per row dropped.  The input gradient is the same
+    routine with the flipped, transposed kernel; the weight gradient is 9 split-K GEMMs over the pixels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _need_cuda(x, weight, bias)
+        B, C, H, W = x.shape
+        O = weight.shape[0]
+        Wp = W + 2
+        taps = [ky * Wp + kx for ky in range(3) for kx in range(3)]
+        xp = _pad_nhwc(x.permute(0, 2, 3, 1))
+        w9 = weight.permute(0, 2, 3, 1).reshape(O, 9 * C).contiguous()
+        full = torch.empty((B, H * Wp, O), dtype=torch.float32, device=x.device)
+        _gemm_taps(xp, w9, full, H * Wp, O, C, B, (H + 3) * Wp, taps, bias=bias, B_lo=split_lo(w9))
+        ctx.save_for_backward(xp, weight)
+        ctx.dims = (B, C, H, W, O)
+        ctx.has_bias = bias is not None
+        return full.view(B, H, Wp, O)[:, :, :W].contiguous().permute(0, 3, 1, 2)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        xp, weight = ctx.saved_tensors
+        B, C, H, W, O = ctx.dims
+        Wp = W + 2
+        taps = [ky * Wp + kx for ky in range(3) for kx in range(3)]
+        gy_nhwc = _c(gy.permute(0, 2, 3, 1))
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gyp = _pad_nhwc(gy_nhwc)
+            w9t = weight.flip(2, 3).permute(1, 2, 3, 0).reshape(C, 9 * O).contiguous()
+            full = torch.empty((B, H * Wp, C), dtype=torch.float32, device=gy.device)
+            _gemm_taps(gyp, w9t, full, H * Wp, C, O, B, (H + 3) * Wp, taps, B_lo=split_lo(w9t))
+            gx = full.view(B, H, Wp, C)[:, :, :W].contiguous().permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            gyf = torch.nn.functional.pad(gy_nhwc, (0, 0, 0, 2))              # zero garbage columns of the padded-width grid
+            gw9 = torch.zeros((O, 9 * C), dtype=torch.float32, device=gy.device)
+            rows, K = (H + 3) * Wp, H * Wp
+            xflat = xp.view(B, rows * C)
+            ks = _split_k(O, C, K)
+            for t, off in enumerate(taps):
+                # gw9[o, t*C + i] = sum_{b,q} gyf[b, q, o] * xp[b, q + off, i]
+                gemm_tf32x3(gyf, xflat[:, off * C:], gw9[:, t * C:], O, C, K, batch=B, lda=O, ldb=C, ldc=9 * C,
+                            sa=K * O, sb=rows * C, sc=0, a_mn=True, b_mn=True, accumulate=True, ksplit=ks)
+            gw = gw9.view(O, 3, 3, C).permute(0, 3, 1, 2)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy_nhwc.sum((0, 1, 2))
+        return gx, gw, gb
+
+
+def conv3x3(x, weight, bias=None):
+    """F.conv2d(kernel 3, stride 1, padding 1) on the tensor cores for fp32 CUDA tensors with channel counts that are
+    multiples of 32; returns the logical NCHW result in channels-last memory."""
+    ok = (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and tuple(weight.shape[2:]) == (3, 3)
+          and x.shape[1] % 32 == 0 and weight.shape[0] % 32 == 0 and weight.shape[1] == x.shape[1])
+    if not ok:
+        return torch.nn.functional.conv2d(x, weight, bias, padding=1)
+    return Conv3x3Function.apply(x, weight, bias)
+
+
 def linear(x, weight, bias=None, relu=False):
     """nn.Linear (optionally fused ReLU) on the tensor cores for fp32 CUDA tensors whose feature sizes are
     multiples of 4; other dtypes (autocast halves, the fp64 classifier) and tiny ragged heads go through
@@ -548,3 +694,23 @@ def group_affinity(feat, centroids, mask, metric="dot"):
                                         H, W, 0 if metric == "dot" else 1, _stream())
     _lib.check(rc, "pdb_group_affinity")
     return labels
+
+
+# --------------------------------------------------------------------------------------------------
+# Swin window attention, forward (frozen backbone)  (modeling/backbone/swin.py:78-176)
+# --------------------------------------------------------------------------------------------------
+def window_attention(qkv, bias, mask, heads, scale):
+    """qkv (Bw, N, 3*heads*32) f32 from the qkv Linear, bias (heads, N, N), mask (nW, N, N) additive or None ->
+    (Bw, N, heads*32).  No autograd: used when the backbone is frozen."""
+    _need_cuda(qkv, bias, mask)
+    qkv, bias = _c(qkv), _c(bias.float())
+    Bw, N, C3 = qkv.shape
+    d = C3 // (3 * heads)
+    if mask is not None:
+        mask = _c(mask.float())
+    out = torch.empty((Bw, N, heads * d), dtype=torch.float32, device=qkv.device)
+    rc = _lib.load().pdb_window_attention_forward(qkv.data_ptr(), bias.data_ptr(), mask.data_ptr() if mask is not None else None,
+                                                  out.data_ptr(), Bw, N, heads, d, mask.shape[0] if mask is not None else 1,
+                                                  float(scale), _stream())
+    _lib.check(rc, "pdb_window_attention_forward")
+    return out

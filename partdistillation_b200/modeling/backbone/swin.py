@@ -75,9 +75,16 @@ class WindowAttention(nn.Module):
     def forward(self, x, mask=None):
         """x (nW*B, N, C); mask (nW, N, N) additive (0 / -100) or None."""
         Bw, N, C = x.shape
-        qkv = PF.linear(x, self.qkv.weight, self.qkv.bias).reshape(Bw, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
-        bias = self.relative_position_bias_table[self.relative_position_index.view(-1)].view(N, N, -1)
-        bias = bias.permute(2, 0, 1).unsqueeze(0)                               # (1, heads, N, N)
+        qkv = PF.linear(x, self.qkv.weight, self.qkv.bias)
+        bias = self.relative_position_bias_table[self.relative_position_index.view(-1)].view(N, N, -1).permute(2, 0, 1)
+        if (x.is_cuda and qkv.dtype == torch.float32 and C // self.num_heads == 32 and N <= 256
+                and not (torch.is_grad_enabled() and (qkv.requires_grad or bias.requires_grad))
+                and not (self.training and self.attn_drop.p > 0)):
+            # frozen backbone: fused window attention kernel (scores, bias, shift mask, softmax, PV, head transpose)
+            o = PF.window_attention(qkv, bias, mask, self.num_heads, self.scale)
+            return self.proj_drop(PF.linear(o, self.proj.weight, self.proj.bias))
+        qkv = qkv.reshape(Bw, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+        bias = bias.unsqueeze(0)                                                # (1, heads, N, N)
         if mask is not None:
             nW = mask.shape[0]
             bias = (bias + mask[:, None]).repeat(Bw // nW, 1, 1, 1)              # (Bw, heads, N, N)

@@ -218,7 +218,8 @@ class MSDeformAttnPixelDecoder(nn.Module):
             srcs, pos = [], []
             for idx, f in enumerate(self.transformer_in_features[::-1]):
                 x = features[f].float()
-                srcs.append(self.input_proj[idx](x))
+                conv, gn = self.input_proj[idx][0], self.input_proj[idx][1]
+                srcs.append(gn(PF.conv1x1(x, conv.weight, conv.bias)))
                 pos.append(self.pe_layer(x))
             y, shapes, starts = self.transformer(srcs, pos)
             bs = y.shape[0]
@@ -227,11 +228,36 @@ class MSDeformAttnPixelDecoder(nn.Module):
                 end = starts[i + 1] if i + 1 < len(starts) else y.shape[1]
                 out.append(y[:, starts[i]:end].transpose(1, 2).reshape(bs, -1, h, w))
             for idx, f in enumerate(self.in_features[:self.num_fpn_levels][::-1]):
-                cur = self.lateral_convs[idx](features[f].float())
+                cur = self._lateral(self.lateral_convs[idx], features[f].float())
                 up = F.interpolate(out[-1], size=cur.shape[-2:], mode="bilinear", align_corners=False)
-                out.append(self.output_convs[idx](cur + up))
+                out.append(self._output_conv(self.output_convs[idx], cur + up))
             multi_scale = out[:self.maskformer_num_feature_levels]
             return self._mask_features_pixel_major(out[-1]), out[0], multi_scale
+
+    @staticmethod
+    def _lateral(conv, x):
+        """1x1 lateral convolution (+ its norm / activation) with the contraction on the tensor cores."""
+        if tuple(conv.kernel_size) != (1, 1):
+            return conv(x)
+        y = PF.conv1x1(x, conv.weight, conv.bias)
+        if getattr(conv, "norm", None) is not None:
+            y = conv.norm(y)
+        if getattr(conv, "activation", None) is not None:
+            y = conv.activation(y)
+        return y
+
+    @staticmethod
+    def _output_conv(conv, x):
+        """3x3 output convolution (+ norm / activation) with the contraction on the tensor cores."""
+        if tuple(conv.kernel_size) != (3, 3) or tuple(conv.stride) != (1, 1) or tuple(conv.padding) != (1, 1) or \
+                tuple(conv.dilation) != (1, 1) or conv.groups != 1:
+            return conv(x)
+        y = PF.conv3x3(x, conv.weight, conv.bias)
+        if getattr(conv, "norm", None) is not None:
+            y = conv.norm(y)
+        if getattr(conv, "activation", None) is not None:
+            y = conv.activation(y)
+        return y
 
     def _mask_features_pixel_major(self, y):
         """The 1x1 ``mask_features`` convolution as a GEMM over pixels: the result is the logical

@@ -231,6 +231,47 @@ def test_linear_forward_backward(fn, rows, K, N, relu):
     assert _rel(gb.double(), rb.double()) < 1e-5
 
 
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_conv1x1(fn, channels_last):
+    """1x1 convolution as a tensor-core GEMM over pixels (NCHW input read in place as an MN-major operand) vs
+    float64 F.conv2d, forward and all three gradients."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 64, 12, 20, generator=g).cuda()
+    if channels_last:
+        x = x.contiguous(memory_format=torch.channels_last)
+    x.requires_grad_()
+    w = (torch.randn(40, 64, 1, 1, generator=g) / 8).cuda().requires_grad_()
+    b = torch.randn(40, generator=g).cuda().requires_grad_()
+    y = fn.conv1x1(x, w, b)
+    ref = F.conv2d(x.double(), w.double(), b.double())
+    assert y.shape == ref.shape and _rel(y.double(), ref) < 1e-5
+    go = torch.randn(ref.shape, generator=g).cuda()
+    gx, gw, gb = torch.autograd.grad(y, (x, w, b), go)
+    rx, rw, rb = torch.autograd.grad(ref, (x, w, b), go.double())
+    assert _rel(gx.double(), rx.double()) < 1e-5
+    assert _rel(gw.double(), rw.double()) < 1e-5
+    assert _rel(gb.double(), rb.double()) < 1e-5
+
+
+@pytest.mark.parametrize("B,C,O,H,W", [(2, 64, 32, 9, 14), (1, 32, 64, 16, 16)])
+def test_conv3x3(fn, B, C, O, H, W):
+    """3x3 convolution as one tap-shifted tensor-core GEMM on the padded-width grid (forward, input gradient with the
+    flipped kernel, weight gradient as 9 split-K GEMMs) vs float64 F.conv2d."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, C, H, W, generator=g).cuda().requires_grad_()
+    w = (torch.randn(O, C, 3, 3, generator=g) / 24).cuda().requires_grad_()
+    b = torch.randn(O, generator=g).cuda().requires_grad_()
+    y = fn.conv3x3(x, w, b)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    assert y.shape == ref.shape and _rel(y.double(), ref) < 1e-5
+    go = torch.randn(ref.shape, generator=g).cuda()
+    gx, gw, gb = torch.autograd.grad(y, (x, w, b), go)
+    rx, rw, rb = torch.autograd.grad(ref, (x, w, b), go.double())
+    assert _rel(gx.double(), rx.double()) < 1e-5
+    assert _rel(gw.double(), rw.double()) < 1e-5
+    assert _rel(gb.double(), rb.double()) < 1e-5
+
+
 # ------------------------------------------------------------------ attention mask (bit-exact)
 @pytest.mark.parametrize("H,W,h,w", [(64, 64, 32, 32), (64, 64, 16, 16), (64, 64, 8, 8), (40, 56, 20, 28), (33, 47, 9, 13)])
 def test_attn_mask_bits(fn, H, W, h, w):
@@ -488,3 +529,42 @@ def test_pixel_grouping_model_forward(fn):
     pm = out[0]["proposals"].pred_masks
     assert pm.dtype == torch.bool and pm.shape[1:] == (H, W) and 1 <= pm.shape[0] <= 4
     assert torch.equal(pm.any(0).cpu(), obj[0]) and int(pm.sum()) == int(obj.sum())      # disjoint cover of the object
+
+
+# ------------------------------------------------------------------ Swin window attention (frozen backbone)
+@pytest.mark.parametrize("Bw,N,heads,nW", [(8, 144, 4, 4), (6, 16, 2, 0), (3, 49, 3, 3)])
+def test_window_attention(fn, Bw, N, heads, nW):
+    """Fused window attention (scores + relative-position bias + shift mask + softmax + PV + head transpose) vs the
+    float64 formula of WindowAttention.forward (swin.py:78-176)."""
+    g = torch.Generator().manual_seed(9)
+    C = heads * 32
+    qkv = torch.randn(Bw, N, 3 * C, generator=g).cuda()
+    bias = torch.randn(heads, N, N, generator=g).cuda()
+    mask = None
+    if nW:
+        mask = torch.where(torch.rand(nW, N, N, generator=g) < 0.3, torch.tensor(-100.0), torch.tensor(0.0)).cuda()
+    scale = 32 ** -0.5
+    out = fn.window_attention(qkv, bias, mask, heads, scale)
+    q, k, v = qkv.double().view(Bw, N, 3, heads, 32).permute(2, 0, 3, 1, 4)
+    att = q @ k.transpose(-1, -2) * scale + bias.double()[None]
+    if mask is not None:
+        att = att + mask.double().repeat(Bw // nW, 1, 1)[:, None]
+    ref = (att.softmax(-1) @ v).transpose(1, 2).reshape(Bw, N, C)
+    assert _rel(out.double(), ref) < 1e-5
+
+
+def test_swin_backbone_frozen_path_vs_golden(fn, golden_dir):
+    """The frozen-backbone configuration (tensor-core linears + fused window attention) reproduces the reference
+    Swin outputs of the golden fixture."""
+    import synth
+    from partdistillation_b200 import compat, presets
+    g = _load(golden_dir, "swin_micro.pt")
+    cfg = presets.make_cfg("ProposalModel", "swin_micro", device="cuda")
+    backbone = compat.build_backbone(cfg)
+    backbone.load_state_dict(synth.synth_state_dict(g["table"], seed=g["weight_seed"]), strict=False)
+    backbone = backbone.cuda().eval()
+    for p in backbone.parameters():
+        p.requires_grad_(False)
+    out = backbone(g["x"].cuda())
+    for k, v in g["out"].items():
+        assert _rel(out[k].cpu(), v) < 1e-4, k

@@ -34,7 +34,7 @@ def main(out_path):
     wall = (time.perf_counter() - t0) / n * 1e3
     # stage split with events
     from torch.profiler import ProfilerActivity, profile
-    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
         for _ in range(2):
             trainer.step(batch)
         torch.cuda.synchronize()
@@ -53,6 +53,15 @@ def main(out_path):
         w.write(f"{'us/step':>10} {'share':>7} {'count':>6}  kernel\n")
         for t, c, k in rows[:70]:
             w.write(f"{t:10.1f} {100 * t / total:6.1f}% {c:6d}  {k[:110]}\n")
+        w.write("\n# ATen / autograd ops by device time (self + children), with input shapes\n")
+        ops = []
+        for e in prof.key_averages(group_by_input_shape=True):
+            t = getattr(e, "device_time_total", 0.0) or 0.0
+            if t > 0 and e.device_type == torch.autograd.DeviceType.CPU:
+                ops.append((t / 2, e.count // 2, e.key, str(e.input_shapes)[:150]))
+        ops.sort(reverse=True)
+        for t, c, k, sh in ops[:60]:
+            w.write(f"{t:10.1f} {c:6d}  {k[:40]:40s} {sh}\n")
     print(open(out_path).read()[:6000])
 
 
