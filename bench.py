@@ -207,7 +207,7 @@ def kernel_rooflines(device):
     with torch.no_grad():
         t = _time_kernel(lambda: fn.mask_einsum(e, f), flush)
     out.append(hbm_entry("gemm_tf32x3_kernel (mask einsum fwd)", 4 * (B * Q * C + B * C * HH * WW + B * Q * HH * WW), t))
-    out[-1]["traffic"] = 191.2e6          # dram read+write per launch from profiles/r01_ncu_einsum_fwd.txt (ncu --set full)
+    out[-1]["traffic"] = 161.5e6          # dram read + write per launch, profiles/r01_ncu_einsum_fwd.txt (ncu --set full; part of the output is still in L2)
 
     # ---- MSDeformAttn gather / scatter at the encoder shape
     shapes = [(H // 32, W // 32), (H // 16, W // 16), (H // 8, W // 8)]

@@ -238,6 +238,15 @@ PDB_API int pdb_adamw_flat(float* param, const float* grad, float* exp_avg, floa
                    float beta2, float eps, const int64_t* step, float grad_scale, float clip_norm, const double* sumsq,
                    void* stream);
 
+/* Whole (shifted-)window attention of a Swin block on the un-partitioned token grid: F.pad, torch.roll,
+ * window_partition, the shift mask, window_reverse, the inverse roll and the crop of SwinTransformerBlock.forward
+ * (modeling/backbone/swin.py:239-300) become index arithmetic of the kernel.
+ *   qkv (B, H, W, 3, heads, 32) f32 (qkv Linear of norm1(x), token order); qkv_bias (3*heads*32) f32 or NULL: the
+ *   qkv of padded tokens (the reference pads the normalised map with zeros); bias (heads, ws*ws, ws*ws);
+ *   out (B, H, W, heads*32).  ws*ws <= 256, 0 <= shift < ws, head dim 32. */
+PDB_API int pdb_swin_window_attention_forward(const float* qkv, const float* qkv_bias, const float* bias, float* out, int B,
+                                      int H, int W, int heads, int d, int ws, int shift, float scale, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Pixel grouping affinity — replaces, inside PixelGroupingModel.generate_part_segments
  * (pixel_grouping_model.py:139-144,197-211), the bilinear up-sampling of the backbone features to image size,

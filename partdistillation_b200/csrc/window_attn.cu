@@ -104,3 +104,139 @@ extern "C" int pdb_window_attention_forward(const float* qkv, const float* bias,
                                                                                        mask ? nW : 1, scale);
     return launched("window_attention");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Whole shifted-window attention of a Swin block on the un-partitioned token grid: folds F.pad, torch.roll,
+// window_partition, the (nW, N, N) shift mask, window_reverse, the inverse roll and the crop of
+// SwinTransformerBlock.forward (swin.py:239-300) into the index arithmetic of the attention kernel.
+//   qkv (B, H, W, 3, heads, 32) f32 = qkv Linear applied to norm1(x) in token order; padded tokens (the reference
+//   pads the NORMALISED map with zeros, so their qkv is the Linear's bias) take qkv_bias (3*heads*32) or zeros;
+//   bias (heads, N, N) relative-position bias, N = ws*ws;  out (B, H, W, heads*32).
+// CTA = (image, window of the shifted frame, head); token t of the window sits at shifted-frame (wy*ws + t/ws,
+// wx*ws + t%ws) = original pixel ((ys + shift) % Hp, (xs + shift) % Wp); the mask is -100 between tokens of
+// different regions (0 | Hp-ws | Hp-shift bands per axis), as the reference's img_mask construction.
+// ------------------------------------------------------------------------------------------------
+namespace pdb {
+
+__global__ void __launch_bounds__(256)
+swin_window_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias, const float* __restrict__ bias,
+                             float* __restrict__ out, int H, int W, int heads, int ws, int shift, int Hp, int Wp, float scale) {
+    extern __shared__ __align__(16) float s_kv[];      // K [N][32] | V [N][32] | region id [N]
+    const int N = ws * ws;
+    float* s_k = s_kv;
+    float* s_v = s_kv + N * kWinD;
+    int* s_id = reinterpret_cast<int*>(s_kv + 2 * N * kWinD);
+    const int nwx = Wp / ws, nwy = Hp / ws;
+    int r = blockIdx.x;
+    const int h = r % heads; r /= heads;
+    const int wx = r % nwx; r /= nwx;
+    const int wy = r % nwy;
+    const int b = r / nwy;
+    const int C = heads * kWinD, C3 = 3 * C;
+    // token -> source row of qkv (or -1 for a padded token)
+    auto source = [&](int t, int& region) -> int64_t {
+        const int ys = wy * ws + t / ws, xs = wx * ws + t % ws;
+        const int hr = ys < Hp - ws ? 0 : (ys < Hp - shift ? 1 : 2);
+        const int wr = xs < Wp - ws ? 0 : (xs < Wp - shift ? 1 : 2);
+        region = shift > 0 ? hr * 3 + wr : 0;
+        int yo = ys + shift, xo = xs + shift;
+        if (yo >= Hp) yo -= Hp;
+        if (xo >= Wp) xo -= Wp;
+        return (yo < H && xo < W) ? ((int64_t)b * H + yo) * W + xo : -1;
+    };
+    for (int i = threadIdx.x; i < N * (kWinD / 4); i += blockDim.x) {
+        const int row = i >> 3, c4 = (i & 7) * 4;
+        int region;
+        const int64_t src = source(row, region);
+        float4 kk, vv;
+        if (src >= 0) {
+            const float* p = qkv + src * C3 + h * kWinD + c4;
+            kk = __ldg(reinterpret_cast<const float4*>(p + C));
+            vv = __ldg(reinterpret_cast<const float4*>(p + 2 * C));
+        } else if (qkv_bias) {
+            kk = __ldg(reinterpret_cast<const float4*>(qkv_bias + C + h * kWinD + c4));
+            vv = __ldg(reinterpret_cast<const float4*>(qkv_bias + 2 * C + h * kWinD + c4));
+        } else {
+            kk = vv = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        *reinterpret_cast<float4*>(s_k + row * kWinD + c4) = kk;
+        *reinterpret_cast<float4*>(s_v + row * kWinD + c4) = vv;
+        if ((i & 7) == 0) s_id[row] = region;
+    }
+    __syncthreads();
+    const int i = threadIdx.x;
+    if (i >= N) return;
+    int my_region;
+    const int64_t src = source(i, my_region);
+    if (src < 0) return;                                  // padded query: its output row is cropped away
+    float q[kWinD], acc[kWinD];
+    {
+        const float4* qp = reinterpret_cast<const float4*>(qkv + src * C3 + h * kWinD);
+#pragma unroll
+        for (int c = 0; c < kWinD / 4; ++c) {
+            const float4 v = __ldg(qp + c);
+            q[4 * c] = v.x * scale; q[4 * c + 1] = v.y * scale; q[4 * c + 2] = v.z * scale; q[4 * c + 3] = v.w * scale;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < kWinD; ++c) acc[c] = 0.f;
+    const float* brow = bias + ((int64_t)h * N + i) * N;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < N; ++j) {
+        const float4* kp = reinterpret_cast<const float4*>(s_k + j * kWinD);
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < kWinD / 4; ++c) {
+            const float4 kv = kp[c];
+            s = fmaf(q[4 * c], kv.x, s); s = fmaf(q[4 * c + 1], kv.y, s);
+            s = fmaf(q[4 * c + 2], kv.z, s); s = fmaf(q[4 * c + 3], kv.w, s);
+        }
+        s += __ldg(brow + j);
+        if (s_id[j] != my_region) s += -100.0f;
+        if (s > m) {
+            const float rsc = expf(m - s);
+            l *= rsc;
+#pragma unroll
+            for (int c = 0; c < kWinD; ++c) acc[c] *= rsc;
+            m = s;
+        }
+        const float p = expf(s - m);
+        l += p;
+        const float4* vp = reinterpret_cast<const float4*>(s_v + j * kWinD);
+#pragma unroll
+        for (int c = 0; c < kWinD / 4; ++c) {
+            const float4 vv = vp[c];
+            acc[4 * c] = fmaf(p, vv.x, acc[4 * c]); acc[4 * c + 1] = fmaf(p, vv.y, acc[4 * c + 1]);
+            acc[4 * c + 2] = fmaf(p, vv.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(p, vv.w, acc[4 * c + 3]);
+        }
+    }
+    const float inv = 1.f / l;
+    float4* op = reinterpret_cast<float4*>(out + src * C + h * kWinD);
+#pragma unroll
+    for (int c = 0; c < kWinD / 4; ++c)
+        op[c] = make_float4(acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv, acc[4 * c + 3] * inv);
+}
+
+}  // namespace pdb
+
+extern "C" int pdb_swin_window_attention_forward(const float* qkv, const float* qkv_bias, const float* bias, float* out, int B,
+                                                 int H, int W, int heads, int d, int ws, int shift, float scale, void* stream) {
+    PDB_REQUIRE(qkv && bias && out, "swin_window_attention: null pointer");
+    PDB_REQUIRE(d == kWinD, "swin_window_attention: head dim %d (only 32)", d);
+    PDB_REQUIRE(B > 0 && H > 0 && W > 0 && heads > 0 && ws > 0 && ws * ws <= 256 && shift >= 0 && shift < ws,
+                "swin_window_attention: bad sizes (ws*ws <= 256, 0 <= shift < ws)");
+    const int Hp = (H + ws - 1) / ws * ws, Wp = (W + ws - 1) / ws * ws;
+    const int64_t ctas = (int64_t)B * (Hp / ws) * (Wp / ws) * heads;
+    PDB_REQUIRE(ctas < (1ll << 31), "swin_window_attention: too many windows");
+    const int N = ws * ws;
+    const int threads = ((N + 31) / 32) * 32;
+    const size_t smem = sizeof(float) * 2 * N * kWinD + sizeof(int) * N;
+    static bool attr = false;
+    if (!attr && smem > 48 * 1024) {
+        cudaFuncSetAttribute(swin_window_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr = true;
+    }
+    swin_window_attention_kernel<<<(unsigned)ctas, threads, smem, as_stream(stream)>>>(qkv, qkv_bias, bias, out, H, W, heads, ws,
+                                                                                    shift, Hp, Wp, scale);
+    return launched("swin_window_attention");
+}

@@ -714,3 +714,19 @@ def window_attention(qkv, bias, mask, heads, scale):
                                                   float(scale), _stream())
     _lib.check(rc, "pdb_window_attention_forward")
     return out
+
+
+def swin_window_attention(qkv, qkv_bias, bias, heads, window_size, shift, scale):
+    """qkv (B, H, W, 3*heads*32) f32 in token order -> (B, H, W, heads*32): the whole shifted-window attention of a Swin
+    block (pad, roll, partition, mask, attention, reverse, roll back, crop) in one kernel.  No autograd."""
+    _need_cuda(qkv, bias)
+    qkv, bias = _c(qkv), _c(bias.float())
+    B, H, W, C3 = qkv.shape
+    d = C3 // (3 * heads)
+    out = torch.empty((B, H, W, heads * d), dtype=torch.float32, device=qkv.device)
+    qb = _c(qkv_bias.float()) if qkv_bias is not None else None
+    rc = _lib.load().pdb_swin_window_attention_forward(qkv.data_ptr(), qb.data_ptr() if qb is not None else None, bias.data_ptr(),
+                                                       out.data_ptr(), B, H, W, heads, d, int(window_size), int(shift),
+                                                       float(scale), _stream())
+    _lib.check(rc, "pdb_swin_window_attention_forward")
+    return out

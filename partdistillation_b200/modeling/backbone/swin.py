@@ -104,9 +104,32 @@ class SwinTransformerBlock(nn.Module):
         self.norm2 = nn.LayerNorm(dim)
         self.mlp = Mlp(dim, int(dim * mlp_ratio), drop)
 
+    def _fused_attention(self, x, H, W):
+        """Frozen-backbone path: qkv Linear on the token grid, then ONE kernel for pad / roll / window partition /
+        shift mask / attention / window reverse / roll back / crop (functional.swin_window_attention)."""
+        a = self.attn
+        B, L, C = x.shape
+        qkv = PF.linear(self.norm1(x), a.qkv.weight, a.qkv.bias)
+        N = self.window_size * self.window_size
+        bias = a.relative_position_bias_table[a.relative_position_index.view(-1)].view(N, N, -1).permute(2, 0, 1)
+        o = PF.swin_window_attention(qkv.view(B, H, W, 3 * C), a.qkv.bias, bias, a.num_heads, self.window_size,
+                                     self.shift_size, a.scale)
+        return PF.linear(o.view(B, L, C), a.proj.weight, a.proj.bias)
+
+    def _can_fuse(self, x):
+        a = self.attn
+        frozen = not (torch.is_grad_enabled() and (x.requires_grad or a.qkv.weight.requires_grad
+                                                   or a.relative_position_bias_table.requires_grad))
+        return (x.is_cuda and x.dtype == torch.float32 and frozen and self.dim // a.num_heads == 32
+                and self.window_size * self.window_size <= 256 and a.attn_drop.p == 0 and a.proj_drop.p == 0
+                and not torch.is_autocast_enabled())
+
     def forward(self, x, H, W, mask_matrix):
         B, L, C = x.shape
         ws = self.window_size
+        if self._can_fuse(x):
+            x = x + self.drop_path(self._fused_attention(x, H, W))
+            return x + self.drop_path(self.mlp(self.norm2(x)))
         h = self.norm1(x).view(B, H, W, C)
         pr, pb = (ws - W % ws) % ws, (ws - H % ws) % ws
         h = F.pad(h, (0, 0, 0, pr, 0, pb))

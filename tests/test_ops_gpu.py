@@ -553,6 +553,45 @@ def test_window_attention(fn, Bw, N, heads, nW):
     assert _rel(out.double(), ref) < 1e-5
 
 
+@pytest.mark.parametrize("H,W,ws,shift,heads", [(24, 24, 12, 6, 2), (20, 30, 12, 6, 1), (16, 16, 4, 0, 2), (9, 7, 4, 2, 1)])
+def test_swin_window_attention_block(fn, H, W, ws, shift, heads):
+    """The one-kernel shifted-window attention on the token grid vs the reference's sequence pad -> roll ->
+    window_partition -> attention with the img_mask-derived shift mask -> window_reverse -> roll -> crop
+    (swin.py:239-300), including maps that are not multiples of the window."""
+    g = torch.Generator().manual_seed(12)
+    B, C, N = 2, heads * 32, ws * ws
+    qkv_w = (torch.randn(3 * C, C, generator=g) / C ** 0.5).double()
+    qkv_b = torch.randn(3 * C, generator=g).double()
+    x = torch.randn(B, H, W, C, generator=g).double()
+    bias = torch.randn(heads, N, N, generator=g)
+    scale = 32 ** -0.5
+    Hp, Wp = (H + ws - 1) // ws * ws, (W + ws - 1) // ws * ws
+    xp = F.pad(x, (0, 0, 0, Wp - W, 0, Hp - H))
+    if shift:
+        xp = torch.roll(xp, (-shift, -shift), (1, 2))
+    win = xp.view(B, Hp // ws, ws, Wp // ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, N, C)
+    q, k, v = (win @ qkv_w.t() + qkv_b).view(-1, N, 3, heads, 32).permute(2, 0, 3, 1, 4)
+    att = q @ k.transpose(-1, -2) * scale + bias.double()[None]
+    if shift:
+        img = torch.zeros(1, Hp, Wp, 1)
+        cnt = 0
+        for hs in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+            for wsl in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+                img[:, hs, wsl, :] = cnt
+                cnt += 1
+        mw = img.view(1, Hp // ws, ws, Wp // ws, ws, 1).permute(0, 1, 3, 2, 4, 5).reshape(-1, N)
+        am = (mw[:, None, :] - mw[:, :, None]).ne(0).double() * -100.0
+        att = att + am.repeat(B, 1, 1)[:, None]
+    o = (att.softmax(-1) @ v).transpose(1, 2).reshape(-1, N, C)
+    o = o.view(B, Hp // ws, Wp // ws, ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B, Hp, Wp, C)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    ref = o[:, :H, :W]
+    qkv_tok = (x @ qkv_w.t() + qkv_b).float().cuda()
+    out = fn.swin_window_attention(qkv_tok, qkv_b.float().cuda(), bias.cuda(), heads, ws, shift, scale)
+    assert _rel(out.double().cpu(), ref) < 1e-5
+
+
 def test_swin_backbone_frozen_path_vs_golden(fn, golden_dir):
     """The frozen-backbone configuration (tensor-core linears + fused window attention) reproduces the reference
     Swin outputs of the golden fixture."""
