@@ -13,6 +13,39 @@ namespace pdb {
 
 constexpr int kWinD = 32;
 
+// One key/value step of the online softmax for a query whose scaled q and accumulator live in registers.  The running
+// reference exponent m is re-based lazily (p stays below 2^16 and the row sum below 2^24, far from fp32 overflow); the
+// normalised result does not depend on the choice of m.  Base-2 softmax: q carries scale * log2(e), `add` (bias + mask)
+// is already multiplied by log2(e).
+__device__ __forceinline__ void attend_step(const float (&q)[kWinD], float (&acc)[kWinD], const float* __restrict__ kj,
+                                            const float* __restrict__ vj, float add, float& m, float& l) {
+    const float4* kp = reinterpret_cast<const float4*>(kj);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;          // four independent chains instead of one 32-long FMA chain
+#pragma unroll
+    for (int c = 0; c < kWinD / 4; ++c) {
+        const float4 kv = kp[c];
+        s0 = fmaf(q[4 * c], kv.x, s0); s1 = fmaf(q[4 * c + 1], kv.y, s1);
+        s2 = fmaf(q[4 * c + 2], kv.z, s2); s3 = fmaf(q[4 * c + 3], kv.w, s3);
+    }
+    const float s = ((s0 + s1) + (s2 + s3)) + add;
+    if (s > m + 16.f) {                 // lazy running maximum: only re-base when the exponent would grow past 2^16
+        const float r = exp2f(m - s);   // exp2f(-inf) = 0 on the first key
+        l *= r;
+#pragma unroll
+        for (int c = 0; c < kWinD; ++c) acc[c] *= r;
+        m = s;
+    }
+    const float p = exp2f(s - m);
+    l += p;
+    const float4* vp = reinterpret_cast<const float4*>(vj);
+#pragma unroll
+    for (int c = 0; c < kWinD / 4; ++c) {
+        const float4 vv = vp[c];
+        acc[4 * c] = fmaf(p, vv.x, acc[4 * c]); acc[4 * c + 1] = fmaf(p, vv.y, acc[4 * c + 1]);
+        acc[4 * c + 2] = fmaf(p, vv.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(p, vv.w, acc[4 * c + 3]);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 window_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ bias, const float* __restrict__ mask,
                         float* __restrict__ out, int N, int heads, int nW, float scale) {
@@ -33,12 +66,14 @@ window_attention_kernel(const float* __restrict__ qkv, const float* __restrict__
     const int i = threadIdx.x;
     if (i >= N) return;
     float q[kWinD], acc[kWinD];
+    constexpr float kLog2e = 1.4426950408889634f;
+    const float qs = scale * kLog2e;
     {
         const float4* qp = reinterpret_cast<const float4*>(base + (int64_t)i * C3);
 #pragma unroll
         for (int c = 0; c < kWinD / 4; ++c) {
             const float4 v = __ldg(qp + c);
-            q[4 * c] = v.x * scale; q[4 * c + 1] = v.y * scale; q[4 * c + 2] = v.z * scale; q[4 * c + 3] = v.w * scale;
+            q[4 * c] = v.x * qs; q[4 * c + 1] = v.y * qs; q[4 * c + 2] = v.z * qs; q[4 * c + 3] = v.w * qs;
         }
     }
 #pragma unroll
@@ -46,33 +81,25 @@ window_attention_kernel(const float* __restrict__ qkv, const float* __restrict__
     const float* brow = bias + ((int64_t)h * N + i) * N;
     const float* mrow = mask ? mask + ((int64_t)(bw % nW) * N + i) * N : nullptr;
     float m = -INFINITY, l = 0.f;
-    for (int j = 0; j < N; ++j) {
-        const float4* kp = reinterpret_cast<const float4*>(s_k + j * kWinD);
-        float s = 0.f;
+    // each thread streams its own bias (and mask) row: 8 columns = one 32-byte sector per load pair, so the row reads
+    // cost 4 L1 wavefronts per key instead of 32
+    const bool vec = (N % 8) == 0;
+    for (int j0 = 0; j0 < N; j0 += 8) {
+        float add[8];
+        if (vec) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(brow + j0)), b1 = __ldg(reinterpret_cast<const float4*>(brow + j0 + 4));
+            add[0] = b0.x; add[1] = b0.y; add[2] = b0.z; add[3] = b0.w; add[4] = b1.x; add[5] = b1.y; add[6] = b1.z; add[7] = b1.w;
+            if (mrow) {
+                const float4 m0 = __ldg(reinterpret_cast<const float4*>(mrow + j0)), m1 = __ldg(reinterpret_cast<const float4*>(mrow + j0 + 4));
+                add[0] += m0.x; add[1] += m0.y; add[2] += m0.z; add[3] += m0.w; add[4] += m1.x; add[5] += m1.y; add[6] += m1.z; add[7] += m1.w;
+            }
+        } else {
 #pragma unroll
-        for (int c = 0; c < kWinD / 4; ++c) {
-            const float4 kv = kp[c];
-            s = fmaf(q[4 * c], kv.x, s); s = fmaf(q[4 * c + 1], kv.y, s);
-            s = fmaf(q[4 * c + 2], kv.z, s); s = fmaf(q[4 * c + 3], kv.w, s);
+            for (int u = 0; u < 8; ++u) add[u] = j0 + u < N ? __ldg(brow + j0 + u) + (mrow ? __ldg(mrow + j0 + u) : 0.f) : 0.f;
         }
-        s += __ldg(brow + j);
-        if (mrow) s += __ldg(mrow + j);
-        if (s > m) {                        // new running maximum: rescale what has been accumulated
-            const float r = expf(m - s);    // expf(-inf) = 0 on the first key
-            l *= r;
 #pragma unroll
-            for (int c = 0; c < kWinD; ++c) acc[c] *= r;
-            m = s;
-        }
-        const float p = expf(s - m);
-        l += p;
-        const float4* vp = reinterpret_cast<const float4*>(s_v + j * kWinD);
-#pragma unroll
-        for (int c = 0; c < kWinD / 4; ++c) {
-            const float4 vv = vp[c];
-            acc[4 * c] = fmaf(p, vv.x, acc[4 * c]); acc[4 * c + 1] = fmaf(p, vv.y, acc[4 * c + 1]);
-            acc[4 * c + 2] = fmaf(p, vv.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(p, vv.w, acc[4 * c + 3]);
-        }
+        for (int u = 0; u < 8; ++u)
+            if (j0 + u < N) attend_step(q, acc, s_k + (j0 + u) * kWinD, s_v + (j0 + u) * kWinD, add[u] * kLog2e, m, l);
     }
     const float inv = 1.f / l;
     float4* op = reinterpret_cast<float4*>(out + ((int64_t)bw * N + i) * heads * kWinD + h * kWinD);
@@ -170,45 +197,35 @@ swin_window_attention_kernel(const float* __restrict__ qkv, const float* __restr
     const int64_t src = source(i, my_region);
     if (src < 0) return;                                  // padded query: its output row is cropped away
     float q[kWinD], acc[kWinD];
+    constexpr float kLog2e = 1.4426950408889634f;
+    const float qs = scale * kLog2e;
     {
         const float4* qp = reinterpret_cast<const float4*>(qkv + src * C3 + h * kWinD);
 #pragma unroll
         for (int c = 0; c < kWinD / 4; ++c) {
             const float4 v = __ldg(qp + c);
-            q[4 * c] = v.x * scale; q[4 * c + 1] = v.y * scale; q[4 * c + 2] = v.z * scale; q[4 * c + 3] = v.w * scale;
+            q[4 * c] = v.x * qs; q[4 * c + 1] = v.y * qs; q[4 * c + 2] = v.z * qs; q[4 * c + 3] = v.w * qs;
         }
     }
 #pragma unroll
     for (int c = 0; c < kWinD; ++c) acc[c] = 0.f;
     const float* brow = bias + ((int64_t)h * N + i) * N;
     float m = -INFINITY, l = 0.f;
-    for (int j = 0; j < N; ++j) {
-        const float4* kp = reinterpret_cast<const float4*>(s_k + j * kWinD);
-        float s = 0.f;
+    const bool vec = (N % 8) == 0;
+    for (int j0 = 0; j0 < N; j0 += 8) {
+        float add[8];
+        if (vec) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(brow + j0)), b1 = __ldg(reinterpret_cast<const float4*>(brow + j0 + 4));
+            add[0] = b0.x; add[1] = b0.y; add[2] = b0.z; add[3] = b0.w; add[4] = b1.x; add[5] = b1.y; add[6] = b1.z; add[7] = b1.w;
+        } else {
 #pragma unroll
-        for (int c = 0; c < kWinD / 4; ++c) {
-            const float4 kv = kp[c];
-            s = fmaf(q[4 * c], kv.x, s); s = fmaf(q[4 * c + 1], kv.y, s);
-            s = fmaf(q[4 * c + 2], kv.z, s); s = fmaf(q[4 * c + 3], kv.w, s);
+            for (int u = 0; u < 8; ++u) add[u] = j0 + u < N ? __ldg(brow + j0 + u) : 0.f;
         }
-        s += __ldg(brow + j);
-        if (s_id[j] != my_region) s += -100.0f;
-        if (s > m) {
-            const float rsc = expf(m - s);
-            l *= rsc;
 #pragma unroll
-            for (int c = 0; c < kWinD; ++c) acc[c] *= rsc;
-            m = s;
-        }
-        const float p = expf(s - m);
-        l += p;
-        const float4* vp = reinterpret_cast<const float4*>(s_v + j * kWinD);
-#pragma unroll
-        for (int c = 0; c < kWinD / 4; ++c) {
-            const float4 vv = vp[c];
-            acc[4 * c] = fmaf(p, vv.x, acc[4 * c]); acc[4 * c + 1] = fmaf(p, vv.y, acc[4 * c + 1]);
-            acc[4 * c + 2] = fmaf(p, vv.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(p, vv.w, acc[4 * c + 3]);
-        }
+        for (int u = 0; u < 8; ++u)
+            if (j0 + u < N)
+                attend_step(q, acc, s_k + (j0 + u) * kWinD, s_v + (j0 + u) * kWinD,
+                            (add[u] + (s_id[j0 + u] != my_region ? -100.0f : 0.f)) * kLog2e, m, l);
     }
     const float inv = 1.f / l;
     float4* op = reinterpret_cast<float4*>(out + src * C + h * kWinD);
