@@ -107,7 +107,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 
 // one CTA per (image, query): cost row over that image's targets
 constexpr int CK = 8;   // targets per pass
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 matcher_cost_kernel(const float* __restrict__ pred_pts, const float* __restrict__ tgt_pts,
                     const float* __restrict__ cls_prob, const int32_t* __restrict__ tgt_label, Offsets off,
                     float* __restrict__ cost, int Q, int Kc, int P, float w_class, float w_mask, float w_dice) {
@@ -273,7 +273,9 @@ lsap_kernel(const float* __restrict__ cost, Offsets off, int64_t* __restrict__ p
 // ------------------------------------------------------------------------------------------------
 // fused point-sampled BCE + dice
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// one CTA of 1024 threads per matched pair: there are only a handful of pairs per layer, so the block is as wide as it
+// can be (12544 points -> 12 per thread)
+__global__ void __launch_bounds__(1024)
 point_loss_fwd(const float* __restrict__ pred, const int64_t* __restrict__ pred_index, const uint8_t* __restrict__ gt,
                const int64_t* __restrict__ gt_index, const float* __restrict__ coords, float* __restrict__ sums, int P,
                int H, int W, int Hg, int Wg) {
@@ -305,7 +307,7 @@ point_loss_fwd(const float* __restrict__ pred, const int64_t* __restrict__ pred_
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 point_loss_bwd(const float* __restrict__ pred, const int64_t* __restrict__ pred_index, const uint8_t* __restrict__ gt,
                const int64_t* __restrict__ gt_index, const float* __restrict__ coords, const float* __restrict__ sums,
                const float* __restrict__ g_bce, const float* __restrict__ g_dice, float* __restrict__ gpred, int P,
@@ -443,7 +445,7 @@ extern "C" int pdb_matcher_cost(const float* pred_pts, const float* tgt_pts, con
     PDB_TRY(fill_offsets(tgt_offset, B, off, "matcher_cost"));
     if (off.v[B] == 0) return PDB_OK;
     dim3 grid((unsigned)Q, (unsigned)B);
-    matcher_cost_kernel<<<grid, 128, 0, as_stream(stream)>>>(pred_pts, tgt_pts, cls_prob, tgt_label, off, cost, Q, Kc,
+    matcher_cost_kernel<<<grid, 512, 0, as_stream(stream)>>>(pred_pts, tgt_pts, cls_prob, tgt_label, off, cost, Q, Kc,
                                                              P, w_class, w_mask, w_dice);
     return launched("matcher_cost");
 }
@@ -471,7 +473,7 @@ extern "C" int pdb_point_loss_forward(const float* pred, const int64_t* pred_ind
     PDB_REQUIRE(pred && pred_index && gt && gt_index && coords && sums, "point_loss_forward: null pointer");
     PDB_REQUIRE(Nm >= 0 && P > 0 && H > 0 && W > 0 && Hg > 0 && Wg > 0, "point_loss_forward: bad shape");
     if (Nm == 0) return PDB_OK;
-    point_loss_fwd<<<(unsigned)Nm, 256, 0, as_stream(stream)>>>(pred, pred_index, gt, gt_index, coords, sums, P, H, W,
+    point_loss_fwd<<<(unsigned)Nm, 1024, 0, as_stream(stream)>>>(pred, pred_index, gt, gt_index, coords, sums, P, H, W,
                                                                 Hg, Wg);
     return launched("point_loss_forward");
 }
@@ -484,7 +486,7 @@ extern "C" int pdb_point_loss_backward(const float* pred, const int64_t* pred_in
                 "point_loss_backward: null pointer");
     PDB_REQUIRE(Nm >= 0 && P > 0 && H > 0 && W > 0 && Hg > 0 && Wg > 0, "point_loss_backward: bad shape");
     if (Nm == 0) return PDB_OK;
-    point_loss_bwd<<<(unsigned)Nm, 256, 0, as_stream(stream)>>>(pred, pred_index, gt, gt_index, coords, sums, g_bce,
+    point_loss_bwd<<<(unsigned)Nm, 1024, 0, as_stream(stream)>>>(pred, pred_index, gt, gt_index, coords, sums, g_bce,
                                                                 g_dice, grad_pred, P, H, W, Hg, Wg);
     return launched("point_loss_backward");
 }
