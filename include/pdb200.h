@@ -268,6 +268,16 @@ PDB_API int pdb_group_affinity(const float* feat, const float* centroids, const 
 PDB_API int pdb_window_attention_forward(const float* qkv, const float* bias, const float* mask, float* out, int Bw, int N,
                                  int heads, int d, int nW, float scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm forward, optionally fused with the residual add in front of it — replaces nn.LayerNorm of the encoder
+ * layers (msdeformattn.py:129-133), decoder layers (mask2former_transformer_decoder.py:44-54,102-114,167-171) and Swin
+ * blocks (swin.py:239-300):   z = x (+ residual);  y = (z - mean) * rstd * weight + bias.
+ *   x, residual (or NULL), y, sum_out (or NULL; receives z): (rows, C) f32; weight, bias (C); mean, rstd (rows) f32
+ *   are saved for the backward pass (same meaning as ATen's native_layer_norm).  C % 4 == 0, C <= 2048.
+ * ---------------------------------------------------------------------------------------------- */
+PDB_API int pdb_layer_norm_forward(const float* x, const float* residual, const float* weight, const float* bias, float* y,
+                           float* sum_out, float* mean, float* rstd, int64_t rows, int C, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

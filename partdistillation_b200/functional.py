@@ -730,3 +730,66 @@ def swin_window_attention(qkv, qkv_bias, bias, heads, window_size, shift, scale)
                                                        float(scale), _stream())
     _lib.check(rc, "pdb_swin_window_attention_forward")
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# LayerNorm (+ fused residual add)
+# --------------------------------------------------------------------------------------------------
+class LayerNormFunction(Function):
+    """y = LayerNorm(x (+ residual)); optionally also returns the sum.  Forward is one pass of the warp-per-row kernel;
+    backward is ATen's native_layer_norm_backward on the saved mean / rstd (the sum is recomputed there)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, eps, want_sum):
+        _need_cuda(x, residual, weight, bias)
+        C = x.shape[-1]
+        x2 = _c(x).view(-1, C)
+        r2 = _c(residual).view(-1, C) if residual is not None else None
+        rows = x2.shape[0]
+        y = torch.empty_like(x2)
+        z = torch.empty_like(x2) if (want_sum and r2 is not None) else None
+        mean = torch.empty((rows,), dtype=torch.float32, device=x.device)
+        rstd = torch.empty((rows,), dtype=torch.float32, device=x.device)
+        rc = _lib.load().pdb_layer_norm_forward(x2.data_ptr(), r2.data_ptr() if r2 is not None else None, weight.data_ptr(),
+                                                bias.data_ptr(), y.data_ptr(), z.data_ptr() if z is not None else None,
+                                                mean.data_ptr(), rstd.data_ptr(), rows, C, float(eps), _stream())
+        _lib.check(rc, "pdb_layer_norm_forward")
+        ctx.save_for_backward(x2, r2, weight, bias, mean, rstd, z)
+        ctx.shape = x.shape
+        ctx.want_sum = want_sum
+        if want_sum:
+            return y.view(x.shape), (z if z is not None else x2).view(x.shape)
+        return y.view(x.shape), None
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy, gz):
+        x2, r2, weight, bias, mean, rstd, z = ctx.saved_tensors
+        C = x2.shape[-1]
+        zin = z if z is not None else (x2 + r2 if r2 is not None else x2)
+        mask = [ctx.needs_input_grad[0] or (r2 is not None and ctx.needs_input_grad[1]), ctx.needs_input_grad[2],
+                ctx.needs_input_grad[3]]
+        gin, gw, gb = torch.ops.aten.native_layer_norm_backward(_c(gy).view(-1, C), zin, [C], mean.view(-1, 1), rstd.view(-1, 1),
+                                                                weight, bias, mask)
+        if gin is not None:
+            if gz is not None:
+                gin = gin + _c(gz).view(-1, C)
+            gin = gin.view(ctx.shape)
+        elif gz is not None:
+            gin = gz
+        return (gin if ctx.needs_input_grad[0] else None, gin if (r2 is not None and ctx.needs_input_grad[1]) else None,
+                gw, gb, None, None)
+
+
+def layer_norm(x, weight, bias, eps=1e-5, residual=None, return_sum=False):
+    """F.layer_norm over the last dimension of ``x + residual`` (``residual`` optional).  With ``return_sum`` also
+    returns the sum (pre-norm residual streams).  fp32 CUDA tensors with C % 4 == 0 use the kernel; anything else goes
+    through torch."""
+    ok = (x.is_cuda and x.dtype == torch.float32 and weight is not None and bias is not None and weight.dtype == torch.float32
+          and x.shape[-1] % 4 == 0 and x.shape[-1] <= 2048 and (residual is None or residual.shape == x.shape))
+    if not ok:
+        z = x if residual is None else x + residual
+        y = torch.nn.functional.layer_norm(z, (x.shape[-1],), weight, bias, eps)
+        return (y, z) if return_sum else y
+    y, z = LayerNormFunction.apply(x, residual, weight, bias, eps, return_sum)
+    return (y, z) if return_sum else y

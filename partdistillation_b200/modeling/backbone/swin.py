@@ -109,7 +109,7 @@ class SwinTransformerBlock(nn.Module):
         shift mask / attention / window reverse / roll back / crop (functional.swin_window_attention)."""
         a = self.attn
         B, L, C = x.shape
-        qkv = PF.linear(self.norm1(x), a.qkv.weight, a.qkv.bias)
+        qkv = PF.linear(PF.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps), a.qkv.weight, a.qkv.bias)
         N = self.window_size * self.window_size
         bias = a.relative_position_bias_table[a.relative_position_index.view(-1)].view(N, N, -1).permute(2, 0, 1)
         o = PF.swin_window_attention(qkv.view(B, H, W, 3 * C), a.qkv.bias, bias, a.num_heads, self.window_size,
@@ -128,8 +128,10 @@ class SwinTransformerBlock(nn.Module):
         B, L, C = x.shape
         ws = self.window_size
         if self._can_fuse(x):
-            x = x + self.drop_path(self._fused_attention(x, H, W))
-            return x + self.drop_path(self.mlp(self.norm2(x)))
+            # residual add fused into norm2: one pass writes both the new residual stream and its normalised copy
+            h, x = PF.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps,
+                                 residual=self.drop_path(self._fused_attention(x, H, W)), return_sum=True)
+            return x + self.drop_path(self.mlp(h))
         h = self.norm1(x).view(B, H, W, C)
         pr, pb = (ws - W % ws) % ws, (ws - H % ws) % ws
         h = F.pad(h, (0, 0, 0, pr, 0, pb))
@@ -159,7 +161,7 @@ class PatchMerging(nn.Module):
         if H % 2 or W % 2:
             x = F.pad(x, (0, 0, 0, W % 2, 0, H % 2))
         x = torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1)
-        return PF.linear(self.norm(x.view(B, -1, 4 * C)), self.reduction.weight, None)
+        return PF.linear(PF.layer_norm(x.view(B, -1, 4 * C), self.norm.weight, self.norm.bias, self.norm.eps), self.reduction.weight, None)
 
 
 class BasicLayer(nn.Module):

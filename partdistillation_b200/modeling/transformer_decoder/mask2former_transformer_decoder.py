@@ -71,7 +71,7 @@ class SelfAttentionLayer(nn.Module):
         v = a.project(x, 2, 3).view(B, Q, a.num_heads, a.head_dim)
         o = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2), v.transpose(1, 2))
         o = PF.linear(o.transpose(1, 2).reshape(B, Q, E), a.out_proj.weight, a.out_proj.bias)
-        return tgt + o if self.normalize_before else self.norm(tgt + o)
+        return tgt + o if self.normalize_before else PF.layer_norm(tgt, self.norm.weight, self.norm.bias, self.norm.eps, residual=o)
 
 
 class CrossAttentionLayer(nn.Module):
@@ -96,7 +96,7 @@ class CrossAttentionLayer(nn.Module):
         mask, row_any = (memory_mask.mask, memory_mask.row_any) if memory_mask is not None else (None, None)
         o = PF.masked_cross_attention(q.float(), k.float(), v.float(), mask, row_any, a.num_heads)
         o = PF.linear(o.to(x.dtype), a.out_proj.weight, a.out_proj.bias)
-        return tgt + o if self.normalize_before else self.norm(tgt + o)
+        return tgt + o if self.normalize_before else PF.layer_norm(tgt, self.norm.weight, self.norm.bias, self.norm.eps, residual=o)
 
 
 class FFNLayer(nn.Module):
@@ -111,7 +111,7 @@ class FFNLayer(nn.Module):
     def forward(self, tgt):
         x = self.norm(tgt) if self.normalize_before else tgt
         y = PF.linear(PF.linear(x, self.linear1.weight, self.linear1.bias, relu=True), self.linear2.weight, self.linear2.bias)
-        return tgt + y if self.normalize_before else self.norm(tgt + y)
+        return tgt + y if self.normalize_before else PF.layer_norm(tgt, self.norm.weight, self.norm.bias, self.norm.eps, residual=y)
 
 
 class MLP(nn.Module):
@@ -241,7 +241,7 @@ class MultiScaleMaskedTransformerDecoder(nn.Module):
     def forward_prediction_heads(self, output, mask_features, attn_mask_target_size, targets=None):
         """output (B, Q, C) -> (class logits, mask logits (B, Q, H, W), AttnMask for the next layer,
         normalised decoder output (B, Q, C))."""
-        decoder_output = self.decoder_norm(output)
+        decoder_output = PF.layer_norm(output, self.decoder_norm.weight, self.decoder_norm.bias, self.decoder_norm.eps)
         outputs_class = self._classify(decoder_output, targets)
         mask_embed = self.mask_embed(decoder_output)
         if self.query_feature_normalize:

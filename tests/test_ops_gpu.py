@@ -607,3 +607,28 @@ def test_swin_backbone_frozen_path_vs_golden(fn, golden_dir):
     out = backbone(g["x"].cuda())
     for k, v in g["out"].items():
         assert _rel(out[k].cpu(), v) < 1e-4, k
+
+
+# ------------------------------------------------------------------ LayerNorm (+ residual)
+@pytest.mark.parametrize("rows,C,res,want_sum", [((2, 300), 256, True, False), ((5, 7), 128, False, False),
+                                                  ((3, 50), 512, True, True), ((9,), 2048, True, True), ((4, 11), 36, False, True)])
+def test_layer_norm_fused(fn, rows, C, res, want_sum):
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(*rows, C, generator=g).cuda().requires_grad_()
+    r = torch.randn(*rows, C, generator=g).cuda().requires_grad_() if res else None
+    w = torch.randn(C, generator=g).cuda().requires_grad_()
+    b = torch.randn(C, generator=g).cuda().requires_grad_()
+    out = fn.layer_norm(x, w, b, 1e-5, residual=r, return_sum=want_sum)
+    y, z = out if want_sum else (out, None)
+    zr = x.double() + (r.double() if res else 0)
+    ref = F.layer_norm(zr, (C,), w.double(), b.double(), 1e-5)
+    assert _rel(y.double(), ref) < 1e-5
+    go = torch.randn(ref.shape, generator=g).cuda()
+    gz = torch.randn(ref.shape, generator=g).cuda()
+    ins = [t for t in (x, r, w, b) if t is not None]
+    loss = (y * go).sum() + ((z * gz).sum() if want_sum else 0)
+    lref = (ref * go.double()).sum() + ((zr * gz.double()).sum() if want_sum else 0)
+    got = torch.autograd.grad(loss, ins)
+    exp = torch.autograd.grad(lref, ins)
+    for a, e in zip(got, exp):
+        assert _rel(a.double(), e.double()) < 1e-5
