@@ -44,7 +44,8 @@ constexpr int G_SPLIT_THREADS = 256;  // warps 2..9
 constexpr int G_EPI_WARP0 = 2 + G_SPLIT_THREADS / 32;
 constexpr int G_EPI_WARPS = 8;          // two warps per TMEM lane quarter, each takes every other column chunk
 constexpr int G_THREADS = (G_EPI_WARP0 + G_EPI_WARPS) * 32;     // 576
-constexpr int G_RS = 3;               // raw ring depth
+constexpr int G_RS = 3;               // raw ring depth (general case)
+constexpr int G_RS_MAX = 6;           // barrier slots; the deep ring of the einsum-shaped problems uses 5 (see launch_gemm_alo)
 constexpr int G_LS = 2;               // A_lo ring depth
 
 struct GemmParams {
@@ -60,10 +61,7 @@ struct GemmParams {
     int presplit;                     // B_lo comes pre-computed from global memory (tm_blo) instead of being split here
     int b_box_rows;                   // rows of the K-major B box (BN, or the 16-multiple covering N when N < BN)
     long long* trace;                 // debug timeline of CTA 0 (pdb_debug_set_trace), normally NULL
-    int pf_a;                         // L2 prefetch distance of the A operand, in k-blocks ahead of the TMA loads (0 = off)
-    int dbg;                          // timing experiments only (pdb_debug_set_gemm_dbg): 1 epilogue skips loads / stores, 2 no correction
-                                      // MMAs, 4 split warps skip their work, 8 no MMAs at all -- results are wrong with any bit set
-    int alo_tmem;                     // A_lo lives in tensor memory (tcgen05.st by the split warps, MMA A operand from TMEM)
+    int stages, stage_bytes;          // raw ring: depth and bytes per stage (A raw/hi | B raw/hi | B lo)
 };
 
 template <int BN>
@@ -74,10 +72,14 @@ struct GemmSmem {
     static constexpr int RAW_TOTAL = G_RS * RAW_STAGE;
     static constexpr int ALO_TOTAL = G_LS * A_BYTES;
     static constexpr int STAGING = G_EPI_WARPS * 32 * 36 * 4;                    // epilogue transpose tiles (row stride 36 floats)
-    static constexpr int BAR_OFF = RAW_TOTAL + ALO_TOTAL + STAGING;
+    // deep ring (ALO kernels with a transposed store: no A_lo ring, no staging tiles): 5 stages of A + 2 x 112 B rows
+    static constexpr int DEEP_STAGE = A_BYTES + 2 * 112 * G_BK * 4;
+    static constexpr int DEEP_STAGES = 5;
+    static constexpr int BAR_OFF = (BN == 128 && DEEP_STAGES * DEEP_STAGE > RAW_TOTAL + ALO_TOTAL + STAGING)
+                                       ? DEEP_STAGES * DEEP_STAGE : RAW_TOTAL + ALO_TOTAL + STAGING;
     static constexpr int TOTAL = BAR_OFF + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int ACC_COLS = 2 * BN;               // main (hi*hi) | correction (lo*hi + hi*lo)
-    // double-buffered accumulators + (alo_tmem) a 2-deep ring of 32-column A_lo k-blocks.  BN = 128 has all 512 columns
+    // double-buffered accumulators + (ALO kernels) a 2-deep ring of 32-column A_lo k-blocks.  BN = 128 has all 512 columns
     // taken by the accumulators unless every tile needs at most 112 columns (N <= 112, e.g. the 100-query mask einsum):
     // then the two accumulators are packed 224 columns apart and A_lo takes columns 448..511.
     static constexpr int TMEM_COLS = BN == 32 ? 256 : 512;
@@ -85,26 +87,10 @@ struct GemmSmem {
     static constexpr int ALO_COL = BN == 128 ? 448 : 4 * BN;
 };
 
-// Issued by the lane(s) whose `issue` is non-zero.  The producer and MMA warps run their loops with all 32 lanes converged and
-// predicate only the asynchronous instructions: every operand is then provably warp-uniform, the compiler keeps addresses,
-// coordinates and descriptors in uniform registers, and UTMALDG / UTCHMMA issue directly instead of through a per-instruction
-// ELECT + R2UR "waterfall" loop (which made the single-lane version issue-bound at ~100 clk per MMA).
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint32_t issue) {
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
-        "{\n\t.reg .pred q;\n\t"
-        "setp.ne.b32 q, %6, 0;\n\t"
-        "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
-        ::"r"(tc::smem_u32(smem_dst)), "l"(map), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(issue) : "memory");
-}
-
-// Pulls the box into L2 only: the TMA load that follows a few k-blocks later then pays the L2 latency instead of the HBM
-// latency (2 000 - 3 000 clk under load), which the 3-deep shared-memory ring is too shallow to cover on a streaming operand.
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2, uint32_t issue) {
-    asm volatile(
-        "{\n\t.reg .pred q;\n\t"
-        "setp.ne.b32 q, %4, 0;\n\t"
-        "@q cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];\n\t}"
-        ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(issue) : "memory");
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(tc::smem_u32(smem_dst)), "l"(map), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 // MN-major SWIZZLE_128B_BASE32B operand: 32-element mn blocks `lbo` bytes apart, 4-k groups `sbo` bytes apart.
@@ -191,12 +177,14 @@ __device__ __forceinline__ void b_layout(const GemmParams& p, int bn_eff, int& b
     stacked = (blo_off == adjacent) && (!B_MN || bn_eff % 32 == 0);
 }
 
-template <int BN, bool A_MN, bool B_MN>
+// ALO: the A_lo k-blocks live in tensor memory instead of shared memory: the split warps write them with tcgen05.st (thread =
+// one row = one TMEM lane) and the correction MMA takes its A operand from TMEM, which removes 16 KB of shared-memory writes and
+// 16 KB of operand reads per k-block.  K-major A only, and the accumulators must leave 64 columns (see GemmSmem).
+template <int BN, bool A_MN, bool B_MN, bool ALO>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const __grid_constant__ CUtensorMap tm_blo, const GemmParams p) {
     using S = GemmSmem<BN>;
-    const long long t_entry = p.trace ? clock64() : 0;
     extern __shared__ uint8_t smem_raw[];
     // 1 KB alignment by pointer arithmetic (no integer round trip), so the compiler keeps the shared state space
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -204,207 +192,184 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     float* staging = reinterpret_cast<float*>(smem + S::RAW_TOTAL + S::ALO_TOTAL);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint64_t* raw_full = bars;                      // TMA bytes landed
-    uint64_t* raw_empty = bars + G_RS;              // MMAs reading the stage completed
-    uint64_t* split_done = bars + 2 * G_RS;         // hi / lo of the stage ready (128 arrivals)
-    uint64_t* acc_full = bars + 3 * G_RS;           // [2]
+    uint64_t* raw_empty = bars + G_RS_MAX;          // MMAs reading the stage completed
+    uint64_t* split_done = bars + 2 * G_RS_MAX;     // hi / lo of the stage ready (128 arrivals)
+    uint64_t* alo_empty = bars + 3 * G_RS_MAX;      // [G_LS]
+    uint64_t* acc_full = alo_empty + G_LS;          // [2]
     uint64_t* acc_empty = acc_full + 2;             // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);       // warp-uniform as far as the compiler can tell
+    const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    auto a_raw = [&](int s) { return smem + s * S::RAW_STAGE; };
-    auto b_raw = [&](int s) { return smem + s * S::RAW_STAGE + S::A_BYTES; };
+    const int nstages = p.stages;
+    const int stage_bytes = p.stage_bytes;
+    // every role walks the raw ring with its own (stage, phase parity) pair
+    auto ring_next = [&](int& s, uint32_t& ph) {
+        if (++s == nstages) {
+            s = 0;
+            ph ^= 1u;
+        }
+    };
+    auto a_raw = [&](int s) { return smem + s * stage_bytes; };
+    auto b_raw = [&](int s) { return smem + s * stage_bytes + S::A_BYTES; };
     auto a_lo = [&](int s) { return alo_ring + s * S::A_BYTES; };
 
     if (threadIdx.x == 0) {
         tc::prefetch_tensormap(&tm_a);
         tc::prefetch_tensormap(&tm_b);
-        for (int s = 0; s < G_RS; ++s) {
+        for (int s = 0; s < G_RS_MAX; ++s) {
             tc::mbar_init(&raw_full[s], 1);
             tc::mbar_init(&raw_empty[s], 1);
             tc::mbar_init(&split_done[s], G_SPLIT_THREADS);
         }
+        for (int s = 0; s < G_LS; ++s) tc::mbar_init(&alo_empty[s], 1);
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&acc_full[s], 1);
             tc::mbar_init(&acc_empty[s], G_EPI_WARPS * 32);
         }
         tc::fence_barrier_init();
+        // SM clock vs wall clock over the kernel (debug trace only).  Keep thread-divergent code like this in front of the
+        // __syncthreads below: a divergent branch after it makes the compiler treat the role loops as non-uniform, and every
+        // UTCHMMA / UTMALDG then issues through an ELECT + R2UR waterfall (measured: all GEMMs 20 % slower).
+        if (p.trace && blockIdx.x == 0) {
+            long long gt;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+            p.trace[(3 * 256 + 200) * 4 + 0] = clock64();
+            p.trace[(3 * 256 + 200) * 4 + 1] = gt;
+        }
     }
     if (warp == 1) tc::tmem_alloc<S::TMEM_COLS>(tmem_slot);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) {      // SM clock vs wall clock over the kernel (debug trace only)
-        long long gt;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-        p.trace[(3 * 256 + 200) * 4 + 0] = clock64();
-        p.trace[(3 * 256 + 200) * 4 + 1] = gt;
-        p.trace[(3 * 256 + 201) * 4 + 0] = t_entry;
-    }
-    const uint32_t acc_stride = p.alo_tmem ? S::ACC_STRIDE_PACKED : S::ACC_COLS;
+    const uint32_t tmem_base = *tmem_slot;
+    static_assert(!(ALO && A_MN), "A_lo in tensor memory needs a K-major A operand");
+    constexpr uint32_t acc_stride = ALO ? S::ACC_STRIDE_PACKED : S::ACC_COLS;
     const uint32_t tmem_alo = tmem_base + S::ALO_COL;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer (warp converged, lane 0 issues)
-        const uint32_t issue = lane == 0;
-        uint32_t it = 0;
-        // L2 prefetch cursor: walks the same (tile, k-block) sequence p.pf_a k-blocks ahead of the loads
-        int pf_tile = blockIdx.x, pf_kb = 0;
-        TileCoord pc = tile_coord<BN>(p, min(pf_tile, p.total_tiles - 1));
-        auto prefetch_step = [&]() {
-            if (pf_tile >= p.total_tiles) return;
-            const int k0 = pc.k_begin + pf_kb * G_BK;
-            if (A_MN) {
-#pragma unroll
-                for (int i = 0; i < G_BM / 32; ++i) tma_prefetch_3d(&tm_a, pc.m0 + 32 * i, k0, pc.b, issue);
-            } else if (p.taps > 1) {
-                const int kbg = k0 / G_BK;
-                const int t = kbg / p.kb_per_tap;
-                tma_prefetch_3d(&tm_a, (kbg - t * p.kb_per_tap) * G_BK, pc.m0 + p.tap_off[t], pc.b, issue);
-            } else {
-                tma_prefetch_3d(&tm_a, k0, pc.m0, pc.b, issue);
-            }
-            if (++pf_kb == pc.num_kb) {
-                pf_kb = 0;
-                pf_tile += gridDim.x;
-                if (pf_tile < p.total_tiles) pc = tile_coord<BN>(p, pf_tile);
-            }
-        };
-        for (int i = 0; i < p.pf_a; ++i) prefetch_step();
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const TileCoord c = tile_coord<BN>(p, tile);
-            int blo_off, hi_bytes;
-            bool stacked;
-            b_layout<BN, B_MN>(p, c.bn_eff, blo_off, hi_bytes, stacked);
-            const int nblk = p.presplit ? (c.bn_eff + 31) / 32 : BN / 32;      // MN-major B: 32-column blocks to load
-            for (int kb = 0; kb < c.num_kb; ++kb, ++it) {
-                if (p.pf_a) prefetch_step();
-                const int s = it % G_RS;
-                const uint32_t ph = (it / G_RS) & 1;
-                const int k0 = c.k_begin + kb * G_BK;
-                tc::mbar_wait(&raw_empty[s], ph ^ 1);
-                if (issue) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord c = tile_coord<BN>(p, tile);
+                int blo_off, hi_bytes;
+                bool stacked;
+                b_layout<BN, B_MN>(p, c.bn_eff, blo_off, hi_bytes, stacked);
+                const int nblk = p.presplit ? (c.bn_eff + 31) / 32 : BN / 32;      // MN-major B: 32-column blocks to load
+                for (int kb = 0; kb < c.num_kb; ++kb, ++it, ring_next(s, ph)) {
+                    const int k0 = c.k_begin + kb * G_BK;
+                    tc::mbar_wait(&raw_empty[s], ph ^ 1);
                     trace_evt(p, 0, it, 0);
                     tc::mbar_expect_tx(&raw_full[s], S::A_BYTES + hi_bytes * (p.presplit ? 2 : 1));
-                }
-                __syncwarp();
-                if (A_MN) {
+                    if (A_MN) {
 #pragma unroll
-                    for (int i = 0; i < G_BM / 32; ++i) tma_load_3d(a_raw(s) + i * 4096, &tm_a, &raw_full[s], c.m0 + 32 * i, k0, c.b, issue);
-                } else if (p.taps > 1) {
-                    // K = taps * C: k-block kbg of tap t reads channels of the A rows shifted by tap_off[t]
-                    const int kbg = k0 / G_BK;
-                    const int t = kbg / p.kb_per_tap;
-                    tma_load_3d(a_raw(s), &tm_a, &raw_full[s], (kbg - t * p.kb_per_tap) * G_BK, c.m0 + p.tap_off[t], c.b, issue);
-                } else {
-                    tma_load_3d(a_raw(s), &tm_a, &raw_full[s], k0, c.m0, c.b, issue);
-                }
-                if (B_MN) {
-                    for (int i = 0; i < nblk; ++i) tma_load_3d(b_raw(s) + i * 4096, &tm_b, &raw_full[s], c.n0 + 32 * i, k0, c.b, issue);
-                    if (p.presplit)
-                        for (int i = 0; i < nblk; ++i)
-                            tma_load_3d(b_raw(s) + blo_off + i * 4096, &tm_blo, &raw_full[s], c.n0 + 32 * i, k0, c.b, issue);
-                } else {
-                    tma_load_3d(b_raw(s), &tm_b, &raw_full[s], k0, c.n0, c.b, issue);
-                    if (p.presplit) tma_load_3d(b_raw(s) + blo_off, &tm_blo, &raw_full[s], k0, c.n0, c.b, issue);
+                        for (int i = 0; i < G_BM / 32; ++i) tma_load_3d(a_raw(s) + i * 4096, &tm_a, &raw_full[s], c.m0 + 32 * i, k0, c.b);
+                    } else if (p.taps > 1) {
+                        // K = taps * C: k-block kbg of tap t reads channels of the A rows shifted by tap_off[t]
+                        const int kbg = k0 / G_BK;
+                        const int t = kbg / p.kb_per_tap;
+                        tma_load_3d(a_raw(s), &tm_a, &raw_full[s], (kbg - t * p.kb_per_tap) * G_BK, c.m0 + p.tap_off[t], c.b);
+                    } else {
+                        tma_load_3d(a_raw(s), &tm_a, &raw_full[s], k0, c.m0, c.b);
+                    }
+                    if (B_MN) {
+                        for (int i = 0; i < nblk; ++i) tma_load_3d(b_raw(s) + i * 4096, &tm_b, &raw_full[s], c.n0 + 32 * i, k0, c.b);
+                        if (p.presplit)
+                            for (int i = 0; i < nblk; ++i)
+                                tma_load_3d(b_raw(s) + blo_off + i * 4096, &tm_blo, &raw_full[s], c.n0 + 32 * i, k0, c.b);
+                    } else {
+                        tma_load_3d(b_raw(s), &tm_b, &raw_full[s], k0, c.n0, c.b);
+                        if (p.presplit) tma_load_3d(b_raw(s) + blo_off, &tm_blo, &raw_full[s], k0, c.n0, c.b);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer (warp converged, lane 0 issues)
-        const uint32_t issue = lane == 0;
-        uint32_t it = 0, t = 0;
-        TileCoord cn = tile_coord<BN>(p, min((int)blockIdx.x, p.total_tiles - 1));
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
-            const TileCoord c = cn;
-            const bool more_tiles = tile + (int)gridDim.x < p.total_tiles;
-            const uint32_t ab = t & 1;
-            const uint32_t tmem_main = tmem_base + ab * acc_stride;
-            const uint32_t tmem_corr = tmem_main + c.bn_eff;
-            // one N = 2*bn_eff MMA when B_lo sits directly behind the bn_eff valid rows / blocks of B_hi
-            int blo_off, hi_bytes;
-            bool stacked;
-            b_layout<BN, B_MN>(p, c.bn_eff, blo_off, hi_bytes, stacked);
-            const uint32_t major = (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
-            const uint32_t idesc1 = tc::umma_idesc_tf32(G_BM, c.bn_eff) | major;
-            const uint32_t idesc2 = tc::umma_idesc_tf32(G_BM, 2 * c.bn_eff) | major;
-            const bool alo_t = !A_MN && p.alo_tmem;
-            if (issue) trace_evt(p, 1, it, 3);
-            tc::mbar_wait(&acc_empty[ab], ((t >> 1) & 1) ^ 1);
-            tc::tc_fence_after();
-            for (int kb = 0; kb < c.num_kb; ++kb, ++it) {
-                const int s = it % G_RS;
-                const int ls = it % G_LS;
-                // the next tile's coordinates (integer divisions) are worked out while this tile's MMAs are still queued
-                if (kb == c.num_kb - 1 && more_tiles) cn = tile_coord<BN>(p, tile + gridDim.x);
-                if (issue) trace_evt(p, 1, it, 0);
-                tc::mbar_wait(&raw_full[s], (it / G_RS) & 1);
-                tc::mbar_wait(&split_done[s], (it / G_RS) & 1);
-                if (issue) trace_evt(p, 1, it, 1);
-                const uint8_t* blo = b_raw(s) + blo_off;
-                auto k_step = [&](int k) {
-                    const uint64_t dah = operand_desc<A_MN>(a_raw(s), k);
-                    const uint64_t dbh = operand_desc<B_MN>(b_raw(s), k);
-                    const uint32_t acc = (kb | k) != 0;
-                    if (p.dbg & 8) return;
-                    if (alo_t) {
-                        const uint32_t tal = tmem_alo + ls * G_BK + k * 8;     // A_lo rows = TMEM lanes, k = columns
-                        if (stacked) {
-                            tc::mma_tf32(tmem_main, dah, dbh, idesc2, acc, issue);
-                            if (!(p.dbg & 2)) tc::mma_tf32_ta(tmem_corr, tal, dbh, idesc1, 1, issue);
-                        } else {
-                            const uint64_t dbl = operand_desc<B_MN>(blo, k);
-                            tc::mma_tf32_ta(tmem_corr, tal, dbh, idesc1, acc, issue);
-                            tc::mma_tf32(tmem_corr, dah, dbl, idesc1, 1, issue);
-                            tc::mma_tf32(tmem_main, dah, dbh, idesc1, acc, issue);
-                        }
-                    } else {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            uint32_t it = 0, t = 0;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+                const TileCoord c = tile_coord<BN>(p, tile);
+                const uint32_t ab = t & 1;
+                const uint32_t tmem_main = tmem_base + ab * acc_stride;
+                const uint32_t tmem_corr = tmem_main + c.bn_eff;
+                // one N = 2*bn_eff MMA when B_lo sits directly behind the bn_eff valid rows / blocks of B_hi
+                int blo_off, hi_bytes;
+                bool stacked;
+                b_layout<BN, B_MN>(p, c.bn_eff, blo_off, hi_bytes, stacked);
+                const uint32_t major = (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+                const uint32_t idesc1 = tc::umma_idesc_tf32(G_BM, c.bn_eff) | major;
+                const uint32_t idesc2 = tc::umma_idesc_tf32(G_BM, 2 * c.bn_eff) | major;
+                trace_evt(p, 1, it, 3);
+                tc::mbar_wait(&acc_empty[ab], ((t >> 1) & 1) ^ 1);
+                tc::tc_fence_after();
+                for (int kb = 0; kb < c.num_kb; ++kb, ++it, ring_next(s, ph)) {
+                    const int ls = it % G_LS;
+                    tc::mbar_wait(&raw_full[s], ph);
+                    trace_evt(p, 1, it, 0);
+                    tc::mbar_wait(&split_done[s], ph);
+                    tc::tc_fence_after();
+                    trace_evt(p, 1, it, 1);
+                    const uint8_t* blo = b_raw(s) + blo_off;
+#pragma unroll
+                    for (int k = 0; k < G_BK / 8; ++k) {
+                        const uint64_t dah = operand_desc<A_MN>(a_raw(s), k);
                         const uint64_t dal = operand_desc<A_MN>(a_lo(ls), k);
-                        if (stacked) {
-                            tc::mma_tf32(tmem_main, dah, dbh, idesc2, acc, issue);      // [main | corr] += A_hi x [B_hi ; B_lo]^T
-                            tc::mma_tf32(tmem_corr, dal, dbh, idesc1, 1, issue);        // corr += A_lo x B_hi^T
+                        const uint64_t dbh = operand_desc<B_MN>(b_raw(s), k);
+                        const uint32_t acc = (kb | k) != 0;
+                        if (ALO) {
+                            const uint32_t tal = tmem_alo + ls * G_BK + k * 8;   // A_lo rows = TMEM lanes, k = columns
+                            if (stacked) {
+                                tc::mma_tf32(tmem_main, dah, dbh, idesc2, acc);
+                                tc::mma_tf32_ta(tmem_corr, tal, dbh, idesc1, 1);
+                            } else {
+                                const uint64_t dbl = operand_desc<B_MN>(blo, k);
+                                tc::mma_tf32_ta(tmem_corr, tal, dbh, idesc1, acc);
+                                tc::mma_tf32(tmem_corr, dah, dbl, idesc1, 1);
+                                tc::mma_tf32(tmem_main, dah, dbh, idesc1, acc);
+                            }
+                        } else if (stacked) {
+                            tc::mma_tf32(tmem_main, dah, dbh, idesc2, acc);      // [main | corr] += A_hi x [B_hi ; B_lo]^T
+                            tc::mma_tf32(tmem_corr, dal, dbh, idesc1, 1);        // corr += A_lo x B_hi^T
                         } else {
                             const uint64_t dbl = operand_desc<B_MN>(blo, k);
-                            tc::mma_tf32(tmem_corr, dal, dbh, idesc1, acc, issue);
-                            tc::mma_tf32(tmem_corr, dah, dbl, idesc1, 1, issue);
-                            tc::mma_tf32(tmem_main, dah, dbh, idesc1, acc, issue);
+                            tc::mma_tf32(tmem_corr, dal, dbh, idesc1, acc);
+                            tc::mma_tf32(tmem_corr, dah, dbl, idesc1, 1);
+                            tc::mma_tf32(tmem_main, dah, dbh, idesc1, acc);
                         }
                     }
-                };
-                tc::tc_fence_after();
-#pragma unroll
-                for (int k = 0; k < G_BK / 8; ++k) k_step(k);
-                tc::tc_commit(&raw_empty[s], issue);   // arrives once the MMAs above have read their operands (raw stage and A_lo stage)
-                if (issue) trace_evt(p, 1, it, 2);
+                    tc::tc_commit(&raw_empty[s]);          // both arrive once the MMAs above have read their operands
+                    tc::tc_commit(&alo_empty[ls]);
+                    trace_evt(p, 1, it, 2);
+                }
+                tc::tc_commit(&acc_full[ab]);
             }
-            tc::tc_commit(&acc_full[ab], issue);
         }
     } else if (warp < G_EPI_WARP0) {
         // ------------------------------------------------------------------ hi / lo split (warps 2..9)
         const int tid = threadIdx.x - 64;
         uint32_t it = 0;
+        int s = 0;
+        uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const TileCoord c = tile_coord<BN>(p, tile);
             int blo_off, hi_bytes;
             bool stacked;
             b_layout<BN, B_MN>(p, c.bn_eff, blo_off, hi_bytes, stacked);
-            for (int kb = 0; kb < c.num_kb; ++kb, ++it) {
-                const int s = it % G_RS;
+            for (int kb = 0; kb < c.num_kb; ++kb, ++it, ring_next(s, ph)) {
                 const int ls = it % G_LS;
                 if (tid == 0) trace_evt(p, 2, it, 0);
-                tc::mbar_wait(&raw_full[s], (it / G_RS) & 1);
+                tc::mbar_wait(&raw_full[s], ph);
                 if (tid == 0) trace_evt(p, 2, it, 1);
-                // A_lo stage ls was last read by the MMAs of k-block it - 2, whose completion is the commit on that k-block's
-                // raw_empty barrier (its next phase cannot complete before this k-block has been split)
-                if (it >= G_LS) tc::mbar_wait(&raw_empty[(it - G_LS) % G_RS], ((it - G_LS) / G_RS) & 1);
+                tc::mbar_wait(&alo_empty[ls], ((it / G_LS) & 1) ^ 1);
                 if (tid == 0) trace_evt(p, 2, it, 2);
-                if (p.dbg & 4) {
-                    tc::mbar_arrive(&split_done[s]);
-                    continue;
-                }
-                if (!A_MN && p.alo_tmem) {
+                if (ALO) {
                     // thread = one row of the tile (TMEM lane 32 * (warp % 4) + lane), 16 of the 32 k columns: four 16-byte chunks
                     // of the 128-byte-swizzled row (chunk j of row r sits at position j ^ (r & 7))
                     tc::tc_fence_after();
@@ -487,28 +452,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 #pragma unroll 1
                 for (int c0 = half * 16; c0 < c.bn_eff; c0 += 32) {
                     uint32_t vr[16], wr[16];
-                    const int ncol = nvalid - c0;              // columns of this group that exist (warp-uniform)
-                    if (p.dbg & 1) {
-                        if (c0 + 32 >= c.bn_eff) {
-                            tc::tc_fence_before();
-                            tc::mbar_arrive(&acc_empty[ab]);
-                        }
-                        continue;
-                    }
-                    if (ncol > 8) {
-                        tc::tmem_ld16_nowait(tbase + c0, vr);
-                        tc::tmem_ld16_nowait(tbase + c.bn_eff + c0, wr);
-                    } else {                                   // ragged last group (e.g. 100 queries = 6 x 16 + 4)
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) vr[i] = wr[i] = 0u;
-                        if (ncol > 4) {
-                            tc::tmem_ld8_nowait(tbase + c0, vr);
-                            tc::tmem_ld8_nowait(tbase + c.bn_eff + c0, wr);
-                        } else if (ncol > 0) {
-                            tc::tmem_ld4_nowait(tbase + c0, vr);
-                            tc::tmem_ld4_nowait(tbase + c.bn_eff + c0, wr);
-                        }
-                    }
+                    tc::tmem_ld16_nowait(tbase + c0, vr);
+                    tc::tmem_ld16_nowait(tbase + c.bn_eff + c0, wr);
                     tc::tmem_ld_wait();
                     if (c0 + 32 >= c.bn_eff) {                 // last read of this accumulator: hand it back to the MMA warp
                         tc::tc_fence_before();
@@ -670,31 +615,41 @@ static int make_operand_map(CUtensorMap* map, const float* base, bool mn_major, 
 }
 
 static long long* g_trace_ptr = nullptr;
-static int g_pf_a = 4;                        // pdb_debug_set_gemm_prefetch
-static int g_dbg = 0;
+static int g_deep_ring = 1;                   // pdb_debug_set_gemm_alo_tmem(2) keeps A_lo in TMEM but the 3-stage ring
 static int g_alo_tmem = 1;                    // pdb_debug_set_gemm_alo_tmem(0) forces A_lo through shared memory
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbl, const GemmParams& p, cudaStream_t st) {
+template <int BN, bool A_MN, bool B_MN, bool ALO>
+static int launch_gemm_alo(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbl, const GemmParams& p, cudaStream_t st) {
     using S = GemmSmem<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, A_MN, B_MN, ALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return fail(PDB_ERR_LAUNCH, "gemm_tf32x3: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
     GemmParams q = p;
     q.trace = g_trace_ptr;
-    // A_lo in tensor memory: K-major A only (the split warps own whole rows), and the accumulators must leave 64 columns
-    q.pf_a = g_pf_a;
-    q.dbg = g_dbg;
-    q.alo_tmem = (g_alo_tmem && !A_MN && (BN < 128 || p.N <= 112)) ? 1 : 0;
+    // Ring depth.  The general kernel fits 3 stages next to the A_lo ring and the epilogue staging tiles.  With A_lo in tensor
+    // memory and a transposed store (the mask einsum) neither is used, and a stage shrinks to A + 2 x 112 B rows: 5 stages, which
+    // is what it takes to keep the HBM stream of A in flight (TMA latency under load is 2 000 - 3 000 clk, a k-block ~700 clk).
+    const bool deep = ALO && !B_MN && BN == 128 && p.c_trans && g_deep_ring;      // (MN-major B blocks are 4 KB apart: 32 KB per stage)
+    q.stages = deep ? S::DEEP_STAGES : G_RS;
+    q.stage_bytes = deep ? S::DEEP_STAGE : S::RAW_STAGE;
     q.mt = (p.M + G_BM - 1) / G_BM;
     q.nt = (p.N + BN - 1) / BN;
     q.total_tiles = q.mt * q.nt * p.batch * p.ksplit;
     const unsigned grid = (unsigned)std::min(q.total_tiles, kNumSMs);        // persistent: one CTA per SM
-    gemm_tf32x3_kernel<BN, A_MN, B_MN><<<grid, G_THREADS, S::TOTAL, st>>>(ta, tb, tbl, q);
+    gemm_tf32x3_kernel<BN, A_MN, B_MN, ALO><<<grid, G_THREADS, S::TOTAL, st>>>(ta, tb, tbl, q);
     return launched("gemm_tf32x3");
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbl, const GemmParams& p, cudaStream_t st) {
+    // A_lo in tensor memory: K-major A only (the split warps own whole rows), and the accumulators must leave 64 columns
+    if constexpr (!A_MN) {
+        if (g_alo_tmem && (BN < 128 || p.N <= 112)) return launch_gemm_alo<BN, A_MN, B_MN, true>(ta, tb, tbl, p, st);
+    }
+    return launch_gemm_alo<BN, A_MN, B_MN, false>(ta, tb, tbl, p, st);
 }
 
 template <int BN>
@@ -791,18 +746,9 @@ extern "C" int pdb_split_lo(const float* x, float* lo, int64_t n, void* stream) 
     return launched("split_lo");
 }
 
-extern "C" PDB_API int pdb_debug_set_gemm_prefetch(int pf_a) {
-    g_pf_a = pf_a;
-    return PDB_OK;
-}
-
-extern "C" PDB_API int pdb_debug_set_gemm_dbg(int flags) {
-    g_dbg = flags;
-    return PDB_OK;
-}
-
 extern "C" PDB_API int pdb_debug_set_gemm_alo_tmem(int on) {
-    g_alo_tmem = on;
+    g_alo_tmem = on != 0;
+    g_deep_ring = on != 2;
     return PDB_OK;
 }
 

@@ -61,33 +61,24 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {           // whol
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // arrives (count 1) on the mbarrier once all previously issued tcgen05.mma of this thread have completed
-// (issued by the lanes whose `issue` is non-zero: see the note at tma_load_3d in gemm_tc.cu)
-__device__ __forceinline__ void tc_commit(uint64_t* bar, uint32_t issue) {
-    asm volatile(
-        "{\n\t.reg .pred q;\n\t"
-        "setp.ne.b32 q, %1, 0;\n\t"
-        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-        ::"r"(smem_u32(bar)), "r"(issue) : "memory");
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], kind::tf32 (fp32 containers, top 19 bits used), fp32 accumulate
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
-                                         uint32_t issue) {
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p, q;\n\t"
+        "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "setp.ne.b32 q, %5, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue) : "memory");
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // same with the A operand in tensor memory: 128 lanes (rows) x 8 consecutive 32-bit columns (k) at a_tmem
-__device__ __forceinline__ void mma_tf32_ta(uint32_t tmem_d, uint32_t a_tmem, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
-                                            uint32_t issue) {
+__device__ __forceinline__ void mma_tf32_ta(uint32_t tmem_d, uint32_t a_tmem, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p, q;\n\t"
+        "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "setp.ne.b32 q, %5, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "r"(a_tmem), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue) : "memory");
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_tmem), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // 16 registers per thread -> 32 lanes x 16 consecutive 32-bit columns (thread t of the warp <-> lane base + t)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
@@ -118,16 +109,6 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
-}
-// narrower variants for ragged column groups (tensor-memory reads are a shared, slow resource: 64 B/clk)
-__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, uint32_t* r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

@@ -1,5 +1,5 @@
 """tcgen05 GEMM at the mask-einsum and step shapes with A_lo in shared memory vs tensor memory
-(pdb_debug_set_gemm_alo_tmem), plus the CTA-0 timeline of the einsum forward.  Usage: python tools/sweep_gemm.py [--trace]"""
+(pdb_debug_set_gemm_alo_tmem: 0 = shared memory, 2 = TMEM with the 3-stage ring, 1 = TMEM with the deep ring), plus the CTA-0 timeline of the einsum forward.  Usage: python tools/sweep_gemm.py [--trace]"""
 import ctypes
 import os
 import sys
@@ -7,14 +7,47 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from test_gemm import gemm, split_lo, timeit  # noqa: E402
+from test_gemm import gemm as gemm_new, split_lo, timeit  # noqa: E402
 from partdistillation_b200 import _lib  # noqa: E402
 
 lib = _lib.load()
 lib.pdb_debug_set_trace.argtypes = [ctypes.c_void_p]
-lib.pdb_debug_set_gemm_alo_tmem.argtypes = [ctypes.c_int]
-lib.pdb_debug_set_gemm_prefetch.argtypes = [ctypes.c_int]
-lib.pdb_debug_set_gemm_dbg.argtypes = [ctypes.c_int]
+if hasattr(lib, "pdb_debug_set_gemm_alo_tmem"):
+    lib.pdb_debug_set_gemm_alo_tmem.argtypes = [ctypes.c_int]
+else:
+    lib.pdb_debug_set_gemm_alo_tmem = lambda v: 0
+HAS_PF = hasattr(lib, "pdb_debug_set_gemm_prefetch")       # experiment knobs: only in experimental builds of the library
+HAS_DBG = hasattr(lib, "pdb_debug_set_gemm_dbg")
+if HAS_PF:
+    lib.pdb_debug_set_gemm_prefetch.argtypes = [ctypes.c_int]
+if HAS_DBG:
+    lib.pdb_debug_set_gemm_dbg.argtypes = [ctypes.c_int]
+
+
+def set_pf(v):
+    if HAS_PF:
+        lib.pdb_debug_set_gemm_prefetch(v)
+
+
+_OLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpdb200_old.so")
+old_lib = None
+if os.path.exists(_OLD):          # optional A/B partner: an earlier build of the library (same C ABI), timed on the same GPU
+    old_lib = ctypes.CDLL(_OLD)
+    old_lib.pdb_gemm_tf32x3.restype, old_lib.pdb_gemm_tf32x3.argtypes = _lib.SIGNATURES["pdb_gemm_tf32x3"]
+USE_OLD = False
+
+
+def gemm(A, B, M, N, K, batch=1, a_mn=0, b_mn=0, c_trans=0, bias=None, relu=0, accumulate=0, ksplit=1, out=None, B_lo=None):
+    if not USE_OLD:
+        return gemm_new(A, B, M, N, K, batch, a_mn, b_mn, c_trans, bias, relu, accumulate, ksplit, out, B_lo)
+    lda, ldb = A.stride(-2), B.stride(-2)
+    sa = A.stride(0) if batch > 1 else 0
+    sb = B.stride(0) if batch > 1 else 0
+    rc = old_lib.pdb_gemm_tf32x3(A.data_ptr(), B.data_ptr(), B_lo.data_ptr() if B_lo is not None else None, out.data_ptr(),
+                                 bias.data_ptr() if bias is not None else None, M, N, K, batch, lda, ldb, out.stride(-2), sa, sb,
+                                 out.stride(0), a_mn, b_mn, c_trans, relu, accumulate, ksplit, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    return out
 
 
 def cases():
@@ -40,7 +73,7 @@ def cases():
 
 def trace_einsum(pf, alo=1):
     lib.pdb_debug_set_gemm_alo_tmem(alo)
-    lib.pdb_debug_set_gemm_prefetch(pf)
+    set_pf(pf)
     e = torch.randn(2, 100, 256, device="cuda"); f = torch.randn(2, 65536, 256, device="cuda")
     o = torch.empty(2, 100, 65536, device="cuda"); el = split_lo(e)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -59,7 +92,6 @@ def trace_einsum(pf, alo=1):
     ck = t[3, 200]
     dclk, dns = int(ck[2] - ck[0]), int(ck[3] - ck[1])
     print(f"=== einsum fwd, A_lo in TMEM {alo}, L2 prefetch {pf}: kernel body {dclk} clk in {dns} ns -> SM clock {dclk / max(dns, 1) * 1e3:.0f} MHz")
-    print(f"    kernel entry -> barriers / TMEM ready: {int(ck[0] - t[3, 201, 0])} clk")
     print(f"=== einsum fwd, it | TMA issue | split: start raw_full alo_empty done | MMA: start ready issued | (clk since first TMA)")
     for it in range(56):
         print(f"{it:3d} | {r(t[0,it,0]):6d} | {r(t[2,it,0]):6d} {r(t[2,it,1]):6d} {r(t[2,it,2]):6d} {r(t[2,it,3]):6d} | {r(t[1,it,0]):6d} {r(t[1,it,1]):6d} {r(t[1,it,2]):6d}  accwait@{r(t[1,it,3])}")
@@ -72,7 +104,7 @@ def check_einsum():
     e = torch.randn(2, 100, 256, device="cuda"); f = torch.randn(2, 65536, 256, device="cuda")
     el = split_lo(e)
     ref = torch.einsum("bqc,bpc->bqp", e.double(), f.double())
-    for alo in (0, 1):
+    for alo in (0, 2, 1):
         lib.pdb_debug_set_gemm_alo_tmem(alo)
         for lo in (None, el):
             o = gemm(f, e, 65536, 100, 256, batch=2, c_trans=1, B_lo=lo)
@@ -88,7 +120,7 @@ def batched_einsum():
     fs = [torch.randn(2, 65536, 256, device="cuda") for _ in range(4)]
     os_ = [torch.empty(2, 100, 65536, device="cuda") for _ in range(4)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    for alo in (0, 1):
+    for alo in (0, 2, 1):
         lib.pdb_debug_set_gemm_alo_tmem(alo)
         ts = []
         for rep in range(12):
@@ -122,22 +154,32 @@ def ablate_einsum():
 
 def main():
     check_einsum()
-    ablate_einsum()
+    if HAS_DBG:
+        ablate_einsum()
     batched_einsum()
+    global USE_OLD
     for name, nbytes, run in cases():
         row = []
-        for alo in (0, 1):
+        if old_lib is not None:
+            for rep in range(2):           # old / new interleaved twice: order effects show up as differing repeats
+                USE_OLD = True
+                t = timeit(run, iters=15)
+                USE_OLD = False
+                row.append(f"old lib: {t * 1e6:6.1f}")
+                t = timeit(run, iters=15)
+                row.append(f"new lib: {t * 1e6:6.1f}")
+        for alo in (0, 2, 1):
             lib.pdb_debug_set_gemm_alo_tmem(alo)
-            for pf in (0, 4):
-                lib.pdb_debug_set_gemm_prefetch(pf)
+            for pf in ((0, 2, 4) if HAS_PF else (0,)):
+                set_pf(pf)
                 t = timeit(run, iters=15)
                 row.append(f"alo{alo} pf{pf}: {t * 1e6:6.1f}")
-        lib.pdb_debug_set_gemm_prefetch(4)
+        set_pf(4)
         print(f"{name:52s} {' | '.join(row)}", flush=True)
     if "--trace" in sys.argv:
         trace_einsum(0, 1)
         trace_einsum(6, 1)
-    lib.pdb_debug_set_gemm_prefetch(4)
+    set_pf(4)
     lib.pdb_debug_set_gemm_alo_tmem(1)
 
 
