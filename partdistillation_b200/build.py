@@ -12,6 +12,8 @@ LIB = os.path.join(CSRC, "libpdb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+if os.environ.get("PDB_GEMM_TRACE"):     # debug timeline of the tcgen05 GEMM (tools/sweep_gemm.py --trace); off in product builds
+    FLAGS.append("-DPDB_GEMM_TRACE")
 
 
 def sources():

@@ -117,8 +117,13 @@ __device__ __forceinline__ void split4(const float4 x, float4& h, float4& l) {
     h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
 }
 
+// Debug timeline (tools/sweep_gemm.py --trace): compiled in only with -DPDB_GEMM_TRACE (PDB_GEMM_TRACE=1 python -m
+// partdistillation_b200.build --force).  Even the `p.trace != NULL` test costs: the single thread that issues the MMAs runs
+// latency-bound scalar code between two tcgen05.mma, and every instruction there shows up in the k-block cadence.
 __device__ __forceinline__ void trace_evt(const GemmParams& p, int role, int idx, int slot) {
+#ifdef PDB_GEMM_TRACE
     if (p.trace && blockIdx.x == 0 && idx < 256) p.trace[(role * 256 + idx) * 4 + slot] = clock64();
+#endif
 }
 
 // Writes lo = x - trunc_tf32(x) for NV float4 per thread of a tile.  The raw tile itself serves as the hi operand:
@@ -232,12 +237,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         // SM clock vs wall clock over the kernel (debug trace only).  Keep thread-divergent code like this in front of the
         // __syncthreads below: a divergent branch after it makes the compiler treat the role loops as non-uniform, and every
         // UTCHMMA / UTMALDG then issues through an ELECT + R2UR waterfall (measured: all GEMMs 20 % slower).
+#ifdef PDB_GEMM_TRACE
         if (p.trace && blockIdx.x == 0) {
             long long gt;
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
             p.trace[(3 * 256 + 200) * 4 + 0] = clock64();
             p.trace[(3 * 256 + 200) * 4 + 1] = gt;
         }
+#endif
     }
     if (warp == 1) tc::tmem_alloc<S::TMEM_COLS>(tmem_slot);
     tc::tc_fence_before();
@@ -563,12 +570,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     }
     tc::tc_fence_before();
     __syncthreads();
+#ifdef PDB_GEMM_TRACE
     if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) {
         long long gt;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
         p.trace[(3 * 256 + 200) * 4 + 2] = clock64();
         p.trace[(3 * 256 + 200) * 4 + 3] = gt;
     }
+#endif
     if (warp == 1) tc::tmem_dealloc<S::TMEM_COLS>(tmem_base);
 }
 

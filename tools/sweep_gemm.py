@@ -1,5 +1,5 @@
 """tcgen05 GEMM at the mask-einsum and step shapes with A_lo in shared memory vs tensor memory
-(pdb_debug_set_gemm_alo_tmem: 0 = shared memory, 2 = TMEM with the 3-stage ring, 1 = TMEM with the deep ring), plus the CTA-0 timeline of the einsum forward.  Usage: python tools/sweep_gemm.py [--trace]"""
+(pdb_debug_set_gemm_alo_tmem: 0 = shared memory, 2 = TMEM with the 3-stage ring, 1 = TMEM with the deep ring), plus the CTA-0 timeline of the einsum forward.  Usage: python tools/sweep_gemm.py [--trace]  (--trace needs a library built with PDB_GEMM_TRACE=1; an optional tools/libpdb200_old.so is timed next to the current build)"""
 import ctypes
 import os
 import sys
@@ -16,6 +16,9 @@ if hasattr(lib, "pdb_debug_set_gemm_alo_tmem"):
     lib.pdb_debug_set_gemm_alo_tmem.argtypes = [ctypes.c_int]
 else:
     lib.pdb_debug_set_gemm_alo_tmem = lambda v: 0
+HAS_LA = hasattr(lib, "pdb_debug_set_gemm_lookahead")
+if HAS_LA:
+    lib.pdb_debug_set_gemm_lookahead.argtypes = [ctypes.c_int]
 HAS_PF = hasattr(lib, "pdb_debug_set_gemm_prefetch")       # experiment knobs: only in experimental builds of the library
 HAS_DBG = hasattr(lib, "pdb_debug_set_gemm_dbg")
 if HAS_PF:
@@ -168,12 +171,13 @@ def main():
                 row.append(f"old lib: {t * 1e6:6.1f}")
                 t = timeit(run, iters=15)
                 row.append(f"new lib: {t * 1e6:6.1f}")
-        for alo in (0, 2, 1):
+        for alo in (0, 1):
             lib.pdb_debug_set_gemm_alo_tmem(alo)
-            for pf in ((0, 2, 4) if HAS_PF else (0,)):
-                set_pf(pf)
+            for la in ((0, 1) if HAS_LA else (0,)):
+                if HAS_LA:
+                    lib.pdb_debug_set_gemm_lookahead(la)
                 t = timeit(run, iters=15)
-                row.append(f"alo{alo} pf{pf}: {t * 1e6:6.1f}")
+                row.append(f"alo{alo} la{la}: {t * 1e6:6.1f}")
         set_pf(4)
         print(f"{name:52s} {' | '.join(row)}", flush=True)
     if "--trace" in sys.argv:
