@@ -77,7 +77,7 @@ struct GemmSmem {
     static constexpr int DEEP_STAGES = 5;
     static constexpr int BAR_OFF = (BN == 128 && DEEP_STAGES * DEEP_STAGE > RAW_TOTAL + ALO_TOTAL + STAGING)
                                        ? DEEP_STAGES * DEEP_STAGE : RAW_TOTAL + ALO_TOTAL + STAGING;
-    static constexpr int TOTAL = BAR_OFF + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int TOTAL = BAR_OFF + 1024 /*align slack*/ + 512 /*barriers, tile-coordinate ring*/;
     static constexpr int ACC_COLS = 2 * BN;               // main (hi*hi) | correction (lo*hi + hi*lo)
     // double-buffered accumulators + (ALO kernels) a 2-deep ring of 32-column A_lo k-blocks.  BN = 128 has all 512 columns
     // taken by the accumulators unless every tile needs at most 112 columns (N <= 112, e.g. the 100-query mask einsum):
@@ -203,6 +203,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     uint64_t* acc_full = alo_empty + G_LS;          // [2]
     uint64_t* acc_empty = acc_full + 2;             // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    // tile coordinates handed from the producer to the MMA thread (which would otherwise spend ~700 clk of dependent integer
+    // divisions between two tiles with the tensor pipe drained): entry t & 7 belongs to this CTA's t-th tile; the producer is at
+    // most G_RS_MAX k-blocks, hence tiles, ahead of the MMA thread
+    TileCoord* coord_ring = reinterpret_cast<TileCoord*>(smem + S::BAR_OFF + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -258,11 +262,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t it = 0, t = 0;
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
                 const TileCoord c = tile_coord<BN>(p, tile);
+                coord_ring[t & 7] = c;          // published by the release of this tile's first mbarrier.arrive.expect_tx
                 int blo_off, hi_bytes;
                 bool stacked;
                 b_layout<BN, B_MN>(p, c.bn_eff, blo_off, hi_bytes, stacked);
@@ -302,7 +307,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             int s = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
-                const TileCoord c = tile_coord<BN>(p, tile);
+                tc::mbar_wait(&raw_full[s], ph);          // first k-block of the tile landed => its coordinates are visible
+                const TileCoord c = coord_ring[t & 7];
                 const uint32_t ab = t & 1;
                 const uint32_t tmem_main = tmem_base + ab * acc_stride;
                 const uint32_t tmem_corr = tmem_main + c.bn_eff;
@@ -351,8 +357,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                             tc::mma_tf32(tmem_main, dah, dbh, idesc1, acc);
                         }
                     }
-                    tc::tc_commit(&raw_empty[s]);          // both arrive once the MMAs above have read their operands
-                    tc::tc_commit(&alo_empty[ls]);
+                    tc::tc_commit(&raw_empty[s]);          // arrives once the MMAs above have read their operands (raw stage and A_lo stage)
                     trace_evt(p, 1, it, 2);
                 }
                 tc::tc_commit(&acc_full[ab]);
@@ -362,8 +367,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         // ------------------------------------------------------------------ hi / lo split (warps 2..9)
         const int tid = threadIdx.x - 64;
         uint32_t it = 0;
-        int s = 0;
-        uint32_t ph = 0;
+        int s = 0, s2 = 0;              // s2 / ph2: stage and parity of k-block it - G_LS
+        uint32_t ph = 0, ph2 = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const TileCoord c = tile_coord<BN>(p, tile);
             int blo_off, hi_bytes;
@@ -374,7 +379,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 if (tid == 0) trace_evt(p, 2, it, 0);
                 tc::mbar_wait(&raw_full[s], ph);
                 if (tid == 0) trace_evt(p, 2, it, 1);
-                tc::mbar_wait(&alo_empty[ls], ((it / G_LS) & 1) ^ 1);
+                // A_lo stage ls was last read by the MMAs of k-block it - G_LS; their completion is that k-block's commit on its
+                // raw_empty barrier (whose next phase cannot complete before this k-block has been split): no second commit per
+                // k-block in the issuing thread
+                if (it >= G_LS) {
+                    tc::mbar_wait(&raw_empty[s2], ph2);
+                    ring_next(s2, ph2);
+                }
                 if (tid == 0) trace_evt(p, 2, it, 2);
                 if (ALO) {
                     // thread = one row of the tile (TMEM lane 32 * (warp % 4) + lane), 16 of the 32 k columns: four 16-byte chunks
