@@ -91,6 +91,7 @@ PDB_API int pdb_mask_einsum_backward(const float* embed, const float* feat, cons
  *   c_trans = 0: C[b*sc + m*ldc + n]                          c_trans = 1: C[b*sc + n*ldc + m]
  *   accumulate != 0: C += (red.add; C must be initialised); ksplit > 1 (split-K) requires accumulate.
  * A, B 16-byte aligned; lda, ldb, sa, sb multiples of 4 floats.  bias may be NULL.
+ * relu: epilogue activation after the bias: 0 none, 1 ReLU, 2 GELU (erf form, as nn.GELU()).
  * B_lo: NULL, or the low parts of B (same layout as B) from pdb_split_lo — worthwhile when B is a weight matrix
  * shared by many row tiles (every 128-row tile would otherwise re-split it).
  * nn.Linear:  y = x W^T + b      -> A = x (K-major), B = W (K-major), bias, relu optional

@@ -110,6 +110,13 @@ __device__ __forceinline__ uint64_t operand_desc(const void* tile, int k8) {
     return MN ? umma_desc_mn_sw128(tile, k8 * 1024, 4096u, 512u) : tc::umma_desc_k_sw128(tile, k8 * 32);
 }
 
+// epilogue activation: 1 = ReLU, 2 = GELU (erf form, the association of ATen's GeluCUDAKernelImpl: x * 0.5 * (1 + erf(x / sqrt 2)))
+__device__ __forceinline__ float epi_act(float x, int mode) {
+    if (mode == 1) return fmaxf(x, 0.f);
+    if (mode == 2) return x * 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+    return x;
+}
+
 __device__ __forceinline__ void split4(const float4 x, float4& h, float4& l) {
     h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
     h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
@@ -482,8 +489,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                     for (int i = 0; i < 16; ++i) {
                         float x = __uint_as_float(vr[i]) + __uint_as_float(wr[i]);
                         if (p.bias) x += __ldg(p.bias + min(c.n0 + c0 + i, p.N - 1));
-                        if (p.relu) x = fmaxf(x, 0.f);
-                        v[i] = x;
+                        v[i] = epi_act(x, p.relu);
                     }
                     if (m_ok) {
                         const int lim = nvalid - c0;           // columns of this group that exist
@@ -551,7 +557,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                             const int r = i * 4 + sub_r;
                             float4 x = *reinterpret_cast<const float4*>(tile_s + r * 36 + sub_c);
                             x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
-                            if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                            if (p.relu) { x.x = epi_act(x.x, p.relu); x.y = epi_act(x.y, p.relu); x.z = epi_act(x.z, p.relu); x.w = epi_act(x.w, p.relu); }
                             if (n_ok && mrow0 + r < p.M) {
                                 if (p.atomic) red_add_v4(dst, x.x, x.y, x.z, x.w);
                                 else *reinterpret_cast<float4*>(dst) = x;
@@ -567,7 +573,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                         for (int r = 0; r < 32; ++r) {
                             if (mrow0 + r < p.M && n_ok) {
                                 float x = tile_s[r * 36 + lane] + bv;
-                                if (p.relu) x = fmaxf(x, 0.f);
+                                x = epi_act(x, p.relu);
                                 if (p.atomic) atomicAdd(dst, x); else *dst = x;
                             }
                             dst += p.ldc;

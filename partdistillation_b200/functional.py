@@ -487,9 +487,9 @@ class LinearFunction(Function):
         if M > 0:
             gemm_tf32x3(x2, weight, out, M, N, K, lda=K, ldb=K, ldc=N, bias=bias, relu=relu, B_lo=w_lo)
         ctx.w_lo = w_lo
-        ctx.relu = relu
+        ctx.relu = int(relu)            # epilogue activation: 0 none, 1 ReLU, 2 GELU (forward-only: see linear())
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(x2, weight, out if relu else None)
+        ctx.save_for_backward(x2, weight, out if ctx.relu == 1 else None)
         return out.view(*x.shape[:-1], N)
 
     @staticmethod
@@ -499,8 +499,10 @@ class LinearFunction(Function):
         N, K = weight.shape
         M = x2.shape[0]
         gy2 = _c(gy).view(M, N)
+        if ctx.relu == 2:
+            raise RuntimeError("LinearFunction: the fused GELU epilogue is forward-only")
         if ctx.relu:
-            gy2 = gy2 * (out > 0)
+            gy2 = torch.ops.aten.threshold_backward(gy2, out, 0.0)      # gy * (out > 0) in one pass
         if gy2.data_ptr() % 16:
             gy2 = gy2.clone()
         gx = gw = gb = None
@@ -665,13 +667,22 @@ def conv3x3(x, weight, bias=None):
     return Conv3x3Function.apply(x, weight, bias)
 
 
-def linear(x, weight, bias=None, relu=False):
+def linear(x, weight, bias=None, relu=False, gelu=False):
     """nn.Linear (optionally fused ReLU) on the tensor cores for fp32 CUDA tensors whose feature sizes are
     multiples of 4; other dtypes (autocast halves, the fp64 classifier) and tiny ragged heads go through
-    the library GEMM."""
+    the library GEMM.  gelu=True applies nn.GELU() (erf form); it is folded into the GEMM epilogue when nothing
+    on the path needs a gradient (the frozen backbone), otherwise it runs as a separate differentiable op."""
     if linear_supported(x, weight):
+        if gelu:
+            needs_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or
+                                                      (bias is not None and bias.requires_grad))
+            if needs_grad:
+                return torch.nn.functional.gelu(LinearFunction.apply(x, weight, bias, False))
+            return LinearFunction.apply(x, weight, bias, 2)
         return LinearFunction.apply(x, weight, bias, relu)
     y = torch.nn.functional.linear(x, weight.to(x.dtype), None if bias is None else bias.to(x.dtype))
+    if gelu:
+        return torch.nn.functional.gelu(y)
     return torch.relu(y) if relu else y
 
 

@@ -22,9 +22,19 @@ class DropPath(nn.Module):
     def forward(self, x):
         if self.p == 0.0 or not self.training:
             return x
+        return x * self.sample_scale(x)
+
+    def sample_scale(self, x):
+        """The per-sample keep / (1 - p) factors (one bernoulli draw per sample, as timm's drop_path)."""
         keep = 1.0 - self.p
         mask = x.new_empty((x.shape[0],) + (1,) * (x.dim() - 1)).bernoulli_(keep)
-        return x * mask.div_(keep)
+        return mask.div_(keep)
+
+    def add_to(self, residual, x):
+        """residual + drop_path(x) in one pass (addcmul) instead of a scale pass and an add pass."""
+        if self.p == 0.0 or not self.training:
+            return residual + x
+        return torch.addcmul(residual, x, self.sample_scale(x))
 
 
 def _trunc_normal_(t, std=0.02):
@@ -40,7 +50,10 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
-        h = self.act(PF.linear(x, self.fc1.weight, self.fc1.bias))
+        if isinstance(self.act, nn.GELU) and getattr(self.act, "approximate", "none") == "none":
+            h = PF.linear(x, self.fc1.weight, self.fc1.bias, gelu=True)       # GELU in the GEMM epilogue when frozen
+        else:
+            h = self.act(PF.linear(x, self.fc1.weight, self.fc1.bias))
         return self.drop(PF.linear(self.drop(h), self.fc2.weight, self.fc2.bias))
 
 
@@ -131,7 +144,7 @@ class SwinTransformerBlock(nn.Module):
             # residual add fused into norm2: one pass writes both the new residual stream and its normalised copy
             h, x = PF.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps,
                                  residual=self.drop_path(self._fused_attention(x, H, W)), return_sum=True)
-            return x + self.drop_path(self.mlp(h))
+            return self._add_drop_path(x, self.mlp(h))
         h = self.norm1(x).view(B, H, W, C)
         pr, pb = (ws - W % ws) % ws, (ws - H % ws) % ws
         h = F.pad(h, (0, 0, 0, pr, 0, pb))
@@ -145,8 +158,12 @@ class SwinTransformerBlock(nn.Module):
         if self.shift_size > 0:
             h = torch.roll(h, shifts=(self.shift_size, self.shift_size), dims=(1, 2))
         h = h[:, :H, :W, :].reshape(B, H * W, C)
-        x = x + self.drop_path(h)
-        return x + self.drop_path(self.mlp(self.norm2(x)))
+        x = self._add_drop_path(x, h)
+        return self._add_drop_path(x, self.mlp(self.norm2(x)))
+
+    def _add_drop_path(self, residual, x):
+        dp = self.drop_path
+        return dp.add_to(residual, x) if isinstance(dp, DropPath) else residual + dp(x)
 
 
 class PatchMerging(nn.Module):

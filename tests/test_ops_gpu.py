@@ -231,6 +231,30 @@ def test_linear_forward_backward(fn, rows, K, N, relu):
     assert _rel(gb.double(), rb.double()) < 1e-5
 
 
+@pytest.mark.parametrize("rows,K,N", [((2, 4096), 128, 512), ((300,), 512, 2048), ((5, 7), 64, 36)])
+def test_linear_gelu_epilogue(fn, rows, K, N):
+    """nn.GELU() folded into the GEMM epilogue (frozen Swin MLP, swin.py:52-66) against float64, and the differentiable
+    route (separate gelu) when a gradient is needed."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(*rows, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    ref = F.gelu(F.linear(x.double(), w.double(), b.double()))
+    with torch.no_grad():
+        y = fn.linear(x, w, b, gelu=True)
+    assert _rel(y.double(), ref) < 1e-5
+    # same association as ATen's kernel on the same fp32 pre-activation: identical up to the last bit or two
+    with torch.no_grad():
+        pre = fn.linear(x, w, b)
+    assert (y - F.gelu(pre)).abs().max() <= 2e-7 * max(1.0, float(pre.abs().max()))
+    xg = x.clone().requires_grad_()
+    yg = fn.linear(xg, w, b, gelu=True)
+    gx, = torch.autograd.grad(yg, xg, torch.ones_like(yg))
+    xr = x.double().requires_grad_()
+    rx, = torch.autograd.grad(F.gelu(F.linear(xr, w.double(), b.double())), xr, torch.ones_like(ref))
+    assert _rel(gx.double(), rx) < 1e-5
+
+
 @pytest.mark.parametrize("channels_last", [False, True])
 def test_conv1x1(fn, channels_last):
     """1x1 convolution as a tensor-core GEMM over pixels (NCHW input read in place as an MN-major operand) vs
