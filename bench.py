@@ -215,7 +215,7 @@ def kernel_rooflines(device):
     with torch.no_grad():
         t = _time_kernel([(lambda f=f: fn.mask_einsum(e, f)) for f in fs], flush)
     out.append(hbm_entry("gemm_tf32x3_kernel (mask einsum fwd)", 4 * (B * Q * C + B * C * HH * WW + B * Q * HH * WW), t))
-    out[-1]["traffic"] = 161.5e6          # dram read + write per launch, profiles/r01_ncu_einsum_fwd.txt (ncu --set full; part of the output is still in L2)
+    out[-1]["traffic"] = 158.9e6          # dram read + write per launch, profiles/r01_ncu_einsum_fwd_v3.txt (ncu --set full; part of the output is still in L2)
     del fs
 
     # ---- MSDeformAttn gather / scatter at the encoder shape
