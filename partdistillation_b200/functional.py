@@ -140,7 +140,7 @@ def _pixel_major(t):
 
 class MaskEinsumFunction(Function):
     @staticmethod
-    def forward(ctx, mask_embed, mask_features):
+    def forward(ctx, mask_embed, mask_features, embed_lo=None):
         _need_cuda(mask_embed, mask_features)
         if mask_embed.dtype != torch.float32 or mask_features.dtype != torch.float32:
             raise RuntimeError("mask_einsum: float32 only")
@@ -150,7 +150,11 @@ class MaskEinsumFunction(Function):
         if B != Bf or C != Cf:
             raise RuntimeError(f"mask_einsum: shapes {tuple(mask_embed.shape)} x {tuple(mask_features.shape)}")
         out = torch.empty((B, Q, H, W), dtype=torch.float32, device=mask_embed.device)
-        embed_lo = None      # the (Q, C) operand is tiny: splitting it inside the kernel is cheaper than a second launch
+        # embed_lo: the tf32 low parts of mask_embed (split_lo), so that the GEMM does not re-split the same (Q, C) operand in
+        # every one of its ~1000 pixel tiles (47 vs 51 us at the BASELINE shape); without it the kernel splits in place
+        if embed_lo is not None and (embed_lo.shape != mask_embed.shape or not embed_lo.is_contiguous()
+                                     or embed_lo.dtype != torch.float32):
+            raise RuntimeError("mask_einsum: embed_lo must be a contiguous float32 tensor shaped like mask_embed")
         rc = _lib.load().pdb_mask_einsum_forward(mask_embed.data_ptr(), embed_lo.data_ptr() if embed_lo is not None else None,
                                                  mask_features.data_ptr(), out.data_ptr(), B, Q, C, H * W, _stream())
         _lib.check(rc, "pdb_mask_einsum_forward")
@@ -172,11 +176,16 @@ class MaskEinsumFunction(Function):
                                                   gf.data_ptr() if gf is not None else None, 0,
                                                   B, Q, C, H * W, _stream())
         _lib.check(rc, "pdb_mask_einsum_backward")
-        return ge, gf
+        return ge, gf, None
 
 
-def mask_einsum(mask_embed, mask_features):
-    return MaskEinsumFunction.apply(mask_embed, mask_features)
+def mask_einsum(mask_embed, mask_features, embed_lo=None, presplit=True):
+    """torch.einsum("bqc,bchw->bqhw") (mask2former_transformer_decoder.py:449).  The tiny embed operand is pre-split into its
+    tf32 hi / lo parts by one extra launch (presplit) unless the caller hands in embed_lo = split_lo(mask_embed) itself."""
+    if embed_lo is None and presplit and mask_embed.is_cuda and mask_embed.dtype == torch.float32 \
+            and mask_embed.numel() % 4 == 0:
+        embed_lo = split_lo(_c(mask_embed.detach()))
+    return MaskEinsumFunction.apply(mask_embed, mask_features, embed_lo)
 
 
 # --------------------------------------------------------------------------------------------------

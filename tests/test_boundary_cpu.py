@@ -24,6 +24,28 @@ def test_cabi_exports_every_declared_symbol():
     assert lib.pdb_last_error() == b""
 
 
+def test_tensor_core_kernels_are_tcgen05_tma_sass():
+    """The GEMM object holds what the design claims (checkable without a GPU): tcgen05 MMAs (UTCHMMA), TMA tensor loads
+    (UTMALDG), tensor-memory loads / stores (LDTM / STTM: epilogue and the A_lo k-blocks of the ALO kernels), tcgen05.commit
+    (UTCBAR) -- and no mma.sync-era HMMA / legacy cp.async pipeline."""
+    import shutil
+    import subprocess
+    from partdistillation_b200 import build
+    build.build()
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    obj = os.path.join(ROOT, "partdistillation_b200", "csrc", "gemm_tc.o")
+    sass = subprocess.run([cuobjdump, "-sass", obj], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "UTCBAR", "SYNCS"):
+        assert mnemonic in sass, mnemonic
+    assert " HMMA." not in sass and "LDGSTS" not in sass
+    # one kernel per (BN, A layout, B layout) and the ALO variants of the K-major-A ones
+    kernels = set(re.findall(r"Function : (\w*gemm_tf32x3_kernel\w*)", sass))
+    assert len(kernels) == 18, sorted(kernels)
+
+
 def test_cabi_rejects_bad_arguments_without_gpu():
     """Argument validation happens before any launch, so it is testable on CPU."""
     from partdistillation_b200 import _lib

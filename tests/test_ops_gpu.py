@@ -149,7 +149,11 @@ def test_msda_rejects_bad_input(fn):
 
 # ------------------------------------------------------------------ mask einsum
 @pytest.mark.parametrize("B,Q,C,H,W", [(2, 10, 256, 32, 32), (1, 100, 256, 24, 40), (2, 131, 64, 7, 9), (1, 200, 256, 16, 24),
-                                       (3, 50, 36, 5, 5)])
+                                       (3, 50, 36, 5, 5),
+                                       # Q <= 112: A_lo in tensor memory + the 5-deep ring; fewer k-blocks than ring stages (C = 32, 64),
+                                       # ragged pixel tiles, more tiles than SMs (3 x 160 x 152 / 128 = 570), Q = 112 / 113 on the boundary
+                                       (2, 100, 64, 60, 52), (1, 37, 32, 33, 20), (3, 100, 256, 160, 152), (1, 112, 128, 40, 40),
+                                       (1, 113, 128, 40, 40), (2, 8, 512, 12, 12)])
 def test_mask_einsum(fn, B, Q, C, H, W):
     g = torch.Generator().manual_seed(0)
     e = torch.randn(B, Q, C, generator=g).cuda().requires_grad_()
@@ -164,6 +168,24 @@ def test_mask_einsum(fn, B, Q, C, H, W):
     rge, rgf = torch.autograd.grad(ref, (e, f), go.double())
     assert _rel(ge.double(), rge.double()) < 1e-5
     assert _rel(gf.double(), rgf.double()) < 1e-5
+
+
+@pytest.mark.parametrize("B,Q,C,H,W", [(2, 100, 256, 24, 40), (1, 37, 32, 33, 20), (2, 131, 64, 7, 9)])
+def test_mask_einsum_embed_split_variants(fn, B, Q, C, H, W):
+    """The three ways the embed's tf32 low parts reach the GEMM give the same logits: split inside the kernel, split by the
+    wrapper's extra launch (default), handed in by the caller."""
+    g = torch.Generator().manual_seed(4)
+    e = torch.randn(B, Q, C, generator=g).cuda()
+    f = torch.randn(B, C, H, W, generator=g).cuda()
+    ref = torch.einsum("bqc,bchw->bqhw", e.double(), f.double())
+    a = fn.mask_einsum(e, f, presplit=False)
+    b = fn.mask_einsum(e, f)
+    c = fn.mask_einsum(e, f, embed_lo=fn.split_lo(e))
+    for out in (a, b, c):
+        assert _rel(out.double(), ref) < 1e-5
+    assert torch.equal(b, c)
+    with pytest.raises(RuntimeError):
+        fn.mask_einsum(e, f, embed_lo=torch.zeros(1, device="cuda"))
 
 
 def test_mask_einsum_full_size(fn):
