@@ -641,6 +641,7 @@ static int make_operand_map(CUtensorMap* map, const float* base, bool mn_major, 
 }
 
 static long long* g_trace_ptr = nullptr;
+static int g_narrow_tiles = 1;                // pdb_debug_set_gemm_alo_tmem(3) switches the narrow-tile heuristic off
 static int g_deep_ring = 1;                   // pdb_debug_set_gemm_alo_tmem(2) keeps A_lo in TMEM but the 3-stage ring
 static int g_alo_tmem = 1;                    // pdb_debug_set_gemm_alo_tmem(0) forces A_lo through shared memory
 
@@ -696,7 +697,6 @@ static int gemm_impl(const float* A, const float* B, const float* B_lo, float* C
     PDB_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && sa % 4 == 0 && sb % 4 == 0,
                 "gemm_tf32x3: leading dimensions / batch strides must be multiples of 4 floats (TMA 16-byte strides)");
     PDB_REQUIRE(ksplit >= 1 && (ksplit == 1 || accumulate), "gemm_tf32x3: split-K needs accumulate mode");
-    const int BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
     GemmParams p;
     p.C = C; p.bias = bias; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.sc = sc; p.batch = batch;
     int kb_total = (K + G_BK - 1) / G_BK;
@@ -704,6 +704,14 @@ static int gemm_impl(const float* A, const float* B, const float* B_lo, float* C
     p.ksplit = ksplit;
     p.kchunk = ((kb_total + ksplit - 1) / ksplit) * G_BK;
     p.ksplit = (K + p.kchunk - 1) / p.kchunk;           // no empty slices
+    // Column-tile width.  Problems with few row tiles (the decoder's 200-row linears: 2 row tiles, and K = 2048 in its FFN)
+    // would occupy a handful of SMs with 128-wide tiles; narrower tiles put up to 4x more SMs to work.  Deterministic, unlike
+    // split-K (which these forward / input-gradient products could not use anyway: bias, fixed summation order).
+    int BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+    if (BN == 128 && taps <= 1 && g_narrow_tiles) {
+        const int64_t row_tiles = (int64_t)((M + G_BM - 1) / G_BM) * batch * p.ksplit;
+        if (row_tiles * ((N + 127) / 128) * 2 <= kNumSMs) BN = (row_tiles * ((N + 63) / 64) * 2 <= kNumSMs) ? 32 : 64;
+    }
     p.c_trans = c_trans; p.relu = relu; p.atomic = accumulate;
     p.taps = taps;
     p.kb_per_tap = taps > 1 ? (K / taps) / G_BK : 0;
@@ -775,6 +783,7 @@ extern "C" int pdb_split_lo(const float* x, float* lo, int64_t n, void* stream) 
 extern "C" PDB_API int pdb_debug_set_gemm_alo_tmem(int on) {
     g_alo_tmem = on != 0;
     g_deep_ring = on != 2;
+    g_narrow_tiles = on != 3;
     return PDB_OK;
 }
 

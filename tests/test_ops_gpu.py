@@ -152,8 +152,9 @@ def test_msda_rejects_bad_input(fn):
                                        (3, 50, 36, 5, 5),
                                        # Q <= 112: A_lo in tensor memory + the 5-deep ring; fewer k-blocks than ring stages (C = 32, 64),
                                        # ragged pixel tiles, more tiles than SMs (3 x 160 x 152 / 128 = 570), Q = 112 / 113 on the boundary
-                                       (2, 100, 64, 60, 52), (1, 37, 32, 33, 20), (3, 100, 256, 160, 152), (1, 112, 128, 40, 40),
-                                       (1, 113, 128, 40, 40), (2, 8, 512, 12, 12)])
+                                       # (small pixel counts take the narrow-tile route of gemm_impl instead: both are covered)
+                                       (2, 100, 64, 128, 100), (1, 37, 32, 133, 120), (3, 100, 256, 160, 152), (1, 112, 128, 128, 80),
+                                       (2, 100, 64, 60, 52), (1, 112, 128, 40, 40), (1, 113, 128, 40, 40), (2, 8, 512, 12, 12)])
 def test_mask_einsum(fn, B, Q, C, H, W):
     g = torch.Generator().manual_seed(0)
     e = torch.randn(B, Q, C, generator=g).cuda().requires_grad_()
