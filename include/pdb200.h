@@ -279,6 +279,23 @@ PDB_API int pdb_window_attention_forward(const float* qkv, const float* bias, co
 PDB_API int pdb_layer_norm_forward(const float* x, const float* residual, const float* weight, const float* bias, float* y,
                            float* sum_out, float* mean, float* rstd, int64_t rows, int C, float eps, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm (+ ReLU) over channels-last maps — replaces nn.GroupNorm(32, C) and the F.relu behind it on the pixel decoder's
+ * input_proj / lateral / output convolutions (msdeformattn.py:249-287 via detectron2 Conv2d(norm=get_norm("GN", C),
+ * activation=F.relu)).  ATen's kernel wants NCHW; the convolutions here produce pixel-major maps.
+ *   x, y, dy, dx: (B, HW, C) f32 = the channels-last memory of the logical (B, C, H, W) tensor; G groups of C / G
+ *   consecutive channels (C / G a multiple of 4, C / 4 a divisor of 256); weight, bias (C) f32; mean, rstd (B, G) f32.
+ * forward:  stats (B, G, 2) f64 workspace, ZERO-FILLED by the caller (sum, sum of squares); relu != 0 applies max(., 0).
+ * backward: chan_sums (B, C, 2) f64, ZERO-FILLED by the caller; on return [b][c][0] = sum_hw dy' * xhat and
+ *   [b][c][1] = sum_hw dy' (dy' = dy, or dy where the forward output was positive): grad_weight = sum_b [..][0],
+ *   grad_bias = sum_b [..][1] (host side); coef (B, G, 2) f32 workspace; dx may be NULL (parameter gradients only).
+ * ---------------------------------------------------------------------------------------------- */
+PDB_API int pdb_group_norm_forward(const float* x, const float* weight, const float* bias, float* y, double* stats, float* mean,
+                           float* rstd, int B, int64_t HW, int C, int G, float eps, int relu, void* stream);
+PDB_API int pdb_group_norm_backward(const float* dy, const float* x, const float* weight, const float* bias, const float* mean,
+                            const float* rstd, double* chan_sums, float* coef, float* dx, int B, int64_t HW, int C, int G,
+                            int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -813,3 +813,71 @@ def layer_norm(x, weight, bias, eps=1e-5, residual=None, return_sum=False):
         return (y, z) if return_sum else y
     y, z = LayerNormFunction.apply(x, residual, weight, bias, eps, return_sum)
     return (y, z) if return_sum else y
+
+
+# --------------------------------------------------------------------------------------------------
+# GroupNorm (+ ReLU) on channels-last maps  (msdeformattn.py:249-287: Conv2d(norm=get_norm("GN", C), activation=F.relu))
+# --------------------------------------------------------------------------------------------------
+class GroupNormFunction(Function):
+    """x: logical (B, C, H, W) in channels-last memory.  Returns the same logical shape, channels-last."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, num_groups, eps, relu):
+        _need_cuda(x, weight, bias)
+        B, C, H, W = x.shape
+        xp = x.permute(0, 2, 3, 1)
+        if not xp.is_contiguous():
+            xp = xp.contiguous()
+        w, b = _c(weight), _c(bias)
+        y = torch.empty_like(xp)
+        stats = torch.zeros((B, num_groups, 2), dtype=torch.float64, device=x.device)
+        mean = torch.empty((B, num_groups), dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        rc = _lib.load().pdb_group_norm_forward(xp.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), stats.data_ptr(),
+                                                mean.data_ptr(), rstd.data_ptr(), B, H * W, C, num_groups, float(eps), int(relu),
+                                                _stream())
+        _lib.check(rc, "pdb_group_norm_forward")
+        ctx.save_for_backward(xp, w, b, mean, rstd)
+        ctx.cfg = (B, C, H, W, num_groups, bool(relu))
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        xp, w, b, mean, rstd = ctx.saved_tensors
+        B, C, H, W, G, relu = ctx.cfg
+        gyp = gy.permute(0, 2, 3, 1)
+        if not gyp.is_contiguous() or gyp.data_ptr() % 16:
+            gyp = gyp.contiguous()
+        sums = torch.zeros((B, C, 2), dtype=torch.float64, device=gy.device)
+        coef = torch.empty((B, G, 2), dtype=torch.float32, device=gy.device)
+        gx = torch.empty_like(xp) if ctx.needs_input_grad[0] else None
+        rc = _lib.load().pdb_group_norm_backward(gyp.data_ptr(), xp.data_ptr(), w.data_ptr(), b.data_ptr(), mean.data_ptr(),
+                                                 rstd.data_ptr(), sums.data_ptr(), coef.data_ptr(),
+                                                 gx.data_ptr() if gx is not None else None, B, H * W, C, G, int(relu), _stream())
+        _lib.check(rc, "pdb_group_norm_backward")
+        gw = gb = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            tot = sums.sum(0).float()
+            gw, gb = tot[:, 0].contiguous(), tot[:, 1].contiguous()
+        return (gx.permute(0, 3, 1, 2) if gx is not None else None), gw, gb, None, None, None
+
+
+def group_norm_supported(x, num_groups, weight, bias):
+    if not (torch.is_tensor(x) and x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and weight is not None
+            and bias is not None and weight.dtype == torch.float32 and bias.dtype == torch.float32):
+        return False
+    C = x.shape[1]
+    if C % num_groups or (C // num_groups) % 4 or C // 4 > 256 or 256 % (C // 4) or num_groups > 256 or x.numel() == 0:
+        return False
+    # channels-last memory (what conv1x1 / conv3x3 of this module return); an NCHW input would need a transposing copy first
+    return x.permute(0, 2, 3, 1).is_contiguous() and x.data_ptr() % 16 == 0
+
+
+def group_norm(x, num_groups, weight, bias, eps=1e-5, relu=False):
+    """F.group_norm (optionally followed by ReLU) for a logical (B, C, H, W) map.  fp32 CUDA maps in channels-last memory
+    use the pixel-major kernels; everything else goes through torch."""
+    if group_norm_supported(x, num_groups, weight, bias) and not torch.is_autocast_enabled():
+        return GroupNormFunction.apply(x, weight, bias, int(num_groups), float(eps), bool(relu))
+    y = torch.nn.functional.group_norm(x, num_groups, weight, bias, eps)
+    return torch.relu(y) if relu else y

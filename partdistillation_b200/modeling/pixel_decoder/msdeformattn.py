@@ -219,7 +219,7 @@ class MSDeformAttnPixelDecoder(nn.Module):
             for idx, f in enumerate(self.transformer_in_features[::-1]):
                 x = features[f].float()
                 conv, gn = self.input_proj[idx][0], self.input_proj[idx][1]
-                srcs.append(gn(PF.conv1x1(x, conv.weight, conv.bias)))
+                srcs.append(self._norm_act(gn, None, PF.conv1x1(x, conv.weight, conv.bias)))
                 pos.append(self.pe_layer(x))
             y, shapes, starts = self.transformer(srcs, pos)
             bs = y.shape[0]
@@ -235,29 +235,33 @@ class MSDeformAttnPixelDecoder(nn.Module):
             return self._mask_features_pixel_major(out[-1]), out[0], multi_scale
 
     @staticmethod
-    def _lateral(conv, x):
+    def _norm_act(norm, activation, y):
+        """norm (+ activation) behind a convolution: GroupNorm (+ ReLU) runs as one pixel-major kernel pair on the
+        channels-last map the convolution GEMMs produce; any other norm / activation goes through its module."""
+        if isinstance(norm, nn.GroupNorm) and norm.affine and (activation is None or activation is F.relu):
+            return PF.group_norm(y, norm.num_groups, norm.weight, norm.bias, norm.eps, relu=activation is F.relu)
+        if norm is not None:
+            y = norm(y)
+        if activation is not None:
+            y = activation(y)
+        return y
+
+    @classmethod
+    def _lateral(cls, conv, x):
         """1x1 lateral convolution (+ its norm / activation) with the contraction on the tensor cores."""
         if tuple(conv.kernel_size) != (1, 1):
             return conv(x)
         y = PF.conv1x1(x, conv.weight, conv.bias)
-        if getattr(conv, "norm", None) is not None:
-            y = conv.norm(y)
-        if getattr(conv, "activation", None) is not None:
-            y = conv.activation(y)
-        return y
+        return cls._norm_act(getattr(conv, "norm", None), getattr(conv, "activation", None), y)
 
-    @staticmethod
-    def _output_conv(conv, x):
+    @classmethod
+    def _output_conv(cls, conv, x):
         """3x3 output convolution (+ norm / activation) with the contraction on the tensor cores."""
         if tuple(conv.kernel_size) != (3, 3) or tuple(conv.stride) != (1, 1) or tuple(conv.padding) != (1, 1) or \
                 tuple(conv.dilation) != (1, 1) or conv.groups != 1:
             return conv(x)
         y = PF.conv3x3(x, conv.weight, conv.bias)
-        if getattr(conv, "norm", None) is not None:
-            y = conv.norm(y)
-        if getattr(conv, "activation", None) is not None:
-            y = conv.activation(y)
-        return y
+        return cls._norm_act(getattr(conv, "norm", None), getattr(conv, "activation", None), y)
 
     def _mask_features_pixel_major(self, y):
         """The 1x1 ``mask_features`` convolution as a GEMM over pixels: the result is the logical

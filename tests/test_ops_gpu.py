@@ -679,3 +679,40 @@ def test_layer_norm_fused(fn, rows, C, res, want_sum):
     exp = torch.autograd.grad(lref, ins)
     for a, e in zip(got, exp):
         assert _rel(a.double(), e.double()) < 1e-5
+
+
+# ------------------------------------------------------------------ GroupNorm (+ ReLU) on channels-last maps
+@pytest.mark.parametrize("B,C,H,W,G,relu", [(2, 256, 64, 64, 32, True), (2, 256, 64, 64, 32, False), (1, 128, 33, 47, 32, True),
+                                            (3, 64, 16, 16, 8, False), (2, 256, 7, 5, 32, True), (1, 512, 24, 24, 32, True)])
+def test_group_norm_channels_last(fn, B, C, H, W, G, relu):
+    """functional.group_norm (pixel-major statistics / apply kernels, msdeformattn.py:249-287 via Conv2d(norm=GN, activation=relu))
+    against float64 F.group_norm (+ relu): output, input gradient, affine gradients.  A non-zero mean (+3) keeps the
+    E[x^2] - mean^2 route honest."""
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(B, C, H, W, generator=g) * 2 + 3).cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+    w = (torch.randn(C, generator=g) * 0.5 + 1).cuda().requires_grad_()
+    b = (torch.randn(C, generator=g) * 0.5).cuda().requires_grad_()
+    assert fn.group_norm_supported(x, G, w, b)
+    y = fn.group_norm(x, G, w, b, 1e-5, relu=relu)
+    assert y.shape == x.shape and y.permute(0, 2, 3, 1).is_contiguous()
+    xd, wd, bd = (t.detach().double().requires_grad_() for t in (x, w, b))
+    ref = F.group_norm(xd, G, wd, bd, 1e-5)
+    if relu:
+        ref = ref.relu()
+    assert _rel(y.double(), ref) < 1e-5
+    go = torch.randn(B, C, H, W, generator=g).cuda()
+    if relu:    # keep the comparison away from the kink: only clearly positive outputs carry an upstream gradient
+        go = go * (ref > 1e-4).float()
+    gx, gw, gb = torch.autograd.grad(y, (x, w, b), go)
+    rx, rw, rb = torch.autograd.grad(ref, (xd, wd, bd), go.double())
+    assert _rel(gx.double(), rx) < 1e-5
+    assert _rel(gw.double(), rw) < 1e-5
+    assert _rel(gb.double(), rb) < 1e-5
+
+
+def test_group_norm_falls_back_for_other_layouts(fn):
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 96, 9, 9, generator=g).cuda()                  # NCHW memory, 96 / 4 = 24 does not divide 256
+    w, b = torch.randn(96, generator=g).cuda(), torch.randn(96, generator=g).cuda()
+    assert not fn.group_norm_supported(x, 32, w, b)
+    assert torch.allclose(fn.group_norm(x, 32, w, b, relu=True), F.group_norm(x, 32, w, b).relu())
