@@ -1,6 +1,6 @@
 // General fp32 GEMM on the 5th-generation tensor cores ("3xTF32"), the dense-contraction engine of the
 // hot path:  for each batch b
-//     C_b[m][n] (+)= sum_k A_b(m,k) * B_b(n,k)  (+ bias[n]) (ReLU)
+//     C_b[m][n] (+)= sum_k A_b(m,k) * B_b(n,k)  (+ bias[n]) (ReLU | GELU)
 // It serves nn.Linear forward / input-gradient / weight-gradient of the encoder and decoder layers
 // (reference: msdeformattn.py:120-135, ops/modules/ms_deform_attn.py:102-130,
 // mask2former_transformer_decoder.py:148-208) and the mask-head einsum with its two gradient products
@@ -30,8 +30,13 @@
 //               hi*hi and hi*lo side by side in TMEM), A_lo into its own 2-deep ring
 //   warp 1      TMEM allocator + tcgen05.mma issuer (one elected lane): per 8-wide k step
 //               [main | corr] += A_hi x [B_hi ; B_lo]^T   and   corr += A_lo x B_hi^T
-//   warps 10..17 epilogue (two per TMEM lane quarter): tcgen05.ld (main + corr) -> (+bias, ReLU) -> coalesced store / red.add, overlapped
-//               with the next tile's main loop through a double-buffered TMEM accumulator
+//   warps 10..17 epilogue (two per TMEM lane quarter): tcgen05.ld (main + corr) -> (+bias, ReLU / GELU) -> coalesced store / red.add,
+//               overlapped with the next tile's main loop through a double-buffered TMEM accumulator
+// ALO kernels (K-major A, N <= 112 or BN < 128): the A_lo k-blocks go to tensor memory (tcgen05.st) instead of shared memory and
+// the correction MMA reads its A operand from there; with a transposed store (the mask einsum) the ring is 5 stages deep.
+// The producer hands each tile's coordinates to the MMA thread through shared memory, and one tcgen05.commit per k-block
+// releases both the raw stage (to the producer) and the A_lo stage (to the split warps).  gemm_impl picks narrower column tiles
+// (BN = 64 / 32) for problems with few row tiles.  Measurements and the dead ends are in DESIGN.md, section 3.2.
 #include <algorithm>
 #include "common.cuh"
 #include "tc_gemm.cuh"
