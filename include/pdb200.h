@@ -296,6 +296,39 @@ PDB_API int pdb_group_norm_backward(const float* dy, const float* x, const float
                             const float* rstd, double* chan_sums, float* coef, float* dx, int B, int64_t HW, int C, int G,
                             int relu, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Inference post-processing (ProposalModel eval branch) — replaces, per image,
+ * F.interpolate(pred_masks -> padded size) (proposal_model.py:225-230), detectron2 sem_seg_postprocess (crop +
+ * second bilinear resize, :243-245), masking_with_object_mask (:369-376), _unique_assignment's `> 0`, top-1 object
+ * map and score * sigmoid argmax (:258-302), and get_iou_all_cocoapi's host RLE round trip (utils/utils.py:35-42).
+ * Masks live bit-packed: `bits` rows are (Ho, Ww) uint32 words, Ww = ceil(Wo / 32), bit i of a word = pixel
+ * 32 * word + i of that image row.
+ *
+ * pdb_postprocess_masks:  logits (Q, h, w) f32 (one image of pred_masks); sel (K) int32 query indices (the top-k);
+ *   scores (K) f32 (NULL unless label != NULL); gate (Ho, Wo) uint8 object mask or NULL;
+ *   bits (K + 1, Ho, Ww) uint32 or NULL: row k = [resized(logits[sel[k]]) * gate > 0], row K = OR of the K rows
+ *   (the reference's `topk(1, dim=0)[0] > 0` object map); label (Ho, Wo) int32 or NULL = argmax_k scores[k] *
+ *   sigmoid(resized * gate) (first maximum).  (h, w) -> bilinear -> (Hp, Wp) -> crop (Hi, Wi) -> bilinear ->
+ *   (Ho, Wo), both passes align_corners=False, composed per output pixel.
+ * pdb_resize_masks_u8:  masks (G, Hp, Wp) uint8 0/1 -> out (G, Ho, Wo) uint8 = [bilinear(float(crop (Hi, Wi))) != 0]
+ *   (sem_seg_postprocess(target["masks"].float(), ...).bool(), :244-245).
+ * pdb_pack_bits / pdb_unpack_bits:  (R, Ho, Wo) uint8 (non-zero = set) <-> (R, Ho, Ww) words; unpack gathers rows[r]
+ *   (int32, NULL = identity).
+ * pdb_bits_popcount:  counts[r] += popcount(bits[r, :words]); counts (rows) int64, ZERO-FILLED by the caller.
+ * pdb_bits_intersect: inter[i, j] += popcount(a[i] & b[j]); inter (Ka, Kb) int64, ZERO-FILLED by the caller.
+ *   IoU (pycocotools rleIou, iscrowd = 0) = inter / (|a| + |b| - inter), exactly 0 where inter == 0.
+ * ---------------------------------------------------------------------------------------------- */
+PDB_API int pdb_postprocess_masks(const float* logits, const int32_t* sel, const float* scores, const uint8_t* gate,
+                          uint32_t* bits, int32_t* label, int Q, int K, int h, int w, int Hp, int Wp, int Hi, int Wi,
+                          int Ho, int Wo, void* stream);
+PDB_API int pdb_resize_masks_u8(const uint8_t* masks, uint8_t* out, int G, int Hp, int Wp, int Hi, int Wi, int Ho, int Wo,
+                        void* stream);
+PDB_API int pdb_pack_bits(const uint8_t* in, uint32_t* bits, int R, int Ho, int Wo, void* stream);
+PDB_API int pdb_unpack_bits(const uint32_t* bits, const int32_t* rows, uint8_t* out, int R, int Ho, int Wo, void* stream);
+PDB_API int pdb_bits_popcount(const uint32_t* bits, int64_t* counts, int rows, int64_t words, void* stream);
+PDB_API int pdb_bits_intersect(const uint32_t* a, const uint32_t* b, int64_t* inter, int Ka, int Kb, int64_t words,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -660,3 +660,95 @@ def pixel_grouping_segments(feature, centroids, mask_resized, metric="dot"):
     labels[mask_resized] = scores[:, mask_resized].argmax(0) + 1
     present = labels[mask_resized].unique()
     return labels, torch.stack([labels == p for p in present]) if len(present) else labels.new_zeros((0, *labels.shape)).bool()
+
+
+# --------------------------------------------------------------------------------------
+# f4  ProposalModel eval branch  (proposal_model.py:220-302 inference / _unique_assignment,
+#     :341-366 _prepare_gt_targets, :381-432 instance_inference / match_gt_labels;
+#     detectron2 sem_seg_postprocess; pycocotools rleIou via utils/utils.py:35-42)
+# --------------------------------------------------------------------------------------
+
+
+def sem_seg_postprocess(result, img_size, out_h, out_w):
+    """detectron2.modeling.postprocessing.sem_seg_postprocess: crop the padding, bilinear resize."""
+    result = result[:, :img_size[0], :img_size[1]][None]
+    return F.interpolate(result, size=(out_h, out_w), mode="bilinear", align_corners=False)[0]
+
+
+def pad_masks(masks, padded):
+    """_prepare_gt_targets' zero padding to the padded batch size (:349-352,355-358)."""
+    out = torch.zeros((masks.shape[0], *padded), dtype=masks.dtype)
+    out[:, :masks.shape[1], :masks.shape[2]] = masks
+    return out
+
+
+def mask_iou(pr, gt):
+    """get_iou_all_cocoapi (utils/utils.py:35-42): float64 |a & b| / |a | b|, exactly 0 when disjoint (rleIou)."""
+    a = pr.flatten(1).to(torch.float64)
+    b = gt.flatten(1).to(torch.float64)
+    inter = a @ b.t()
+    union = a.sum(1)[:, None] + b.sum(1)[None] - inter
+    return torch.where(inter > 0, inter / union.clamp(min=1), torch.zeros_like(inter))
+
+
+def proposal_unique_assignment(masks, scores, per_pixel, min_ratio, min_score):
+    """_unique_assignment (:258-302)."""
+    obj = masks.topk(1, dim=0)[0] > 0.0
+    if per_pixel:
+        pred = scores[:, None, None] * masks.sigmoid()
+        score_map = pred.topk(1, dim=0)[1]
+        ids = score_map.unique()
+        new = torch.stack([((score_map == c) & obj)[0] for c in ids]).to(masks.dtype)
+        scores = scores[ids]
+        valid = new.flatten(1).sum(1) / obj.flatten(1).sum(1) > min_ratio
+        if valid.any():
+            new, scores = new[valid], scores[valid]
+        valid = scores > min_score
+        if valid.any():
+            new, scores = new[valid], scores[valid]
+        return new.bool(), scores
+    valid = (masks > 0).flatten(1).sum(1) / obj.flatten(1).sum(1) > min_ratio
+    if valid.any():
+        masks, scores = masks[valid], scores[valid]
+    valid = scores > min_score
+    if valid.any():
+        masks, scores = masks[valid], scores[valid]
+    return masks > 0, scores
+
+
+def proposal_instance_inference(mask_cls, mask_pred, target_masks, target_object_masks, target_labels, topk,
+                                per_pixel=False, min_ratio=0.0, min_score=0.0, gate=True, iou_thr=0.001):
+    """instance_inference + match_gt_labels (:381-432) -> (bool masks, scores, gt part labels)."""
+    scores = mask_cls.softmax(-1)[:, :-1].topk(1, dim=1)[0].flatten()
+    scores, idx = scores.topk(topk, sorted=False)
+    mask_pred = mask_pred[idx]
+    if gate:
+        mask_pred = mask_pred * target_object_masks.sum(dim=0, keepdim=True).bool()         # (:369-376)
+    masks, scores = proposal_unique_assignment(mask_pred, scores, per_pixel, min_ratio, min_score)
+    ious = mask_iou(masks, target_masks)
+    top1, top1_idx = ious.topk(1, dim=1)
+    fg = (top1 > iou_thr).flatten()
+    labels = target_labels[top1_idx.flatten()[fg]]
+    masks, scores = masks[fg], scores[fg]
+    if masks.shape[0] == 0:                                                                  # (:402-406)
+        masks = torch.zeros((1, *mask_pred.shape[1:]), dtype=torch.bool)
+        scores = scores.new_zeros(1)
+        labels = labels.new_zeros(1)
+    return masks, scores, labels
+
+
+def proposal_inference(pred_logits, pred_masks, items, padded, topk, **flags):
+    """inference (:220-254).  ``items``: per image dict(size, out, object_mask (1,H,W) bool, part_masks (G,H,W) bool,
+    part_classes (G,)).  Returns per image dict(pred_masks, scores, pred_classes, gt_masks, gt_classes)."""
+    up = F.interpolate(pred_masks, size=padded, mode="bilinear", align_corners=False)
+    out = []
+    for b, it in enumerate(items):
+        size, (oh, ow) = it["size"], it["out"]
+        mp = sem_seg_postprocess(up[b], size, oh, ow)
+        tm = sem_seg_postprocess(pad_masks(it["part_masks"], padded).float(), size, oh, ow).bool()
+        tom = sem_seg_postprocess(pad_masks(it["object_mask"], padded).float(), size, oh, ow).bool()
+        masks, scores, labels = proposal_instance_inference(pred_logits[b].to(mp), mp, tm, tom, it["part_classes"],
+                                                            topk, **flags)
+        out.append(dict(pred_masks=masks, scores=scores, pred_classes=labels, gt_masks=tm,
+                        gt_classes=it["part_classes"]))
+    return out

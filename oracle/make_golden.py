@@ -229,12 +229,98 @@ def golden_pixel_grouping(ref):
     print("pixel_grouping.pt", {m: tuple(out[m]["binary_mask"].shape) for m in ("dot", "l2")})
 
 
+INFER_CASES = {
+    # name: attribute overrides on the reference ProposalModel (set_postprocess_type / from_config keys,
+    # proposal_model.py:55-103,139-168)
+    "prop": dict(use_unique_per_pixel_label=False, minimum_pseudo_mask_score=0.0, minimum_pseudo_mask_ratio=0.0,
+                 apply_masking_with_object_mask=True),
+    "prop_filtered": dict(use_unique_per_pixel_label=False, minimum_pseudo_mask_score=0.3,
+                          minimum_pseudo_mask_ratio=0.05, apply_masking_with_object_mask=True),
+    "prop_nomask": dict(use_unique_per_pixel_label=False, minimum_pseudo_mask_score=0.0,
+                        minimum_pseudo_mask_ratio=0.0, apply_masking_with_object_mask=False),
+    "semseg": dict(use_unique_per_pixel_label=True, minimum_pseudo_mask_score=0.0, minimum_pseudo_mask_ratio=0.0,
+                   apply_masking_with_object_mask=True),
+    "semseg_filtered": dict(use_unique_per_pixel_label=True, minimum_pseudo_mask_score=0.3,
+                            minimum_pseudo_mask_ratio=0.05, apply_masking_with_object_mask=True),
+}
+
+
+def synth_inference_inputs(seed=21, Q=12):
+    """Two images of different sizes (padding to a multiple of 32), one of them evaluated at a different output
+    size (second bilinear pass of sem_seg_postprocess), ground-truth parts inside an elliptic object mask."""
+    g = torch.Generator().manual_seed(seed)
+    sizes = [(96, 128), (128, 112)]
+    outs = [(144, 192), (128, 112)]
+    Hp, Wp = 128, 128
+    items = []
+    for (H, W), (Ho, Wo) in zip(sizes, outs):
+        yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+        obj = ((yy - H / 2) ** 2 / (H * 0.42) ** 2 + (xx - W / 2) ** 2 / (W * 0.38) ** 2) < 1.0
+        lab = torch.randint(0, 4, (H // 16, W // 16), generator=g).repeat_interleave(16, 0).repeat_interleave(16, 1)
+        parts = torch.stack([(lab == k) & obj for k in range(4)])
+        parts = parts[parts.flatten(1).any(1)]
+        items.append(dict(size=(H, W), out=(Ho, Wo), object_mask=obj[None], part_masks=parts,
+                          part_classes=torch.arange(parts.shape[0]) % 3))
+    low = torch.randn(2, Q, Hp // 16, Wp // 16, generator=g) * 3.0
+    pred_masks = torch.nn.functional.interpolate(low, size=(Hp // 4, Wp // 4), mode="bicubic", align_corners=False)
+    pred_masks = pred_masks + 0.3 * torch.randn(2, Q, Hp // 4, Wp // 4, generator=g)
+    pred_masks[0, 3] = -4.0                     # a query that claims nothing
+    pred_masks[1, 5, :8] = 0.0                  # exact zeros: not > 0
+    pred_logits = torch.randn(2, Q, 2, generator=g) * 1.5
+    return dict(items=items, padded=(Hp, Wp), pred_masks=pred_masks, pred_logits=pred_logits)
+
+
+def golden_proposal_inference(ref):
+    """ProposalModel eval branch of the UNMODIFIED reference (proposal_model.py:220-302,341-420: inference,
+    _prepare_gt_targets, instance_inference, _unique_assignment, match_gt_labels) on synthetic head outputs.
+    pycocotools is absent: get_iou_all_cocoapi runs on oracle/shims/pycocotools (restated rleIou semantics)."""
+    from detectron2.structures import ImageList, Instances, BitMasks
+    Q = 12
+    cfg = rl.make_cfg("ProposalModel", "swin_micro", num_queries=Q, dec_layers=3, num_points=64)
+    model = rl.build_model(cfg, "/tmp/pd_oracle_work")
+    model.eval()
+    inp = synth_inference_inputs(Q=Q)
+    Hp, Wp = inp["padded"]
+    bi = []
+    for it in inp["items"]:
+        H, W = it["size"]
+        inst = Instances((H, W)); inst.gt_masks = BitMasks(it["object_mask"]); inst.gt_classes = torch.zeros(1, dtype=torch.long)
+        pinst = Instances((H, W)); pinst.gt_masks = BitMasks(it["part_masks"]); pinst.gt_classes = it["part_classes"]
+        bi.append({"image": torch.zeros(3, H, W, dtype=torch.uint8), "instances": inst, "part_instances": pinst,
+                   "height": it["out"][0], "width": it["out"][1]})
+    il = ImageList(torch.zeros(2, 3, Hp, Wp), [it["size"] for it in inp["items"]])
+    outputs = {"pred_logits": inp["pred_logits"], "pred_masks": inp["pred_masks"]}
+    g = dict(inputs=inp, cases={})
+    for name, over in INFER_CASES.items():
+        for k, v in over.items():
+            assert hasattr(model, k), k
+            setattr(model, k, v)
+        with torch.no_grad():
+            targets = model.prepare_targets(bi, il)
+            res = model.inference(bi, targets, il, outputs, vis=False)
+        rec = []
+        for r in res:
+            p, t = r["proposals"], r["gt_masks"]
+            rec.append(dict(pred_masks=np.packbits(p.pred_masks.numpy(), axis=-1), pred_shape=tuple(p.pred_masks.shape),
+                            scores=p.scores.clone(), pred_classes=p.pred_classes.clone(),
+                            image_size=tuple(p.image_size),
+                            gt_masks=np.packbits(t.gt_masks.numpy(), axis=-1), gt_shape=tuple(t.gt_masks.shape),
+                            gt_classes=t.gt_classes.clone()))
+        g["cases"][name] = dict(overrides=over, results=rec)
+    torch.save(g, os.path.join(OUT, "proposal_inference.pt"))
+    print("proposal_inference.pt", {n: [r["pred_shape"] for r in c["results"]] for n, c in g["cases"].items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = rl.load()
     if "--pixel-grouping-only" in sys.argv:
         golden_pixel_grouping(ref)
         return
+    if "--inference-only" in sys.argv:
+        golden_proposal_inference(ref)
+        return
+    golden_proposal_inference(ref)
     golden_pixel_grouping(ref)
     golden_msda(ref)
     golden_swin(ref)

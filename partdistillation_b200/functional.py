@@ -717,6 +717,120 @@ def group_affinity(feat, centroids, mask, metric="dot"):
 
 
 # --------------------------------------------------------------------------------------------------
+# Inference post-processing on bit-packed masks  (proposal_model.py:220-302,369-432; utils/utils.py:35-42)
+# --------------------------------------------------------------------------------------------------
+def _u8(mask):
+    return _c(mask).view(torch.uint8) if mask.dtype == torch.bool else _c(mask.to(torch.uint8))
+
+
+def postprocess_masks(logits, sel, padded_size, image_size, out_size, gate=None, scores=None, want_bits=True,
+                      want_label=False):
+    """logits (Q, h, w) f32 of ONE image, sel (K) query indices -> (bits (K + 1, Ho, ceil(Wo / 32)) int32 words or
+    None, label (Ho, Wo) int32 or None).  Row k of ``bits`` is ``resize(logits[sel[k]]) * gate > 0`` with ``resize`` =
+    bilinear to ``padded_size``, crop to ``image_size``, bilinear to ``out_size`` (both align_corners=False); row K is
+    the OR over k.  ``label`` = argmax_k scores[k] * sigmoid(resize * gate)."""
+    _need_cuda(logits, sel, gate, scores)
+    if logits.dtype != torch.float32 or logits.dim() != 3:
+        raise RuntimeError("postprocess_masks: logits must be float32 (Q, h, w)")
+    logits = _c(logits)
+    sel = _c(sel.to(torch.int32))
+    Q, h, w = logits.shape
+    K = sel.shape[0]
+    (Hp, Wp), (Hi, Wi), (Ho, Wo) = [(int(a), int(b)) for a, b in (padded_size, image_size, out_size)]
+    if gate is not None:
+        gate = _u8(gate)
+        if tuple(gate.shape[-2:]) != (Ho, Wo) or gate.numel() != Ho * Wo:
+            raise RuntimeError(f"postprocess_masks: gate shape {tuple(gate.shape)} != output size {(Ho, Wo)}")
+    if want_label:
+        if scores is None:
+            raise RuntimeError("postprocess_masks: the label map needs the scores")
+        scores = _c(scores.float())
+    Ww = (Wo + 31) // 32
+    bits = torch.empty((K + 1, Ho, Ww), dtype=torch.int32, device=logits.device) if want_bits else None
+    label = torch.empty((Ho, Wo), dtype=torch.int32, device=logits.device) if want_label else None
+    rc = _lib.load().pdb_postprocess_masks(logits.data_ptr(), sel.data_ptr(),
+                                           scores.data_ptr() if want_label else None,
+                                           gate.data_ptr() if gate is not None else None,
+                                           bits.data_ptr() if want_bits else None,
+                                           label.data_ptr() if want_label else None,
+                                           Q, K, h, w, Hp, Wp, Hi, Wi, Ho, Wo, _stream())
+    _lib.check(rc, "pdb_postprocess_masks")
+    return bits, label
+
+
+def resize_bool_masks(masks, image_size, out_size):
+    """Zero-padded bool / uint8 (G, Hp, Wp) -> bool (G, Ho, Wo): ``sem_seg_postprocess(masks.float(), image_size, Ho,
+    Wo).bool()`` (crop, bilinear, non-zero)."""
+    _need_cuda(masks)
+    masks = _u8(masks)
+    G, Hp, Wp = masks.shape
+    (Hi, Wi), (Ho, Wo) = [(int(a), int(b)) for a, b in (image_size, out_size)]
+    out = torch.empty((G, Ho, Wo), dtype=torch.uint8, device=masks.device)
+    if G:
+        rc = _lib.load().pdb_resize_masks_u8(masks.data_ptr(), out.data_ptr(), G, Hp, Wp, Hi, Wi, Ho, Wo, _stream())
+        _lib.check(rc, "pdb_resize_masks_u8")
+    return out.view(torch.bool)
+
+
+def pack_bits(masks):
+    """bool / uint8 (R, Ho, Wo) -> int32 words (R, Ho, ceil(Wo / 32)); bit i of a word = pixel 32 * word + i."""
+    _need_cuda(masks)
+    masks = _u8(masks)
+    R, Ho, Wo = masks.shape
+    bits = torch.empty((R, Ho, (Wo + 31) // 32), dtype=torch.int32, device=masks.device)
+    if R:
+        rc = _lib.load().pdb_pack_bits(masks.data_ptr(), bits.data_ptr(), R, Ho, Wo, _stream())
+        _lib.check(rc, "pdb_pack_bits")
+    return bits
+
+
+def unpack_bits(bits, width, rows=None):
+    """int32 words (R0, Ho, Ww) -> bool (R, Ho, width), gathering ``rows`` (int tensor) if given."""
+    _need_cuda(bits, rows)
+    bits = _c(bits)
+    _, Ho, Ww = bits.shape
+    if (int(width) + 31) // 32 != Ww:
+        raise RuntimeError(f"unpack_bits: width {width} does not match {Ww} words per row")
+    if rows is not None:
+        rows = _c(rows.to(torch.int32))
+    R = rows.shape[0] if rows is not None else bits.shape[0]
+    out = torch.empty((R, Ho, int(width)), dtype=torch.uint8, device=bits.device)
+    if R:
+        rc = _lib.load().pdb_unpack_bits(bits.data_ptr(), rows.data_ptr() if rows is not None else None, out.data_ptr(),
+                                         R, Ho, int(width), _stream())
+        _lib.check(rc, "pdb_unpack_bits")
+    return out.view(torch.bool)
+
+
+def bits_popcount(bits):
+    """int32 words (R, ...) -> int64 (R,) number of set bits per row."""
+    _need_cuda(bits)
+    bits = _c(bits)
+    R = bits.shape[0]
+    counts = torch.zeros((R,), dtype=torch.int64, device=bits.device)
+    if R and bits[0].numel():
+        rc = _lib.load().pdb_bits_popcount(bits.data_ptr(), counts.data_ptr(), R, bits[0].numel(), _stream())
+        _lib.check(rc, "pdb_bits_popcount")
+    return counts
+
+
+def bits_iou(a, b):
+    """Pairwise mask IoU of packed masks a (Ka, Ho, Ww), b (Kb, Ho, Ww) -> float64 (Ka, Kb) with pycocotools' rleIou
+    semantics for iscrowd = 0: |a & b| / |a | b|, exactly 0 where the intersection is empty."""
+    _need_cuda(a, b)
+    a, b = _c(a), _c(b)
+    if a.shape[1:] != b.shape[1:]:
+        raise RuntimeError(f"bits_iou: packed shapes differ: {tuple(a.shape)} vs {tuple(b.shape)}")
+    Ka, Kb = a.shape[0], b.shape[0]
+    inter = torch.zeros((Ka, Kb), dtype=torch.int64, device=a.device)
+    if Ka and Kb:
+        rc = _lib.load().pdb_bits_intersect(a.data_ptr(), b.data_ptr(), inter.data_ptr(), Ka, Kb, a[0].numel(), _stream())
+        _lib.check(rc, "pdb_bits_intersect")
+    union = bits_popcount(a)[:, None] + bits_popcount(b)[None] - inter
+    return torch.where(inter > 0, inter.double() / union.clamp(min=1).double(), torch.zeros((), dtype=torch.float64, device=a.device))
+
+
+# --------------------------------------------------------------------------------------------------
 # Swin window attention, forward (frozen backbone)  (modeling/backbone/swin.py:78-176)
 # --------------------------------------------------------------------------------------------------
 def window_attention(qkv, bias, mask, heads, scale):

@@ -1,4 +1,5 @@
-"""``ProposalModel`` meta-architecture — training branch (reference: part_distillation/proposal_model.py:30-204,313-338).
+"""``ProposalModel`` meta-architecture — training branch (reference: part_distillation/proposal_model.py:30-204,313-338)
+and eval branch (:205-302,341-432; ``postprocess.ProposalInferenceMixin``).
 
 Registered under the reference's name so ``cfg.MODEL.META_ARCHITECTURE = "ProposalModel"`` resolves here;
 same ``from_config`` keys and ``forward(batched_inputs) -> dict of weighted losses``."""
@@ -8,10 +9,11 @@ from torch import nn
 
 from .compat import META_ARCH_REGISTRY, build_backbone, build_sem_seg_head, configurable
 from .meta_base import Mask2FormerTrainingArch, build_criterion
+from .postprocess import ProposalInferenceMixin
 
 
 @META_ARCH_REGISTRY.register()
-class ProposalModel(Mask2FormerTrainingArch):
+class ProposalModel(ProposalInferenceMixin, Mask2FormerTrainingArch):
     @configurable
     def __init__(self, *, backbone, sem_seg_head: nn.Module, criterion: nn.Module, num_queries: int, num_classes: int,
                  size_divisibility: int, pixel_mean: Tuple[float], pixel_std: Tuple[float], test_topk_per_image: int,
@@ -64,6 +66,14 @@ class ProposalModel(Mask2FormerTrainingArch):
                     minimum_pseudo_mask_ratio=p.MIN_AREA_RATIO, minimum_pseudo_mask_score=p.MIN_SCORE)
 
     def forward(self, batched_inputs):
-        losses = super().forward(batched_inputs)
-        self.num_train_iterations += 1
-        return losses
+        if self.training:
+            losses = super().forward(batched_inputs)
+            self.num_train_iterations += 1
+            return losses
+        images = self.preprocess_images(batched_inputs)
+        features = self.backbone(images.tensor)
+        targets = self._prepare_gt_targets(batched_inputs, images)
+        outputs = self.run_head(features, targets)
+        processed_results = self.inference(batched_inputs, targets, images, outputs, vis=False)
+        self.num_test_iterations += 1
+        return processed_results

@@ -1,0 +1,81 @@
+"""Shared by the CPU host-logic test and the GPU parity test of the ProposalModel eval branch: builds the batched inputs
+of tests/golden/proposal_inference.pt and compares results with the reference's recorded outputs."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+import m2f_oracle as O
+
+NEAR = 1e-4     # |interpolated logit| below which a threshold bit may differ between two fp32 bilinear implementations
+
+
+def oracle_resize(logits, padded, image_size, out_size):
+    up = F.interpolate(logits[None], size=padded, mode="bilinear", align_corners=False)[0]
+    return O.sem_seg_postprocess(up, image_size, *out_size)
+
+
+def unpack_golden(packed, shape):
+    return torch.from_numpy(np.unpackbits(packed, axis=-1)[..., :shape[-1]]).bool()
+
+
+def proposal_stub(overrides, topk, device):
+    """The eval-branch methods of ProposalModel bound to a bare object (no backbone / head needed: the golden inputs are
+    head outputs)."""
+    from partdistillation_b200.postprocess import ProposalInferenceMixin
+
+    class Stub(ProposalInferenceMixin):
+        pass
+    s = Stub()
+    s.device = torch.device(device)
+    s.test_topk_per_image = topk
+    s.wandb_vis_topk = topk
+    for k, v in overrides.items():
+        setattr(s, k, v)
+    return s
+
+
+def run_case(golden, case, device):
+    from partdistillation_b200.compat import BitMasks, ImageList, Instances
+    inp, c = golden["inputs"], golden["cases"][case]
+    Q = inp["pred_logits"].shape[1]
+    model = proposal_stub(c["overrides"], Q, device)
+    padded = inp["padded"]
+    bi = []
+    for it in inp["items"]:
+        H, W = it["size"]
+        inst = Instances((H, W))
+        inst.gt_masks = BitMasks(it["object_mask"])
+        inst.gt_classes = torch.zeros(1, dtype=torch.long)
+        pinst = Instances((H, W))
+        pinst.gt_masks = BitMasks(it["part_masks"])
+        pinst.gt_classes = it["part_classes"]
+        bi.append({"instances": inst, "part_instances": pinst, "height": it["out"][0], "width": it["out"][1]})
+    images = ImageList(torch.zeros(len(bi), 3, *padded, device=device), [it["size"] for it in inp["items"]])
+    outputs = {"pred_logits": inp["pred_logits"].to(device), "pred_masks": inp["pred_masks"].to(device)}
+    targets = model._prepare_gt_targets(bi, images)
+    res = model.inference(bi, targets, images, outputs)
+    assert len(res) == len(c["results"])
+    for b, (r, ref, it) in enumerate(zip(res, c["results"], inp["items"])):
+        dense = oracle_resize(inp["pred_masks"][b], padded, it["size"], it["out"])
+        prop = r["proposals"]
+        assert tuple(prop.image_size) == ref["image_size"]
+        pm = prop.pred_masks.cpu()
+        ref_masks = unpack_golden(ref["pred_masks"], ref["pred_shape"])
+        assert pm.dtype == torch.bool
+        assert tuple(pm.shape) == tuple(ref_masks.shape)
+        assert torch.allclose(prop.scores.cpu(), ref["scores"], rtol=1e-6, atol=1e-7)
+        assert torch.equal(prop.pred_classes.cpu(), ref["pred_classes"])
+        near = (dense.abs() < NEAR).any(0)
+        if c["overrides"]["use_unique_per_pixel_label"]:
+            # per-pixel labels: a pixel may also change owner where the two best score * sigmoid values nearly tie
+            scores = inp["pred_logits"][b].softmax(-1)[:, :-1].topk(1, dim=1)[0].flatten()
+            gated = dense
+            if c["overrides"]["apply_masking_with_object_mask"]:
+                tom = O.sem_seg_postprocess(O.pad_masks(it["object_mask"], padded).float(), it["size"], *it["out"]).bool()
+                gated = dense * tom.sum(0, keepdim=True).bool()
+            top2 = (scores[:, None, None] * gated.sigmoid()).topk(2, dim=0)[0]
+            near = near | ((top2[0] - top2[1]) < 1e-5)
+        assert not ((pm != ref_masks) & ~near[None]).any()
+        assert torch.equal(r["gt_masks"].gt_masks.cpu(), unpack_golden(ref["gt_masks"], ref["gt_shape"]))
+        assert torch.equal(r["gt_masks"].gt_classes.cpu(), ref["gt_classes"])
+    return res

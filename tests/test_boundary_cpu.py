@@ -54,6 +54,21 @@ def test_cabi_rejects_bad_arguments_without_gpu():
     assert rc == -1 and b"null pointer" in lib.pdb_last_error()
     assert lib.pdb_masked_xattn_workspace_bytes(2, 8, 100, 1024, 64) == -1      # head dim must be 32
     assert lib.pdb_masked_xattn_workspace_bytes(2, 8, 100, 1024, 32) > 0
+    # post-processing entry points (a non-null dummy address is never dereferenced: the checks reject first)
+    import ctypes
+    buf = ctypes.create_string_buffer(64)
+    ptr = ctypes.cast(buf, ctypes.c_void_p)
+    rc = lib.pdb_postprocess_masks(ptr, ptr, None, None, ptr, None, 4, 2, 8, 8, 32, 32, 40, 32, 32, 32, None)
+    assert rc == -1 and b"outside the padded size" in lib.pdb_last_error()
+    rc = lib.pdb_postprocess_masks(ptr, ptr, None, None, None, ptr, 4, 2, 8, 8, 32, 32, 32, 32, 32, 32, None)
+    assert rc == -1 and b"needs the scores" in lib.pdb_last_error()
+    rc = lib.pdb_postprocess_masks(ptr, ptr, None, None, None, None, 4, 2, 8, 8, 32, 32, 32, 32, 32, 32, None)
+    assert rc == -1 and b"neither bits nor label" in lib.pdb_last_error()
+    assert lib.pdb_bits_intersect(ptr, ptr, ptr, 0, 3, 10, None) == -1
+    assert lib.pdb_bits_popcount(ptr, None, 1, 10, None) == -1
+    assert lib.pdb_pack_bits(ptr, ptr, 70000, 8, 8, None) == -1
+    assert lib.pdb_unpack_bits(None, None, ptr, 1, 8, 8, None) == -1
+    assert lib.pdb_resize_masks_u8(ptr, ptr, 1, 32, 32, 33, 32, 8, 8, None) == -1
 
 
 def test_registries_resolve_reference_names():

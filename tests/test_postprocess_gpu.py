@@ -1,0 +1,134 @@
+"""GPU: the ProposalModel eval branch on bit-packed masks — the post-processing kernels against
+the CPU oracle (m2f_oracle.proposal_inference, pinned to goldens of the unmodified reference) through the C ABI, and
+the host branch end to end on the golden inputs.
+
+Threshold bits are compared exactly except where the interpolated logit is within fp32 interpolation noise of 0
+(|v| < NEAR: the oracle's ATen CPU kernel and this kernel round the source coordinates differently; measured max
+difference 1.6e-5 on these shapes)."""
+import os
+import pytest
+import torch
+import torch.nn.functional as F
+
+import m2f_oracle as O
+from postprocess_cases import NEAR, oracle_resize, run_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fn():
+    from partdistillation_b200 import functional
+    return functional
+
+
+def unpack_words(bits, width):
+    """int32 words (..., Ww) on any device -> bool (..., width) with torch ops (independent of pdb_unpack_bits)."""
+    b = bits.cpu().to(torch.int64) & 0xFFFFFFFF
+    out = ((b[..., None] >> torch.arange(32)) & 1).bool().flatten(-2)
+    return out[..., :width]
+
+
+GEOMETRIES = [
+    # (h, w), padded, image size, output size
+    ((32, 32), (128, 128), (96, 128), (144, 192)),      # padding cropped + second pass up
+    ((32, 32), (128, 128), (128, 112), (128, 112)),     # second pass is the identity, ragged last word (112 = 3.5 words)
+    ((40, 56), (160, 224), (150, 200), (75, 101)),      # second pass down, odd width
+    ((8, 8), (32, 32), (32, 32), (32, 32)),             # one word per row
+]
+
+
+@pytest.mark.parametrize("geom", GEOMETRIES)
+@pytest.mark.parametrize("gated", [True, False])
+def test_postprocess_masks_bits_and_label(fn, geom, gated):
+    (h, w), padded, image_size, out_size = geom
+    g = torch.Generator().manual_seed(5)
+    Q, K = 9, 6
+    logits = torch.randn(Q, h, w, generator=g) * 2.0
+    logits[4] = -3.0
+    logits[7, : h // 2] = 0.0
+    sel = torch.tensor([7, 0, 4, 2, 8, 5])
+    scores = torch.rand(K, generator=g)
+    yy, xx = torch.meshgrid(torch.arange(out_size[0]), torch.arange(out_size[1]), indexing="ij")
+    gate = ((yy - out_size[0] / 2) ** 2 / (out_size[0] * 0.4) ** 2 + (xx - out_size[1] / 2) ** 2 / (out_size[1] * 0.4) ** 2) < 1
+    bits, label = fn.postprocess_masks(logits.cuda(), sel.cuda(), padded, image_size, out_size,
+                                       gate=gate.cuda() if gated else None, scores=scores.cuda(), want_bits=True,
+                                       want_label=True)
+    assert tuple(bits.shape) == (K + 1, out_size[0], (out_size[1] + 31) // 32)
+    ref = oracle_resize(logits, padded, image_size, out_size)[sel]
+    if gated:
+        ref = ref * gate
+    got = unpack_words(bits, out_size[1])
+    exp = ref > 0
+    flips = got[:K] != exp
+    assert not (flips & (ref.abs() > NEAR)).any()
+    assert flips.float().mean() < 1e-3
+    # padding bits of a ragged last word are zero
+    full = unpack_words(bits, 32 * bits.shape[-1])
+    assert not full[..., out_size[1]:].any()
+    # object map row = OR of the rows the kernel wrote (exact), = topk(1, dim=0)[0] > 0 of the oracle up to the flips
+    assert torch.equal(got[K], got[:K].any(0))
+    # label map: argmax of score * sigmoid; mismatches only at numerical near-ties
+    sm = scores[:, None, None] * ref.sigmoid()
+    exp_label = sm.argmax(0)
+    lab = label.cpu().long()
+    bad = lab != exp_label
+    top2 = sm.topk(2, dim=0)[0]
+    assert not (bad & ((top2[0] - top2[1]) > 1e-5)).any()
+    # popcounts and IoU on the packed words against dense counting of the SAME bits
+    counts = fn.bits_popcount(bits).cpu()
+    assert torch.equal(counts, got.flatten(1).sum(1))
+
+
+@pytest.mark.parametrize("shape", [((5, 64, 96), (3, 64, 96)), ((70, 33, 45), (67, 33, 45)), ((2, 300, 2100), (1, 300, 2100))])
+def test_pack_unpack_popcount_iou(fn, shape):
+    g = torch.Generator().manual_seed(8)
+    a = torch.rand(*shape[0], generator=g) > 0.7
+    b = torch.rand(*shape[1], generator=g) > 0.4
+    a[1] = False
+    b[0] = ~a[0]
+    pa, pb = fn.pack_bits(a.cuda()), fn.pack_bits(b.cuda())
+    assert torch.equal(unpack_words(pa, a.shape[-1]), a)
+    assert torch.equal(fn.unpack_bits(pa, a.shape[-1]).cpu(), a)
+    rows = torch.tensor([a.shape[0] - 1, 0])
+    assert torch.equal(fn.unpack_bits(pa, a.shape[-1], rows.cuda()).cpu(), a[rows])
+    assert torch.equal(fn.bits_popcount(pa).cpu(), a.flatten(1).sum(1))
+    iou = fn.bits_iou(pa, pb).cpu()
+    assert iou.dtype == torch.float64
+    assert torch.equal(iou, O.mask_iou(a, b))
+
+
+@pytest.mark.parametrize("geom", [((128, 128), (96, 128), (144, 192)), ((128, 128), (128, 112), (128, 112)),
+                                  ((160, 224), (150, 200), (75, 101))])
+def test_resize_bool_masks(fn, geom):
+    padded, image_size, out_size = geom
+    g = torch.Generator().manual_seed(2)
+    m = torch.zeros(4, *padded, dtype=torch.bool)
+    lab = torch.randint(0, 4, (image_size[0] // 8 + 1, image_size[1] // 8 + 1), generator=g)
+    lab = lab.repeat_interleave(8, 0).repeat_interleave(8, 1)[:image_size[0], :image_size[1]]
+    for k in range(3):
+        m[k, :image_size[0], :image_size[1]] = lab == k           # m[3] stays empty
+    got = fn.resize_bool_masks(m.cuda(), image_size, out_size).cpu()
+    exp = O.sem_seg_postprocess(m.float(), image_size, *out_size).bool()
+    assert got.dtype == torch.bool and got.shape == exp.shape
+    assert torch.equal(got, exp)
+    assert not got[3].any()
+
+
+@pytest.mark.parametrize("case", ["prop", "prop_filtered", "prop_nomask", "semseg", "semseg_filtered"])
+def test_proposal_inference_vs_golden(fn, golden_dir, case):
+    """ProposalInferenceMixin.inference on the golden inputs against the outputs of the UNMODIFIED reference
+    (tests/golden/proposal_inference.pt, produced by oracle/make_golden.py)."""
+    g = torch.load(os.path.join(golden_dir, "proposal_inference.pt"), weights_only=False)
+    run_case(g, case, "cuda")
+
+
+def test_postprocess_rejects_bad_arguments(fn):
+    x = torch.zeros(3, 8, 8, device="cuda")
+    sel = torch.arange(3, device="cuda")
+    with pytest.raises(RuntimeError):
+        fn.postprocess_masks(x, sel, (32, 32), (40, 32), (32, 32))            # image larger than the padded size
+    with pytest.raises(RuntimeError):
+        fn.postprocess_masks(x, sel, (32, 32), (32, 32), (32, 32), want_label=True)   # label without scores
+    with pytest.raises(RuntimeError):
+        fn.postprocess_masks(x.cpu(), sel.cpu(), (32, 32), (32, 32), (32, 32))        # CUDA only
