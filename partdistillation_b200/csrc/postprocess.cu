@@ -14,51 +14,9 @@
 // depend on the compiler).  When the output size equals the cropped size the second pass has lambda = 0 and is the
 // identity, bit for bit; it is skipped.
 #include "common.cuh"
+#include "postprocess_math.cuh"
 
 namespace pdb {
-
-struct Tap1D {          // one bilinear source coordinate: indices i, i + p and weights (1 - l), l
-    int i, p;
-    float l0, l1;
-};
-
-__device__ __forceinline__ Tap1D make_tap(float scale, int dst, int in_size) {
-    float r = fmaxf(__fadd_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), -0.5f), 0.f);
-    Tap1D t;
-    t.i = (int)r;
-    if (t.i > in_size - 1) t.i = in_size - 1;       // only reachable through rounding when up-sampling by < 1 ulp
-    t.p = (t.i < in_size - 1) ? 1 : 0;
-    t.l1 = __fadd_rn(r, -(float)t.i);
-    t.l0 = __fadd_rn(1.f, -t.l1);
-    return t;
-}
-
-__device__ __forceinline__ float bilerp(float a, float b, float c, float d, float h0, float h1, float w0, float w1) {
-    float top = __fadd_rn(__fmul_rn(w0, a), __fmul_rn(w1, b));
-    float bot = __fadd_rn(__fmul_rn(w0, c), __fmul_rn(w1, d));
-    return __fadd_rn(__fmul_rn(h0, top), __fmul_rn(h1, bot));
-}
-
-// One stage-1 sample (value of the padded-size map at row Y, column X) needs a 2x2 patch of the logits.
-struct Patch {
-    int o00, o01, o10, o11;     // offsets into one query's (h, w) logit plane
-    float h0, h1, w0, w1;
-};
-
-__device__ __forceinline__ Patch make_patch(const Tap1D& ty, const Tap1D& tx, int w) {
-    Patch p;
-    p.o00 = ty.i * w + tx.i;
-    p.o01 = p.o00 + tx.p;
-    p.o10 = (ty.i + ty.p) * w + tx.i;
-    p.o11 = p.o10 + tx.p;
-    p.h0 = ty.l0; p.h1 = ty.l1; p.w0 = tx.l0; p.w1 = tx.l1;
-    return p;
-}
-
-__device__ __forceinline__ float sample_patch(const float* __restrict__ plane, const Patch& p) {
-    return bilerp(__ldg(plane + p.o00), __ldg(plane + p.o01), __ldg(plane + p.o10), __ldg(plane + p.o11),
-                  p.h0, p.h1, p.w0, p.w1);
-}
 
 // grid (Ww, ceil(Ho / 8)), block (32, 8): a warp owns 32 consecutive pixels of one output row = one packed word.
 template <bool TWO_STAGE>
@@ -74,20 +32,7 @@ postprocess_masks_kernel(const float* __restrict__ logits, const int32_t* __rest
     const bool inside = ox < Wo;
     const int cx = inside ? ox : Wo - 1;                    // lanes past the row end compute a valid pixel, then drop it
 
-    Patch p00, p01, p10, p11;
-    float H0 = 1.f, H1 = 0.f, W0 = 1.f, W1 = 0.f;
-    if (TWO_STAGE) {
-        Tap1D ty = make_tap(s2h, oy, Hi), tx = make_tap(s2w, cx, Wi);
-        H0 = ty.l0; H1 = ty.l1; W0 = tx.l0; W1 = tx.l1;
-        Tap1D y0 = make_tap(s1h, ty.i, h), y1 = make_tap(s1h, ty.i + ty.p, h);
-        Tap1D x0 = make_tap(s1w, tx.i, w), x1 = make_tap(s1w, tx.i + tx.p, w);
-        p00 = make_patch(y0, x0, w); p01 = make_patch(y0, x1, w);
-        p10 = make_patch(y1, x0, w); p11 = make_patch(y1, x1, w);
-    } else {
-        Tap1D y0 = make_tap(s1h, oy, h), x0 = make_tap(s1w, cx, w);
-        p00 = make_patch(y0, x0, w);
-        p01 = p10 = p11 = p00;
-    }
+    const PixelTaps taps = make_pixel_taps<TWO_STAGE>(oy, cx, h, w, Hi, Wi, s1h, s1w, s2h, s2w);
     const bool open = inside && (gate == nullptr || gate[(int64_t)oy * Wo + ox] != 0);
     const int64_t plane = (int64_t)h * w;
     const int64_t row_words = (int64_t)Ho * Ww;
@@ -98,21 +43,15 @@ postprocess_masks_kernel(const float* __restrict__ logits, const int32_t* __rest
     int best_k = 0;
     for (int k = 0; k < K; ++k) {
         const float* src = logits + (int64_t)__ldg(sel + k) * plane;
-        float v;
-        if (TWO_STAGE) {
-            v = bilerp(sample_patch(src, p00), sample_patch(src, p01), sample_patch(src, p10), sample_patch(src, p11),
-                       H0, H1, W0, W1);
-        } else {
-            v = sample_patch(src, p00);
-        }
-        if (!open) v = __fmul_rn(v, 0.f);                   // masks_per_image * object_target_mask (:375)
+        float v = sample_pixel<TWO_STAGE>(src, taps);
+        if (!open) v = mul_rn(v, 0.f);                   // masks_per_image * object_target_mask (:375)
         const bool on = inside && (v > 0.f);
         const unsigned wbits = __ballot_sync(0xffffffffu, on);
         any_word |= wbits;
         if (bits != nullptr && threadIdx.x == 0) bits[(int64_t)k * row_words + word] = wbits;
         if (label != nullptr) {
             // scores[:, None, None] * masks.sigmoid() -> topk(1, dim=0)[1]  (:262-264); first maximum wins
-            float s = __fmul_rn(__ldg(scores + k), 1.0f / (1.0f + expf(-v)));
+            float s = mul_rn(__ldg(scores + k), 1.0f / (1.0f + expf(-v)));
             if (k == 0 || s > best) { best = s; best_k = k; }
         }
     }
@@ -128,14 +67,8 @@ resize_masks_u8_kernel(const uint8_t* __restrict__ masks, uint8_t* __restrict__ 
     const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= (int64_t)Ho * Wo) return;
     const int oy = (int)(o / Wo), ox = (int)(o - (int64_t)oy * Wo);
-    Tap1D ty = make_tap(sh, oy, Hi), tx = make_tap(sw, ox, Wi);
     const uint8_t* src = masks + (int64_t)g * Hp * Wp;
-    float a = src[(int64_t)ty.i * Wp + tx.i] ? 1.f : 0.f;
-    float b = src[(int64_t)ty.i * Wp + tx.i + tx.p] ? 1.f : 0.f;
-    float c = src[(int64_t)(ty.i + ty.p) * Wp + tx.i] ? 1.f : 0.f;
-    float d = src[(int64_t)(ty.i + ty.p) * Wp + tx.i + tx.p] ? 1.f : 0.f;
-    float v = bilerp(a, b, c, d, ty.l0, ty.l1, tx.l0, tx.l1);
-    out[(int64_t)g * Ho * Wo + o] = (v != 0.f) ? 1 : 0;
+    out[(int64_t)g * Ho * Wo + o] = resized_mask_bit(src, Wp, Hi, Wi, oy, ox, sh, sw) ? 1 : 0;
 }
 
 // grid (Ww, ceil(Ho / 8), R), block (32, 8)

@@ -72,3 +72,68 @@ def test_eval_branch_has_no_cpu_path(golden_dir):
     g = torch.load(os.path.join(golden_dir, "proposal_inference.pt"), weights_only=False)
     with pytest.raises(RuntimeError, match="CUDA-only"):
         run_case(g, "prop", "cpu")
+
+
+# ------------------------------------------------------------------ the kernels' per-pixel arithmetic, compiled for the host
+GEOMETRIES = [
+    # (h, w), padded, image size, output size
+    ((32, 32), (128, 128), (96, 128), (144, 192)),
+    ((32, 32), (128, 128), (128, 112), (128, 112)),
+    ((40, 56), (160, 224), (150, 200), (75, 101)),
+    ((40, 56), (160, 224), (150, 200), (333, 517)),
+    ((8, 8), (32, 32), (32, 32), (32, 32)),
+    ((256, 256), (1024, 1024), (1024, 1024), (1024, 1024)),      # BASELINE configs[1] geometry
+]
+
+
+@pytest.fixture(scope="module")
+def host_math(tmp_path_factory):
+    """tests/native/postprocess_host.cpp + csrc/postprocess_math.cuh built with g++ into a temporary directory."""
+    import ctypes
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = str(tmp_path_factory.mktemp("pp_host") / "libpp_host.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-x", "c++",
+                           os.path.join(here, "native", "postprocess_host.cpp"), "-o", so])
+    lib = ctypes.CDLL(so)
+    ints = [ctypes.c_int] * 9
+    lib.pp_host_resize.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + ints
+    lib.pp_host_resize.restype = None
+    lib.pp_host_resize_masks.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + ints[:7]
+    lib.pp_host_resize_masks.restype = None
+    return lib
+
+
+@pytest.mark.parametrize("geom", GEOMETRIES)
+def test_kernel_pixel_math_matches_oracle(host_math, geom):
+    """The composed two-pass bilinear value of postprocess_math.cuh (host build) against F.interpolate o crop o
+    F.interpolate: within fp32 interpolation noise everywhere, identical threshold bits outside |v| < 1e-4."""
+    (h, w), padded, image_size, out_size = geom
+    g = torch.Generator().manual_seed(5)
+    K = 3 if h < 100 else 1
+    logits = (torch.randn(K, h, w, generator=g) * 2.0).contiguous()
+    logits[0, : h // 2] = 0.0
+    out = torch.empty(K, *out_size)
+    host_math.pp_host_resize(logits.data_ptr(), out.data_ptr(), K, h, w, *padded, *image_size, *out_size)
+    ref = oracle_resize(logits, padded, image_size, out_size)
+    assert (out - ref).abs().max() < 5e-5
+    flips = (out > 0) != (ref > 0)
+    assert not (flips & (ref.abs() > 1e-4)).any()
+    assert flips.float().mean() < 1e-3
+    assert torch.equal(out[0, : out_size[0] // 4] == 0, ref[0, : out_size[0] // 4] == 0)    # exact zeros stay exact
+
+
+@pytest.mark.parametrize("geom", GEOMETRIES)
+def test_kernel_mask_resize_math_matches_oracle(host_math, geom):
+    _, padded, image_size, out_size = geom
+    g = torch.Generator().manual_seed(2)
+    G = 3
+    m = torch.zeros(G, *padded, dtype=torch.uint8)
+    lab = torch.randint(0, 4, (image_size[0] // 8 + 1, image_size[1] // 8 + 1), generator=g)
+    lab = lab.repeat_interleave(8, 0).repeat_interleave(8, 1)[:image_size[0], :image_size[1]]
+    for k in range(G - 1):
+        m[k, :image_size[0], :image_size[1]] = (lab == k).to(torch.uint8)
+    out = torch.empty(G, *out_size, dtype=torch.uint8)
+    host_math.pp_host_resize_masks(m.data_ptr(), out.data_ptr(), G, *padded, *image_size, *out_size)
+    exp = O.sem_seg_postprocess(m.float(), image_size, *out_size).bool()
+    assert torch.equal(out.bool(), exp)
