@@ -305,11 +305,13 @@ PDB_API int pdb_group_norm_backward(const float* dy, const float* x, const float
  * 32 * word + i of that image row.
  *
  * pdb_postprocess_masks:  logits (Q, h, w) f32 (one image of pred_masks); sel (K) int32 query indices (the top-k);
- *   scores (K) f32 (NULL unless label != NULL); gate (Ho, Wo) uint8 object mask or NULL;
+ *   scores (K) f32 (NULL unless label or score_bits is requested); gate (Ho, Wo) uint8 object mask or NULL;
  *   bits (K + 1, Ho, Ww) uint32 or NULL: row k = [resized(logits[sel[k]]) * gate > 0], row K = OR of the K rows
  *   (the reference's `topk(1, dim=0)[0] > 0` object map); label (Ho, Wo) int32 or NULL = argmax_k scores[k] *
  *   sigmoid(resized * gate) (first maximum).  (h, w) -> bilinear -> (Hp, Wp) -> crop (Hi, Wi) -> bilinear ->
- *   (Ho, Wo), both passes align_corners=False, composed per output pixel.
+ *   (Ho, Wo), both passes align_corners=False, composed per output pixel.  score_bits (K, Ho, Ww) uint32 or NULL:
+ *   row k = [scores[k] * sigmoid(resized * gate) > score_thr] (PartDistillationModel's `predmask > 0.5` area filter and
+ *   its `predmask > 0` masks, part_distillation_model.py:379-394).
  * pdb_resize_masks_u8:  masks (G, Hp, Wp) uint8 0/1 -> out (G, Ho, Wo) uint8 = [bilinear(float(crop (Hi, Wi))) != 0]
  *   (sem_seg_postprocess(target["masks"].float(), ...).bool(), :244-245).
  * pdb_pack_bits / pdb_unpack_bits:  (R, Ho, Wo) uint8 (non-zero = set) <-> (R, Ho, Ww) words; unpack gathers rows[r]
@@ -319,8 +321,8 @@ PDB_API int pdb_group_norm_backward(const float* dy, const float* x, const float
  *   IoU (pycocotools rleIou, iscrowd = 0) = inter / (|a| + |b| - inter), exactly 0 where inter == 0.
  * ---------------------------------------------------------------------------------------------- */
 PDB_API int pdb_postprocess_masks(const float* logits, const int32_t* sel, const float* scores, const uint8_t* gate,
-                          uint32_t* bits, int32_t* label, int Q, int K, int h, int w, int Hp, int Wp, int Hi, int Wi,
-                          int Ho, int Wo, void* stream);
+                          uint32_t* bits, int32_t* label, uint32_t* score_bits, float score_thr, int Q, int K, int h,
+                          int w, int Hp, int Wp, int Hi, int Wi, int Ho, int Wo, void* stream);
 PDB_API int pdb_resize_masks_u8(const uint8_t* masks, uint8_t* out, int G, int Hp, int Wp, int Hi, int Wi, int Ho, int Wo,
                         void* stream);
 PDB_API int pdb_pack_bits(const uint8_t* in, uint32_t* bits, int R, int Ho, int Wo, void* stream);

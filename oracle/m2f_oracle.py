@@ -752,3 +752,84 @@ def proposal_inference(pred_logits, pred_masks, items, padded, topk, **flags):
         out.append(dict(pred_masks=masks, scores=scores, pred_classes=labels, gt_masks=tm,
                         gt_classes=it["part_classes"]))
     return out
+
+
+# --------------------------------------------------------------------------------------
+# f4  PartDistillationModel eval branch  (part_distillation_model.py:239-283 inference,
+#     :329-394 match_gt_labels / _unique_assignment_with_classes, :431-501 _prepare_gt_targets /
+#     instance_inference_with_classification)
+# --------------------------------------------------------------------------------------
+
+
+def pd_unique_assignment_with_classes(masks, scores, class_labels, per_pixel, min_ratio, min_score):
+    """_unique_assignment_with_classes (:346-394), including its quirk in the proposal setting: once the area
+    filter keeps anything, the returned masks are ``score * sigmoid(logit) > 0`` instead of ``logit > 0`` (:385-394)."""
+    obj = masks.topk(1, dim=0)[0] > 0.0
+    pred = scores[:, None, None] * masks.sigmoid()
+    if per_pixel:
+        score_map = pred.topk(1, dim=0)[1]
+        ids = score_map.unique()
+        seg = torch.stack([((score_map == c) & obj)[0] for c in ids]).to(masks.dtype)
+        scores, class_labels = scores[ids], class_labels[ids]
+        new_labels = class_labels.unique()
+        new = torch.stack([seg[class_labels == c].sum(dim=0).bool() for c in new_labels]).to(masks.dtype)
+        new_scores = torch.stack([scores[class_labels == c].topk(1, dim=0)[0].flatten()[0] for c in new_labels])
+        valid = new.flatten(1).sum(1) / obj.flatten(1).sum(1) > min_ratio
+        if valid.any():
+            new, new_scores, new_labels = new[valid], new_scores[valid], new_labels[valid]
+        valid = new_scores > min_score
+        if valid.any():
+            new, new_scores, new_labels = new[valid], new_scores[valid], new_labels[valid]
+        return new.bool(), new_scores, new_labels
+    valid = (pred > 0.5).flatten(1).sum(1) / obj.flatten(1).sum(1) > min_ratio
+    if valid.any():
+        masks, scores, class_labels = pred[valid], scores[valid], class_labels[valid]
+    valid = scores > min_score
+    if valid.any():
+        masks, scores, class_labels = masks[valid], scores[valid], class_labels[valid]
+    return masks > 0, scores, class_labels
+
+
+def pd_instance_inference(mask_cls, mask_pred, target_mask, target_object_mask, target_labels, num_classes, topk,
+                          mapping=None, per_pixel=False, min_ratio=0.0, min_score=0.0, gate=True, fg_thr=0.1,
+                          oracle_classifier=False):
+    """instance_inference_with_classification (:456-501) -> (bool masks, scores, pred classes)."""
+    Q = mask_cls.shape[0]
+    scores = mask_cls.softmax(-1)[:, :-1]
+    labels = torch.arange(num_classes).unsqueeze(0).repeat(Q, 1).flatten(0, 1)
+    scores, idx = scores.flatten(0, 1).topk(topk, sorted=False)
+    labels = labels[idx]
+    if mapping is not None:                                                                   # mode == "eval" (:467-469)
+        labels = mapping[labels]
+    idx = torch.div(idx, num_classes, rounding_mode="floor")
+    mask_pred = mask_pred[idx]
+    if gate:
+        mask_pred = mask_pred * target_object_mask.sum(dim=0, keepdim=True).bool()           # (:319-326)
+    masks, scores, labels = pd_unique_assignment_with_classes(mask_pred, scores, labels, per_pixel, min_ratio, min_score)
+    ious = mask_iou(masks, target_mask)                                                       # (:329-343)
+    top1, top1_idx = ious.topk(1, dim=1)
+    fg = (top1 > fg_thr).flatten()
+    gt_labels = target_labels[top1_idx.flatten()[fg]]
+    masks, scores, labels = masks[fg], scores[fg], labels[fg]
+    if masks.shape[0] == 0:                                                                   # (:481-486)
+        masks = torch.zeros((1, *mask_pred.shape[1:]), dtype=torch.bool)
+        scores = scores.new_zeros(1)
+        labels = scores.new_ones(1).long() * num_classes
+        gt_labels = scores.new_ones(1).long() * num_classes
+    return masks, scores, (gt_labels if oracle_classifier else labels)
+
+
+def pd_inference(pred_logits, pred_masks, items, padded, object_classes, num_classes, topk, mappings=None, **flags):
+    """inference (:239-283).  ``mappings``: {object class: (num_classes,) long} when mode == "eval", else None."""
+    up = F.interpolate(pred_masks, size=padded, mode="bilinear", align_corners=False)
+    out = []
+    for b, it in enumerate(items):
+        size, (oh, ow) = it["size"], it["out"]
+        mp = sem_seg_postprocess(up[b], size, oh, ow)
+        tm = sem_seg_postprocess(pad_masks(it["part_masks"], padded).float(), size, oh, ow).bool()
+        tom = sem_seg_postprocess(pad_masks(it["object_mask"], padded).float(), size, oh, ow).bool()
+        mapping = mappings[int(object_classes[b])] if mappings is not None else None
+        masks, scores, labels = pd_instance_inference(pred_logits[b].to(mp), mp, tm, tom, it["part_classes"], num_classes,
+                                                      topk, mapping=mapping, **flags)
+        out.append(dict(pred_masks=masks, scores=scores, pred_classes=labels, gt_masks=tm, gt_classes=it["part_classes"]))
+    return out

@@ -311,6 +311,75 @@ def golden_proposal_inference(ref):
     print("proposal_inference.pt", {n: [r["pred_shape"] for r in c["results"]] for n, c in g["cases"].items()})
 
 
+PD_INFER_CASES = {
+    # name: (mode, attribute overrides on the reference PartDistillationModel; part_distillation_model.py:36-97)
+    "prop": ("eval", dict(use_unique_per_pixel_label=False, min_pseudo_mask_score=0.0, min_pseudo_mask_ratio=0.0,
+                          apply_masking_with_object_mask=True, use_oracle_classifier=False)),
+    "prop_filtered": ("eval", dict(use_unique_per_pixel_label=False, min_pseudo_mask_score=0.2, min_pseudo_mask_ratio=0.9,
+                                   apply_masking_with_object_mask=True, use_oracle_classifier=False)),
+    "prop_none_valid": ("eval", dict(use_unique_per_pixel_label=False, min_pseudo_mask_score=0.0, min_pseudo_mask_ratio=50.0,
+                                     apply_masking_with_object_mask=True, use_oracle_classifier=False)),
+    "semseg": ("eval", dict(use_unique_per_pixel_label=True, min_pseudo_mask_score=0.0, min_pseudo_mask_ratio=0.0,
+                            apply_masking_with_object_mask=True, use_oracle_classifier=False)),
+    "semseg_filtered": ("eval", dict(use_unique_per_pixel_label=True, min_pseudo_mask_score=0.2, min_pseudo_mask_ratio=0.05,
+                                     apply_masking_with_object_mask=True, use_oracle_classifier=False)),
+    "semseg_oracle_cls": ("", dict(use_unique_per_pixel_label=True, min_pseudo_mask_score=0.0, min_pseudo_mask_ratio=0.0,
+                                   apply_masking_with_object_mask=False, use_oracle_classifier=True)),
+}
+
+
+def golden_pd_inference(ref):
+    """PartDistillationModel eval branch of the UNMODIFIED reference (part_distillation_model.py:239-283,329-394,
+    431-501: inference, _prepare_gt_targets, instance_inference_with_classification,
+    _unique_assignment_with_classes, match_gt_labels) on synthetic head outputs."""
+    from detectron2.structures import ImageList, Instances, BitMasks
+    Q, P, TOPK = 12, 8, 20
+    cfg = rl.make_cfg("PartDistillationModel", "swin_micro", num_queries=Q, dec_layers=3, num_points=64,
+                      num_object_classes=50, num_part_classes=P)
+    cfg.TEST.DETECTIONS_PER_IMAGE = TOPK
+    model = rl.build_model(cfg, "/tmp/pd_oracle_work")
+    model.eval()
+    inp = synth_inference_inputs(seed=23, Q=Q)
+    g = torch.Generator().manual_seed(77)
+    inp["pred_logits"] = torch.randn(2, Q, P + 1, generator=g) * 2.0
+    inp["object_classes"] = [7, 31]
+    inp["majority_vote_mapping"] = {7: torch.randint(0, 5, (P,), generator=g), 31: torch.randint(0, 5, (P,), generator=g)}
+    inp["topk"] = TOPK
+    inp["fg_score_threshold"] = float(model.fg_score_threshold)
+    Hp, Wp = inp["padded"]
+    bi = []
+    for it, oc in zip(inp["items"], inp["object_classes"]):
+        H, W = it["size"]
+        inst = Instances((H, W)); inst.gt_masks = BitMasks(it["object_mask"]); inst.gt_classes = torch.tensor([oc])
+        pinst = Instances((H, W)); pinst.gt_masks = BitMasks(it["part_masks"]); pinst.gt_classes = it["part_classes"]
+        bi.append({"image": torch.zeros(3, H, W, dtype=torch.uint8), "instances": inst, "part_instances": pinst,
+                   "height": it["out"][0], "width": it["out"][1]})
+    il = ImageList(torch.zeros(2, 3, Hp, Wp), [it["size"] for it in inp["items"]])
+    outputs = {"pred_logits": inp["pred_logits"], "pred_masks": inp["pred_masks"]}
+    import logging
+    model.logger = logging.getLogger("oracle")      # the reference never sets it (AttributeError at :192 otherwise)
+    model.update_majority_vote_mapping(inp["majority_vote_mapping"])
+    out = dict(inputs=inp, cases={})
+    for name, (mode, over) in PD_INFER_CASES.items():
+        model.mode = mode
+        for k, v in over.items():
+            assert hasattr(model, k), k
+            setattr(model, k, v)
+        with torch.no_grad():
+            targets = model.prepare_targets(bi, il)
+            res = model.inference(bi, targets, il, outputs, vis=False)
+        rec = []
+        for r in res:
+            p, t = r["predictions"], r["gt_instances"]
+            rec.append(dict(pred_masks=np.packbits(p.pred_masks.numpy(), axis=-1), pred_shape=tuple(p.pred_masks.shape),
+                            scores=p.scores.clone(), pred_classes=p.pred_classes.clone(), image_size=tuple(p.image_size),
+                            gt_masks=np.packbits(t.gt_masks.numpy(), axis=-1), gt_shape=tuple(t.gt_masks.shape),
+                            gt_classes=t.gt_classes.clone(), gt_object_label=torch.as_tensor(r["gt_object_label"]).clone()))
+        out["cases"][name] = dict(mode=mode, overrides=over, results=rec)
+    torch.save(out, os.path.join(OUT, "pd_inference.pt"))
+    print("pd_inference.pt", {n: [(r["pred_shape"], r["pred_classes"].tolist()) for r in c["results"]] for n, c in out["cases"].items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = rl.load()
@@ -319,8 +388,10 @@ def main():
         return
     if "--inference-only" in sys.argv:
         golden_proposal_inference(ref)
+        golden_pd_inference(ref)
         return
     golden_proposal_inference(ref)
+    golden_pd_inference(ref)
     golden_pixel_grouping(ref)
     golden_msda(ref)
     golden_swin(ref)

@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256)
 postprocess_masks_kernel(const float* __restrict__ logits, const int32_t* __restrict__ sel,
                          const float* __restrict__ scores, const uint8_t* __restrict__ gate,
                          uint32_t* __restrict__ bits, int32_t* __restrict__ label,
+                         uint32_t* __restrict__ score_bits, float score_thr,
                          int K, int h, int w, int Hi, int Wi, int Ho, int Wo, int Ww,
                          float s1h, float s1w, float s2h, float s2w) {
     const int ox = blockIdx.x * 32 + threadIdx.x;
@@ -49,10 +50,14 @@ postprocess_masks_kernel(const float* __restrict__ logits, const int32_t* __rest
         const unsigned wbits = __ballot_sync(0xffffffffu, on);
         any_word |= wbits;
         if (bits != nullptr && threadIdx.x == 0) bits[(int64_t)k * row_words + word] = wbits;
-        if (label != nullptr) {
+        if (scores != nullptr) {
             // scores[:, None, None] * masks.sigmoid() -> topk(1, dim=0)[1]  (:262-264); first maximum wins
             float s = mul_rn(__ldg(scores + k), 1.0f / (1.0f + expf(-v)));
             if (k == 0 || s > best) { best = s; best_k = k; }
+            if (score_bits != nullptr) {        // (predmask > thr) of part_distillation_model.py:379,385,391
+                const unsigned sb = __ballot_sync(0xffffffffu, inside && (s > score_thr));
+                if (threadIdx.x == 0) score_bits[(int64_t)k * row_words + word] = sb;
+            }
         }
     }
     if (bits != nullptr && threadIdx.x == 0) bits[(int64_t)K * row_words + word] = any_word;   // topk(1, dim=0)[0] > 0 (:259)
@@ -166,11 +171,14 @@ bits_intersect_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict
 using namespace pdb;
 
 extern "C" int pdb_postprocess_masks(const float* logits, const int32_t* sel, const float* scores, const uint8_t* gate,
-                                     uint32_t* bits, int32_t* label, int Q, int K, int h, int w, int Hp, int Wp,
-                                     int Hi, int Wi, int Ho, int Wo, void* stream) {
+                                     uint32_t* bits, int32_t* label, uint32_t* score_bits, float score_thr, int Q,
+                                     int K, int h, int w, int Hp, int Wp, int Hi, int Wi, int Ho, int Wo,
+                                     void* stream) {
     PDB_REQUIRE(logits && sel, "postprocess_masks: null pointer");
-    PDB_REQUIRE(bits || label, "postprocess_masks: neither bits nor label requested");
-    PDB_REQUIRE(label == nullptr || scores != nullptr, "postprocess_masks: label map needs the scores");
+    PDB_REQUIRE(bits || label || score_bits, "postprocess_masks: neither bits nor label requested");
+    PDB_REQUIRE((label == nullptr && score_bits == nullptr) || scores != nullptr,
+                "postprocess_masks: label map / score bits needs the scores");
+    if (label == nullptr && score_bits == nullptr) scores = nullptr;     // the kernel keys the sigmoid work on `scores`
     PDB_REQUIRE(Q > 0 && K > 0 && h > 0 && w > 0 && Hp > 0 && Wp > 0 && Ho > 0 && Wo > 0,
                 "postprocess_masks: non-positive dimension");
     PDB_REQUIRE(Hi > 0 && Wi > 0 && Hi <= Hp && Wi <= Wp, "postprocess_masks: image size (%d, %d) outside the padded size (%d, %d)",
@@ -186,10 +194,10 @@ extern "C" int pdb_postprocess_masks(const float* logits, const int32_t* sel, co
     dim3 grid((unsigned)Ww, gy), block(32, 8);
     if (Hi == Ho && Wi == Wo)
         postprocess_masks_kernel<false><<<grid, block, 0, as_stream(stream)>>>(
-            logits, sel, scores, gate, bits, label, K, h, w, Hi, Wi, Ho, Wo, Ww, s1h, s1w, s2h, s2w);
+            logits, sel, scores, gate, bits, label, score_bits, score_thr, K, h, w, Hi, Wi, Ho, Wo, Ww, s1h, s1w, s2h, s2w);
     else
         postprocess_masks_kernel<true><<<grid, block, 0, as_stream(stream)>>>(
-            logits, sel, scores, gate, bits, label, K, h, w, Hi, Wi, Ho, Wo, Ww, s1h, s1w, s2h, s2w);
+            logits, sel, scores, gate, bits, label, score_bits, score_thr, K, h, w, Hi, Wi, Ho, Wo, Ww, s1h, s1w, s2h, s2w);
     return launched("postprocess_masks");
 }
 

@@ -724,11 +724,12 @@ def _u8(mask):
 
 
 def postprocess_masks(logits, sel, padded_size, image_size, out_size, gate=None, scores=None, want_bits=True,
-                      want_label=False):
+                      want_label=False, score_threshold=None):
     """logits (Q, h, w) f32 of ONE image, sel (K) query indices -> (bits (K + 1, Ho, ceil(Wo / 32)) int32 words or
     None, label (Ho, Wo) int32 or None).  Row k of ``bits`` is ``resize(logits[sel[k]]) * gate > 0`` with ``resize`` =
     bilinear to ``padded_size``, crop to ``image_size``, bilinear to ``out_size`` (both align_corners=False); row K is
-    the OR over k.  ``label`` = argmax_k scores[k] * sigmoid(resize * gate)."""
+    the OR over k.  ``label`` = argmax_k scores[k] * sigmoid(resize * gate).  With ``score_threshold`` a third result is
+    returned: words (K, Ho, Ww) of ``scores[k] * sigmoid(resize * gate) > score_threshold``."""
     _need_cuda(logits, sel, gate, scores)
     if logits.dtype != torch.float32 or logits.dim() != 3:
         raise RuntimeError("postprocess_masks: logits must be float32 (Q, h, w)")
@@ -741,20 +742,26 @@ def postprocess_masks(logits, sel, padded_size, image_size, out_size, gate=None,
         gate = _u8(gate)
         if tuple(gate.shape[-2:]) != (Ho, Wo) or gate.numel() != Ho * Wo:
             raise RuntimeError(f"postprocess_masks: gate shape {tuple(gate.shape)} != output size {(Ho, Wo)}")
-    if want_label:
+    need_scores = want_label or score_threshold is not None
+    if need_scores:
         if scores is None:
-            raise RuntimeError("postprocess_masks: the label map needs the scores")
+            raise RuntimeError("postprocess_masks: the label map / score bits need the scores")
         scores = _c(scores.float())
     Ww = (Wo + 31) // 32
     bits = torch.empty((K + 1, Ho, Ww), dtype=torch.int32, device=logits.device) if want_bits else None
     label = torch.empty((Ho, Wo), dtype=torch.int32, device=logits.device) if want_label else None
+    sbits = torch.empty((K, Ho, Ww), dtype=torch.int32, device=logits.device) if score_threshold is not None else None
     rc = _lib.load().pdb_postprocess_masks(logits.data_ptr(), sel.data_ptr(),
-                                           scores.data_ptr() if want_label else None,
+                                           scores.data_ptr() if need_scores else None,
                                            gate.data_ptr() if gate is not None else None,
                                            bits.data_ptr() if want_bits else None,
                                            label.data_ptr() if want_label else None,
+                                           sbits.data_ptr() if sbits is not None else None,
+                                           float(score_threshold) if score_threshold is not None else 0.0,
                                            Q, K, h, w, Hp, Wp, Hi, Wi, Ho, Wo, _stream())
     _lib.check(rc, "pdb_postprocess_masks")
+    if score_threshold is not None:
+        return bits, label, sbits
     return bits, label
 
 

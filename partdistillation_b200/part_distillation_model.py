@@ -1,5 +1,6 @@
 """``PartDistillationModel`` meta-architecture — training branch
-(reference: part_distillation/part_distillation_model.py:32-226,405-428).
+(reference: part_distillation/part_distillation_model.py:32-226,405-428) and eval branch (:227-283,319-394,431-501;
+``postprocess.PartDistillationInferenceMixin``).
 
 Differences from ProposalModel, as in the reference: the head receives the targets (``mask=targets``,
 :205) because the float64 classifier needs each image's object class; the matcher and the loss may
@@ -10,10 +11,11 @@ from torch import nn
 
 from .compat import META_ARCH_REGISTRY, build_backbone, build_sem_seg_head, configurable
 from .meta_base import Mask2FormerTrainingArch, build_criterion
+from .postprocess import PartDistillationInferenceMixin
 
 
 @META_ARCH_REGISTRY.register()
-class PartDistillationModel(Mask2FormerTrainingArch):
+class PartDistillationModel(PartDistillationInferenceMixin, Mask2FormerTrainingArch):
     part_distillation = True
 
     @configurable
@@ -22,7 +24,8 @@ class PartDistillationModel(Mask2FormerTrainingArch):
                  train_dataset_name: str = "", use_wandb: bool = True, wandb_vis_period_train: int = 200,
                  wandb_vis_period_test: int = 20, wandb_vis_topk: int = 200, use_unique_per_pixel_label: bool = False,
                  min_pseudo_mask_ratio: float = 0.0, min_pseudo_mask_score: float = 0.0,
-                 use_oracle_classifier: bool = False, apply_masking_with_object_mask: bool = True):
+                 use_oracle_classifier: bool = False, apply_masking_with_object_mask: bool = True,
+                 fg_score_threshold: float = 0.1):
         super().__init__()
         self._init_common(backbone, sem_seg_head, criterion, num_queries, num_classes, size_divisibility, pixel_mean,
                           pixel_std, test_topk_per_image, use_wandb)
@@ -31,6 +34,8 @@ class PartDistillationModel(Mask2FormerTrainingArch):
         self.wandb_vis_period_test = wandb_vis_period_test
         self.wandb_vis_topk = wandb_vis_topk
         self.current_train_iteration = 0
+        self.current_test_iteration = 0
+        self.fg_score_threshold = fg_score_threshold
         self.use_unique_per_pixel_label = use_unique_per_pixel_label
         self.min_pseudo_mask_ratio = min_pseudo_mask_ratio
         self.min_pseudo_mask_score = min_pseudo_mask_score
@@ -63,6 +68,17 @@ class PartDistillationModel(Mask2FormerTrainingArch):
                     apply_masking_with_object_mask=pd.APPLY_MASKING_WITH_OBJECT_MASK)
 
     def forward(self, batched_inputs):
-        losses = super().forward(batched_inputs)
-        self.current_train_iteration += 1
-        return losses
+        if self.training:
+            losses = super().forward(batched_inputs)
+            self.current_train_iteration += 1
+            return losses
+        if self.mode == "save":
+            raise NotImplementedError("PartDistillationModel mode 'save' (pseudo-label dump, part_distillation_model.py:"
+                                      "285-306) is outside the accelerated path")
+        images = self.preprocess_images(batched_inputs)
+        features = self.backbone(images.tensor)
+        targets = self._prepare_gt_targets(batched_inputs, images)
+        outputs = self.run_head(features, targets)
+        processed_results = self.inference(batched_inputs, targets, images, outputs, vis=False)
+        self.current_test_iteration += 1
+        return processed_results

@@ -58,11 +58,11 @@ def test_cabi_rejects_bad_arguments_without_gpu():
     import ctypes
     buf = ctypes.create_string_buffer(64)
     ptr = ctypes.cast(buf, ctypes.c_void_p)
-    rc = lib.pdb_postprocess_masks(ptr, ptr, None, None, ptr, None, 4, 2, 8, 8, 32, 32, 40, 32, 32, 32, None)
+    rc = lib.pdb_postprocess_masks(ptr, ptr, None, None, ptr, None, None, 0.0, 4, 2, 8, 8, 32, 32, 40, 32, 32, 32, None)
     assert rc == -1 and b"outside the padded size" in lib.pdb_last_error()
-    rc = lib.pdb_postprocess_masks(ptr, ptr, None, None, None, ptr, 4, 2, 8, 8, 32, 32, 32, 32, 32, 32, None)
+    rc = lib.pdb_postprocess_masks(ptr, ptr, None, None, None, ptr, None, 0.0, 4, 2, 8, 8, 32, 32, 32, 32, 32, 32, None)
     assert rc == -1 and b"needs the scores" in lib.pdb_last_error()
-    rc = lib.pdb_postprocess_masks(ptr, ptr, None, None, None, None, 4, 2, 8, 8, 32, 32, 32, 32, 32, 32, None)
+    rc = lib.pdb_postprocess_masks(ptr, ptr, None, None, None, None, None, 0.0, 4, 2, 8, 8, 32, 32, 32, 32, 32, 32, None)
     assert rc == -1 and b"neither bits nor label" in lib.pdb_last_error()
     assert lib.pdb_bits_intersect(ptr, ptr, ptr, 0, 3, 10, None) == -1
     assert lib.pdb_bits_popcount(ptr, None, 1, 10, None) == -1

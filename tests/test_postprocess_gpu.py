@@ -11,7 +11,7 @@ import torch
 import torch.nn.functional as F
 
 import m2f_oracle as O
-from postprocess_cases import NEAR, oracle_resize, run_case
+from postprocess_cases import NEAR, oracle_resize, run_case, run_pd_case
 
 pytestmark = pytest.mark.gpu
 
@@ -121,6 +121,36 @@ def test_proposal_inference_vs_golden(fn, golden_dir, case):
     (tests/golden/proposal_inference.pt, produced by oracle/make_golden.py)."""
     g = torch.load(os.path.join(golden_dir, "proposal_inference.pt"), weights_only=False)
     run_case(g, case, "cuda")
+
+
+@pytest.mark.parametrize("case", ["prop", "prop_filtered", "prop_none_valid", "semseg", "semseg_filtered", "semseg_oracle_cls"])
+def test_pd_inference_vs_golden(fn, golden_dir, case):
+    """PartDistillationInferenceMixin.inference against the outputs of the UNMODIFIED reference
+    (tests/golden/pd_inference.pt)."""
+    g = torch.load(os.path.join(golden_dir, "pd_inference.pt"), weights_only=False)
+    run_pd_case(g, case, "cuda")
+
+
+def test_score_threshold_bits(fn):
+    """score_bits rows = scores[k] * sigmoid(resized * gate) > thr, against the oracle away from the threshold."""
+    g = torch.Generator().manual_seed(12)
+    Q, K = 7, 10
+    logits = torch.randn(Q, 24, 40, generator=g) * 2.0
+    sel = torch.randint(0, Q, (K,), generator=g)              # repeated queries, as (query, class) pairs produce
+    scores = torch.rand(K, generator=g) * 0.5 + 0.5
+    padded, image_size, out_size = (96, 160), (90, 150), (120, 200)
+    gate = torch.rand(*out_size, generator=g) > 0.3
+    bits, label, sb = fn.postprocess_masks(logits.cuda(), sel.cuda(), padded, image_size, out_size, gate=gate.cuda(),
+                                           scores=scores.cuda(), want_bits=True, want_label=False, score_threshold=0.5)
+    assert label is None and tuple(sb.shape) == (K, out_size[0], (out_size[1] + 31) // 32)
+    ref = oracle_resize(logits, padded, image_size, out_size)[sel] * gate
+    pred = scores[:, None, None] * ref.sigmoid()
+    got = unpack_words(sb, out_size[1])
+    assert not ((got != (pred > 0.5)) & ((pred - 0.5).abs() > 1e-5)).any()
+    _, _, sb0 = fn.postprocess_masks(logits.cuda(), sel.cuda(), padded, image_size, out_size, gate=gate.cuda(),
+                                     scores=scores.cuda(), want_bits=False, score_threshold=0.0)
+    assert unpack_words(sb0, out_size[1]).all()               # score * sigmoid > 0 everywhere for finite logits
+    assert not (unpack_words(bits, out_size[1])[:K] != (ref > 0))[(ref.abs() > NEAR)].any()
 
 
 def test_postprocess_rejects_bad_arguments(fn):

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 import m2f_oracle as O
-from postprocess_cases import oracle_resize, run_case
+from postprocess_cases import oracle_resize, run_case, run_pd_case
 
 
 def _pack(m):
@@ -27,13 +27,16 @@ def _unpack(bits, width, rows=None):
     return out if rows is None else out[rows.long()]
 
 
-def _postprocess_masks(logits, sel, padded, image_size, out_size, gate=None, scores=None, want_bits=True, want_label=False):
+def _postprocess_masks(logits, sel, padded, image_size, out_size, gate=None, scores=None, want_bits=True, want_label=False,
+                       score_threshold=None):
     v = oracle_resize(logits, padded, image_size, out_size)[sel.long()]
     if gate is not None:
         v = v * gate
     on = v > 0
     bits = _pack(torch.cat([on, on.any(0, keepdim=True)])) if want_bits else None
     label = (scores[:, None, None] * v.sigmoid()).argmax(0).to(torch.int32) if want_label else None
+    if score_threshold is not None:
+        return bits, label, _pack(scores[:, None, None] * v.sigmoid() > score_threshold)
     return bits, label
 
 
@@ -60,6 +63,15 @@ def torch_ops(monkeypatch):
 def test_eval_branch_host_logic(torch_ops, golden_dir, case):
     g = torch.load(os.path.join(golden_dir, "proposal_inference.pt"), weights_only=False)
     run_case(g, case, "cpu")
+
+
+PD_CASES = ["prop", "prop_filtered", "prop_none_valid", "semseg", "semseg_filtered", "semseg_oracle_cls"]
+
+
+@pytest.mark.parametrize("case", PD_CASES)
+def test_pd_eval_branch_host_logic(torch_ops, golden_dir, case):
+    g = torch.load(os.path.join(golden_dir, "pd_inference.pt"), weights_only=False)
+    run_pd_case(g, case, "cpu")
 
 
 def test_pack_helpers_round_trip():
