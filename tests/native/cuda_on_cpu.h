@@ -1,0 +1,148 @@
+// TEST INFRASTRUCTURE ONLY.  A minimal "CUDA on the CPU" shim: enough of the CUDA C++ surface to compile the simple
+// byte / bit kernels of partdistillation_b200/csrc/postprocess_kernels.cuh with g++ and execute them with CUDA's
+// semantics — one OS thread per CUDA thread of a block (a pool per launch), blocks run one after the other, __syncthreads and the warp
+// collectives (__ballot_sync, __reduce_add_sync, __syncthreads_or) implemented with std::barrier so that divergent
+// exits behave as on the device (a thread that returns drops out of its warp's and its block's barriers).
+// Used by tests/test_postprocess_host_cpu.py in the build container, which has no GPU.  Never part of the product.
+#pragma once
+#include <stdint.h>
+
+#include <algorithm>
+#include <atomic>
+#include <barrier>
+#include <cmath>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static          // blocks run one at a time, so one static instance = one block's shared memory
+
+namespace cpu_cuda {
+
+struct Warp {
+    std::unique_ptr<std::barrier<>> bar;
+    unsigned pred[32];
+    int val[32];
+};
+
+struct Block {
+    std::unique_ptr<std::barrier<>> bar;
+    std::vector<Warp> warps;
+    std::atomic<int> or_flag[2];
+};
+
+inline thread_local Block* t_block = nullptr;
+inline thread_local Warp* t_warp = nullptr;
+inline thread_local int t_lane = 0;
+inline thread_local int t_or_phase = 0;
+
+}  // namespace cpu_cuda
+
+inline thread_local dim3 threadIdx, blockIdx;
+inline dim3 blockDim, gridDim;
+
+inline void __syncthreads() { cpu_cuda::t_block->bar->arrive_and_wait(); }
+
+inline int __syncthreads_or(int pred) {
+    auto* b = cpu_cuda::t_block;
+    const int ph = cpu_cuda::t_or_phase;
+    cpu_cuda::t_or_phase ^= 1;
+    if (pred) b->or_flag[ph].store(1);
+    b->bar->arrive_and_wait();
+    const int r = b->or_flag[ph].load();
+    b->bar->arrive_and_wait();
+    if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) b->or_flag[ph].store(0);   // next use of this phase is two barriers away
+    return r;
+}
+
+inline unsigned __ballot_sync(unsigned, int pred) {
+    auto* w = cpu_cuda::t_warp;
+    w->pred[cpu_cuda::t_lane] = pred ? 1u : 0u;
+    w->bar->arrive_and_wait();
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) r |= w->pred[i] << i;
+    w->bar->arrive_and_wait();
+    return r;
+}
+
+inline int __reduce_add_sync(unsigned, int v) {
+    auto* w = cpu_cuda::t_warp;
+    w->val[cpu_cuda::t_lane] = v;
+    w->bar->arrive_and_wait();
+    int r = 0;
+    for (int i = 0; i < 32; ++i) r += w->val[i];
+    w->bar->arrive_and_wait();
+    return r;
+}
+
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+template <typename T> inline T __ldg(const T* p) { return *p; }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+using std::min;
+using std::max;
+
+namespace cpu_cuda {
+
+// kernel<<<grid, block>>>(args...)  ==  launch(grid, block, [&] { kernel(args...); })
+// One pool of blockDim OS threads per launch walks over the blocks in order; a launch-wide barrier separates two
+// blocks (the `static` shared memory of a kernel belongs to one block at a time).
+template <typename F>
+void launch(dim3 grid, dim3 block, F body) {
+    const int nthreads = (int)(block.x * block.y * block.z);
+    const int nwarps = (nthreads + 31) / 32;
+    blockDim = block;
+    gridDim = grid;
+    const int64_t nblocks = (int64_t)grid.x * grid.y * grid.z;
+    std::barrier<> between_blocks(nthreads);
+    Block blk[2];                                   // block i uses blk[i & 1]; re-armed by thread 0 while nobody uses it
+    auto arm = [&](Block& b) {
+        b.bar = std::make_unique<std::barrier<>>(nthreads);
+        b.or_flag[0] = 0;
+        b.or_flag[1] = 0;
+        b.warps.clear();
+        b.warps.resize(nwarps);
+        for (int wi = 0; wi < nwarps; ++wi) {
+            b.warps[wi].bar = std::make_unique<std::barrier<>>(std::min(32, nthreads - 32 * wi));
+            std::fill(b.warps[wi].pred, b.warps[wi].pred + 32, 0u);
+            std::fill(b.warps[wi].val, b.warps[wi].val + 32, 0);
+        }
+    };
+    arm(blk[0]);
+    std::vector<std::thread> threads;
+    threads.reserve(nthreads);
+    for (int t = 0; t < nthreads; ++t)
+        threads.emplace_back([&, t] {
+            threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+            for (int64_t i = 0; i < nblocks; ++i) {
+                Block& b = blk[i & 1];
+                if (t == 0 && i + 1 < nblocks) arm(blk[(i + 1) & 1]);      // idle since the barrier that ended block i - 1
+                blockIdx = dim3((unsigned)(i % grid.x), (unsigned)((i / grid.x) % grid.y), (unsigned)(i / ((int64_t)grid.x * grid.y)));
+                t_block = &b;
+                t_warp = &b.warps[t / 32];
+                t_lane = t % 32;
+                t_or_phase = 0;
+                body();
+                // the thread has exited the kernel: it no longer takes part in any collective of this block
+                t_warp->pred[t_lane] = 0;
+                t_warp->val[t_lane] = 0;
+                t_warp->bar->arrive_and_drop();
+                b.bar->arrive_and_drop();
+                between_blocks.arrive_and_wait();
+            }
+        });
+    for (auto& th : threads) th.join();
+}
+
+}  // namespace cpu_cuda

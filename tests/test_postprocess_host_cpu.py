@@ -149,3 +149,115 @@ def test_kernel_mask_resize_math_matches_oracle(host_math, geom):
     host_math.pp_host_resize_masks(m.data_ptr(), out.data_ptr(), G, *padded, *image_size, *out_size)
     exp = O.sem_seg_postprocess(m.float(), image_size, *out_size).bool()
     assert torch.equal(out.bool(), exp)
+
+
+# ------------------------------------------------------------------ the kernels themselves, compiled for the host
+@pytest.fixture(scope="module")
+def host_kernels(tmp_path_factory):
+    """csrc/postprocess_kernels.cuh compiled with g++ through tests/native/cuda_on_cpu.h (one OS thread per CUDA thread,
+    std::barrier for the warp / block collectives), exposed with the ctypes signatures of the C ABI minus the stream."""
+    import ctypes
+    import subprocess
+    from partdistillation_b200 import _lib
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = str(tmp_path_factory.mktemp("pp_kernels") / "libpp_kernels_host.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", "-ffp-contract=off",
+                           os.path.join(here, "native", "postprocess_kernels_host.cpp"), "-o", so])
+    cdll = ctypes.CDLL(so)
+
+    class HostLib:
+        """Stands in for the loaded libpdb200.so: pdb_<op>(..., stream) -> host_<op>(...)."""
+        def pdb_last_error(self):
+            return b"host build"
+
+    lib = HostLib()
+    for name in ("postprocess_masks", "resize_masks_u8", "pack_bits", "unpack_bits", "bits_popcount", "bits_intersect"):
+        f = getattr(cdll, "host_" + name)
+        res, args = _lib.SIGNATURES["pdb_" + name]
+        f.restype, f.argtypes = res, args[:-1]
+        setattr(lib, "pdb_" + name, (lambda f: lambda *a: f(*a[:-1]))(f))
+    return lib
+
+
+@pytest.fixture
+def kernels_on_host(monkeypatch, host_kernels):
+    """Runs partdistillation_b200.functional's post-processing wrappers UNMODIFIED on CPU tensors: the library handle
+    is the host build of the kernels, the CUDA-only guard and the stream lookup are disabled for the test."""
+    from partdistillation_b200 import _lib
+    from partdistillation_b200 import functional as fn
+    monkeypatch.setattr(_lib, "load", lambda: host_kernels)
+    monkeypatch.setattr(fn, "_need_cuda", lambda *a: None)
+    monkeypatch.setattr(fn, "_stream", lambda: None)
+    return fn
+
+
+def _words_to_bool(bits, width):
+    return _unpack(bits, width)
+
+
+SMALL_GEOMETRIES = [
+    ((8, 8), (32, 32), (32, 32), (32, 32)),             # second pass is the identity, one word per row
+    ((8, 10), (32, 40), (28, 36), (42, 54)),            # padding cropped, second pass up, ragged last word
+    ((10, 14), (40, 56), (38, 50), (19, 27)),           # second pass down, less than one word per row
+]
+
+
+@pytest.mark.parametrize("geom", SMALL_GEOMETRIES)
+@pytest.mark.parametrize("gated", [True, False])
+def test_host_built_kernel_postprocess_masks(kernels_on_host, geom, gated):
+    fn = kernels_on_host
+    (h, w), padded, image_size, out_size = geom
+    g = torch.Generator().manual_seed(5)
+    Q, K = 9, 6
+    logits = torch.randn(Q, h, w, generator=g) * 2.0
+    logits[4] = -3.0
+    logits[7, : h // 2] = 0.0
+    sel = torch.tensor([7, 0, 4, 2, 8, 5])
+    scores = torch.rand(K, generator=g)
+    yy, xx = torch.meshgrid(torch.arange(out_size[0]), torch.arange(out_size[1]), indexing="ij")
+    gate = ((yy - out_size[0] / 2) ** 2 / (out_size[0] * 0.4) ** 2 + (xx - out_size[1] / 2) ** 2 / (out_size[1] * 0.4) ** 2) < 1
+    bits, label, sbits = fn.postprocess_masks(logits, sel, padded, image_size, out_size, gate=gate if gated else None,
+                                              scores=scores, want_bits=True, want_label=True, score_threshold=0.5)
+    ref = oracle_resize(logits, padded, image_size, out_size)[sel]
+    if gated:
+        ref = ref * gate
+    got = _words_to_bool(bits, out_size[1])
+    flips = got[:K] != (ref > 0)
+    assert not (flips & (ref.abs() > 1e-4)).any()
+    assert not _words_to_bool(bits, 32 * bits.shape[-1])[..., out_size[1]:].any()       # padding bits of ragged words
+    assert torch.equal(got[K], got[:K].any(0))
+    sm = scores[:, None, None] * ref.sigmoid()
+    top2 = sm.topk(2, dim=0)[0]
+    assert not ((label.long() != sm.argmax(0)) & ((top2[0] - top2[1]) > 1e-5)).any()
+    assert not ((_words_to_bool(sbits, out_size[1]) != (sm > 0.5)) & ((sm - 0.5).abs() > 1e-5)).any()
+    assert torch.equal(fn.bits_popcount(bits), got.flatten(1).sum(1))
+
+
+@pytest.mark.parametrize("shape", [((5, 16, 96), (3, 16, 96)), ((70, 9, 45), (67, 9, 45)), ((2, 36, 2100), (1, 36, 2100))])
+def test_host_built_kernels_pack_popcount_iou(kernels_on_host, shape):
+    fn = kernels_on_host
+    g = torch.Generator().manual_seed(8)
+    a = torch.rand(*shape[0], generator=g) > 0.7
+    b = torch.rand(*shape[1], generator=g) > 0.4
+    a[1] = False
+    b[0] = ~a[0]
+    pa, pb = fn.pack_bits(a), fn.pack_bits(b)
+    assert torch.equal(_unpack(pa, a.shape[-1]), a)
+    assert torch.equal(fn.unpack_bits(pa, a.shape[-1]), a)
+    rows = torch.tensor([a.shape[0] - 1, 0])
+    assert torch.equal(fn.unpack_bits(pa, a.shape[-1], rows), a[rows])
+    assert torch.equal(fn.bits_popcount(pa), a.flatten(1).sum(1))
+    assert torch.equal(fn.bits_iou(pa, pb), O.mask_iou(a, b))
+
+
+@pytest.mark.parametrize("case", ["prop_filtered", "semseg_filtered"])
+def test_host_built_kernels_proposal_eval_branch(kernels_on_host, golden_dir, case):
+    """Host branch + functional wrappers + the kernels' own code (host build) against the reference's recorded outputs."""
+    g = torch.load(os.path.join(golden_dir, "proposal_inference.pt"), weights_only=False)
+    run_case(g, case, "cpu")
+
+
+@pytest.mark.parametrize("case", ["prop", "prop_none_valid", "semseg_oracle_cls"])
+def test_host_built_kernels_pd_eval_branch(kernels_on_host, golden_dir, case):
+    g = torch.load(os.path.join(golden_dir, "pd_inference.pt"), weights_only=False)
+    run_pd_case(g, case, "cpu")
