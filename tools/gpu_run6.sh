@@ -1,0 +1,11 @@
+#!/bin/bash
+# First GPU call for the f4 eval-branch kernels (written after round 1's GPU budget was spent):
+# parity tests, the per-image microbenchmark against the dense PyTorch expression, launch list + one ncu --set full capture.
+#   gpurun --timeout 900 -- 'bash tools/gpu_run6.sh'
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_postprocess_gpu.py -x -q > gpurun_out/pp_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pp_tests.log
+timeout 300 python tools/bench_postprocess.py > gpurun_out/pp_bench.json 2> gpurun_out/pp_bench.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/pp_launches.csv python tools/bench_postprocess.py > /dev/null 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:postprocess_masks_kernel -s 3 -c 1 -o gpurun_out/prof_postprocess_v1 -f python tools/bench_postprocess.py > gpurun_out/ncu_pp.log 2>&1
+timeout 120 ncu -i gpurun_out/prof_postprocess_v1.ncu-rep --page raw --csv > gpurun_out/ncu_pp_raw.csv 2>/dev/null
+tail -3 gpurun_out/pp_tests.log; cat gpurun_out/pp_bench.json
