@@ -261,3 +261,92 @@ def test_host_built_kernels_proposal_eval_branch(kernels_on_host, golden_dir, ca
 def test_host_built_kernels_pd_eval_branch(kernels_on_host, golden_dir, case):
     g = torch.load(os.path.join(golden_dir, "pd_inference.pt"), weights_only=False)
     run_pd_case(g, case, "cpu")
+
+
+# ------------------------------------------------------------------ eval-mode forward() wiring of the registered classes
+class _StubBackbone(torch.nn.Module):
+    size_divisibility = 32
+
+    def forward(self, x):
+        return {"res2": x}
+
+
+class _StubHead(torch.nn.Module):
+    num_classes = 1
+
+    def __init__(self, outputs):
+        super().__init__()
+        self.outputs = outputs
+        self.calls = []
+
+    def forward(self, features, mask=None):
+        self.calls.append(mask)
+        return self.outputs
+
+
+def _batched_inputs(inp, object_classes=None):
+    from partdistillation_b200.compat import BitMasks, Instances
+    bi = []
+    for i, it in enumerate(inp["items"]):
+        H, W = it["size"]
+        inst = Instances((H, W))
+        inst.gt_masks = BitMasks(it["object_mask"])
+        inst.gt_classes = torch.tensor([object_classes[i]]) if object_classes else torch.zeros(1, dtype=torch.long)
+        pinst = Instances((H, W))
+        pinst.gt_masks = BitMasks(it["part_masks"])
+        pinst.gt_classes = it["part_classes"]
+        bi.append({"image": torch.zeros(3, H, W, dtype=torch.uint8), "instances": inst, "part_instances": pinst,
+                   "height": it["out"][0], "width": it["out"][1]})
+    return bi
+
+
+def test_proposal_model_eval_forward_wiring(torch_ops, golden_dir):
+    """ProposalModel(...).eval()(batched_inputs) -> the reference's list of {"proposals", "gt_masks"} (proposal_model.py:
+    205-218), with the backbone / head replaced by stubs that return the golden head outputs."""
+    from partdistillation_b200.proposal_model import ProposalModel
+    g = torch.load(os.path.join(golden_dir, "proposal_inference.pt"), weights_only=False)
+    inp, c = g["inputs"], g["cases"]["prop_filtered"]
+    Q = inp["pred_logits"].shape[1]
+    head = _StubHead({"pred_logits": inp["pred_logits"], "pred_masks": inp["pred_masks"]})
+    model = ProposalModel(backbone=_StubBackbone(), sem_seg_head=head, criterion=torch.nn.Identity(), num_queries=Q,
+                          num_classes=1, size_divisibility=32, pixel_mean=(0.0, 0.0, 0.0), pixel_std=(1.0, 1.0, 1.0),
+                          test_topk_per_image=Q, use_wandb=False, use_unique_per_pixel_label=False,
+                          minimum_pseudo_mask_score=0.3, minimum_pseudo_mask_ratio=0.05)
+    model.eval()
+    res = model(_batched_inputs(inp))
+    assert model.num_test_iterations == 1 and model.num_train_iterations == 0
+    assert head.calls == [None]
+    for r, ref in zip(res, c["results"]):
+        assert set(r) == {"proposals", "gt_masks"}
+        assert tuple(r["proposals"].pred_masks.shape) == ref["pred_shape"]
+        assert torch.equal(r["proposals"].pred_classes, ref["pred_classes"])
+        assert torch.allclose(r["proposals"].scores, ref["scores"])
+    model.set_postprocess_type("semseg")
+    res = model(_batched_inputs(inp))
+    assert [tuple(r["proposals"].pred_masks.shape) for r in res] == [x["pred_shape"] for x in g["cases"]["semseg_filtered"]["results"]]
+
+
+def test_part_distillation_model_eval_forward_wiring(torch_ops, golden_dir):
+    from partdistillation_b200.part_distillation_model import PartDistillationModel
+    g = torch.load(os.path.join(golden_dir, "pd_inference.pt"), weights_only=False)
+    inp, c = g["inputs"], g["cases"]["semseg_filtered"]
+    Q, P = inp["pred_logits"].shape[1], inp["pred_logits"].shape[2] - 1
+    head = _StubHead({"pred_logits": inp["pred_logits"], "pred_masks": inp["pred_masks"]})
+    model = PartDistillationModel(backbone=_StubBackbone(), sem_seg_head=head, criterion=torch.nn.Identity(), num_queries=Q,
+                                  num_classes=P, size_divisibility=32, pixel_mean=(0.0, 0.0, 0.0), pixel_std=(1.0, 1.0, 1.0),
+                                  test_topk_per_image=inp["topk"], use_wandb=False, use_unique_per_pixel_label=True,
+                                  min_pseudo_mask_score=0.2, min_pseudo_mask_ratio=0.05)
+    model.eval()
+    model.mode = "eval"
+    model.update_majority_vote_mapping(inp["majority_vote_mapping"])
+    res = model(_batched_inputs(inp, inp["object_classes"]))
+    assert model.current_test_iteration == 1
+    assert len(head.calls) == 1 and [int(t["gt_object_class"]) for t in head.calls[0]] == inp["object_classes"]
+    for r, ref in zip(res, c["results"]):
+        assert set(r) == {"predictions", "gt_instances", "gt_object_label"}
+        assert tuple(r["predictions"].pred_masks.shape) == ref["pred_shape"]
+        assert torch.equal(r["predictions"].pred_classes, ref["pred_classes"])
+        assert torch.allclose(r["predictions"].scores, ref["scores"])
+    model.mode = "save"
+    with pytest.raises(NotImplementedError):
+        model(_batched_inputs(inp, inp["object_classes"]))
