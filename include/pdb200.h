@@ -259,6 +259,12 @@ PDB_API int pdb_swin_window_attention_forward(const float* qkv, const float* qkv
  * ---------------------------------------------------------------------------------------------- */
 PDB_API int pdb_group_affinity(const float* feat, const float* centroids, const uint8_t* mask, int32_t* labels,
                        int C, int Kc, int h, int w, int H, int W, int metric, void* stream);
+/* Same, for an evaluation size different from the padded batch size (pixel_grouping_model.py:139-160,
+ * proposal_generation_model.py:139-155): feat (C, h, w) -> bilinear -> (Hp, Wp) -> crop (Hi, Wi) -> bilinear -> (Ho, Wo)
+ * (detectron2 sem_seg_postprocess), both passes composed per output pixel; mask and labels are (Ho, Wo). */
+PDB_API int pdb_group_affinity_resized(const float* feat, const float* centroids, const uint8_t* mask, int32_t* labels,
+                               int C, int Kc, int h, int w, int Hp, int Wp, int Hi, int Wi, int Ho, int Wo, int metric,
+                               void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Swin window attention, forward only (frozen backbone) — replaces q @ k^T * scale + relative-position bias

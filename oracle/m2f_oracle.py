@@ -641,9 +641,16 @@ def head_and_loss(sd, features, targets, hp, rand=torch.rand, record=None, core=
 # --------------------------------------------------------------------------------------
 
 
-def pixel_grouping_scores(feature, centroids, out_size, metric="dot"):
-    """(C, h, w) features -> (Kc, H, W) affinity of every image-resolution pixel to every centroid."""
-    up = F.interpolate(feature[None], size=out_size, mode="bilinear", align_corners=False)[0]     # (:139-144)
+def pixel_grouping_scores(feature, centroids, out_size, metric="dot", geometry=None):
+    """(C, h, w) features -> (Kc, H, W) affinity of every image-resolution pixel to every centroid.  ``geometry`` =
+    (padded size, image size, output size): up-sample to the padded size, crop, resize (sem_seg_postprocess, :146-158)."""
+    if geometry is None:
+        up = F.interpolate(feature[None], size=out_size, mode="bilinear", align_corners=False)[0]     # (:139-144)
+    else:
+        padded, image_size, out_size = geometry
+        up = F.interpolate(feature[None], size=padded, mode="bilinear", align_corners=False)[0]
+        up = up[:, :image_size[0], :image_size[1]][None]
+        up = F.interpolate(up, size=out_size, mode="bilinear", align_corners=False)[0]
     A = up.flatten(1).t()
     B = centroids
     if metric == "dot":
@@ -653,9 +660,9 @@ def pixel_grouping_scores(feature, centroids, out_size, metric="dot"):
     return d.t().reshape(centroids.shape[0], *out_size)
 
 
-def pixel_grouping_segments(feature, centroids, mask_resized, metric="dot"):
+def pixel_grouping_segments(feature, centroids, mask_resized, metric="dot", geometry=None):
     """generate_part_segments with given centroids (:205-218): -> (label map (H, W) int64, bool (P, H, W))."""
-    scores = pixel_grouping_scores(feature, centroids, tuple(mask_resized.shape), metric)
+    scores = pixel_grouping_scores(feature, centroids, tuple(mask_resized.shape), metric, geometry)
     labels = torch.zeros(mask_resized.shape, dtype=torch.long)
     labels[mask_resized] = scores[:, mask_resized].argmax(0) + 1
     present = labels[mask_resized].unique()

@@ -380,11 +380,52 @@ def golden_pd_inference(ref):
     print("pd_inference.pt", {n: [(r["pred_shape"], r["pred_classes"].tolist()) for r in c["results"]] for n, c in out["cases"].items()})
 
 
+def golden_pixel_grouping_resized(ref):
+    """As golden_pixel_grouping, for an evaluation size that differs from the padded size: the features go through the
+    reference forward's F.interpolate(-> padded) + sem_seg_postprocess(crop, -> (height, width)) (pixel_grouping_model.py:
+    139-160) before generate_part_segments; the object mask through sem_seg_postprocess(...).bool() and the nearest
+    down-sampling to the feature size (:158-160)."""
+    import importlib
+    import types
+    from detectron2.modeling.postprocessing import sem_seg_postprocess
+    pg = importlib.import_module("part_distillation.pixel_grouping_model").PixelGroupingModel
+    g = torch.Generator().manual_seed(13)
+    C3, C4, h, w, Kc = 16, 24, 12, 16, 4
+    padded, image_size, out_size = (96, 128), (90, 120), (135, 180)
+    feats = {"res3": torch.randn(1, C3, h, w, generator=g), "res4": torch.randn(1, C4, h // 2, w // 2, generator=g)}
+    yy, xx = torch.meshgrid(torch.arange(image_size[0]), torch.arange(image_size[1]), indexing="ij")
+    obj = ((yy - image_size[0] / 2) ** 2 / (image_size[0] * 0.4) ** 2 + (xx - image_size[1] / 2) ** 2 / (image_size[1] * 0.35) ** 2) < 1.0
+    masks = torch.zeros(1, *padded)
+    masks[0, :image_size[0], :image_size[1]] = obj.float()
+    out = {}
+    for metric in ("dot", "l2"):
+        self = types.SimpleNamespace(backbone_feature_key_list=["res3", "res4"], feature_normalize=False,
+                                     distance_metric=metric, num_superpixel_clusters=Kc)
+        features = pg._prepare_features(self, feats)                                       # (1, C, h, w)
+        features_resized = torch.nn.functional.interpolate(features, size=padded, mode="bilinear", align_corners=False)
+        resized = sem_seg_postprocess(features_resized[0], image_size, *out_size)
+        mask_resized = sem_seg_postprocess(masks, image_size, *out_size)[0].bool()
+        mask_feat = torch.nn.functional.interpolate(masks[None], size=features.shape[-2:], mode="nearest")[0, 0].bool()
+        centroids = torch.randn(Kc, features.shape[1], generator=g)
+        self.get_pixel_grouping = lambda f, m: centroids
+        self.measure_distance = types.MethodType(pg.measure_distance, self)
+        binary = pg.generate_part_segments(self, {}, features[0], resized, mask_feat, mask_resized)
+        out[metric] = dict(feature=features[0], centroids=centroids, binary_mask=binary, mask_resized=mask_resized,
+                           mask_feat=mask_feat)
+    out.update(feats=feats, object_mask=obj, geometry=(padded, image_size, out_size))
+    torch.save(out, os.path.join(OUT, "pixel_grouping_resized.pt"))
+    print("pixel_grouping_resized.pt", {m: tuple(out[m]["binary_mask"].shape) for m in ("dot", "l2")})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = rl.load()
     if "--pixel-grouping-only" in sys.argv:
         golden_pixel_grouping(ref)
+        golden_pixel_grouping_resized(ref)
+        return
+    if "--pixel-grouping-resized-only" in sys.argv:
+        golden_pixel_grouping_resized(ref)
         return
     if "--inference-only" in sys.argv:
         golden_proposal_inference(ref)
@@ -393,6 +434,7 @@ def main():
     golden_proposal_inference(ref)
     golden_pd_inference(ref)
     golden_pixel_grouping(ref)
+    golden_pixel_grouping_resized(ref)
     golden_msda(ref)
     golden_swin(ref)
     for name in HEAD_CASES:

@@ -64,6 +64,16 @@ _PIXEL_GROUPING = {
 }
 
 
+_PROPOSAL_GENERATION = {      # config.py:188-205 of the reference
+    "PROPOSAL_GENERATION": dict(
+        DATASET_NAME="imagenet_22k_train", OBJECT_MASK_TYPE="detic",
+        OBJECT_MASK_PATH="pseudo_labels/object_labels/imagenet_22k_train/detic_predictions/", NUM_SUPERPIXEL_CLUSTERS=4,
+        DISTANCE_METRIC="l2", FEATURE_NORMALIZE=False, BACKBONE_FEATURE_KEY_LIST=["res4"], TOTAL_PARTITIONS=-1,
+        PARTITION_INDEX=-1, BATCH_SIZE=4, WITH_GIVEN_MASK=False, USE_PART_IMAGENET_CLASSES=False,
+        FILTERED_CODE_PATH_LIST=[], EXCLUDE_CODE_PATH="", SINGLE_CLASS_CODE="", DEBUG=False),
+}
+
+
 def _install(node, table):
     for key, val in table.items():
         if isinstance(val, dict):
@@ -92,3 +102,7 @@ def add_part_distillation_config(cfg):
 
 def add_pixel_grouping_confing(cfg):          # (sic) the reference's spelling, config.py:255
     _install(cfg, _PIXEL_GROUPING)
+
+
+def add_proposal_generation_config(cfg):
+    _install(cfg, _PROPOSAL_GENERATION)

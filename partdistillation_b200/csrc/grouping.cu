@@ -11,6 +11,7 @@
 // One thread per output pixel; the C x Kc centroid table sits in shared memory (broadcast reads); neighbouring
 // pixels share their 4 source texels, so the feature reads are L1 hits after the first touch.
 #include "common.cuh"
+#include "grouping_resized.cuh"
 
 namespace pdb {
 
@@ -92,4 +93,38 @@ extern "C" int pdb_group_affinity(const float* feat, const float* centroids, con
     dim3 grid((unsigned)((W + 31) / 32), (unsigned)((H + 7) / 8));
     group_affinity_kernel<<<grid, 256, smem, as_stream(stream)>>>(feat, centroids, mask, labels, C, Kc, h, w, H, W, metric);
     return launched("group_affinity");
+}
+
+// General geometry: features (C, h, w) -> bilinear -> padded (Hp, Wp) -> crop (Hi, Wi) -> bilinear -> (Ho, Wo); mask and
+// labels at (Ho, Wo).  With Hp == Hi == Ho and Wp == Wi == Wo this computes what pdb_group_affinity computes (up to the
+// FMA contraction the older kernel leaves to the compiler).
+extern "C" int pdb_group_affinity_resized(const float* feat, const float* centroids, const uint8_t* mask, int32_t* labels,
+                                          int C, int Kc, int h, int w, int Hp, int Wp, int Hi, int Wi, int Ho, int Wo,
+                                          int metric, void* stream) {
+    PDB_REQUIRE(feat && centroids && mask && labels, "group_affinity_resized: null pointer");
+    PDB_REQUIRE(C > 0 && Kc > 0 && Kc <= kMaxGroupCentroids && h > 0 && w > 0 && Hp > 0 && Wp > 0 && Ho > 0 && Wo > 0,
+                "group_affinity_resized: bad sizes (1 <= Kc <= %d)", kMaxGroupCentroids);
+    PDB_REQUIRE(Hi > 0 && Wi > 0 && Hi <= Hp && Wi <= Wp, "group_affinity_resized: image size outside the padded size");
+    PDB_REQUIRE(metric == 0 || metric == 1, "group_affinity_resized: metric %d (0 = dot, 1 = l2)", metric);
+    PDB_REQUIRE((Ho + 7) / 8 <= 65535, "group_affinity_resized: output height %d exceeds grid.y", Ho);
+    const size_t smem = group_affinity_smem(C, Kc);
+    PDB_REQUIRE(smem <= 200 * 1024, "group_affinity_resized: centroid table of %zu bytes does not fit shared memory", smem);
+    const bool two = !(Hi == Ho && Wi == Wo);
+    static size_t attr_smem[2] = {0, 0};
+    if (smem > 48 * 1024 && smem > attr_smem[two]) {
+        cudaError_t e = two ? cudaFuncSetAttribute(group_affinity_resized_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(group_affinity_resized_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(PDB_ERR_LAUNCH, "group_affinity_resized: smem attribute: %s", cudaGetErrorString(e));
+        attr_smem[two] = smem;
+    }
+    const float s1h = (float)h / (float)Hp, s1w = (float)w / (float)Wp;
+    const float s2h = (float)Hi / (float)Ho, s2w = (float)Wi / (float)Wo;
+    const dim3 grid = group_affinity_grid(Ho, Wo);
+    if (two)
+        group_affinity_resized_kernel<true><<<grid, 256, smem, as_stream(stream)>>>(feat, centroids, mask, labels, C, Kc, h, w, Hi, Wi,
+                                                                                  Ho, Wo, s1h, s1w, s2h, s2w, metric);
+    else
+        group_affinity_resized_kernel<false><<<grid, 256, smem, as_stream(stream)>>>(feat, centroids, mask, labels, C, Kc, h, w, Hi, Wi,
+                                                                                   Ho, Wo, s1h, s1w, s2h, s2w, metric);
+    return launched("group_affinity_resized");
 }

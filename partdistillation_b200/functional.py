@@ -698,9 +698,11 @@ def linear(x, weight, bias=None, relu=False, gelu=False):
 # --------------------------------------------------------------------------------------------------
 # pixel grouping affinity  (pixel_grouping_model.py:139-144,197-211)
 # --------------------------------------------------------------------------------------------------
-def group_affinity(feat, centroids, mask, metric="dot"):
+def group_affinity(feat, centroids, mask, metric="dot", geometry=None):
     """feat (C, h, w) f32, centroids (Kc, C) f32, mask (H, W) bool/uint8 -> labels (H, W) int32: 0 outside the mask,
-    1 + argmax_k affinity(bilinear(feat) at the pixel, centroid k) inside."""
+    1 + argmax_k affinity(bilinear(feat) at the pixel, centroid k) inside.  ``geometry`` = (padded size, image size,
+    output size) when the features are up-sampled to the padded size, cropped and resized again (sem_seg_postprocess);
+    ``mask`` is then at the output size.  Default: one bilinear pass to the size of ``mask``."""
     _need_cuda(feat, centroids, mask)
     if metric not in ("dot", "l2"):
         raise ValueError(f"distance metric {metric!r} (dot / l2)")
@@ -710,6 +712,16 @@ def group_affinity(feat, centroids, mask, metric="dot"):
     Kc = centroids.shape[0]
     H, W = mask.shape
     labels = torch.empty((H, W), dtype=torch.int32, device=feat.device)
+    if geometry is not None:
+        (Hp, Wp), (Hi, Wi), (Ho, Wo) = [(int(a), int(b)) for a, b in geometry]
+        if (Ho, Wo) != (H, W):
+            raise RuntimeError(f"group_affinity: mask shape {(H, W)} != output size {(Ho, Wo)}")
+        if not ((Hp, Wp) == (Hi, Wi) == (Ho, Wo)):
+            rc = _lib.load().pdb_group_affinity_resized(feat.data_ptr(), centroids.data_ptr(), mask.data_ptr(),
+                                                        labels.data_ptr(), C, Kc, h, w, Hp, Wp, Hi, Wi, Ho, Wo,
+                                                        0 if metric == "dot" else 1, _stream())
+            _lib.check(rc, "pdb_group_affinity_resized")
+            return labels
     rc = _lib.load().pdb_group_affinity(feat.data_ptr(), centroids.data_ptr(), mask.data_ptr(), labels.data_ptr(), C, Kc, h, w,
                                         H, W, 0 if metric == "dot" else 1, _stream())
     _lib.check(rc, "pdb_group_affinity")

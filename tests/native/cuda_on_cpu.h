@@ -42,6 +42,7 @@ struct Block {
     std::atomic<int> or_flag[2];
 };
 
+inline void* g_dyn_smem = nullptr;           // dynamic shared memory of the running launch (one block at a time)
 inline thread_local Block* t_block = nullptr;
 inline thread_local Warp* t_warp = nullptr;
 inline thread_local int t_lane = 0;
@@ -146,3 +147,16 @@ void launch(dim3 grid, dim3 block, F body) {
 }
 
 }  // namespace cpu_cuda
+
+namespace cpu_cuda {
+// kernel<<<grid, block, smem_bytes>>>(args...) for kernels that declare PDB_DYNAMIC_SMEM(type, name)
+template <typename F>
+void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
+    std::vector<float> smem(smem_bytes / sizeof(float) + 4);
+    g_dyn_smem = smem.data();
+    launch(grid, block, body);
+    g_dyn_smem = nullptr;
+}
+}  // namespace cpu_cuda
+
+#define PDB_DYNAMIC_SMEM(type, name) type* name = reinterpret_cast<type*>(cpu_cuda::g_dyn_smem)

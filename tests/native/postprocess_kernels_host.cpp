@@ -3,6 +3,7 @@
 // the launch geometry of postprocess.cu.  tests/test_postprocess_host_cpu.py runs them against the oracle.
 #include "cuda_on_cpu.h"
 #include "../../partdistillation_b200/csrc/postprocess_kernels.cuh"
+#include "../../partdistillation_b200/csrc/grouping_resized.cuh"
 
 using namespace pdb;
 using cpu_cuda::launch;
@@ -56,5 +57,22 @@ extern "C" int host_bits_popcount(const uint32_t* bits, int64_t* counts, int row
 extern "C" int host_bits_intersect(const uint32_t* a, const uint32_t* b, int64_t* inter, int Ka, int Kb, int64_t words) {
     launch(chunk_grid(words, Ka), dim3(256),
            [&] { bits_intersect_kernel(a, b, reinterpret_cast<unsigned long long*>(inter), Kb, words); });
+    return 0;
+}
+
+extern "C" int host_group_affinity_resized(const float* feat, const float* centroids, const uint8_t* mask, int32_t* labels,
+                                           int C, int Kc, int h, int w, int Hp, int Wp, int Hi, int Wi, int Ho, int Wo,
+                                           int metric) {
+    const float s1h = (float)h / (float)Hp, s1w = (float)w / (float)Wp;
+    const float s2h = (float)Hi / (float)Ho, s2w = (float)Wi / (float)Wo;
+    const size_t smem = group_affinity_smem(C, Kc);
+    if (Hi == Ho && Wi == Wo)
+        launch(group_affinity_grid(Ho, Wo), dim3(256), smem, [&] {
+            group_affinity_resized_kernel<false>(feat, centroids, mask, labels, C, Kc, h, w, Hi, Wi, Ho, Wo, s1h, s1w, s2h, s2w, metric);
+        });
+    else
+        launch(group_affinity_grid(Ho, Wo), dim3(256), smem, [&] {
+            group_affinity_resized_kernel<true>(feat, centroids, mask, labels, C, Kc, h, w, Hi, Wi, Ho, Wo, s1h, s1w, s2h, s2w, metric);
+        });
     return 0;
 }

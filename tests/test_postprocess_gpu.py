@@ -162,3 +162,40 @@ def test_postprocess_rejects_bad_arguments(fn):
         fn.postprocess_masks(x, sel, (32, 32), (32, 32), (32, 32), want_label=True)   # label without scores
     with pytest.raises(RuntimeError):
         fn.postprocess_masks(x.cpu(), sel.cpu(), (32, 32), (32, 32), (32, 32))        # CUDA only
+
+
+# ------------------------------------------------------------------ pixel grouping at a resized evaluation size
+@pytest.mark.parametrize("metric", ["dot", "l2"])
+def test_group_affinity_resized_vs_reference_golden(fn, golden_dir, metric):
+    """pdb_group_affinity_resized against the segments of the UNMODIFIED reference at padded (96, 128) / image (90, 120) /
+    output (135, 180) (tests/golden/pixel_grouping_resized.pt); label flips only at numerical near-ties."""
+    g = torch.load(os.path.join(golden_dir, "pixel_grouping_resized.pt"), weights_only=False)
+    c = g[metric]
+    labels = fn.group_affinity(c["feature"].cuda(), c["centroids"].cuda(), c["mask_resized"].cuda(), metric,
+                               geometry=g["geometry"]).cpu().long()
+    exp_labels, exp_seg = O.pixel_grouping_segments(c["feature"], c["centroids"], c["mask_resized"], metric, geometry=g["geometry"])
+    assert torch.equal(exp_seg, c["binary_mask"])
+    scores = O.pixel_grouping_scores(c["feature"], c["centroids"], tuple(c["mask_resized"].shape), metric, g["geometry"])
+    top2 = scores.topk(2, dim=0)[0]
+    bad = labels != exp_labels
+    assert not (bad & ((top2[0] - top2[1]) > 1e-3 * scores.abs().max())).any()
+    assert bad.float().mean() < 1e-3
+    assert (labels[~c["mask_resized"]] == 0).all()
+
+
+def test_group_affinity_resized_equals_one_pass_kernel(fn, golden_dir):
+    """With padded == image == output size the general-geometry kernel and pdb_group_affinity label the same pixels
+    (they differ only in FMA contraction of the interpolation)."""
+    from partdistillation_b200 import _lib
+    g = torch.load(os.path.join(golden_dir, "pixel_grouping.pt"), weights_only=False)
+    c = g["dot"]
+    H, W = g["mask_resized"].shape
+    feat, cent = c["feature"].cuda().contiguous(), c["centroids"].cuda().contiguous()
+    mask = g["mask_resized"].cuda()
+    old = fn.group_affinity(feat, cent, mask, "dot")
+    new = torch.empty_like(old)
+    rc = _lib.load().pdb_group_affinity_resized(feat.data_ptr(), cent.data_ptr(), mask.view(torch.uint8).data_ptr(),
+                                                new.data_ptr(), feat.shape[0], cent.shape[0], feat.shape[1], feat.shape[2],
+                                                H, W, H, W, H, W, 0, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    assert (old != new).float().mean() < 1e-3

@@ -171,7 +171,8 @@ def host_kernels(tmp_path_factory):
             return b"host build"
 
     lib = HostLib()
-    for name in ("postprocess_masks", "resize_masks_u8", "pack_bits", "unpack_bits", "bits_popcount", "bits_intersect"):
+    for name in ("postprocess_masks", "resize_masks_u8", "pack_bits", "unpack_bits", "bits_popcount", "bits_intersect",
+                 "group_affinity_resized"):
         f = getattr(cdll, "host_" + name)
         res, args = _lib.SIGNATURES["pdb_" + name]
         f.restype, f.argtypes = res, args[:-1]
@@ -350,3 +351,123 @@ def test_part_distillation_model_eval_forward_wiring(torch_ops, golden_dir):
     model.mode = "save"
     with pytest.raises(NotImplementedError):
         model(_batched_inputs(inp, inp["object_classes"]))
+
+
+# ------------------------------------------------------------------ pixel grouping at a resized evaluation size
+@pytest.mark.parametrize("metric", ["dot", "l2"])
+def test_host_built_kernel_group_affinity_resized(kernels_on_host, golden_dir, metric):
+    """pdb_group_affinity_resized's kernel (host build) through functional.group_affinity against the segments the
+    UNMODIFIED reference produced (tests/golden/pixel_grouping_resized.pt); label flips only at near-ties."""
+    fn = kernels_on_host
+    g = torch.load(os.path.join(golden_dir, "pixel_grouping_resized.pt"), weights_only=False)
+    c = g[metric]
+    labels = fn.group_affinity(c["feature"], c["centroids"], c["mask_resized"], metric, geometry=g["geometry"]).long()
+    exp_labels, exp_seg = O.pixel_grouping_segments(c["feature"], c["centroids"], c["mask_resized"], metric, geometry=g["geometry"])
+    assert torch.equal(exp_seg, c["binary_mask"])
+    scores = O.pixel_grouping_scores(c["feature"], c["centroids"], tuple(c["mask_resized"].shape), metric, g["geometry"])
+    top2 = scores.topk(2, dim=0)[0]
+    bad = labels != exp_labels
+    assert not (bad & ((top2[0] - top2[1]) > 1e-3 * scores.abs().max())).any()
+    assert bad.float().mean() < 1e-3
+    assert (labels[~c["mask_resized"]] == 0).all()
+
+
+def test_host_built_kernel_group_affinity_same_size_matches_oracle(kernels_on_host, golden_dir):
+    """geometry with padded == image == output size takes the older kernel in the product; the resized kernel's
+    one-pass branch must agree with the oracle on the same golden (tests/golden/pixel_grouping.pt)."""
+    from partdistillation_b200 import _lib
+    g = torch.load(os.path.join(golden_dir, "pixel_grouping.pt"), weights_only=False)
+    c = g["dot"]
+    H, W = g["mask_resized"].shape
+    feat, cent = c["feature"].contiguous(), c["centroids"].contiguous()
+    mask = g["mask_resized"].to(torch.uint8).contiguous()
+    labels = torch.empty((H, W), dtype=torch.int32)
+    rc = _lib.load().pdb_group_affinity_resized(feat.data_ptr(), cent.data_ptr(), mask.data_ptr(), labels.data_ptr(),
+                                                feat.shape[0], cent.shape[0], feat.shape[1], feat.shape[2], H, W, H, W, H, W, 0, None)
+    assert rc == 0
+    exp_labels, _ = O.pixel_grouping_segments(c["feature"], c["centroids"], g["mask_resized"], "dot")
+    assert (labels.long() != exp_labels).float().mean() < 1e-3
+
+
+class _FeatureBackbone(torch.nn.Module):
+    size_divisibility = 32
+
+    def __init__(self, feats):
+        super().__init__()
+        self.feats = feats
+
+    def forward(self, x):
+        return self.feats
+
+
+def _grouping_inputs(g, small_object=False):
+    from partdistillation_b200.compat import BitMasks, Instances
+    padded, image_size, out_size = g["geometry"]
+    obj = g["object_mask"].clone()
+    if small_object:
+        obj[:] = False
+        obj[40:44, 50:54] = True          # covers < 1 backbone pixel after the nearest down-sampling
+    inst = Instances(image_size)
+    inst.gt_masks = BitMasks(obj[None])
+    pinst = Instances(image_size)
+    pinst.gt_masks = BitMasks(torch.stack([obj & (torch.arange(image_size[1])[None] < 60), obj & (torch.arange(image_size[1])[None] >= 60)]))
+    return [{"image": torch.zeros(3, *image_size, dtype=torch.uint8), "instances": inst, "part_instances": pinst,
+             "height": out_size[0], "width": out_size[1], "file_name": "img0", "file_path": "/x/img0", "class_code": "n01",
+             "class_name": "thing", "gt_object_class": 3}]
+
+
+def test_pixel_grouping_model_resized_forward(kernels_on_host, golden_dir):
+    """PixelGroupingModel.forward at an evaluation size != padded size (the case that used to raise): the grouping kernel
+    (host build) against the oracle with the model's own k-means centroids."""
+    from partdistillation_b200.pixel_grouping_model import PixelGroupingModel
+    g = torch.load(os.path.join(golden_dir, "pixel_grouping_resized.pt"), weights_only=False)
+    padded, image_size, out_size = g["geometry"]
+    model = PixelGroupingModel(backbone=_FeatureBackbone(g["feats"]), size_divisibility=32, pixel_mean=(0.0, 0.0, 0.0),
+                               pixel_std=(1.0, 1.0, 1.0), distance_metric="dot", backbone_feature_key_list=["res3", "res4"],
+                               num_superpixel_clusters=4)
+    model.eval()
+    res = model(_grouping_inputs(g))
+    assert len(res) == 1 and set(res[0]) == {"proposals", "gt_masks"}
+    pm = res[0]["proposals"].pred_masks
+    c = g["dot"]
+    assert tuple(pm.shape[-2:]) == out_size
+    assert torch.equal(pm.any(0), c["mask_resized"]) and int(pm.sum()) == int(c["mask_resized"].sum())    # a partition of the object
+    centroids = model.get_pixel_grouping(c["feature"], c["mask_feat"])
+    _, seg = O.pixel_grouping_segments(c["feature"], centroids, c["mask_resized"], "dot", geometry=g["geometry"])
+    assert pm.shape == seg.shape and (pm != seg).float().mean() < 1e-3
+    gt = res[0]["gt_masks"].gt_masks
+    assert tuple(gt.shape) == (2, *out_size) and torch.equal(gt.any(0), c["mask_resized"])
+
+
+def test_proposal_generation_model(kernels_on_host, golden_dir, tmp_path, monkeypatch):
+    """ProposalGenerationModel: registered name, None for objects too small to cluster, the reference's on-disk record
+    (proposal_generation_model.py:185-199) through a stand-in pycocotools.encode."""
+    import sys
+    import types
+    import partdistillation_b200 as pkg
+    from partdistillation_b200.compat import META_ARCH_REGISTRY
+    assert META_ARCH_REGISTRY.get("ProposalGenerationModel") is pkg.ProposalGenerationModel
+    g = torch.load(os.path.join(golden_dir, "pixel_grouping_resized.pt"), weights_only=False)
+    make = lambda path: pkg.ProposalGenerationModel(
+        backbone=_FeatureBackbone(g["feats"]), size_divisibility=32, dataset_name="synthetic", pixel_mean=(0.0, 0.0, 0.0),
+        pixel_std=(1.0, 1.0, 1.0), distance_metric="l2", backbone_feature_key_list=["res3", "res4"],
+        num_superpixel_clusters=4, root_save_path=path).eval()
+    model = make(None)
+    assert model.generate(_grouping_inputs(g, small_object=True), save=False) == [None]
+    res = model.generate(_grouping_inputs(g), save=False)
+    assert res[0]["proposals"].pred_masks.any(0).equal(g["l2"]["mask_resized"])
+    with pytest.raises(RuntimeError, match="root_save_path"):
+        model(_grouping_inputs(g))
+    fake = types.ModuleType("pycocotools.mask")
+    fake.encode = lambda m: [{"size": list(m.shape[:2]), "counts": b"rle%d" % int(m.sum())}]
+    parent = types.ModuleType("pycocotools")
+    parent.mask = fake
+    monkeypatch.setitem(sys.modules, "pycocotools", parent)
+    monkeypatch.setitem(sys.modules, "pycocotools.mask", fake)
+    model = make(str(tmp_path))
+    assert model(_grouping_inputs(g)) is None
+    rec = torch.load(os.path.join(str(tmp_path), "n01", "img0"), weights_only=False)
+    assert rec["height"] == g["geometry"][2][0] and rec["width"] == g["geometry"][2][1] and rec["class_index"] == 3
+    assert len(rec["part_mask"]) == res[0]["proposals"].pred_masks.shape[0]
+    assert all(isinstance(p["segmentation"]["counts"], str) for p in rec["part_mask"])
+    assert rec["object_ratio"] == int(g["l2"]["mask_resized"].sum()) / g["l2"]["mask_resized"].numel()
