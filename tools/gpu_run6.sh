@@ -9,3 +9,4 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --c
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:postprocess_masks_kernel -s 3 -c 1 -o gpurun_out/prof_postprocess_v1 -f python tools/bench_postprocess.py > gpurun_out/ncu_pp.log 2>&1
 timeout 120 ncu -i gpurun_out/prof_postprocess_v1.ncu-rep --page raw --csv > gpurun_out/ncu_pp_raw.csv 2>/dev/null
 tail -3 gpurun_out/pp_tests.log; cat gpurun_out/pp_bench.json
+timeout 600 python tools/bench_reference_ops.py > gpurun_out/reference_ops.log 2>&1; tail -40 gpurun_out/reference_ops.log
