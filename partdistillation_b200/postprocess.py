@@ -57,13 +57,9 @@ class ProposalInferenceMixin:
         new_targets = []
         for x in inputs:
             parts, objects = x["part_instances"], x["instances"]
-            gt = parts.gt_masks.tensor.to(dev, non_blocking=True)
-            padded = torch.zeros((gt.shape[0], h_pad, w_pad), dtype=gt.dtype, device=dev)
-            padded[:, :gt.shape[1], :gt.shape[2]] = gt
-            go = objects.gt_masks.tensor.to(dev, non_blocking=True)
-            padded_obj = torch.zeros((go.shape[0], h_pad, w_pad), dtype=go.dtype, device=dev)
-            padded_obj[:, :go.shape[1], :go.shape[2]] = go
-            new_targets.append({"labels": parts.gt_classes.to(dev), "masks": padded, "object_masks": padded_obj})
+            new_targets.append({"labels": parts.gt_classes.to(dev),
+                                "masks": _zero_pad(parts.gt_masks.tensor, h_pad, w_pad, dev),
+                                "object_masks": _zero_pad(objects.gt_masks.tensor, h_pad, w_pad, dev)})
         return new_targets
 
     def inference(self, batched_inputs, targets, images, outputs, vis=False):
@@ -71,15 +67,13 @@ class ProposalInferenceMixin:
         gt_classes, pred_masks, pred_classes)} at each image's evaluation size (:220-254)."""
         mask_cls_results = outputs["pred_logits"]
         mask_pred_results = outputs["pred_masks"]                       # (B, Q, h, w) logits, never up-sampled densely
-        padded = tuple(int(v) for v in images.tensor.shape[-2:])
         processed_results = []
         for mask_cls, logits, target, inp, image_size in zip(mask_cls_results, mask_pred_results, targets,
                                                              batched_inputs, images.image_sizes):
-            image_size = (int(image_size[0]), int(image_size[1]))
-            out_size = (int(inp.get("height", image_size[0])), int(inp.get("width", image_size[1])))
+            geometry = _sizes(images, inp, image_size)
+            _, image_size, out_size = geometry
             target_masks = fn.resize_bool_masks(target["masks"], image_size, out_size)
             target_object_masks = fn.resize_bool_masks(target["object_masks"], image_size, out_size)
-            geometry = (padded, image_size, out_size)
             instance_r = self.instance_inference(mask_cls.float(), logits.float(), target_masks, target_object_masks,
                                                  target["labels"], vis=vis, geometry=geometry)
             target_inst = Instances(out_size)
