@@ -199,3 +199,30 @@ def test_group_affinity_resized_equals_one_pass_kernel(fn, golden_dir):
                                                 H, W, H, W, H, W, 0, torch.cuda.current_stream().cuda_stream)
     assert rc == 0
     assert (old != new).float().mean() < 1e-3
+
+
+def test_pixel_grouping_model_resized_forward(fn):
+    """The registered PixelGroupingModel on a micro Swin trunk with an image that needs padding (120 x 104 -> 128 x 128) and
+    an evaluation size of 1.5x: the proposals partition the resized object mask exactly."""
+    from partdistillation_b200 import compat, presets
+    from partdistillation_b200.config import add_pixel_grouping_confing
+    cfg = presets.make_cfg("PixelGroupingModel", "swin_micro", device="cuda")
+    add_pixel_grouping_confing(cfg)
+    cfg.PIXEL_GROUPING.DISTANCE_METRIC = "l2"
+    cfg.PIXEL_GROUPING.BACKBONE_FEATURE_KEY_LIST = ["res3", "res4"]
+    torch.manual_seed(0)
+    model = compat.build_model(cfg).eval()
+    H, W, Ho, Wo = 120, 104, 180, 156
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    obj = (((yy - 60) ** 2 + (xx - 52) ** 2) < 36 ** 2)[None]
+    inst = compat.Instances((H, W))
+    inst.gt_masks = compat.BitMasks(obj)
+    inst.gt_classes = torch.zeros(1, dtype=torch.long)
+    img = torch.randint(0, 256, (3, H, W), generator=torch.Generator().manual_seed(1), dtype=torch.uint8)
+    out = model([{"image": img, "instances": inst, "height": Ho, "width": Wo}])
+    pm = out[0]["proposals"].pred_masks.cpu()
+    padded = torch.zeros(1, 128, 128)
+    padded[:, :H, :W] = obj.float()
+    exp_obj = O.sem_seg_postprocess(padded, (H, W), Ho, Wo)[0].bool()
+    assert pm.dtype == torch.bool and tuple(pm.shape[1:]) == (Ho, Wo) and 1 <= pm.shape[0] <= 4
+    assert torch.equal(pm.any(0), exp_obj) and int(pm.sum()) == int(exp_obj.sum())
