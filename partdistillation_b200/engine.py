@@ -42,6 +42,62 @@ def build_param_groups(model, base_lr=1e-4, weight_decay=0.05, weight_decay_norm
     return groups
 
 
+class WarmupMultiStepLR:
+    """Learning-rate factor of detectron2's ``WarmupMultiStepLR`` (detectron2==0.6 solver/lr_scheduler.py, un-vendored;
+    selected by SOLVER.LR_SCHEDULER_NAME's default and configured by SOLVER.STEPS / GAMMA / WARMUP_* — the reference builds
+    it in base_trainer.py:57-62; recipe values: STEPS (40000, 45000) of 50000 iterations, sh_files/proposal_learning/
+    train_multi.sh:55-58; WARMUP_FACTOR 1.0, WARMUP_ITERS 10, Base-COCO-InstanceSegmentation.yaml:24-25):
+    ``lr(it) = base_lr * warmup(it) * gamma ** #{milestones <= it}``."""
+
+    def __init__(self, milestones, gamma=0.1, warmup_factor=0.001, warmup_iters=1000, warmup_method="linear"):
+        if list(milestones) != sorted(milestones):
+            raise ValueError(f"Milestones should be a list of increasing integers. Got {milestones}")
+        if warmup_method not in ("constant", "linear"):
+            raise ValueError(f"Unknown warmup method: {warmup_method}")
+        self.milestones, self.gamma = list(milestones), gamma
+        self.warmup_factor, self.warmup_iters, self.warmup_method = warmup_factor, warmup_iters, warmup_method
+
+    def warmup(self, it):
+        if it >= self.warmup_iters:
+            return 1.0
+        if self.warmup_method == "constant":
+            return self.warmup_factor
+        alpha = it / self.warmup_iters
+        return self.warmup_factor * (1 - alpha) + alpha
+
+    def factor(self, it):
+        import bisect
+        return self.warmup(it) * self.gamma ** bisect.bisect_right(self.milestones, it)
+
+
+class WarmupPolyLR(WarmupMultiStepLR):
+    """detectron2.projects.deeplab ``WarmupPolyLR`` (SOLVER.LR_SCHEDULER_NAME = "WarmupPolyLR", the Mask2Former semantic /
+    panoptic configs): ``warmup(it) * (1 - it / max_iters) ** power``, held at ``constant_ending`` once below it."""
+
+    def __init__(self, max_iters, power=0.9, constant_ending=0.0, warmup_factor=0.001, warmup_iters=1000,
+                 warmup_method="linear"):
+        super().__init__([], 1.0, warmup_factor, warmup_iters, warmup_method)
+        self.max_iters, self.power, self.constant_ending = max_iters, power, constant_ending
+
+    def factor(self, it):
+        poly = (1.0 - it / self.max_iters) ** self.power
+        if self.constant_ending > 0 and poly < self.constant_ending:
+            return self.constant_ending          # detectron2 drops the warm-up factor here as well
+        return self.warmup(it) * poly
+
+
+def build_lr_schedule(cfg):
+    """SOLVER.* -> schedule object (detectron2.projects.deeplab.build_lr_scheduler, used at base_trainer.py:62)."""
+    s = cfg.SOLVER
+    name = getattr(s, "LR_SCHEDULER_NAME", "WarmupMultiStepLR")
+    warm = dict(warmup_factor=s.WARMUP_FACTOR, warmup_iters=s.WARMUP_ITERS, warmup_method=getattr(s, "WARMUP_METHOD", "linear"))
+    if name == "WarmupMultiStepLR":
+        return WarmupMultiStepLR([x for x in s.STEPS if x <= s.MAX_ITER], getattr(s, "GAMMA", 0.1), **warm)
+    if name == "WarmupPolyLR":
+        return WarmupPolyLR(s.MAX_ITER, getattr(s, "POLY_LR_POWER", 0.9), getattr(s, "POLY_LR_CONSTANT_ENDING", 0.0), **warm)
+    raise ValueError(f"Unknown LR scheduler: {name}")
+
+
 class DataParallelTrainer:
     """model(batched_inputs) -> loss dict; backward; ONE flat gradient all-reduce; clip; AdamW.
 
@@ -108,6 +164,36 @@ class DataParallelTrainer:
             self.optimizer = torch.optim.AdamW(other_groups, lr=base_lr, betas=betas, eps=eps, fused=fused,
                                                capturable=fused and self.cuda_graph)
         self.grad_bytes = sum(b.numel() * b.element_size() for b in self.flat.values())
+        self.lr_schedule = None
+        self.iteration = 0                  # optimizer steps taken through step() (graph replays included)
+
+    def set_lr_schedule(self, schedule):
+        """``schedule.factor(iteration)`` scales every group's learning rate before each step.  The rates live in device
+        memory (``seg_lr`` for the flat kernel, tensor ``lr`` for the torch groups), so a captured step picks the new
+        value up at replay; graphs captured with python-float rates are dropped."""
+        self.lr_schedule = schedule
+        if self.flat_param is not None and not hasattr(self, "seg_lr_base"):
+            self.seg_lr_base = self.seg_lr.clone()
+        if self.optimizer is not None:
+            for g in self.optimizer.param_groups:
+                if "base_lr" not in g:
+                    g["base_lr"] = float(g["lr"])
+                    if g["params"][0].is_cuda:
+                        g["lr"] = torch.tensor(g["base_lr"], dtype=torch.float32, device=g["params"][0].device)
+            self._graphs.clear()
+
+    def _apply_lr_factor(self, factor):
+        if self.flat_param is not None:
+            torch.mul(self.seg_lr_base, float(factor), out=self.seg_lr)
+        if self.optimizer is not None:
+            for g in self.optimizer.param_groups:
+                if torch.is_tensor(g["lr"]):
+                    g["lr"].fill_(g["base_lr"] * float(factor))
+                else:
+                    g["lr"] = g["base_lr"] * float(factor)
+
+    def current_lr_factor(self):
+        return 1.0 if self.lr_schedule is None else float(self.lr_schedule.factor(self.iteration))
 
     def zero_grad(self):
         for b in self.flat.values():
@@ -195,6 +281,9 @@ class DataParallelTrainer:
         counts) after two eager steps, and replayed afterwards: the inputs are copied into the graph's static
         buffers, the returned tensors are the graph's static outputs."""
         from . import _lib
+        if self.lr_schedule is not None:
+            self._apply_lr_factor(self.lr_schedule.factor(self.iteration))
+        self.iteration += 1
         if not self.cuda_graph:
             n0 = _lib.launch_count()
             out = self._eager_step(batched_inputs)

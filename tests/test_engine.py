@@ -103,3 +103,59 @@ def test_flat_adamw_matches_torch():
         opt.step()
     for (k, v), (_, w) in zip(a.state_dict().items(), b.state_dict().items()):
         assert torch.allclose(v, w, rtol=2e-5, atol=2e-6), k
+
+
+def test_lr_schedules_follow_detectron2_formulas():
+    """WarmupMultiStepLR / WarmupPolyLR factors against the published detectron2==0.6 expressions (un-vendored third
+    party; restated independently here) and against torch's MultiStepLR after the warm-up."""
+    import bisect
+    from partdistillation_b200.engine import WarmupMultiStepLR, WarmupPolyLR, build_lr_schedule
+    from partdistillation_b200.compat import CfgNode
+    s = WarmupMultiStepLR([40, 45], gamma=0.1, warmup_factor=0.001, warmup_iters=10, warmup_method="linear")
+    for it in (0, 1, 5, 9, 10, 39, 40, 44, 45, 60):
+        alpha = it / 10
+        warm = 1.0 if it >= 10 else 0.001 * (1 - alpha) + alpha
+        assert s.factor(it) == pytest.approx(warm * 0.1 ** bisect.bisect_right([40, 45], it), rel=1e-12)
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0)
+    ref = torch.optim.lr_scheduler.MultiStepLR(opt, [40, 45], 0.1)
+    for it in range(60):
+        if it >= 10:
+            assert s.factor(it) == pytest.approx(ref.get_last_lr()[0], rel=1e-9)
+        opt.step()
+        ref.step()
+    c = WarmupMultiStepLR([3], warmup_factor=0.5, warmup_iters=4, warmup_method="constant")
+    assert [c.factor(i) for i in range(6)] == [0.5, 0.5, 0.5, pytest.approx(0.05), pytest.approx(0.1), pytest.approx(0.1)]
+    p = WarmupPolyLR(100, power=0.9, constant_ending=0.05, warmup_factor=1.0, warmup_iters=10)
+    assert p.factor(0) == 1.0 and p.factor(50) == pytest.approx(0.5 ** 0.9)
+    assert p.factor(99) == 0.05                                     # (1 - 0.99) ** 0.9 = 0.0158 < constant ending
+    with pytest.raises(ValueError):
+        WarmupMultiStepLR([5, 3])
+    cfg = CfgNode({"SOLVER": {"STEPS": (40000, 45000, 70000), "MAX_ITER": 50000, "WARMUP_FACTOR": 1.0, "WARMUP_ITERS": 10}})
+    b = build_lr_schedule(cfg)                                      # the recipe of sh_files/proposal_learning/train_multi.sh
+    assert b.milestones == [40000, 45000] and b.factor(0) == 1.0 and b.factor(45000) == pytest.approx(0.01)
+
+
+def test_trainer_applies_lr_schedule_cpu():
+    """DataParallelTrainer.set_lr_schedule on a CPU model (torch.optim.AdamW groups): same trajectory as torch AdamW
+    driven by LambdaLR with the same factors and the same clipping."""
+    from partdistillation_b200.engine import DataParallelTrainer, WarmupMultiStepLR, build_param_groups
+    sched = WarmupMultiStepLR([2], gamma=0.1, warmup_factor=0.1, warmup_iters=2)
+    torch.manual_seed(0)
+    a, b = _Tiny(), _Tiny()
+    b.load_state_dict(a.state_dict())
+    tr = DataParallelTrainer(a, base_lr=1e-2, weight_decay=0.05, clip_norm=0.5, freeze_keys=())
+    tr.set_lr_schedule(sched)
+    groups = build_param_groups(b, 1e-2, 0.05, freeze_keys=())
+    opt = torch.optim.AdamW(groups, lr=1e-2)
+    lam = torch.optim.lr_scheduler.LambdaLR(opt, sched.factor)
+    for step in range(4):
+        assert tr.current_lr_factor() == pytest.approx(sched.factor(step))
+        tr.step(_data(step))
+        opt.zero_grad()
+        sum(b(_data(step)).values()).backward()
+        torch.nn.utils.clip_grad_norm_([p for g in groups for p in g["params"]], 0.5)
+        opt.step()
+        lam.step()
+    assert tr.iteration == 4
+    for (k, va), vb in zip(a.state_dict().items(), b.state_dict().values()):
+        assert torch.allclose(va, vb, rtol=1e-5, atol=1e-7), k
