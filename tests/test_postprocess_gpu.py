@@ -226,3 +226,42 @@ def test_pixel_grouping_model_resized_forward(fn):
     exp_obj = O.sem_seg_postprocess(padded, (H, W), Ho, Wo)[0].bool()
     assert pm.dtype == torch.bool and tuple(pm.shape[1:]) == (Ho, Wo) and 1 <= pm.shape[0] <= 4
     assert torch.equal(pm.any(0), exp_obj) and int(pm.sum()) == int(exp_obj.sum())
+
+
+def test_postprocess_full_size_properties(fn):
+    """BASELINE geometry (Q = 100, 256^2 logits -> 1024^2): the packed path against the reference expression evaluated by
+    PyTorch on the same GPU (F.interpolate -> gate -> > 0; dense areas and IoU), plus size-independent properties."""
+    g = torch.Generator().manual_seed(3)
+    Q, S, G = 100, 1024, 6
+    low = torch.randn(Q, S // 16, S // 16, generator=g) * 3
+    logits = (F.interpolate(low[None], size=(S // 4, S // 4), mode="bicubic")[0]
+              + 0.3 * torch.randn(Q, S // 4, S // 4, generator=g)).cuda()
+    scores = torch.rand(Q, generator=g).cuda()
+    sel = torch.randperm(Q, generator=g).cuda()
+    yy, xx = torch.meshgrid(torch.arange(S), torch.arange(S), indexing="ij")
+    gate = (((yy - S / 2) ** 2 + (xx - S / 2) ** 2) < (0.4 * S) ** 2).cuda()
+    lab = torch.randint(0, G, (S // 16, S // 16), generator=g).repeat_interleave(16, 0).repeat_interleave(16, 1)
+    gt = torch.stack([lab == k for k in range(G)]).cuda() & gate
+    bits, label = fn.postprocess_masks(logits, sel, (S, S), (S, S), (S, S), gate=gate, scores=scores, want_bits=True,
+                                       want_label=True)
+    dense = F.interpolate(logits[sel][None], size=(S, S), mode="bilinear", align_corners=False)[0] * gate
+    masks = fn.unpack_bits(bits, S)
+    flips = masks[:Q] != (dense > 0)
+    assert not (flips & (dense.abs() > NEAR)).any()
+    assert flips.float().mean() < 1e-4
+    assert torch.equal(masks[Q], masks[:Q].any(0))                                   # object map = OR of the candidates
+    assert not (masks[:Q] & ~gate).any()                                             # nothing outside the gate
+    counts = fn.bits_popcount(bits)
+    assert torch.equal(counts, masks.flatten(1).sum(1))
+    a = masks[:Q].flatten(1).double()
+    b = gt.flatten(1).double()
+    inter = a @ b.t()
+    union = a.sum(1)[:, None] + b.sum(1)[None] - inter
+    exp_iou = torch.where(inter > 0, inter / union.clamp(min=1), torch.zeros_like(inter))
+    assert torch.equal(fn.bits_iou(bits[:Q], fn.pack_bits(gt)), exp_iou)
+    assert torch.equal(fn.unpack_bits(fn.pack_bits(gt), S), gt)                      # pack / unpack round trip
+    # every pixel is owned by exactly one candidate; inside the object the owner's own logit is the largest score * sigmoid
+    sm = scores[:, None, None] * dense.sigmoid()
+    top2 = sm.topk(2, dim=0)[0]
+    bad = label.long() != sm.argmax(0)
+    assert not (bad & ((top2[0] - top2[1]) > 1e-5)).any()
