@@ -43,6 +43,9 @@ class PartDistillationModel(PartDistillationInferenceMixin, Mask2FormerTrainingA
         self.apply_masking_with_object_mask = apply_masking_with_object_mask
         self.majority_vote_mapping = {}
         self.mode = "train"
+        # part_distillation_model.py:91-92
+        self.root_save_path = "pseudo_labels/part_labels/part_distillation_predictions/{}/{}_{}/".format(
+            train_dataset_name, min_pseudo_mask_score, min_pseudo_mask_ratio)
 
     def update_majority_vote_mapping(self, mapping_dict):
         for cid, mapping in mapping_dict.items():
@@ -72,12 +75,9 @@ class PartDistillationModel(PartDistillationInferenceMixin, Mask2FormerTrainingA
             losses = super().forward(batched_inputs)
             self.current_train_iteration += 1
             return losses
-        if self.mode == "save":
-            raise NotImplementedError("PartDistillationModel mode 'save' (pseudo-label dump, part_distillation_model.py:"
-                                      "285-306) is outside the accelerated path")
         images = self.preprocess_images(batched_inputs)
         features = self.backbone(images.tensor)
-        targets = self._prepare_gt_targets(batched_inputs, images)
+        targets = (self._prepare_save_targets if self.mode == "save" else self._prepare_gt_targets)(batched_inputs, images)
         outputs = self.run_head(features, targets)
         processed_results = self.inference(batched_inputs, targets, images, outputs, vis=False)
         self.current_test_iteration += 1

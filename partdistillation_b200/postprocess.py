@@ -163,11 +163,8 @@ class PartDistillationInferenceMixin:
 
     def inference(self, batched_inputs, targets, images, outputs, vis=False):
         """-> list of {"predictions": Instances(pred_masks, scores, pred_classes), "gt_instances": Instances,
-        "gt_object_label"} (:239-283).  ``mode == "save"`` (writing pseudo labels to disk, :285-306) is outside this
-        library."""
-        if self.mode == "save":
-            raise NotImplementedError("PartDistillationModel mode 'save' (pseudo-label dump, part_distillation_model.py:"
-                                      "285-306) is outside the accelerated path")
+        "gt_object_label"} (:239-283).  With ``mode == "save"`` every image's prediction is also written to disk in the
+        reference's record format (``save_part_segmentation``, :285-306)."""
         processed_results = []
         for mask_cls, logits, target, inp, image_size in zip(outputs["pred_logits"], outputs["pred_masks"], targets,
                                                              batched_inputs, images.image_sizes):
@@ -178,6 +175,8 @@ class PartDistillationInferenceMixin:
             instance_r = self.instance_inference_with_classification(
                 mask_cls.float(), logits.float(), target_mask, target_object_mask, target["labels"],
                 target["gt_object_class"], vis=vis, geometry=geometry)
+            if self.mode == "save" and not vis:
+                self.save_part_segmentation(inp, instance_r)
             target_inst = Instances(out_size)
             target_inst.gt_masks = target_mask
             target_inst.gt_classes = target["labels"]
@@ -186,6 +185,46 @@ class PartDistillationInferenceMixin:
             processed_results.append({"predictions": instance_r, "gt_instances": target_inst,
                                       "gt_object_label": target["gt_object_class"]})
         return processed_results
+
+    def _prepare_save_targets(self, inputs, images):
+        """mode == "save": the pseudo labels of the training set stand in for the ground truth (prepare_targets, :397-402;
+        _prepare_pseudo_targets, :405-428), with the object mask = union of the image's part masks."""
+        h_pad, w_pad = images.tensor.shape[-2:]
+        dev = self.device
+        new_targets = []
+        for x in inputs:
+            inst = x["instances"]
+            masks = _zero_pad(inst.gt_masks.tensor, h_pad, w_pad, dev)
+            new_targets.append({"labels": inst.gt_classes.to(dev), "masks": masks,
+                                "object_mask": masks.sum(dim=0, keepdim=True), "gt_object_class": x["gt_object_class"]})
+        return new_targets
+
+    def save_part_segmentation(self, input_per_image, instance):
+        """The reference's on-disk record of one image's part prediction (:285-306); RLE strings from pycocotools, as in
+        the reference (utils/utils.py:15-33)."""
+        import os
+        import numpy as np
+        if instance is None:
+            return
+        root = getattr(self, "root_save_path", None)
+        if root is None:
+            raise RuntimeError("PartDistillationModel.save_part_segmentation: no root_save_path")
+        from pycocotools import mask as mask_util
+        masks = instance.pred_masks
+        H, W = masks.shape[1:]
+        object_area = int(masks.sum())
+        part_areas = masks.flatten(1).sum(-1).long().cpu()
+        rles = [mask_util.encode(np.asfortranarray(m.numpy()[:, :, None].astype(np.uint8)))[0] for m in masks.cpu()]
+        for rle in rles:
+            rle["counts"] = rle["counts"].decode("utf-8")
+        res = {"file_name": input_per_image["file_name"], "image_id": input_per_image["image_id"],
+               "class_code": input_per_image["class_code"], "height": H, "width": W,
+               "part_masks": [{"segmentation": rle} for rle in rles], "part_labels": instance.pred_classes.cpu(),
+               "part_area_ratios": part_areas / object_area, "object_ratio": object_area / (H * W),
+               "part_scores": instance.scores.cpu().numpy()}
+        folder = os.path.join(root, input_per_image["class_code"])
+        os.makedirs(folder, exist_ok=True)
+        torch.save(res, os.path.join(folder, input_per_image["image_id"]))
 
     def instance_inference_with_classification(self, mask_cls, mask_pred, target_mask, target_object_mask, target_labels,
                                                target_object_label, vis=False, geometry=None):

@@ -348,9 +348,47 @@ def test_part_distillation_model_eval_forward_wiring(torch_ops, golden_dir):
         assert tuple(r["predictions"].pred_masks.shape) == ref["pred_shape"]
         assert torch.equal(r["predictions"].pred_classes, ref["pred_classes"])
         assert torch.allclose(r["predictions"].scores, ref["scores"])
+
+
+def test_part_distillation_model_save_mode(torch_ops, golden_dir, tmp_path, monkeypatch):
+    """mode == "save": pseudo labels as targets (object mask = union of the parts), one record per image on disk in the
+    reference's format (part_distillation_model.py:285-306), through a stand-in pycocotools.encode."""
+    import sys
+    import types
+    from partdistillation_b200.part_distillation_model import PartDistillationModel
+    g = torch.load(os.path.join(golden_dir, "pd_inference.pt"), weights_only=False)
+    inp = g["inputs"]
+    Q, P = inp["pred_logits"].shape[1], inp["pred_logits"].shape[2] - 1
+    head = _StubHead({"pred_logits": inp["pred_logits"], "pred_masks": inp["pred_masks"]})
+    model = PartDistillationModel(backbone=_StubBackbone(), sem_seg_head=head, criterion=torch.nn.Identity(), num_queries=Q,
+                                  num_classes=P, size_divisibility=32, pixel_mean=(0.0, 0.0, 0.0), pixel_std=(1.0, 1.0, 1.0),
+                                  test_topk_per_image=inp["topk"], use_wandb=False, use_unique_per_pixel_label=True,
+                                  train_dataset_name="synthetic", min_pseudo_mask_score=0.0, min_pseudo_mask_ratio=0.0)
+    assert model.root_save_path == "pseudo_labels/part_labels/part_distillation_predictions/synthetic/0.0_0.0/"
+    model.root_save_path = str(tmp_path)
+    model.eval()
     model.mode = "save"
-    with pytest.raises(NotImplementedError):
-        model(_batched_inputs(inp, inp["object_classes"]))
+    fake = types.ModuleType("pycocotools.mask")
+    fake.encode = lambda m: [{"size": list(m.shape[:2]), "counts": b"rle%d" % int(m.sum())}]
+    parent = types.ModuleType("pycocotools")
+    parent.mask = fake
+    monkeypatch.setitem(sys.modules, "pycocotools", parent)
+    monkeypatch.setitem(sys.modules, "pycocotools.mask", fake)
+    bi = []
+    for i, (x, it) in enumerate(zip(_batched_inputs(inp, inp["object_classes"]), inp["items"])):
+        x["instances"] = x.pop("part_instances")                # training-set format: the pseudo part masks are the instances
+        x.update(gt_object_class=inp["object_classes"][i], file_name=f"f{i}", image_id=f"id{i}", class_code="n01")
+        bi.append(x)
+    res = model(bi)
+    assert [int(t["gt_object_class"]) for t in head.calls[0]] == inp["object_classes"]
+    for i, r in enumerate(res):
+        rec = torch.load(os.path.join(str(tmp_path), "n01", f"id{i}"), weights_only=False)
+        pred = r["predictions"]
+        assert (rec["height"], rec["width"]) == tuple(pred.pred_masks.shape[1:])
+        assert len(rec["part_masks"]) == pred.pred_masks.shape[0] and torch.equal(rec["part_labels"], pred.pred_classes)
+        assert [p["segmentation"]["counts"] for p in rec["part_masks"]] == ["rle%d" % int(m.sum()) for m in pred.pred_masks]
+        assert rec["object_ratio"] == int(pred.pred_masks.sum()) / pred.pred_masks[0].numel()
+        assert torch.allclose(rec["part_area_ratios"].sum(), torch.tensor(1.0))
 
 
 # ------------------------------------------------------------------ pixel grouping at a resized evaluation size
