@@ -289,10 +289,11 @@ class PointSampleFunction(Function):
         else:
             raise RuntimeError("point_sample: maps must be float32 or uint8/bool")
         out = torch.empty((R, P), dtype=torch.float32, device=src.device)
-        rc = _lib.load().pdb_point_sample_forward(src.data_ptr(), sd, map_index.data_ptr() if map_index is not None else None,
-                                                  coords.data_ptr(), coord_index.data_ptr() if coord_index is not None else None,
-                                                  out.data_ptr(), R, P, H, W, _stream())
-        _lib.check(rc, "pdb_point_sample_forward")
+        if R:       # nothing to sample for an empty row set (a batch without targets): empty tensors have null pointers
+            rc = _lib.load().pdb_point_sample_forward(src.data_ptr(), sd, map_index.data_ptr() if map_index is not None else None,
+                                                      coords.data_ptr(), coord_index.data_ptr() if coord_index is not None else None,
+                                                      out.data_ptr(), R, P, H, W, _stream())
+            _lib.check(rc, "pdb_point_sample_forward")
         ctx.save_for_backward(coords)
         ctx.meta = (map_index, coord_index, tuple(src.shape), sd)
         return out
@@ -307,10 +308,11 @@ class PointSampleFunction(Function):
         grad_out = _c(grad_out)
         R, P = grad_out.shape
         gs = torch.zeros(shape, dtype=torch.float32, device=grad_out.device)
-        rc = _lib.load().pdb_point_sample_backward(grad_out.data_ptr(), map_index.data_ptr() if map_index is not None else None,
-                                                   coords.data_ptr(), coord_index.data_ptr() if coord_index is not None else None,
-                                                   gs.data_ptr(), R, P, shape[1], shape[2], _stream())
-        _lib.check(rc, "pdb_point_sample_backward")
+        if R:
+            rc = _lib.load().pdb_point_sample_backward(grad_out.data_ptr(), map_index.data_ptr() if map_index is not None else None,
+                                                       coords.data_ptr(), coord_index.data_ptr() if coord_index is not None else None,
+                                                       gs.data_ptr(), R, P, shape[1], shape[2], _stream())
+            _lib.check(rc, "pdb_point_sample_backward")
         return gs, None, None, None
 
 
@@ -359,9 +361,10 @@ class PointLossFunction(Function):
         _, Hg, Wg = gt.shape
         Nm, P = coords.shape[0], coords.shape[1]
         sums = torch.empty((Nm, 4), dtype=torch.float32, device=pred.device)
-        rc = _lib.load().pdb_point_loss_forward(pred.data_ptr(), pred_index.data_ptr(), gt.data_ptr(), gt_index.data_ptr(),
-                                                coords.data_ptr(), sums.data_ptr(), Nm, P, H, W, Hg, Wg, _stream())
-        _lib.check(rc, "pdb_point_loss_forward")
+        if Nm:      # no matched pair (a batch without targets): the losses are empty sums, as in the reference
+            rc = _lib.load().pdb_point_loss_forward(pred.data_ptr(), pred_index.data_ptr(), gt.data_ptr(), gt_index.data_ptr(),
+                                                    coords.data_ptr(), sums.data_ptr(), Nm, P, H, W, Hg, Wg, _stream())
+            _lib.check(rc, "pdb_point_loss_forward")
         ctx.save_for_backward(pred, pred_index, gt, gt_index, coords, sums)
         bce = sums[:, 0] / P
         dice = 1 - (2 * sums[:, 1] + 1) / (sums[:, 2] + sums[:, 3] + 1)
@@ -376,10 +379,11 @@ class PointLossFunction(Function):
         Nm, P = coords.shape[0], coords.shape[1]
         g_bce, g_dice = _c(g_bce.float()), _c(g_dice.float())
         gp = torch.zeros_like(pred)
-        rc = _lib.load().pdb_point_loss_backward(pred.data_ptr(), pred_index.data_ptr(), gt.data_ptr(), gt_index.data_ptr(),
-                                                 coords.data_ptr(), sums.data_ptr(), g_bce.data_ptr(), g_dice.data_ptr(),
-                                                 gp.data_ptr(), Nm, P, H, W, Hg, Wg, _stream())
-        _lib.check(rc, "pdb_point_loss_backward")
+        if Nm:
+            rc = _lib.load().pdb_point_loss_backward(pred.data_ptr(), pred_index.data_ptr(), gt.data_ptr(), gt_index.data_ptr(),
+                                                     coords.data_ptr(), sums.data_ptr(), g_bce.data_ptr(), g_dice.data_ptr(),
+                                                     gp.data_ptr(), Nm, P, H, W, Hg, Wg, _stream())
+            _lib.check(rc, "pdb_point_loss_backward")
         return gp, None, None, None, None
 
 
