@@ -34,6 +34,7 @@ struct Warp {
     std::unique_ptr<std::barrier<>> bar;
     unsigned pred[32];
     int val[32];
+    unsigned long long xchg[32];        // __shfl_*_sync payloads (up to 8 bytes per lane)
 };
 
 struct Block {
@@ -84,6 +85,24 @@ inline int __reduce_add_sync(unsigned, int v) {
     int r = 0;
     for (int i = 0; i < 32; ++i) r += w->val[i];
     w->bar->arrive_and_wait();
+    return r;
+}
+
+inline void __syncwarp(unsigned = 0xffffffffu) { cpu_cuda::t_warp->bar->arrive_and_wait(); }
+
+// value held by lane (lane ^ lane_mask); every lane of the warp takes part (full-mask use only)
+template <typename T>
+inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+    static_assert(sizeof(T) <= sizeof(unsigned long long), "shuffle payload");
+    auto* w = cpu_cuda::t_warp;
+    unsigned long long raw = 0;
+    __builtin_memcpy(&raw, &v, sizeof(T));
+    w->xchg[cpu_cuda::t_lane] = raw;
+    w->bar->arrive_and_wait();
+    raw = w->xchg[(cpu_cuda::t_lane ^ lane_mask) & 31];
+    w->bar->arrive_and_wait();
+    T r;
+    __builtin_memcpy(&r, &raw, sizeof(T));
     return r;
 }
 
