@@ -109,6 +109,7 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 template <typename T> inline T __ldg(const T* p) { return *p; }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 using std::min;
 using std::max;
