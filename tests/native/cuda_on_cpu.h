@@ -21,7 +21,14 @@ struct dim3 {
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+
 #define __global__
+#define __grid_constant__
+#define __align__(n) alignas(n)
 #define __device__
 #define __host__
 #define __forceinline__ inline
@@ -109,6 +116,23 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 template <typename T> inline T __ldg(const T* p) { return *p; }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline float atomicAdd(float* p, float v) {
+    float old = *p, next;
+    do { next = old + v; } while (!__atomic_compare_exchange(p, &old, &next, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+    return old;
+}
+inline double atomicAdd(double* p, double v) {
+    double old = *p, next;
+    do { next = old + v; } while (!__atomic_compare_exchange(p, &old, &next, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+    return old;
+}
+// round-to-nearest single operations that the compiler must not contract (build with -ffp-contract=off as well)
+inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+using std::floor;
+inline float __int_as_float(int v) { float r; __builtin_memcpy(&r, &v, 4); return r; }
+inline int __float_as_int(float v) { int r; __builtin_memcpy(&r, &v, 4); return r; }
 inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 using std::min;
