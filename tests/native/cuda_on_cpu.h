@@ -21,6 +21,10 @@ struct dim3 {
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 
+struct uint2 { unsigned x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct int2 { int x, y; };
+struct alignas(16) int4 { int x, y, z, w; };
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
@@ -28,7 +32,7 @@ inline float4 make_float4(float x, float y, float z, float w) { return float4{x,
 
 #define __global__
 #define __grid_constant__
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 #define __device__
 #define __host__
 #define __forceinline__ inline

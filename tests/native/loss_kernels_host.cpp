@@ -3,17 +3,7 @@
 // tests/test_loss_kernels_host_cpu.py cuts the whole `namespace pdb { ... }` block out of loss.cu into loss_section.inc;
 // the entry points below restate the launch geometry of the pdb_* launchers at the end of loss.cu, with the C ABI's argument
 // order minus the stream, so that partdistillation_b200/functional.py's wrappers can drive them unmodified.
-#include "cuda_on_cpu.h"
-
-#define PDB_OK 0
-#define PDB_REQUIRE(cond, ...) do { if (!(cond)) return -1; } while (0)
-#define PDB_TRY(expr) do { int _rc = (expr); if (_rc != PDB_OK) return _rc; } while (0)
-
-namespace pdb {
-// common.cuh's warp reductions
-inline float warp_sum(float v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
-inline float warp_max(float v) { for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
-}  // namespace pdb
+#include "pdb_common_host.h"
 
 #include "loss_section.inc"
 

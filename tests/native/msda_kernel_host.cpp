@@ -3,18 +3,9 @@
 // tests/test_msda_host_cpu.py cuts the kernel part of msda.cu (everything inside `namespace pdb` ahead of the launch
 // helpers) into msda_section.inc, rewriting only the `extern __shared__` declarations to the shim's dynamic shared
 // memory pointer.  The dispatch below restates pdb_msda_forward / pdb_msda_backward (msda.cu) line by line.
-#include "cuda_on_cpu.h"
-
-#define PDB_OK 0
-#define PDB_REQUIRE(cond, ...) do { if (!(cond)) return -1; } while (0)
+#include "pdb_common_host.h"
 
 namespace pdb {
-constexpr int kMaxLevels = 8;               // as in common.cuh
-struct LevelTable { int h[kMaxLevels]; int w[kMaxLevels]; int start[kMaxLevels]; };
-// common.cuh's red.global.add.v4.f32: four float reductions into global memory
-inline void red_add_v4(float* addr, float a, float b, float c, float d) {
-    atomicAdd(addr, a); atomicAdd(addr + 1, b); atomicAdd(addr + 2, c); atomicAdd(addr + 3, d);
-}
 #include "msda_section.inc"
 }  // namespace pdb
 
