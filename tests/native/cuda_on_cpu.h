@@ -135,6 +135,12 @@ inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 using std::floor;
+inline float rsqrtf(float v) { return 1.0f / sqrtf(v); }
+inline double rsqrt(double v) { return 1.0 / sqrt(v); }
+inline float __expf(float v) { return expf(v); }
+inline float __fdividef(float a, float b) { return a / b; }
+inline float __frcp_rn(float v) { return 1.0f / v; }
+inline float exp2f_(float v) { return exp2f(v); }
 inline float __int_as_float(int v) { float r; __builtin_memcpy(&r, &v, 4); return r; }
 inline int __float_as_int(float v) { int r; __builtin_memcpy(&r, &v, 4); return r; }
 inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
