@@ -16,9 +16,9 @@ def build_host_library(tmp, cu_file, inc_name, harness, ops, section_regex=NAMES
     returns an object exposing pdb_<op>(..., stream) -> host_<op>(...) with the ctypes signatures of _lib.SIGNATURES."""
     from partdistillation_b200 import _lib
     src = open(os.path.join(ROOT, "partdistillation_b200", "csrc", cu_file)).read()
-    m = re.search(section_regex, src, re.S)
-    assert m, f"kernel section not found in {cu_file}"
-    section = m.group(1)
+    blocks = re.findall(section_regex, src, re.S)          # a file may interleave several namespace blocks with launchers
+    assert blocks, f"kernel section not found in {cu_file}"
+    section = "\n".join(blocks)
     if rewrite is not None:
         section = rewrite(section)
     assert "<<<" not in section
@@ -39,6 +39,12 @@ def build_host_library(tmp, cu_file, inc_name, harness, ops, section_regex=NAMES
         f.restype, f.argtypes = res, (args[:-1] if stream_arg else args)
         setattr(lib, "pdb_" + name, (lambda f, s: lambda *a: f(*(a[:-1] if s else a)))(f, stream_arg))
     return lib
+
+
+def dynamic_smem(section):
+    """`extern __shared__ [__align__(n)] T name[];` -> the shim's dynamic shared memory pointer."""
+    return re.sub(r"extern __shared__ (?:__align__\(\d+\) )?(\w+) (\w+)\[\];",
+                  r"\1* \2 = reinterpret_cast<\1*>(cpu_cuda::g_dyn_smem);", section)
 
 
 def patch_functional(monkeypatch, host_lib):
