@@ -29,8 +29,13 @@ def build_host_library(tmp, cu_file, inc_name, harness, ops, section_regex=NAMES
     cdll = ctypes.CDLL(so)
 
     class HostLib:
+        launches = 0
+
         def pdb_last_error(self):
             return b"host build"
+
+        def pdb_launch_count(self):
+            return self.launches
     lib = HostLib()
     for name in ops:
         f = getattr(cdll, "host_" + name)
