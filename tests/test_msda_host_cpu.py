@@ -133,3 +133,35 @@ def test_msda_kernel_fast_paths_vs_oracle(msda, shapes, N, Lq, expect):
     assert bpath == expect
     assert _rel(out, ref.detach()) < 1e-5
     assert _rel(gv, rgv) < 1e-5 and _rel(ga, rga) < 1e-5 and _rel(gl, rgl) < 1e-4
+
+
+@pytest.mark.parametrize("shapes,N,Lq,expect,loc_kind", [
+    ([(12, 9), (6, 5), (3, 3), (2, 2)], 1, None, "tiled", "wild"),       # 4 levels (L * P = 16), offsets far outside the maps
+    ([(5, 4), (3, 2)], 2, 3, "slot-ordered", "uniform"),                 # fewer slots than one CTA holds
+    ([(7, 3)], 1, None, "tiled", "edges"),                               # one level; locations exactly on the borders
+])
+def test_msda_kernel_edge_cases_vs_oracle(msda, shapes, N, Lq, expect, loc_kind):
+    forward, backward = msda
+    g = torch.Generator().manual_seed(17)
+    S = sum(h * w for h, w in shapes)
+    L, M, D, P = len(shapes), 8, 32, 4
+    Lq = S if Lq is None else Lq
+    value = torch.randn(N, S, M, D, generator=g)
+    if loc_kind == "wild":
+        loc = torch.randn(N, Lq, M, L, P, 2, generator=g) * 3.0            # many samples entirely outside [0, 1]
+    elif loc_kind == "uniform":
+        loc = torch.rand(N, Lq, M, L, P, 2, generator=g)
+    else:
+        loc = torch.randint(0, 3, (N, Lq, M, L, P, 2), generator=g).float() / 2      # 0, 0.5, 1
+    attn = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g), -1).view(N, Lq, M, L, P)
+    v, l, a = (t.clone().requires_grad_() for t in (value, loc, attn))
+    ref = O.ms_deform_attn_core(v, shapes, l, a)
+    go = torch.randn(ref.shape, generator=g)
+    rgv, rgl, rga = torch.autograd.grad(ref, (v, l, a), go)
+    out, path = forward(value, shapes, loc, attn)
+    gv, gl, ga, bpath = backward(value, shapes, loc, attn, go)
+    assert path == expect and bpath == expect
+    assert _rel(out, ref.detach()) < 1e-5
+    assert _rel(gv, rgv) < 1e-5 and _rel(ga, rga) < 1e-5
+    if loc_kind != "edges":          # on exact pixel borders the one-sided derivative is a convention (floor side), not a value
+        assert _rel(gl, rgl) < 1e-4

@@ -18,6 +18,7 @@ def fn(monkeypatch, host_lib):
     return patch_functional(monkeypatch, host_lib)
 
 
-@pytest.mark.parametrize("B,Q,Lk,masked", [(1, 37, 200, True), (2, 130, 77, True), (1, 20, 300, False)])
+@pytest.mark.parametrize("B,Q,Lk,masked", [(1, 37, 200, True), (2, 130, 77, True), (1, 20, 300, False),
+                                           (1, 5, 2, False), (1, 129, 65, True), (1, 3, 8, True)])
 def test_masked_cross_attention(fn, B, Q, Lk, masked):
     gpu_tests.test_masked_cross_attention(fn, B, Q, Lk, masked)
