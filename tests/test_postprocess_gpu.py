@@ -14,6 +14,7 @@ import m2f_oracle as O
 from postprocess_cases import NEAR, oracle_resize, run_case, run_pd_case
 
 pytestmark = pytest.mark.gpu
+DEV = "cuda"        # tests/test_postprocess_host_cpu.py re-runs these test bodies on the kernels' host build with DEV = "cpu"
 
 
 @pytest.fixture(scope="module")
@@ -120,7 +121,7 @@ def test_proposal_inference_vs_golden(fn, golden_dir, case):
     """ProposalInferenceMixin.inference on the golden inputs against the outputs of the UNMODIFIED reference
     (tests/golden/proposal_inference.pt, produced by oracle/make_golden.py)."""
     g = torch.load(os.path.join(golden_dir, "proposal_inference.pt"), weights_only=False)
-    run_case(g, case, "cuda")
+    run_case(g, case, DEV)
 
 
 @pytest.mark.parametrize("case", ["prop", "prop_filtered", "prop_none_valid", "semseg", "semseg_filtered", "semseg_oracle_cls"])
@@ -128,7 +129,7 @@ def test_pd_inference_vs_golden(fn, golden_dir, case):
     """PartDistillationInferenceMixin.inference against the outputs of the UNMODIFIED reference
     (tests/golden/pd_inference.pt)."""
     g = torch.load(os.path.join(golden_dir, "pd_inference.pt"), weights_only=False)
-    run_pd_case(g, case, "cuda")
+    run_pd_case(g, case, DEV)
 
 
 def test_score_threshold_bits(fn):
@@ -228,11 +229,10 @@ def test_pixel_grouping_model_resized_forward(fn):
     assert torch.equal(pm.any(0), exp_obj) and int(pm.sum()) == int(exp_obj.sum())
 
 
-def test_postprocess_full_size_properties(fn):
+def test_postprocess_full_size_properties(fn, Q=100, S=1024, G=6):
     """BASELINE geometry (Q = 100, 256^2 logits -> 1024^2): the packed path against the reference expression evaluated by
     PyTorch on the same GPU (F.interpolate -> gate -> > 0; dense areas and IoU), plus size-independent properties."""
     g = torch.Generator().manual_seed(3)
-    Q, S, G = 100, 1024, 6
     low = torch.randn(Q, S // 16, S // 16, generator=g) * 3
     logits = (F.interpolate(low[None], size=(S // 4, S // 4), mode="bicubic")[0]
               + 0.3 * torch.randn(Q, S // 4, S // 4, generator=g)).cuda()

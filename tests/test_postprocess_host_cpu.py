@@ -509,3 +509,53 @@ def test_proposal_generation_model(kernels_on_host, golden_dir, tmp_path, monkey
     assert len(rec["part_mask"]) == res[0]["proposals"].pred_masks.shape[0]
     assert all(isinstance(p["segmentation"]["counts"], str) for p in rec["part_mask"])
     assert rec["object_ratio"] == int(g["l2"]["mask_resized"].sum()) / g["l2"]["mask_resized"].numel()
+
+
+# ------------------------------------------------------------------ the GPU tests' own bodies on the kernels' host build
+@pytest.fixture
+def gpu_bodies(monkeypatch, kernels_on_host):
+    """tests/test_postprocess_gpu.py with Tensor.cuda() = identity and DEV = "cpu": the very assertions (and tolerances)
+    the B200 run will evaluate, checked here first against the kernels' host build."""
+    import test_postprocess_gpu as gpu_pp
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(gpu_pp, "DEV", "cpu")
+    return gpu_pp, kernels_on_host
+
+
+@pytest.mark.parametrize("geom", [1, 3])
+@pytest.mark.parametrize("gated", [True, False])
+def test_gpu_body_postprocess_masks_bits_and_label(gpu_bodies, geom, gated):
+    gpu_pp, fn = gpu_bodies
+    gpu_pp.test_postprocess_masks_bits_and_label(fn, gpu_pp.GEOMETRIES[geom], gated)
+
+
+def test_gpu_body_pack_unpack_popcount_iou(gpu_bodies):
+    gpu_pp, fn = gpu_bodies
+    gpu_pp.test_pack_unpack_popcount_iou(fn, ((5, 64, 96), (3, 64, 96)))
+
+
+def test_gpu_body_resize_bool_masks(gpu_bodies):
+    gpu_pp, fn = gpu_bodies
+    gpu_pp.test_resize_bool_masks(fn, ((128, 128), (96, 128), (144, 192)))
+
+
+def test_gpu_body_score_threshold_bits(gpu_bodies):
+    gpu_pp, fn = gpu_bodies
+    gpu_pp.test_score_threshold_bits(fn)
+
+
+def test_gpu_body_inference_vs_golden(gpu_bodies, golden_dir):
+    gpu_pp, fn = gpu_bodies
+    gpu_pp.test_proposal_inference_vs_golden(fn, golden_dir, "prop")
+    gpu_pp.test_pd_inference_vs_golden(fn, golden_dir, "semseg")
+
+
+@pytest.mark.parametrize("metric", ["dot", "l2"])
+def test_gpu_body_group_affinity_resized(gpu_bodies, golden_dir, metric):
+    gpu_pp, fn = gpu_bodies
+    gpu_pp.test_group_affinity_resized_vs_reference_golden(fn, golden_dir, metric)
+
+
+def test_gpu_body_full_size_properties_at_reduced_size(gpu_bodies):
+    gpu_pp, fn = gpu_bodies
+    gpu_pp.test_postprocess_full_size_properties(fn, Q=5, S=64, G=3)
