@@ -52,6 +52,61 @@ def dynamic_smem(section):
                   r"\1* \2 = reinterpret_cast<\1*>(cpu_cuda::g_dyn_smem);", section)
 
 
+HARNESSES = [
+    # (csrc file, section file, harness, entry points, extra sections [(csrc file, section file)], rewrite dynamic smem)
+    ("msda.cu", "msda_section.inc", "msda_abi_host.cpp", ("msda_forward", "msda_backward"), [], True),
+    ("loss.cu", "loss_section.inc", "loss_kernels_host.cpp",
+     ("point_sample_forward", "point_sample_backward", "matcher_cost", "lsap_batched", "point_loss_forward",
+      "point_loss_backward", "class_rows_forward", "class_rows_backward"), [], False),
+    ("xattn.cu", "xattn_section.inc", "xattn_kernels_host.cpp",
+     ("masked_xattn_workspace_bytes", "masked_xattn_forward", "masked_xattn_backward"), [], False),
+    ("groupnorm.cu", "groupnorm_section.inc", "norm_kernels_host.cpp",
+     ("layer_norm_forward", "group_norm_forward", "group_norm_backward"), [("layernorm.cu", "layernorm_section.inc")], False),
+    ("window_attn.cu", "window_attn_section.inc", "window_attn_kernels_host.cpp",
+     ("window_attention_forward", "swin_window_attention_forward"), [], True),
+    ("optim.cu", "optim_section.inc", "misc_kernels_host.cpp",
+     ("grad_sumsq", "adamw_flat", "group_affinity", "attn_mask_build", "attn_mask_reset_rows"),
+     [("grouping.cu", "grouping_section.inc"), ("attn_mask.cu", "attn_mask_section.inc")], True),
+]
+
+
+def msda_section(src):
+    """msda.cu's kernels: everything inside `namespace pdb` ahead of the launch helpers (which use <<< >>>)."""
+    a = src.index("namespace pdb {") + len("namespace pdb {")
+    b = src.index("template <typename T>\nstatic int fwd_generic")
+    return dynamic_smem(src[a:b])
+
+
+def full_host_library(tmp_path_factory):
+    """Every SIMT kernel file's own code built for the host + the restated GEMM interface (host_gemm_abi): enough to run
+    the whole head, loss and optimizer step on CPU tensors."""
+    import host_gemm_abi
+
+    class Composite:
+        launches = 0
+
+        def pdb_last_error(self):
+            return b"host build"
+
+        def pdb_launch_count(self):
+            return self.launches
+    lib = Composite()
+    for cu, inc, harness, ops, extra, dyn in HARNESSES:
+        tmp = tmp_path_factory.mktemp(os.path.splitext(harness)[0])
+        for cu2, inc2 in extra:
+            src = open(os.path.join(ROOT, "partdistillation_b200", "csrc", cu2)).read()
+            (tmp / inc2).write_text(dynamic_smem("\n".join(re.findall(NAMESPACE_BLOCK, src, re.S))))
+        if cu == "msda.cu":
+            part = build_host_library(tmp, cu, inc, harness, ops, section_regex=r"(?s)(.*)", rewrite=msda_section)
+        else:
+            part = build_host_library(tmp, cu, inc, harness, ops, rewrite=dynamic_smem if dyn else None)
+        for name in ops:
+            setattr(lib, "pdb_" + name, getattr(part, "pdb_" + name))
+    for name, f in host_gemm_abi.ENTRY_POINTS.items():
+        setattr(lib, name, f)
+    return lib
+
+
 def patch_functional(monkeypatch, host_lib):
     """functional.py's wrappers on CPU tensors: library handle = host build, CUDA-only guard and stream lookup disabled,
     Tensor.cuda() = identity (so the GPU tests' own code runs as is)."""

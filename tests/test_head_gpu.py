@@ -15,9 +15,11 @@ import torch.nn.functional as F
 import synth
 
 pytestmark = pytest.mark.gpu
+DEV = "cuda"        # tests/test_head_host_cpu.py re-runs these test bodies on the kernels' host builds with DEV = "cpu"
 
 
-def _build(g, device="cuda"):
+def _build(g, device=None):
+    device = device or DEV
     from partdistillation_b200 import compat, presets
     c = g["case"]
     cfg = presets.make_cfg(c["arch"], "swin_micro", num_queries=c["Q"], dec_layers=c["dec_layers"],
@@ -47,18 +49,18 @@ def _inputs(model, c):
         if pd:
             e["gt_object_class"] = d["gt_object_class"]
         bi.append(e)
-    il = ImageList(torch.zeros(c["B"], 3, c["H"], c["W"], device="cuda"), [(c["H"], c["W"])] * c["B"])
+    il = ImageList(torch.zeros(c["B"], 3, c["H"], c["W"], device=DEV), [(c["H"], c["W"])] * c["B"])
     return feats, model.prepare_targets(bi, il)
 
 
 @pytest.mark.parametrize("name", ["proposal_micro", "proposal_micro_uniform", "pd_micro"])
 def test_head_and_loss_vs_reference_golden(golden_dir, name):
-    if not torch.cuda.is_available():
+    if DEV == "cuda" and not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
     g = torch.load(os.path.join(golden_dir, f"head_{name}.pt"), weights_only=False)
     model, c = _build(g)
     feats, targets = _inputs(model, c)
-    replay = synth.ReplayRand(g["rand_draws"], device="cuda")
+    replay = synth.ReplayRand(g["rand_draws"], device=DEV)
     model.criterion.rand = replay
     model.criterion.matcher.rand = replay
 
