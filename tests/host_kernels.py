@@ -52,6 +52,30 @@ def dynamic_smem(section):
                   r"\1* \2 = reinterpret_cast<\1*>(cpu_cuda::g_dyn_smem);", section)
 
 
+POSTPROCESS_OPS = ("postprocess_masks", "resize_masks_u8", "pack_bits", "unpack_bits", "bits_popcount", "bits_intersect",
+                   "group_affinity_resized")
+
+
+def build_plain_harness(tmp, harness, ops):
+    """A harness that includes header-only kernels directly (csrc/postprocess_kernels.cuh, grouping_resized.cuh)."""
+    from partdistillation_b200 import _lib
+    so = str(tmp / ("lib" + os.path.splitext(harness)[0] + ".so"))
+    subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", "-ffp-contract=off",
+                           os.path.join(HERE, "native", harness), "-o", so])
+    cdll = ctypes.CDLL(so)
+
+    class HostLib:
+        def pdb_last_error(self):
+            return b"host build"
+    lib = HostLib()
+    for name in ops:
+        f = getattr(cdll, "host_" + name)
+        res, args = _lib.SIGNATURES["pdb_" + name]
+        f.restype, f.argtypes = res, args[:-1]
+        setattr(lib, "pdb_" + name, (lambda f: lambda *a: f(*a[:-1]))(f))
+    return lib
+
+
 HARNESSES = [
     # (csrc file, section file, harness, entry points, extra sections [(csrc file, section file)], rewrite dynamic smem)
     ("msda.cu", "msda_section.inc", "msda_abi_host.cpp", ("msda_forward", "msda_backward"), [], True),
@@ -102,6 +126,9 @@ def full_host_library(tmp_path_factory):
             part = build_host_library(tmp, cu, inc, harness, ops, rewrite=dynamic_smem if dyn else None)
         for name in ops:
             setattr(lib, "pdb_" + name, getattr(part, "pdb_" + name))
+    pp = build_plain_harness(tmp_path_factory.mktemp("pp_kernels"), "postprocess_kernels_host.cpp", POSTPROCESS_OPS)
+    for name in POSTPROCESS_OPS:
+        setattr(lib, "pdb_" + name, getattr(pp, "pdb_" + name))
     for name, f in host_gemm_abi.ENTRY_POINTS.items():
         setattr(lib, name, f)
     return lib

@@ -25,6 +25,86 @@ def on_host(monkeypatch, host_lib):
     monkeypatch.setattr(head_tests, "DEV", "cpu")
 
 
-@pytest.mark.parametrize("name", ["proposal_micro", "pd_micro"])
+@pytest.mark.parametrize("name", ["pd_micro"])       # PartDistillationModel: the ProposalModel path + the float64 classifier rows
 def test_head_and_loss_vs_reference_golden(on_host, golden_dir, name):
     head_tests.test_head_and_loss_vs_reference_golden(golden_dir, name)
+
+
+def _eval_inputs(H, W, out, seed=0):
+    from partdistillation_b200.compat import BitMasks, Instances
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    obj = ((yy - H / 2) ** 2 / (H * 0.42) ** 2 + (xx - W / 2) ** 2 / (W * 0.38) ** 2) < 1.0
+    lab = torch.randint(0, 3, (H // 16, W // 16), generator=g).repeat_interleave(16, 0).repeat_interleave(16, 1)
+    parts = torch.stack([(lab == k) & obj for k in range(3)])
+    parts = parts[parts.flatten(1).any(1)]
+    inst = Instances((H, W))
+    inst.gt_masks = BitMasks(obj[None])
+    inst.gt_classes = torch.tensor([4])
+    pinst = Instances((H, W))
+    pinst.gt_masks = BitMasks(parts)
+    pinst.gt_classes = torch.arange(parts.shape[0])
+    item = dict(size=(H, W), out=out, object_mask=obj[None], part_masks=parts, part_classes=pinst.gt_classes)
+    return {"image": torch.randint(0, 256, (3, H, W), generator=g, dtype=torch.uint8), "instances": inst,
+            "part_instances": pinst, "height": out[0], "width": out[1]}, item
+
+
+@pytest.mark.parametrize("arch,per_pixel", [("ProposalModel", False), ("PartDistillationModel", True)])
+def test_eval_forward_end_to_end(on_host, arch, per_pixel):
+    """model.eval()(batched_inputs) of the registered meta-architectures with a micro Swin trunk and the real head: images of
+    different sizes (padding), one evaluated at a different output size.  The post-processing of the model's OWN head outputs
+    is compared with the oracle's restatement of the reference's inference() on those outputs."""
+    import m2f_oracle as O
+    from partdistillation_b200 import compat, presets
+    from postprocess_cases import NEAR, oracle_resize
+    Q = 8
+    cfg = presets.make_cfg(arch, "swin_micro", num_queries=Q, dec_layers=3, num_points=64, num_object_classes=10,
+                           num_part_classes=4, device="cpu")
+    cfg.TEST.DETECTIONS_PER_IMAGE = Q
+    torch.manual_seed(3)
+    model = compat.build_model(cfg).eval()
+    pd = arch == "PartDistillationModel"
+    if pd:
+        model.use_unique_per_pixel_label = per_pixel
+        model.mode = ""
+        model.fg_score_threshold = 0.0
+    else:
+        model.use_unique_per_pixel_label = per_pixel
+    (x0, it0), (x1, it1) = _eval_inputs(96, 128, (144, 192), 0), _eval_inputs(128, 96, (128, 96), 1)
+    captured = {}
+    head_forward = model.sem_seg_head.forward
+
+    def capture(*a, **k):
+        captured["out"] = head_forward(*a, **k)
+        return captured["out"]
+    model.sem_seg_head.forward = capture
+    with torch.no_grad():
+        res = model([x0, x1])
+    out = captured["out"]
+    logits, masks = out["pred_logits"].float(), out["pred_masks"].float()
+    assert tuple(masks.shape) == (2, Q, 32, 32) and len(res) == 2
+    padded = (128, 128)
+    if pd:
+        ref = O.pd_inference(logits, masks, [it0, it1], padded, [4, 4], 4, Q, mappings=None, per_pixel=per_pixel,
+                             min_ratio=model.min_pseudo_mask_ratio, min_score=model.min_pseudo_mask_score, fg_thr=0.0)
+        key = "predictions"
+    else:
+        ref = O.proposal_inference(logits, masks, [it0, it1], padded, Q, per_pixel=per_pixel,
+                                   min_ratio=model.minimum_pseudo_mask_ratio, min_score=model.minimum_pseudo_mask_score)
+        key = "proposals"
+    for b, (r, e, it) in enumerate(zip(res, ref, (it0, it1))):
+        got = r[key]
+        assert tuple(got.pred_masks.shape) == tuple(e["pred_masks"].shape), (got.pred_masks.shape, e["pred_masks"].shape)
+        assert torch.allclose(got.scores, e["scores"], rtol=1e-5, atol=1e-7)
+        assert torch.equal(got.pred_classes, e["pred_classes"])
+        dense = oracle_resize(masks[b], padded, it["size"], it["out"])
+        near = (dense.abs() < NEAR).any(0)
+        if per_pixel:
+            P = logits.shape[-1] - 1
+            sc = logits[b].softmax(-1)[:, :-1]
+            sc = sc.flatten() if pd else sc.topk(1, dim=1)[0].flatten()
+            idx = torch.arange(sc.numel()) // (P if pd else 1)
+            tom = O.sem_seg_postprocess(O.pad_masks(it["object_mask"], padded).float(), it["size"], *it["out"]).bool()
+            top2 = (sc[:, None, None] * (dense[idx] * tom.sum(0, keepdim=True).bool()).sigmoid()).topk(2, dim=0)[0]
+            near = near | ((top2[0] - top2[1]) < 1e-5)
+        assert not ((got.pred_masks != e["pred_masks"]) & ~near[None]).any()
