@@ -77,7 +77,7 @@ class PartDistillationModel(PartDistillationInferenceMixin, Mask2FormerTrainingA
             return losses
         images = self.preprocess_images(batched_inputs)
         features = self.backbone(images.tensor)
-        targets = (self._prepare_save_targets if self.mode == "save" else self._prepare_gt_targets)(batched_inputs, images)
+        targets = self.prepare_targets(batched_inputs, images)
         outputs = self.run_head(features, targets)
         processed_results = self.inference(batched_inputs, targets, images, outputs, vis=False)
         self.current_test_iteration += 1

@@ -72,7 +72,7 @@ class ProposalModel(ProposalInferenceMixin, Mask2FormerTrainingArch):
             return losses
         images = self.preprocess_images(batched_inputs)
         features = self.backbone(images.tensor)
-        targets = self._prepare_gt_targets(batched_inputs, images)
+        targets = self.prepare_targets(batched_inputs, images)
         outputs = self.run_head(features, targets)
         processed_results = self.inference(batched_inputs, targets, images, outputs, vis=False)
         self.num_test_iterations += 1
