@@ -43,25 +43,28 @@ def synth_image_and_masks(seed, h=H, w=W, k=K_MASKS, block=16):
     return img, m[m.flatten(1).any(1)]
 
 
-def make_batch(rank, n, device=None, pin=False):
-    from partdistillation_b200.compat import BitMasks, Instances
+def make_batch(rank, n, device=None, pin=False, packed=False):
+    """``packed``: hand the masks over as PackedBitMasks (1 bit / pixel) instead of BitMasks bools."""
+    from partdistillation_b200.compat import BitMasks, Instances, PackedBitMasks
     out = []
     for i in range(n):
         img, m = synth_image_and_masks(rank * 1000 + i)
+        if packed:
+            m = PackedBitMasks.from_bool(m).tensor
         if pin:
             img, m = img.pin_memory(), m.pin_memory()
         if device is not None:
             img, m = img.to(device), m.to(device)
         inst = Instances((H, W))
-        inst.gt_masks = BitMasks(m)
+        inst.gt_masks = PackedBitMasks(m, W) if packed else BitMasks(m)
         inst.gt_classes = torch.zeros(m.shape[0], dtype=torch.long, device=m.device)
         out.append({"image": img, "instances": inst, "height": H, "width": W})
     return out
 
 
 def batch_bytes(batch):
-    return sum(d["image"].numel() * d["image"].element_size() + d["instances"].gt_masks.tensor.numel()
-               for d in batch)
+    return sum(d["image"].numel() * d["image"].element_size()
+               + d["instances"].gt_masks.tensor.numel() * d["instances"].gt_masks.tensor.element_size() for d in batch)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -291,6 +294,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="run the step eagerly instead of replaying its CUDA graph")
+    ap.add_argument("--packed-masks", action="store_true",
+                    help="e2e leg: feed the target masks bit-packed (PackedBitMasks, 1 bit/pixel over PCIe) instead of bools")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -318,7 +323,7 @@ def main():
     cpu_sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()} if rank == 0 else None
 
     dev_batch = make_batch(rank, PER_GPU_BATCH, device=device)
-    host_batch = make_batch(rank, PER_GPU_BATCH, pin=True)
+    host_batch = make_batch(rank, PER_GPU_BATCH, pin=True, packed=args.packed_masks)
 
     def barrier():
         if world > 1:
@@ -357,7 +362,8 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms, _, launches, _ = timed(dev_batch, args.steps, args.warmup, read_loss=False)
     clocks = sampler.stop() if sampler else None
-    ms_e2e, wall_e2e, _, last_loss = timed(host_batch, args.steps, 1, read_loss=True)
+    # packed masks have another batch signature than dev_batch: their graph is captured during the (untimed) warm-up
+    ms_e2e, wall_e2e, _, last_loss = timed(host_batch, args.steps, 4 if args.packed_masks else 1, read_loss=True)
     e2e_ms = max(ms_e2e, wall_e2e)          # the loss read-back makes wall clock the honest end-to-end time
 
     images = PER_GPU_BATCH * world * args.steps
@@ -379,6 +385,7 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": round(images / (e2e_ms * 1e-3), 3), "unit": "images/s",
                         "h2d_bytes_per_step": batch_bytes(host_batch), "d2h_bytes_per_step": 4,
+                        **({"packed_masks": True} if args.packed_masks else {}),
                         "ms_per_step": round(e2e_ms / args.steps, 3), "last_loss": last_loss},
                 "gpu_launches": int(launches),
                 "roofline": roof, "roofline_kernels": roofs}

@@ -224,6 +224,49 @@ else:
     SEM_SEG_HEADS_REGISTRY = Registry("SEM_SEG_HEADS")
     BACKBONE_REGISTRY = Registry("BACKBONE")
 
+class PackedBitMasks:
+    """Instance masks at one bit per pixel: ``tensor`` holds int32 words (K, H, ceil(W / 32)), bit i of
+    a word = pixel 32 * word + i of that row — the layout of ``functional.pack_bits`` / ``unpack_bits``.  A dataset mapper
+    that decodes the RLE pseudo labels (proposal_dataset_mapper.py:113-139,201-235) can emit this instead of the
+    ``BitMasks`` bool tensor: the host->device copy of the targets shrinks 8x and the meta-architectures expand the words
+    on the device straight into their padded uint8 target buffer (``meta_base._prepare_pseudo_targets``).  Quacks like
+    ``BitMasks`` where the training step needs it (``tensor``, ``to``, ``len``)."""
+
+    def __init__(self, tensor, width=None):
+        tensor = torch.as_tensor(tensor)
+        if tensor.dtype != torch.int32 or tensor.dim() != 3:
+            raise ValueError("PackedBitMasks: int32 words of shape (K, H, ceil(W / 32))")
+        self.tensor = tensor
+        self.width = int(width) if width is not None else 32 * tensor.shape[-1]
+        if (self.width + 31) // 32 != tensor.shape[-1]:
+            raise ValueError(f"PackedBitMasks: width {self.width} does not match {tensor.shape[-1]} words per row")
+
+    @property
+    def image_size(self):
+        return (int(self.tensor.shape[1]), self.width)
+
+    @classmethod
+    def from_bool(cls, masks):
+        """Host-side packing of a bool (K, H, W) tensor (what a mapper would do once per sample)."""
+        masks = torch.as_tensor(masks).to(torch.bool)
+        K, H, W = masks.shape
+        Ww = (W + 31) // 32
+        padded = torch.zeros((K, H, Ww * 32), dtype=torch.int64)
+        padded[..., :W] = masks
+        words = (padded.view(K, H, Ww, 32) << torch.arange(32)).sum(-1)
+        words = torch.where(words >= 2 ** 31, words - 2 ** 32, words)
+        return cls(words.to(torch.int32), W)
+
+    def like(self, tensor):
+        return PackedBitMasks(tensor, self.width)
+
+    def to(self, *a, **k):
+        return PackedBitMasks(self.tensor.to(*a, **k), self.width)
+
+    def __len__(self):
+        return self.tensor.shape[0]
+
+
 # Mask2Former's own registry (maskformer_transformer_decoder.py:19) lives in the reference package,
 # not in detectron2, so it is always ours.
 TRANSFORMER_DECODER_REGISTRY = Registry("TRANSFORMER_MODULE")

@@ -339,7 +339,8 @@ def _clone_batch(batch, device):
         e["image"] = d["image"].to(device, copy=True)
         src = d["instances"]
         inst = type(src)(src.image_size)
-        inst.gt_masks = type(src.gt_masks)(src.gt_masks.tensor.to(device, copy=True))
+        t = src.gt_masks.tensor.to(device, copy=True)
+        inst.gt_masks = src.gt_masks.like(t) if hasattr(src.gt_masks, "like") else type(src.gt_masks)(t)
         inst.gt_classes = src.gt_classes.to(device, copy=True)
         e["instances"] = inst
         out.append(e)

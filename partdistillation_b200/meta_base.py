@@ -6,7 +6,7 @@ from typing import Tuple
 import torch
 from torch import nn
 
-from .compat import ImageList
+from .compat import ImageList, PackedBitMasks
 from .functional import host_table
 from .modeling.targets import TargetList
 
@@ -75,9 +75,15 @@ class Mask2FormerTrainingArch(nn.Module):
         out = TargetList()
         labels = []
         for b, (x, i) in enumerate(zip(inputs, inst)):
-            m = i.gt_masks.tensor.to(dev, non_blocking=True)
             view = packed[offs[b]:offs[b + 1]]
-            view[:, :m.shape[1], :m.shape[2]] = m
+            if isinstance(i.gt_masks, PackedBitMasks):      # 1 bit / pixel over the wire, expanded on the device (f3)
+                if counts[b]:
+                    from .functional import unpack_bits
+                    m = unpack_bits(i.gt_masks.tensor.to(dev, non_blocking=True), i.gt_masks.width)
+                    view[:, :m.shape[1], :m.shape[2]] = m
+            else:
+                m = i.gt_masks.tensor.to(dev, non_blocking=True)
+                view[:, :m.shape[1], :m.shape[2]] = m
             if self.part_distillation:
                 lab = i.gt_classes.to(dev, non_blocking=True).long()
                 t = {"labels": lab, "masks": view.view(torch.bool), "gt_object_class": x["gt_object_class"]}

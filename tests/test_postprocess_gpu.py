@@ -265,3 +265,32 @@ def test_postprocess_full_size_properties(fn, Q=100, S=1024, G=6):
     top2 = sm.topk(2, dim=0)[0]
     bad = label.long() != sm.argmax(0)
     assert not (bad & ((top2[0] - top2[1]) > 1e-5)).any()
+
+
+def test_packed_bit_masks_ingestion(fn):
+    """f3: PackedBitMasks targets (1 bit / pixel over PCIe) give the same padded target buffer as BitMasks bools — widths
+    that are not multiples of 32, padding, an image without targets (device-side pdb_unpack_bits)."""
+    from partdistillation_b200.compat import BitMasks, ImageList, Instances, PackedBitMasks
+    from partdistillation_b200.meta_base import Mask2FormerTrainingArch
+
+    class Arch(Mask2FormerTrainingArch):
+        pass
+    arch = Arch()
+    arch._init_common(torch.nn.Identity(), torch.nn.Identity(), torch.nn.Identity(), 4, 1, 32, (0.0, 0.0, 0.0),
+                      (1.0, 1.0, 1.0), 4, False)
+    arch.to(DEV)
+    g = torch.Generator().manual_seed(4)
+    sizes, counts = [(70, 45), (64, 96), (50, 33)], [3, 0, 2]
+    plain, packed = [], []
+    for (H, W), k in zip(sizes, counts):
+        m = torch.rand(k, H, W, generator=g) > 0.5
+        for store, masks in ((plain, BitMasks(m)), (packed, PackedBitMasks.from_bool(m))):
+            inst = Instances((H, W))
+            inst.gt_masks = masks
+            inst.gt_classes = torch.zeros(k, dtype=torch.long)
+            store.append({"image": torch.zeros(3, H, W), "instances": inst})
+    images = ImageList(torch.zeros(3, 3, 96, 96, device=DEV), sizes)
+    ta, tb = arch._prepare_pseudo_targets(plain, images), arch._prepare_pseudo_targets(packed, images)
+    assert ta.offsets == tb.offsets == [0, 3, 3, 5]
+    assert str(tb.packed_masks.device).startswith(DEV)
+    assert torch.equal(ta.packed_masks, tb.packed_masks) and torch.equal(ta.packed_labels, tb.packed_labels)

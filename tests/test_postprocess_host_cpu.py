@@ -559,3 +559,55 @@ def test_gpu_body_group_affinity_resized(gpu_bodies, golden_dir, metric):
 def test_gpu_body_full_size_properties_at_reduced_size(gpu_bodies):
     gpu_pp, fn = gpu_bodies
     gpu_pp.test_postprocess_full_size_properties(fn, Q=5, S=64, G=3)
+
+
+# ------------------------------------------------------------------ f3: bit-packed target ingestion
+def test_packed_bit_masks_ingestion(kernels_on_host):
+    """PackedBitMasks (1 bit / pixel from the mapper) -> the same padded uint8 target buffer, labels and offsets as BitMasks,
+    through the device-side unpack kernel (host build); widths that are not multiples of 32, padding, an image without
+    targets; and the static-batch clone / copy of the CUDA-graph path keeps the width."""
+    from partdistillation_b200.compat import BitMasks, ImageList, Instances, PackedBitMasks
+    from partdistillation_b200.engine import _clone_batch, _copy_batch
+    from partdistillation_b200.meta_base import Mask2FormerTrainingArch
+
+    class Arch(Mask2FormerTrainingArch):
+        pass
+    arch = Arch()
+    arch._init_common(torch.nn.Identity(), torch.nn.Identity(), torch.nn.Identity(), 4, 1, 32, (0.0, 0.0, 0.0),
+                      (1.0, 1.0, 1.0), 4, False)
+    g = torch.Generator().manual_seed(4)
+    sizes, counts = [(70, 45), (64, 96), (50, 33)], [3, 0, 2]
+    plain, packed = [], []
+    for (H, W), k in zip(sizes, counts):
+        m = torch.rand(k, H, W, generator=g) > 0.5
+        for store, masks in ((plain, BitMasks(m)), (packed, PackedBitMasks.from_bool(m))):
+            inst = Instances((H, W))
+            inst.gt_masks = masks
+            inst.gt_classes = torch.zeros(k, dtype=torch.long)
+            store.append({"image": torch.zeros(3, H, W), "instances": inst})
+        assert packed[-1]["instances"].gt_masks.image_size == (H, W)
+    images = ImageList(torch.zeros(3, 3, 96, 96), sizes)
+    ta, tb = arch._prepare_pseudo_targets(plain, images), arch._prepare_pseudo_targets(packed, images)
+    assert ta.offsets == tb.offsets == [0, 3, 3, 5]
+    assert torch.equal(ta.packed_masks, tb.packed_masks) and ta.packed_masks.shape == (5, 96, 96)
+    assert torch.equal(ta.packed_labels, tb.packed_labels)
+    for a, b in zip(ta, tb):
+        assert torch.equal(a["masks"], b["masks"])
+    static = _clone_batch(packed, torch.device("cpu"))
+    assert all(s["instances"].gt_masks.width == p["instances"].gt_masks.width for s, p in zip(static, packed))
+    assert all(s["instances"].gt_masks.tensor.data_ptr() != p["instances"].gt_masks.tensor.data_ptr() or len(p["instances"].gt_masks) == 0
+               for s, p in zip(static, packed))
+    for s in static:
+        s["instances"].gt_masks.tensor.zero_()
+    _copy_batch(static, packed)
+    tc = arch._prepare_pseudo_targets(static, images)
+    assert torch.equal(tc.packed_masks, ta.packed_masks)
+    static_plain = _clone_batch(plain, torch.device("cpu"))                 # BitMasks path of the clone is unchanged
+    assert all(type(s["instances"].gt_masks) is BitMasks for s in static_plain)
+    with pytest.raises(ValueError):
+        PackedBitMasks(torch.zeros(1, 4, 2, dtype=torch.int32), width=20)
+
+
+def test_gpu_body_packed_bit_masks_ingestion(gpu_bodies):
+    gpu_pp, fn = gpu_bodies
+    gpu_pp.test_packed_bit_masks_ingestion(fn)
