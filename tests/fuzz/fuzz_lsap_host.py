@@ -1,10 +1,10 @@
 """Differential fuzzing of the Hungarian-assignment kernel's own code (csrc/loss.cu, host build through
 tests/native/cuda_on_cpu.h) against scipy.optimize.linear_sum_assignment + the reference's ascending-cost order
 (matcher.py:159-163): random batch sizes, Q in [1, 40), K in [0, 50), float / heavily tied / rounded / duplicated costs.
-    python tools/fuzz_lsap_host.py [seconds]        # round 1: 11 821 cases in 240 s, 0 mismatches
+    python tests/fuzz/fuzz_lsap_host.py [seconds]        # round 1: 11 821 cases in 240 s, 0 mismatches
 No GPU needed; nothing here is part of the product."""
 import sys, os, re, subprocess, ctypes, numpy as np, pathlib, tempfile
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from scipy.optimize import linear_sum_assignment
 tmp = pathlib.Path(tempfile.mkdtemp())
 src = open(ROOT+'/partdistillation_b200/csrc/loss.cu').read()

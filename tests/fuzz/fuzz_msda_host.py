@@ -2,10 +2,10 @@
 against the oracle (ms_deform_attn_core_pytorch restated, pinned to the reference's ops/test.py vectors): random level
 pyramids incl. 1-pixel-wide levels, encoder- and decoder-style queries, locations partly outside the maps, the D = 32 paths
 and the generic path with random heads / channels / points in f32 and f64; forward and all three gradients.
-    python tools/fuzz_msda_host.py [seconds]        # round 1: 749 cases in 200 s over all four paths, worst error 4 % of tolerance
+    python tests/fuzz/fuzz_msda_host.py [seconds]        # round 1: 749 cases in 200 s over all four paths, worst error 4 % of tolerance
 No GPU needed.  TEST TOOLING: imports oracle/ as the checker; nothing here is part of the product."""
 import sys, os, re, subprocess, ctypes, pathlib, tempfile, time, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT+'/oracle')
 import m2f_oracle as O
 tmp = pathlib.Path(tempfile.mkdtemp())
