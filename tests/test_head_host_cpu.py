@@ -194,3 +194,14 @@ def test_training_steps_end_to_end(on_host, monkeypatch):
             assert not torch.equal(v, before[k]), k
             moved += 1
     assert frozen > 10 and moved > 50
+
+
+def test_swin_backbone_frozen_path_vs_golden(on_host, golden_dir, monkeypatch):
+    """f2 on the CPU tier: the frozen-backbone configuration (fused window-attention kernels from their own source, linears
+    on the restated GEMM interface) reproduces the reference Swin outputs of the golden fixture — the body of the GPU test."""
+    import test_ops_gpu as gpu_tests
+    from partdistillation_b200 import functional, presets
+    monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, *a, **k: self)
+    make_cfg = presets.make_cfg
+    monkeypatch.setattr(presets, "make_cfg", lambda *a, **k: make_cfg(*a, **{**k, "device": "cpu"}))
+    gpu_tests.test_swin_backbone_frozen_path_vs_golden(functional, golden_dir)
