@@ -165,3 +165,33 @@ def test_msda_kernel_edge_cases_vs_oracle(msda, shapes, N, Lq, expect, loc_kind)
     assert _rel(gv, rgv) < 1e-5 and _rel(ga, rga) < 1e-5
     if loc_kind != "edges":          # on exact pixel borders the one-sided derivative is a convention (floor side), not a value
         assert _rel(gl, rgl) < 1e-4
+
+
+# ------------------------------------------------------------------ the GPU tests' own bodies through functional.py's wrappers
+@pytest.fixture(scope="module")
+def msda_abi_lib(tmp_path_factory):
+    from host_kernels import build_host_library, msda_section
+    return build_host_library(tmp_path_factory.mktemp("msda_abi"), "msda.cu", "msda_section.inc", "msda_abi_host.cpp",
+                              ("msda_forward", "msda_backward"), section_regex=r"(?s)(.*)", rewrite=msda_section)
+
+
+@pytest.fixture
+def fn(monkeypatch, msda_abi_lib):
+    from host_kernels import patch_functional
+    return patch_functional(monkeypatch, msda_abi_lib)
+
+
+def test_gpu_body_msda_known_answers(fn, golden_dir):
+    import test_ops_gpu as gpu_tests
+    gpu_tests.test_msda_known_answers(fn, golden_dir)
+
+
+@pytest.mark.parametrize("case", ["grad_D32", "grad_D71", "cfg_like"])
+def test_gpu_body_msda_gradients(fn, golden_dir, case):
+    import test_ops_gpu as gpu_tests
+    gpu_tests.test_msda_gradients(fn, golden_dir, case)
+
+
+def test_gpu_body_msda_decoder_style_queries(fn):
+    import test_ops_gpu as gpu_tests
+    gpu_tests.test_msda_decoder_style_queries(fn)
