@@ -247,6 +247,10 @@ msda_bwd_d32(const float* __restrict__ value, const __grid_constant__ LevelTable
     __syncthreads();
     const int sl = threadIdx.x >> 3;
     const int j = threadIdx.x & 7;
+    // Lanes whose slot lies beyond the problem skip the body below but do NOT exit (they wait at the barrier after it),
+    // so the butterfly shuffles inside must name only the participating lanes: with a full mask a warp that mixes valid
+    // and invalid slots (slots % 4 != 0, i.e. a head count that is not a multiple of 4) would deadlock.
+    const unsigned lanes = __ballot_sync(0xffffffffu, sl < nslots);
     if (sl < nslots) {
         const int64_t g = slot0 + sl;
         const int m = (int)(g % M);
@@ -285,9 +289,9 @@ msda_bwd_d32(const float* __restrict__ value, const __grid_constant__ LevelTable
                 float gy = (wx0 * (dot[2] - dot[0]) + wx1 * (dot[3] - dot[1])) * a * (float)H;
 #pragma unroll
                 for (int o = 4; o > 0; o >>= 1) {
-                    ga += __shfl_xor_sync(0xffffffffu, ga, o);
-                    gx += __shfl_xor_sync(0xffffffffu, gx, o);
-                    gy += __shfl_xor_sync(0xffffffffu, gy, o);
+                    ga += __shfl_xor_sync(lanes, ga, o);
+                    gx += __shfl_xor_sync(lanes, gx, o);
+                    gy += __shfl_xor_sync(lanes, gy, o);
                 }
                 if (j == 0) {
                     s_gattn[sl * LP + l * P + p] = ga;

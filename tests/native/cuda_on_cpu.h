@@ -46,6 +46,8 @@ struct Warp {
     unsigned pred[32];
     int val[32];
     unsigned long long xchg[32];        // __shfl_*_sync payloads (up to 8 bytes per lane)
+    unsigned sub_arrived = 0;           // rendezvous of a SUBSET of the lanes (collectives with a partial member mask)
+    unsigned sub_gen = 0;
 };
 
 struct Block {
@@ -99,19 +101,41 @@ inline int __reduce_add_sync(unsigned, int v) {
     return r;
 }
 
-inline void __syncwarp(unsigned = 0xffffffffu) { cpu_cuda::t_warp->bar->arrive_and_wait(); }
+namespace cpu_cuda {
+// Convergence point of a warp collective.  Full mask: every non-exited lane takes part (std::barrier with drop-on-exit).
+// Partial mask: exactly the named lanes meet — lanes outside the mask are somewhere else (e.g. already waiting at a
+// __syncthreads), as CUDA's *_sync semantics require; naming a lane that never arrives deadlocks here as it does on the GPU.
+inline void warp_converge(unsigned mask) {
+    Warp* w = t_warp;
+    if (mask == 0xffffffffu) {
+        w->bar->arrive_and_wait();
+        return;
+    }
+    const unsigned me = 1u << t_lane;
+    const unsigned gen = __atomic_load_n(&w->sub_gen, __ATOMIC_ACQUIRE);
+    const unsigned seen = __atomic_fetch_or(&w->sub_arrived, me, __ATOMIC_ACQ_REL) | me;
+    if (seen == mask) {
+        __atomic_store_n(&w->sub_arrived, 0u, __ATOMIC_RELEASE);
+        __atomic_fetch_add(&w->sub_gen, 1u, __ATOMIC_ACQ_REL);
+    } else {
+        while (__atomic_load_n(&w->sub_gen, __ATOMIC_ACQUIRE) == gen) std::this_thread::yield();
+    }
+}
+}  // namespace cpu_cuda
+
+inline void __syncwarp(unsigned mask = 0xffffffffu) { cpu_cuda::warp_converge(mask); }
 
 // value held by lane (lane ^ lane_mask); every lane of the warp takes part (full-mask use only)
 template <typename T>
-inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+inline T __shfl_xor_sync(unsigned mask, T v, int lane_mask) {
     static_assert(sizeof(T) <= sizeof(unsigned long long), "shuffle payload");
     auto* w = cpu_cuda::t_warp;
     unsigned long long raw = 0;
     __builtin_memcpy(&raw, &v, sizeof(T));
     w->xchg[cpu_cuda::t_lane] = raw;
-    w->bar->arrive_and_wait();
+    cpu_cuda::warp_converge(mask);
     raw = w->xchg[(cpu_cuda::t_lane ^ lane_mask) & 31];
-    w->bar->arrive_and_wait();
+    cpu_cuda::warp_converge(mask);
     T r;
     __builtin_memcpy(&r, &raw, sizeof(T));
     return r;

@@ -195,3 +195,25 @@ def test_gpu_body_msda_gradients(fn, golden_dir, case):
 def test_gpu_body_msda_decoder_style_queries(fn):
     import test_ops_gpu as gpu_tests
     gpu_tests.test_msda_decoder_style_queries(fn)
+
+
+@pytest.mark.parametrize("M,Lq", [(1, 29), (3, 7), (2, 33)])
+def test_msda_kernel_d32_partial_warps(msda, M, Lq):
+    """Head counts that are not multiples of 4 leave warps that mix valid and out-of-range slots in the last CTA of the
+    D = 32 fallback path (levels thinner than 2 pixels).  Its backward kernel used to run its butterfly shuffles with a full
+    member mask while the out-of-range lanes waited at the next barrier — a deadlock by CUDA's *_sync rules, found by
+    tests/fuzz/fuzz_msda_host.py on this host build (the shim deadlocks exactly where the GPU would)."""
+    forward, backward = msda
+    shapes = [(8, 1)]
+    g = torch.Generator().manual_seed(3)
+    value = torch.randn(2, 8, M, 32, generator=g)
+    loc = torch.rand(2, Lq, M, 1, 4, 2, generator=g) * 1.4 - 0.2
+    attn = torch.softmax(torch.randn(2, Lq, M, 4, generator=g), -1).view(2, Lq, M, 1, 4)
+    v, l, a = (t.clone().requires_grad_() for t in (value, loc, attn))
+    ref = O.ms_deform_attn_core(v, shapes, l, a)
+    go = torch.randn(ref.shape, generator=g)
+    rgv, rgl, rga = torch.autograd.grad(ref, (v, l, a), go)
+    out, path = forward(value, shapes, loc, attn)
+    gv, gl, ga, bpath = backward(value, shapes, loc, attn, go)
+    assert path == "d32" and bpath == "d32"
+    assert _rel(out, ref.detach()) < 1e-5 and _rel(gv, rgv) < 1e-5 and _rel(ga, rga) < 1e-5 and _rel(gl, rgl) < 1e-4
