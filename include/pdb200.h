@@ -63,6 +63,19 @@ PDB_API int pdb_msda_backward(const void* value, const int64_t* shapes_hw, const
                       void* grad_value, void* grad_loc, void* grad_attn,
                       int N, int S, int M, int D, int Lq, int L, int P, int dtype, void* stream);
 
+/* Encoder path (Lq == S: the queries are the pixels of the value pyramid; D == 32, P == 4, L <= 4) with the value stored
+ * as fp16, head-major (N, M, S, 32): pdb_msda_pack_value_h repacks the fp32 (N, S, M, 32) value once, pdb_msda_forward_h
+ * is pdb_msda_forward on that copy (fp32 locations, weights, products and accumulation; out fp32 (N, Lq, M*32)).
+ * Opt-in reduced-precision staging: halves the shared-memory bytes per tap corner. */
+PDB_API int pdb_msda_pack_value_h(const float* value, void* value_h, int N, int S, int M, int D, void* stream);
+PDB_API int pdb_msda_forward_h(const void* value_h, const int64_t* shapes_hw, const int64_t* level_start,
+                       const float* loc, const float* attn, float* out,
+                       int N, int S, int M, int D, int Lq, int L, int P, void* stream);
+/* Debug / A-B timing of the encoder forward: 0 = measured dispatch (TMA-staged value tiles on >= 4 levels, L1-resident tiled
+ * kernel otherwise), 1 = L1-resident kernels only, 4 = TMA-staged tiles wherever eligible; bit 1 (value 2): experimental launch
+ * shape of the fp16-staged kernel (2 CTAs / SM). */
+PDB_API int pdb_debug_set_msda_path(int path);
+
 /* ------------------------------------------------------------------------------------------------
  * Mask head einsum — replaces torch.einsum("bqc,bchw->bqhw")
  * (mask2former_transformer_decoder.py:449, part_distillation_transformer_decoder.py:244).

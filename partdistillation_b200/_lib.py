@@ -23,6 +23,9 @@ SIGNATURES = {
     "pdb_launch_count": (_l, []),
     "pdb_msda_forward": (_i, [_p, _hp64, _hp64, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "pdb_msda_backward": (_i, [_p, _hp64, _hp64, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "pdb_msda_pack_value_h": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "pdb_msda_forward_h": (_i, [_p, _hp64, _hp64, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "pdb_debug_set_msda_path": (_i, [_i]),
     "pdb_mask_einsum_forward": (_i, [_p, _p, _p, _p, _i, _i, _i, _l, _p]),
     "pdb_mask_einsum_backward": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _l, _p]),
     "pdb_gemm_tf32x3": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _l, _l, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _p]),

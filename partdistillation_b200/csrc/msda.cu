@@ -644,7 +644,22 @@ static int bwd_generic(const void* value, const LevelTable& lt, const void* loc,
 
 }  // namespace pdb
 
+// msda_tile.cu: the encoder path with TMA-staged value tiles
+namespace pdb {
+bool msda_tma_eligible(const LevelTable& lt, int L, int S, int M, int D, int Lq, int P);
+int msda_forward_tma_f32(const void* value, const LevelTable& lt, const float* loc, const float* attn, float* out, int N, int S,
+                         int M, int L, cudaStream_t st);
+int g_tma_variant_set(int v);
+static int g_msda_path = 0;     // pdb_debug_set_msda_path: 0 = measured dispatch (below), 1 = L1-resident tiled kernels only, 4 = TMA tiles wherever eligible
+}
+
 using namespace pdb;
+
+extern "C" int pdb_debug_set_msda_path(int path) {
+    g_msda_path = path & 5;
+    g_tma_variant_set((path >> 1) & 1);    // bit 1: experimental launch shape of the fp16-staged kernel
+    return PDB_OK;
+}
 
 extern "C" int pdb_msda_forward(const void* value, const int64_t* shapes_hw, const int64_t* level_start,
                                 const void* loc, const void* attn, void* out, int N, int S, int M, int D, int Lq,
@@ -656,6 +671,10 @@ extern "C" int pdb_msda_forward(const void* value, const int64_t* shapes_hw, con
     cudaStream_t st = as_stream(stream);
     if (dtype == PDB_F64) return fwd_generic<double>(value, lt, loc, attn, out, N, S, M, D, Lq, L, P, st);
     PDB_REQUIRE(dtype == PDB_F32, "msda_forward: dtype %d (only f32/f64, as ms_deform_attn_cuda.cu:70)", dtype);
+    // Measured dispatch (profiles/r02_bench_msda_v*.json): the persistent TMA-staged kernel wins on the 4-level pyramid
+    // (C5(i): 298 vs 322 us) and ties on 3 levels (C2: 126 vs 124 us), where the L1-resident kernel stays.
+    if ((g_msda_path == 4 || (g_msda_path == 0 && L >= 4)) && msda_tma_eligible(lt, L, S, M, D, Lq, P))
+        return msda_forward_tma_f32(value, lt, (const float*)loc, (const float*)attn, (float*)out, N, S, M, L, st);
     if (D == 32 && P == 4 && (int64_t)S * M * 32 < (1ll << 31) && levels_at_least_2x2(lt, L)) {
         int64_t slots = (int64_t)N * Lq * M;
         PatchTable pt;

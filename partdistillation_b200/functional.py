@@ -3,6 +3,8 @@
 Every function here requires CUDA tensors and the compiled library; nothing falls back to PyTorch
 or to the CPU (the reference's native op is CUDA-only as well: ops/src/ms_deform_attn.h:44).
 """
+import os
+
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -76,6 +78,24 @@ def _host_levels(spatial_shapes, level_start_index):
     return shapes, starts
 
 
+# Opt-in reduced-precision staging of the encoder's value pyramid (csrc/msda_tile.cu): the forward gathers
+# from an fp16 head-major copy of `value` (weights, products, accumulation fp32); the backward is unchanged (fp32 value).
+# Off by default: the fp32 parity contract of the mask logits is stated for exact fp32 staging.
+msda_value_half = bool(int(os.environ.get("PDB_MSDA_HALF", "0")))
+
+
+def _msda_half_eligible(value, shapes, starts, Lq, L, P):
+    N, S, M, D = value.shape
+    if not (msda_value_half and value.dtype == torch.float32 and D == 32 and P == 4 and Lq == S and 1 <= L <= 4):
+        return False
+    s = 0
+    for (h, w), st in zip(shapes, starts):
+        if h < 2 or w < 2 or st != s:
+            return False
+        s += h * w
+    return s == S
+
+
 class MSDeformAttnFunction(Function):
     @staticmethod
     def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations,
@@ -98,10 +118,18 @@ class MSDeformAttnFunction(Function):
         out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
         hs = _lib.host_i64([v for hw in shapes for v in hw])
         st = _lib.host_i64(starts)
-        rc = _lib.load().pdb_msda_forward(value.data_ptr(), hs, st, sampling_locations.data_ptr(),
-                                          attention_weights.data_ptr(), out.data_ptr(), N, S, M, D, Lq, L, P,
-                                          _DT[value.dtype], _stream())
-        _lib.check(rc, "pdb_msda_forward")
+        if _msda_half_eligible(value, shapes, starts, Lq, L, P):
+            value_h = torch.empty((N, M, S, D), dtype=torch.float16, device=value.device)
+            _lib.check(_lib.load().pdb_msda_pack_value_h(value.data_ptr(), value_h.data_ptr(), N, S, M, D, _stream()),
+                       "pdb_msda_pack_value_h")
+            rc = _lib.load().pdb_msda_forward_h(value_h.data_ptr(), hs, st, sampling_locations.data_ptr(),
+                                                attention_weights.data_ptr(), out.data_ptr(), N, S, M, D, Lq, L, P, _stream())
+            _lib.check(rc, "pdb_msda_forward_h")
+        else:
+            rc = _lib.load().pdb_msda_forward(value.data_ptr(), hs, st, sampling_locations.data_ptr(),
+                                              attention_weights.data_ptr(), out.data_ptr(), N, S, M, D, Lq, L, P,
+                                              _DT[value.dtype], _stream())
+            _lib.check(rc, "pdb_msda_forward")
         ctx.save_for_backward(value, sampling_locations, attention_weights)
         ctx.levels = (shapes, starts)
         return out

@@ -716,3 +716,52 @@ def test_group_norm_falls_back_for_other_layouts(fn):
     w, b = torch.randn(96, generator=g).cuda(), torch.randn(96, generator=g).cuda()
     assert not fn.group_norm_supported(x, 32, w, b)
     assert torch.allclose(fn.group_norm(x, 32, w, b, relu=True), F.group_norm(x, 32, w, b).relu())
+
+
+# ------------------------------------------------------------------ round 2: TMA-staged value tiles (csrc/msda_tile.cu)
+@pytest.mark.parametrize("shapes,N,spread", [([(32, 32), (64, 64), (128, 128)], 2, 4.0),       # C2 order (coarse first)
+                                              ([(64, 48), (32, 24), (16, 12), (8, 6)], 1, 9.0),   # ragged patches, far taps
+                                              ([(40, 56), (20, 28)], 1, 2.0)])
+def test_msda_tma_path_equals_l1_path(fn, shapes, N, spread):
+    """The encoder kernel with TMA-staged tiles and the L1-resident tiled kernel take different routes to the same
+    corners (zero-filled tile vs clamped footprint) and form the same products; only the order in which the left and
+    right pixel columns are summed differs: outputs agree to fp32 rounding."""
+    from partdistillation_b200 import _lib
+    S = sum(h * w for h, w in shapes)
+    value, loc, attn = _msda_inputs(N, shapes, S, seed=11, spread=spread)
+    vc, lc, ac = value.cuda(), loc.cuda(), attn.cuda()
+    lib = _lib.load()
+    try:
+        lib.pdb_debug_set_msda_path(1)
+        ref = fn.ms_deform_attn(vc, shapes, None, lc, ac)
+        lib.pdb_debug_set_msda_path(4)
+        out = fn.ms_deform_attn(vc, shapes, None, lc, ac)
+    finally:
+        lib.pdb_debug_set_msda_path(0)
+    assert _rel(out, ref) < 2e-6
+    assert _rel(out.cpu(), O.ms_deform_attn_core(value, shapes, loc, attn)) < 1e-5
+
+
+@pytest.mark.parametrize("shapes,N,spread", [([(32, 32), (64, 64), (128, 128)], 2, 4.0),
+                                              ([(64, 48), (32, 24), (16, 12), (8, 6)], 1, 9.0)])
+def test_msda_half_staged_value(fn, shapes, N, spread):
+    """Opt-in fp16 staging of the value pyramid: equals the fp32 kernel run on the fp16-rounded value (the rounding of
+    the stored value is the ONLY difference), and stays within 1e-3 of the exact result."""
+    S = sum(h * w for h, w in shapes)
+    value, loc, attn = _msda_inputs(N, shapes, S, seed=12, spread=spread)
+    vc, lc, ac = value.cuda(), loc.cuda(), attn.cuda()
+    exact = fn.ms_deform_attn(vc, shapes, None, lc, ac)
+    rounded = fn.ms_deform_attn(vc.half().float(), shapes, None, lc, ac)
+    old = fn.msda_value_half
+    try:
+        fn.msda_value_half = True
+        vg = vc.clone().requires_grad_()
+        out = fn.ms_deform_attn(vg, shapes, None, lc, ac)
+        (gv,) = torch.autograd.grad(out, vg, torch.ones_like(out))
+    finally:
+        fn.msda_value_half = old
+    assert _rel(out, rounded) < 2e-6            # same products; only the summation order across the corner pair differs
+    assert _rel(out, exact) < 1e-3
+    vg2 = vc.clone().requires_grad_()
+    (gv2,) = torch.autograd.grad(fn.ms_deform_attn(vg2, shapes, None, lc, ac), vg2, torch.ones_like(out))
+    assert torch.allclose(gv, gv2, rtol=1e-5, atol=1e-6)          # backward is the fp32 one
