@@ -403,8 +403,8 @@ def hungarian_matcher(outputs, targets, num_points, w_class, w_mask, w_dice, ran
                               targets[b]["labels"], targets[b]["masks"], coords, w_class, w_mask, w_dice)
             C = C.reshape(C.shape[0], -1).cpu()
             row, col = lsap(C.numpy())
-            row = torch.as_tensor(np.asarray(row), dtype=torch.int64)
-            col = torch.as_tensor(np.asarray(col), dtype=torch.int64)
+            row = torch.as_tensor(np.asarray(row), dtype=torch.int64, device=C.device)     # CPU indices, as in the reference
+            col = torch.as_tensor(np.asarray(col), dtype=torch.int64, device=C.device)
             order = C[row, col].topk(len(row), largest=False)[1]
             if record is not None:
                 record.setdefault("cost", []).append(C.clone())
