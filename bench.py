@@ -7,7 +7,9 @@ sh_files/proposal_learning/train_multi.sh:8,46 of the reference).
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 N > 1 is launched by torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON line.
-``--impl reference`` times the reference algorithm on the host CPU (the oracle port under oracle/).
+``--impl reference`` times the reference's own implementation of the same step on the host CPU: the unmodified
+reference through oracle/ref_loader.py when a reference tree resolves (/root/reference, or baseline/_ref on the GPU box),
+else the oracle port under oracle/.
 """
 import argparse
 import json
@@ -111,47 +113,103 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle port (reference algorithm) on the host cores
+# CPU baseline / reference arm: the reference's own implementation of the step on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step_time(state_dict, steps=1, warmup=0, budget_s=240.0):
-    """fwd + loss + bwd of ONE 1024^2 image through oracle/m2f_oracle.py (Swin-B + head + criterion).
-    Returns (seconds per step, steps actually timed, cores)."""
+def make_cpu_reference_step(n_images, state_dict=None):
+    """-> (step(), kind, cores, what).  One step = forward + loss + backward + full-model clip + AdamW over `n_images`
+    synthetic 1024^2 images (configs[1]: Swin-B, 100 queries, 10 decoder layers, 12 544 points, recipe freeze), all host threads.
+    kind "reference": the UNMODIFIED reference ProposalModel (proposal_model.py:177-204) built through oracle/ref_loader.py from
+    /root/reference or from baseline/_ref (baseline/install_reference.sh; that copy is what exists on the GPU box), detectron2 /
+    fvcore / timm provided by oracle/shims, optimizer = torch.optim.AdamW + clip_grad_norm_ as base_trainer.py:118-147.
+    kind "port": oracle/m2f_oracle.py (the restatement pinned to the reference by tests/test_oracle_golden.py) when no
+    reference tree resolves."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import m2f_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    import ref_loader as rl
+    if rl.available():
+        import warnings
+        warnings.filterwarnings("ignore")
+        rl.load()
+        from detectron2.structures import BitMasks, Instances
+        cfg = rl.make_cfg("ProposalModel", "swin_b", num_queries=QUERIES, dec_layers=10, num_points=POINTS,
+                          importance_sample_ratio=0.0)
+        torch.manual_seed(0)
+        model = rl.build_model(cfg, os.path.join(tempfile.gettempdir(), "pdb_ref_work")).train()
+        trainable = []
+        for name, p_ in model.named_parameters():
+            if "backbone" in name or "encoder" in name:          # train_multi.sh:8,46 (FREEZE_KEYS)
+                p_.requires_grad_(False)
+            else:
+                trainable.append(p_)
+        opt = torch.optim.AdamW(trainable, lr=1e-4, weight_decay=0.05)
+        batch = []
+        for i in range(n_images):
+            img, m = synth_image_and_masks(i)
+            inst = Instances((H, W))
+            inst.gt_masks = BitMasks(m)
+            inst.gt_classes = torch.zeros(m.shape[0], dtype=torch.long)
+            batch.append({"image": img, "instances": inst, "height": H, "width": W})
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            losses = model(batch)
+            sum(losses.values()).backward()
+            torch.nn.utils.clip_grad_norm_(trainable, 0.01)
+            opt.step()
+        return step, "reference", cores, (f"{n_images} x 1024^2 per step, fwd+loss+bwd+clip+AdamW, the unmodified reference "
+                                          f"ProposalModel from {os.path.relpath(rl.REF_ROOT, ROOT) if rl.REF_ROOT.startswith(ROOT) else rl.REF_ROOT}")
+    import m2f_oracle as O
+    if state_dict is None:
+        from partdistillation_b200 import compat, presets
+        cfg = presets.make_cfg("ProposalModel", "swin_b", QUERIES, 10, POINTS, 0.0, device="cpu")
+        torch.manual_seed(0)
+        state_dict = compat.META_ARCH_REGISTRY.get("ProposalModel")(cfg).state_dict()
     sd = {k: v.detach().cpu().clone() for k, v in state_dict.items()}
     for k, v in sd.items():
-        if k.startswith("sem_seg_head.") and v.is_floating_point():
+        if k.startswith("sem_seg_head.") and v.is_floating_point() and "encoder" not in k:
             v.requires_grad_(True)
+    trainable = [v for v in sd.values() if v.requires_grad]
+    opt = torch.optim.AdamW(trainable, lr=1e-4, weight_decay=0.05)
     hp = dict(num_classes=1, dec_layers=10, num_points_match=POINTS, num_points_loss=POINTS, w_class=2.0,
               w_mask=5.0, w_dice=5.0, eos_coef=0.1, oversample_ratio=3.0, importance_ratio=0.0)
-    img, m = synth_image_and_masks(0)
-    batch = [{"image": img.float(), "gt_masks": m}]
+    batch = []
+    for i in range(n_images):
+        img, m = synth_image_and_masks(i)
+        batch.append({"image": img.float(), "gt_masks": m})
     mean, std = [123.675, 116.280, 103.530], [58.395, 57.120, 57.375]
 
-    def one():
-        for v in sd.values():
-            v.grad = None
+    def step():
+        opt.zero_grad(set_to_none=True)
         x = O.prepare_images(batch, mean, std, 32)
         with torch.no_grad():
             feats = O.swin_forward(sd, "backbone.", x, 128, [2, 2, 18, 2], [4, 8, 16, 32], 12)
-        targets = O.prepare_targets(batch, H, W)
-        losses = O.head_and_loss(sd, feats, targets, hp)
+        losses = O.head_and_loss(sd, feats, O.prepare_targets(batch, H, W), hp)
         sum(losses.values()).backward()
+        torch.nn.utils.clip_grad_norm_(trainable, 0.01)
+        opt.step()
+    return step, "port", cores, f"{n_images} x 1024^2 per step, fwd+loss+bwd+clip+AdamW, oracle/m2f_oracle.py (no reference tree on this box)"
 
-    t_used, done, times = 0.0, 0, []
+
+def time_cpu_reference(step, steps, warmup, budget_s=420.0):
+    """Seconds per step over `steps` timed steps after `warmup` untimed ones; stops early (after >= 1 timed step) only when
+    the wall-clock budget would be exceeded.  Returns (seconds per step, timed steps, warm-up steps done)."""
+    t_start = time.perf_counter()
+    times, wdone = [], 0
+    last = 0.0
     for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        one()
-        dt = time.perf_counter() - t0
-        t_used += dt
-        if i >= warmup:
-            times.append(dt)
-            done += 1
-        if t_used + dt > budget_s and done >= 1:
+        if times and time.perf_counter() - t_start + last > budget_s:
             break
-    return sum(times) / len(times), done, cores
+        if i < warmup and wdone >= 1 and time.perf_counter() - t_start + last * (1 + steps) > budget_s:
+            continue                                     # budget: skip the remaining warm-up steps, keep the timed ones
+        t0 = time.perf_counter()
+        step()
+        last = time.perf_counter() - t0
+        if i < warmup:
+            wdone += 1
+        else:
+            times.append(last)
+    return sum(times) / len(times), len(times), wdone
 
 
 # ------------------------------------------------------------------------------------------------
@@ -163,6 +221,17 @@ def measured_peak():
         return float(p["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel from the committed `ncu --set full` summary
+    of THIS round (profiles/r02_kernel_traffic.json, written by tools/ncu_traffic.py from the raw export); (None, None) if the
+    summary does not hold the kernel.  bench.py cannot read DRAM counters itself: never measured under a profiler here."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_kernel_traffic.json")))[key]
+        return float(d["dram_bytes"]), d["source"]
+    except Exception:
+        return None, None
 
 
 def _time_kernel(calls, flush, iters=10, warmup=3, per_event=8):
@@ -219,7 +288,7 @@ def kernel_rooflines(device):
     with torch.no_grad():
         t = _time_kernel([(lambda f=f: fn.mask_einsum(e, f, embed_lo=e_lo)) for f in fs], flush)
     out.append(hbm_entry("gemm_tf32x3_kernel (mask einsum fwd)", 4 * (B * Q * C + B * C * HH * WW + B * Q * HH * WW), t))
-    out[-1]["traffic"] = 158.9e6          # dram read + write per launch, profiles/r01_ncu_einsum_fwd_v3.txt (ncu --set full; part of the output is still in L2)
+    out[-1]["traffic"], out[-1]["traffic_source"] = ncu_traffic("mask_einsum_fwd")
     del fs
 
     # ---- MSDeformAttn gather / scatter at the encoder shape
@@ -241,12 +310,51 @@ def kernel_rooflines(device):
     fwd_bytes = 4 * (N * S * M * D + N * S * M * L * P * 3 + N * S * M * D)
     with torch.no_grad():
         t = _time_kernel([(lambda v=v, lo=lo, a=a: fn.ms_deform_attn(v, shapes, None, lo, a)) for v, lo, a in sets], flush)
-    out.append(hbm_entry("msda_fwd_tiled", fwd_bytes, t))
+    out.append(hbm_entry("msda_fwd_tiled (C2: 3 levels, N=2)", fwd_bytes, t))
+    out[-1]["traffic"], out[-1]["traffic_source"] = ncu_traffic("msda_fwd_C2")
     outs = [fn.ms_deform_attn(v, shapes, None, lo, a) for v, lo, a in sets]
     go = torch.randn_like(outs[0])
     t = _time_kernel([(lambda o=o, st=st: torch.autograd.grad(o, st, go, retain_graph=True)) for o, st in zip(outs, sets)], flush)
-    out.append(hbm_entry("msda_bwd_tiled (+ grad_value zero fill)", 2 * fwd_bytes - 4 * N * S * M * D, t))
+    out.append(hbm_entry("msda_bwd_tiled (+ grad_value zero fill) (C2)", 2 * fwd_bytes - 4 * N * S * M * D, t))
+    out[-1]["traffic"], out[-1]["traffic_source"] = ncu_traffic("msda_bwd_C2")
     del sets, outs
+
+    # ---- BASELINE configs[4] = C5(i): 4-scale pyramid 256^2 .. 32^2, N = 1, Lq = S = 87 040 (two buffer sets of 312 MB each)
+    shapes5 = [(H // 4, W // 4), (H // 8, W // 8), (H // 16, W // 16), (H // 32, W // 32)]
+    S5, L5 = sum(h * w for h, w in shapes5), 4
+    refs = []
+    for (hh, ww) in shapes5:
+        ys, xs = torch.meshgrid((torch.arange(hh) + 0.5) / hh, (torch.arange(ww) + 0.5) / ww, indexing="ij")
+        refs.append(torch.stack((xs.reshape(-1), ys.reshape(-1)), -1))
+    ref5 = torch.cat(refs)[None, :, None, None, None, :]
+    norm5 = torch.tensor([[w_, h_] for h_, w_ in shapes5], dtype=torch.float32)[None, None, None, :, None, :]
+    sets = []
+    for _ in range(2):
+        value = torch.randn(1, S5, M, D, generator=g).to(device).requires_grad_()
+        loc = (ref5 + (torch.rand(1, S5, M, L5, P, 2, generator=g) * 2 - 1) * 4.0 / norm5).contiguous().to(device).requires_grad_()
+        attn = torch.softmax(torch.randn(1, S5, M, L5 * P, generator=g), -1).view(1, S5, M, L5, P).contiguous().to(device).requires_grad_()
+        sets.append((value, loc, attn))
+    fwd5 = 4 * (S5 * M * D + S5 * M * L5 * P * 3 + S5 * M * D)
+    with torch.no_grad():
+        t = _time_kernel([(lambda v=v, lo=lo, a=a: fn.ms_deform_attn(v, shapes5, None, lo, a)) for v, lo, a in sets], flush)
+    out.append(hbm_entry("msda_fwd_tma (C5(i): 4 levels 256^2..32^2, N=1, TMA-staged value tiles)", fwd5, t))
+    out[-1]["traffic"], out[-1]["traffic_source"] = ncu_traffic("msda_fwd_C5i")
+    outs = [fn.ms_deform_attn(v, shapes5, None, lo, a) for v, lo, a in sets]
+    go = torch.randn_like(outs[0])
+    t = _time_kernel([(lambda o=o, st=st: torch.autograd.grad(o, st, go, retain_graph=True)) for o, st in zip(outs, sets)], flush)
+    out.append(hbm_entry("msda_bwd_tiled (+ grad_value zero fill) (C5(i))", 2 * fwd5 - 4 * S5 * M * D, t))
+    out[-1]["traffic"], out[-1]["traffic_source"] = ncu_traffic("msda_bwd_C5i")
+    del sets, outs
+
+    # ---- BASELINE configs[3] = C4: pixel grouping, res3 + res4 features (768 ch at 64^2) of a 512^2 image, 4 centroids
+    feats = [torch.randn(768, 64, 64, generator=g).to(device) for _ in range(16)]        # 16 x 12.6 MB > L2
+    cent = torch.randn(4, 768, generator=g).to(device)
+    yy, xx = torch.meshgrid(torch.arange(512), torch.arange(512), indexing="ij")
+    gmask = (((yy - 256) ** 2 + (xx - 256) ** 2) < 200 ** 2).to(device)
+    t = _time_kernel([(lambda f=f: fn.group_affinity(f, cent, gmask, "dot")) for f in feats], flush, per_event=16)
+    out.append(hbm_entry("group_affinity_kernel (C4: 768 ch 64^2 -> 512^2 labels, 4 centroids)", 4 * 768 * 64 * 64 + 512 * 512 * 5, t))
+    out[-1]["images_per_s"] = round(1.0 / t, 1)
+    del feats
 
     # ---- encoder FFN linear on the tensor cores (3 tf32 MMAs per fp32 product: ceiling = tf32 dense / 3 ~ bf16 peak / 6)
     rows = N * S
@@ -266,24 +374,102 @@ def kernel_rooflines(device):
 
 # ------------------------------------------------------------------------------------------------
 def run_reference(args, rank):
+    """The reference arm: rank 0 alone times the reference's CPU implementation of the same step (same batch of
+    PER_GPU_BATCH images, same freeze, clip and optimizer) on all host cores; the other ranks exit."""
     if rank != 0:
         return
-    from partdistillation_b200 import compat, presets
-    cfg = presets.make_cfg("ProposalModel", "swin_b", QUERIES, 10, POINTS, 0.0, device="cpu")
-    torch.manual_seed(0)
-    model = compat.META_ARCH_REGISTRY.get("ProposalModel")(cfg)
-    t, done, cores = cpu_reference_step_time(model.state_dict(), steps=args.steps, warmup=min(args.warmup, 1))
-    ips = 1.0 / t
+    step, kind, cores, what = make_cpu_reference_step(PER_GPU_BATCH)
+    t, done, wdone = time_cpu_reference(step, args.steps, args.warmup)
+    ips = PER_GPU_BATCH / t
     line = {"impl": "reference", "metric": METRIC, "value": round(ips, 5), "unit": "images/s", "n_gpus": args.gpus,
-            "steps": done, "steps_requested": args.steps, "warmup": min(args.warmup, 1),
+            "steps": done, "steps_requested": args.steps, "warmup": wdone,
             "ms_per_step": round(t * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "proposal_learning Swin-B 100q 1024x1024 (configs[1]); each reference step = 1 image "
-                                   "(bounded sample) on the host CPU"},
-            "cpu_baseline": {"value": round(ips, 5), "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": "1 image 1024x1024 per step, fwd+loss+bwd, oracle/m2f_oracle.py"},
+            "config": {"workload": "proposal_learning Swin-B 100q 1024x1024 bs=2 fwd+bwd (BASELINE configs[1]) on the host CPU",
+                       "global_batch": PER_GPU_BATCH, "queries": QUERIES, "dec_layers": 10, "train_num_points": POINTS,
+                       "importance_sample_ratio": 0.0, "freeze_keys": ["backbone", "encoder"],
+                       "optimizer": "AdamW + full-model clip 0.01"},
+            "cpu_baseline": {"value": round(ips, 5), "unit": "images/s", "cores": cores, "kind": kind, "sample": what},
             "e2e": {"value": round(ips, 5), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def run_c4(args, rank, local_rank, world, device):
+    """BASELINE configs[3]: PixelGroupingModel's dot-affinity grouping (pixel_grouping_model.py:129-218) on synthetic Swin-B
+    res3 + res4 features (768 channels at 64 x 64) of 512 x 512 images, 4 centroids; images are independent, so ranks are
+    replicas over disjoint images (no data-path collective).  Step = one batch of 16 images per GPU through
+    pdb_group_affinity.  value: features, centroids and masks resident; e2e: the batch's object masks copied in from pinned
+    host memory and the label maps read back every step."""
+    from partdistillation_b200 import functional as fn
+    IMGS = 16
+    g = torch.Generator().manual_seed(100 + rank)
+    feats = [torch.randn(768, 64, 64, generator=g).to(device) for _ in range(32)]       # 32 x 12.6 MB: never L2-resident
+    cents = [torch.randn(4, 768, generator=g).to(device) for _ in range(IMGS)]
+    yy, xx = torch.meshgrid(torch.arange(512), torch.arange(512), indexing="ij")
+    host_masks = torch.stack([((yy - 256) ** 2 + (xx - 200 - 7 * i) ** 2) < (150 + 5 * i) ** 2 for i in range(IMGS)]).pin_memory()
+    dev_masks = host_masks.to(device)
+    host_labels = torch.empty((IMGS, 512, 512), dtype=torch.int32).pin_memory()
+    state = {"i": 0}
+
+    def step(masks, read_back):
+        labs = []
+        for j in range(IMGS):
+            labs.append(fn.group_affinity(feats[(state["i"] + j) % len(feats)], cents[j], masks[j], "dot"))
+        state["i"] += IMGS
+        if read_back:
+            host_labels.copy_(torch.stack(labs), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    def timed(e2e):
+        for _ in range(max(args.warmup, 3)):
+            step(host_masks.to(device, non_blocking=True) if e2e else dev_masks, e2e)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s_, e_ = torch.cuda.Event(True), torch.cuda.Event(True)
+        t0 = time.perf_counter()
+        s_.record()
+        for _ in range(args.steps):
+            step(host_masks.to(device, non_blocking=True) if e2e else dev_masks, e2e)
+        e_.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([s_.elapsed_time(e_), wall], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms, _ = timed(False)
+    clocks = sampler.stop() if sampler else None
+    ms_e, wall_e = timed(True)
+    ms_e = max(ms_e, wall_e)
+    if rank == 0:
+        images = IMGS * world * args.steps
+        peak, how = measured_peak()
+        alg = 4 * 768 * 64 * 64 + 512 * 512 * 5
+        per_launch = ms * 1e-3 / (args.steps * IMGS)
+        line = {"metric": "pixel grouping images/sec (res3+res4 dot affinity, 512^2 images; BASELINE configs[3])",
+                "value": round(images / (ms * 1e-3), 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "pixel_grouping_model res3/res4 dot-affinity grouping, 768 ch x 64^2 features -> 512^2 labels, "
+                                       "4 centroids, 16 images per GPU per step (BASELINE configs[3])", "parallelism": f"replicas x{world}",
+                           "l2": "features rotate over 32 maps of 12.6 MB per GPU (403 MB > 126 MB L2)"},
+                "clocks": clocks,
+                "e2e": {"value": round(images / (ms_e * 1e-3), 1), "unit": "images/s", "h2d_bytes_per_step": int(host_masks.numel()),
+                        "d2h_bytes_per_step": int(host_labels.numel() * 4)},
+                "gpu_launches": args.steps * IMGS,
+                "roofline": {"kernel": "group_affinity_kernel", "bound": "hbm", "achieved": round(alg / per_launch / 1e9, 1), "peak": peak,
+                             "peak_source": how, "unit": "GB/s", "frac": round(alg / per_launch / 1e9 / peak, 4), "traffic": None,
+                             "algorithmic_bytes": alg, "avg_launch_us": round(per_launch * 1e6, 2),
+                             "note": "launches timed back to back inside the step (includes launch gaps of the eager loop)"}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
@@ -292,6 +478,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+                    help="c2 (default): the training step of BASELINE configs[1]; c4: the pixel-grouping throughput sweep of configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="run the step eagerly instead of replaying its CUDA graph")
     ap.add_argument("--packed-masks", action="store_true",
@@ -312,6 +500,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
 
+    if args.workload == "c4":
+        run_c4(args, rank, local_rank, world, device)
+        return
     from partdistillation_b200 import _lib, compat, presets
     from partdistillation_b200.engine import DataParallelTrainer
     cfg = presets.make_cfg("ProposalModel", "swin_b", QUERIES, 10, POINTS, 0.0, device=str(device))
@@ -393,10 +584,10 @@ def main():
         dist.barrier()
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            t, done, cores = cpu_reference_step_time(cpu_sd, steps=1, warmup=0)
-            line["cpu_baseline"] = {"value": round(1.0 / t, 5), "unit": "images/s", "cores": cores, "kind": "port",
-                                    "sample": "1 image 1024x1024, fwd+loss+bwd once (oracle/m2f_oracle.py: Swin-B + head "
-                                              f"+ criterion), {t:.1f} s"}
+            step, kind, cores, what = make_cpu_reference_step(PER_GPU_BATCH, cpu_sd)
+            t, _, _ = time_cpu_reference(step, steps=1, warmup=0)
+            line["cpu_baseline"] = {"value": round(PER_GPU_BATCH / t, 5), "unit": "images/s", "cores": cores, "kind": kind,
+                                    "sample": f"ONE step ({t:.1f} s): {what}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -272,6 +272,13 @@ PDB_API int pdb_swin_window_attention_forward(const float* qkv, const float* qkv
  * ---------------------------------------------------------------------------------------------- */
 PDB_API int pdb_group_affinity(const float* feat, const float* centroids, const uint8_t* mask, int32_t* labels,
                        int C, int Kc, int h, int w, int H, int W, int metric, void* stream);
+/* Stage 1 of the two-stage grouping (what functional.group_affinity runs): bilinear up-sampling is linear, so the contraction
+ * with the centroids is done once at feature resolution, scores (Kc, h, w): <f, c_k> (metric 0) or 2<f, c_k> - |c_k|^2
+ * (metric 1); pdb_group_affinity[_resized] is then called on the Kc score maps with the identity as centroids (metric 0):
+ * C*h*w reads instead of 4*C reads per output pixel.  Labels can differ from the one-stage evaluation only at numerical
+ * near-ties of the two best scores (different rounding order). */
+PDB_API int pdb_group_scores(const float* feat, const float* centroids, float* scores, int C, int Kc, int h, int w, int metric,
+                     void* stream);
 /* Same, for an evaluation size different from the padded batch size (pixel_grouping_model.py:139-160,
  * proposal_generation_model.py:139-155): feat (C, h, w) -> bilinear -> (Hp, Wp) -> crop (Hi, Wi) -> bilinear -> (Ho, Wo)
  * (detectron2 sem_seg_postprocess), both passes composed per output pixel; mask and labels are (Ho, Wo). */

@@ -2,8 +2,8 @@
 
 Used in the build container (which has /root/reference but no GPU) by
 ``oracle/make_golden.py`` to generate the committed fixtures under ``tests/golden/``
-and by ``tests/test_oracle_vs_reference.py`` (skipped when the reference tree is absent,
-e.g. on the GPU box).  Nothing in the product package imports this file.
+and by ``bench.py --impl reference`` / its ``cpu_baseline`` leg, which time the real reference on the host cores
+when a reference tree resolves (see ``_resolve_root``).  Nothing in the product package imports this file.
 
 Mechanism: the reference's ``part_distillation/__init__.py``
 imports Detic / pycocotools / pydensecrf consumers, so we never execute it; instead we
@@ -16,7 +16,20 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("PD_REFERENCE_ROOT", "/root/reference")
+def _resolve_root():
+    """$PD_REFERENCE_ROOT, else the reference checkout of the build container, else the copy baseline/install_reference.sh
+    made under baseline/_ref (git-ignored; it is what exists on the GPU box)."""
+    env = os.environ.get("PD_REFERENCE_ROOT")
+    if env:
+        return env
+    local = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    for root in ("/root/reference", local):
+        if os.path.isdir(os.path.join(root, "part_distillation")):
+            return root
+    return "/root/reference"
+
+
+REF_ROOT = _resolve_root()
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
 
 _NAMESPACES = [

@@ -95,6 +95,17 @@ extern "C" int pdb_group_affinity(const float* feat, const float* centroids, con
     return launched("group_affinity");
 }
 
+extern "C" int pdb_group_scores(const float* feat, const float* centroids, float* scores, int C, int Kc, int h, int w, int metric,
+                                void* stream) {
+    PDB_REQUIRE(feat && centroids && scores, "group_scores: null pointer");
+    PDB_REQUIRE(C > 0 && Kc > 0 && Kc <= kMaxGroupCentroids && h > 0 && w > 0, "group_scores: bad sizes (1 <= Kc <= %d)",
+                kMaxGroupCentroids);
+    PDB_REQUIRE(metric == 0 || metric == 1, "group_scores: metric %d (0 = dot, 1 = l2)", metric);
+    const int hw = h * w;
+    group_scores_kernel<<<(unsigned)((hw + 31) / 32), 256, 0, as_stream(stream)>>>(feat, centroids, scores, C, Kc, hw, metric);
+    return launched("group_scores");
+}
+
 // General geometry: features (C, h, w) -> bilinear -> padded (Hp, Wp) -> crop (Hi, Wi) -> bilinear -> (Ho, Wo); mask and
 // labels at (Ho, Wo).  With Hp == Hi == Ho and Wp == Wi == Wo this computes what pdb_group_affinity computes (up to the
 // FMA contraction the older kernel leaves to the compiler).

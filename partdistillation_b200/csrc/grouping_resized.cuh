@@ -15,6 +15,47 @@ namespace pdb {
 
 constexpr int kMaxGroupCentroids = 16;
 
+// Stage 1 of the grouping (linearity of the bilinear up-sampling): the affinity of an up-sampled feature with a centroid is
+// the up-sampled affinity, sum_c bilinear(f_c) c_kc = bilinear(sum_c f_c c_kc), so the contraction over the C channels is
+// done ONCE at feature resolution (C h w reads instead of 4 C reads per output pixel) and the per-pixel kernels interpolate
+// Kc score maps.  scores[k][p] = <f_p, c_k> (dot) or 2 <f_p, c_k> - |c_k|^2 (l2; interpolation weights sum to 1, so the
+// constant passes through both bilinear passes unchanged).
+// grid ceil(h w / 32), block 256 = 32 pixels x 8 channel groups (channel c belongs to group c % 8: a warp reads 32
+// consecutive pixels of one channel plane = one 128-byte line); the 8 partial sums of a pixel are reduced in shared memory.
+__global__ void __launch_bounds__(256)
+group_scores_kernel(const float* __restrict__ feat, const float* __restrict__ centroids, float* __restrict__ scores, int C,
+                    int Kc, int hw, int l2) {
+    __shared__ float s_part[8][kMaxGroupCentroids][33];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int p = blockIdx.x * 32 + lane;
+    float acc[kMaxGroupCentroids], nrm[kMaxGroupCentroids];
+#pragma unroll
+    for (int k = 0; k < kMaxGroupCentroids; ++k) acc[k] = nrm[k] = 0.f;
+    if (p < hw) {
+        for (int c = grp; c < C; c += 8) {
+            const float v = __ldg(feat + (int64_t)c * hw + p);
+#pragma unroll
+            for (int k = 0; k < kMaxGroupCentroids; ++k)
+                if (k < Kc) {
+                    const float ck = __ldg(centroids + k * C + c);
+                    acc[k] = fmaf(v, ck, acc[k]);
+                    nrm[k] = fmaf(ck, ck, nrm[k]);
+                }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxGroupCentroids; ++k)
+        if (k < Kc) s_part[grp][k][lane] = l2 ? 2.f * acc[k] - nrm[k] : acc[k];
+    __syncthreads();
+    // thread (grp, lane): centroids grp, grp + 8 of pixel lane
+    for (int k = grp; k < Kc; k += 8) {
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) s += s_part[g][k][lane];
+        if (p < hw) scores[(int64_t)k * hw + p] = s;
+    }
+}
+
 // grid (ceil(Wo / 32), ceil(Ho / 8)), block 256, dynamic shared memory (C * Kc + Kc) floats
 template <bool TWO_STAGE>
 __global__ void __launch_bounds__(256)

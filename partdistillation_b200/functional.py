@@ -730,11 +730,12 @@ def linear(x, weight, bias=None, relu=False, gelu=False):
 # --------------------------------------------------------------------------------------------------
 # pixel grouping affinity  (pixel_grouping_model.py:139-144,197-211)
 # --------------------------------------------------------------------------------------------------
-def group_affinity(feat, centroids, mask, metric="dot", geometry=None):
+def group_affinity(feat, centroids, mask, metric="dot", geometry=None, two_stage=True):
     """feat (C, h, w) f32, centroids (Kc, C) f32, mask (H, W) bool/uint8 -> labels (H, W) int32: 0 outside the mask,
     1 + argmax_k affinity(bilinear(feat) at the pixel, centroid k) inside.  ``geometry`` = (padded size, image size,
     output size) when the features are up-sampled to the padded size, cropped and resized again (sem_seg_postprocess);
-    ``mask`` is then at the output size.  Default: one bilinear pass to the size of ``mask``."""
+    ``mask`` is then at the output size.  Default: one bilinear pass to the size of ``mask``.  ``two_stage`` (default):
+    the C-channel contraction runs once at feature resolution (linearity of the interpolation; include/pdb200.h)."""
     _need_cuda(feat, centroids, mask)
     if metric not in ("dot", "l2"):
         raise ValueError(f"distance metric {metric!r} (dot / l2)")
@@ -743,6 +744,12 @@ def group_affinity(feat, centroids, mask, metric="dot", geometry=None):
     C, h, w = feat.shape
     Kc = centroids.shape[0]
     H, W = mask.shape
+    if two_stage and C > Kc:
+        # contraction with the centroids at feature resolution (pdb_group_scores), then the per-pixel kernels on Kc score maps
+        scores = torch.empty((Kc, h, w), dtype=torch.float32, device=feat.device)
+        _lib.check(_lib.load().pdb_group_scores(feat.data_ptr(), centroids.data_ptr(), scores.data_ptr(), C, Kc, h, w,
+                                                0 if metric == "dot" else 1, _stream()), "pdb_group_scores")
+        feat, centroids, metric, C = scores, host_table(torch.eye(Kc).flatten().tolist(), torch.float32, feat.device).view(Kc, Kc), "dot", Kc
     labels = torch.empty((H, W), dtype=torch.int32, device=feat.device)
     if geometry is not None:
         (Hp, Wp), (Hi, Wi), (Ho, Wo) = [(int(a), int(b)) for a, b in geometry]

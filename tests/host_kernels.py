@@ -53,7 +53,7 @@ def dynamic_smem(section):
 
 
 POSTPROCESS_OPS = ("postprocess_masks", "resize_masks_u8", "pack_bits", "unpack_bits", "bits_popcount", "bits_intersect",
-                   "group_affinity_resized")
+                   "group_affinity_resized", "group_scores")
 
 
 def build_plain_harness(tmp, harness, ops):
@@ -89,7 +89,7 @@ HARNESSES = [
     ("window_attn.cu", "window_attn_section.inc", "window_attn_kernels_host.cpp",
      ("window_attention_forward", "swin_window_attention_forward"), [], True),
     ("optim.cu", "optim_section.inc", "misc_kernels_host.cpp",
-     ("grad_sumsq", "adamw_flat", "group_affinity", "attn_mask_build", "attn_mask_reset_rows"),
+     ("grad_sumsq", "adamw_flat", "group_affinity", "group_scores", "attn_mask_build", "attn_mask_reset_rows"),
      [("grouping.cu", "grouping_section.inc"), ("attn_mask.cu", "attn_mask_section.inc")], True),
 ]
 

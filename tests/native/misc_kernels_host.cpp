@@ -4,6 +4,7 @@
 // points restate the launchers of the three files (C ABI argument order minus the stream).
 #include "pdb_common_host.h"
 
+#include "../../partdistillation_b200/csrc/grouping_resized.cuh"     // group_scores_kernel (stage 1 of the grouping)
 #include "optim_section.inc"
 #include "grouping_section.inc"
 #include "attn_mask_section.inc"
@@ -42,6 +43,13 @@ extern "C" int host_group_affinity(const float* feat, const float* centroids, co
     const size_t smem = sizeof(float) * ((size_t)C * Kc + Kc);
     launch(dim3((unsigned)((W + 31) / 32), (unsigned)((H + 7) / 8)), dim3(256), smem,
            [&] { group_affinity_kernel(feat, centroids, mask, labels, C, Kc, h, w, H, W, metric); });
+    return 0;
+}
+
+extern "C" int host_group_scores(const float* feat, const float* centroids, float* scores, int C, int Kc, int h, int w, int metric) {
+    if (!(C > 0 && Kc > 0 && Kc <= kMaxGroupCentroids)) return -1;
+    const int hw = h * w;
+    launch(dim3((unsigned)((hw + 31) / 32)), dim3(256), [&] { group_scores_kernel(feat, centroids, scores, C, Kc, hw, metric); });
     return 0;
 }
 

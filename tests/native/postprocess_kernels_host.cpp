@@ -60,6 +60,13 @@ extern "C" int host_bits_intersect(const uint32_t* a, const uint32_t* b, int64_t
     return 0;
 }
 
+extern "C" int host_group_scores(const float* feat, const float* centroids, float* scores, int C, int Kc, int h, int w, int metric) {
+    if (!(C > 0 && Kc > 0 && Kc <= kMaxGroupCentroids)) return -1;
+    const int hw = h * w;
+    launch(dim3((unsigned)((hw + 31) / 32)), dim3(256), [&] { group_scores_kernel(feat, centroids, scores, C, Kc, hw, metric); });
+    return 0;
+}
+
 extern "C" int host_group_affinity_resized(const float* feat, const float* centroids, const uint8_t* mask, int32_t* labels,
                                            int C, int Kc, int h, int w, int Hp, int Wp, int Hi, int Wi, int Ho, int Wo,
                                            int metric) {

@@ -136,8 +136,10 @@ def test_product_never_imports_oracle():
 
 
 def test_bench_reference_arm_contract():
-    """`bench.py --impl reference` (the oracle port on the host cores; no GPU needed) prints ONE JSON line with the keys
-    the driver reads, and under a multi-rank launch only rank 0 works."""
+    """`bench.py --impl reference` (the reference's CPU implementation of the step on the host cores; no GPU needed) prints
+    ONE JSON line with the keys the driver reads, and under a multi-rank launch only rank 0 works.  kind = "reference" (the
+    unmodified reference through oracle/ref_loader.py) when a reference tree resolves, "port" (oracle/m2f_oracle.py) otherwise;
+    both arms are run."""
     import json
     import subprocess
     import sys
@@ -146,17 +148,23 @@ def test_bench_reference_arm_contract():
     out = subprocess.run([sys.executable, bench, "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and out.stdout.strip() == ""
-    out = subprocess.run([sys.executable, bench, "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                         capture_output=True, text=True, timeout=900)
-    assert out.returncode == 0, out.stderr[-2000:]
-    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
-    assert len(lines) == 1
-    line = json.loads(lines[0])
-    assert line["impl"] == "reference" and line["unit"] == "images/s" and line["higher_is_better"] is True
-    assert line["value"] > 0 and line["steps"] == 1 and line["n_gpus"] == 1
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
-    assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in line["config"] and "model" not in line["config"]
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_loader
+    arms = [({}, "reference" if ref_loader.available() else "port")]
+    if ref_loader.available():
+        arms.append(({"PD_REFERENCE_ROOT": "/nonexistent"}, "port"))
+    for extra, kind in arms:
+        out = subprocess.run([sys.executable, bench, "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                             capture_output=True, text=True, timeout=900, env=dict(os.environ, **extra))
+        assert out.returncode == 0, out.stderr[-2000:]
+        lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+        assert len(lines) == 1
+        line = json.loads(lines[0])
+        assert line["impl"] == "reference" and line["unit"] == "images/s" and line["higher_is_better"] is True
+        assert line["value"] > 0 and line["steps"] == 1 and line["warmup"] == 0 and line["n_gpus"] == 1
+        assert line["cpu_baseline"]["kind"] == kind and line["cpu_baseline"]["cores"] >= 1
+        assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        assert "workload" in line["config"] and "model" not in line["config"] and line["config"]["global_batch"] == 2
 
 
 def test_criterion_batch_without_targets(monkeypatch):

@@ -12,7 +12,7 @@ import test_engine as engine_tests
 import test_ops_gpu as gpu_tests
 from host_kernels import NAMESPACE_BLOCK, ROOT, build_host_library, dynamic_smem, patch_functional
 
-OPS = ("grad_sumsq", "adamw_flat", "group_affinity", "attn_mask_build", "attn_mask_reset_rows")
+OPS = ("grad_sumsq", "adamw_flat", "group_affinity", "group_scores", "attn_mask_build", "attn_mask_reset_rows")
 
 
 @pytest.fixture(scope="module")

@@ -172,7 +172,7 @@ def host_kernels(tmp_path_factory):
 
     lib = HostLib()
     for name in ("postprocess_masks", "resize_masks_u8", "pack_bits", "unpack_bits", "bits_popcount", "bits_intersect",
-                 "group_affinity_resized"):
+                 "group_affinity_resized", "group_scores"):
         f = getattr(cdll, "host_" + name)
         res, args = _lib.SIGNATURES["pdb_" + name]
         f.restype, f.argtypes = res, args[:-1]

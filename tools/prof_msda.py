@@ -34,4 +34,14 @@ for _ in range(3):
     if which in ("all", "bwd"):
         out = fn.ms_deform_attn(value, shapes, None, loc, attn)
         torch.autograd.grad(out, (value, loc, attn), torch.ones_like(out))
+if which in ("all", "einsum"):
+    B, Q, C, H, W = 2, 100, 256, 256, 256
+    e = torch.randn(B, Q, C, device="cuda")
+    e_lo = fn.split_lo(e)
+    fs = [torch.randn(B, C, H, W, device="cuda").contiguous(memory_format=torch.channels_last) for _ in range(3)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    with torch.no_grad():
+        for f in fs:
+            flush.zero_()
+            fn.mask_einsum(e, f, embed_lo=e_lo)
 torch.cuda.synchronize()
