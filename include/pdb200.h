@@ -279,6 +279,11 @@ PDB_API int pdb_group_affinity(const float* feat, const float* centroids, const 
  * near-ties of the two best scores (different rounding order). */
 PDB_API int pdb_group_scores(const float* feat, const float* centroids, float* scores, int C, int Kc, int h, int w, int metric,
                      void* stream);
+/* B images of one geometry in TWO launches (both stages batched over the grid): feat (B, C, h, w), centroids (B, Kc, C),
+ * mask / labels (B, H, W); scores: workspace of B*Kc*h*w floats; identity: the Kc x Kc identity matrix (device). */
+PDB_API int pdb_group_affinity_batched(const float* feat, const float* centroids, const uint8_t* mask, int32_t* labels,
+                               float* scores, const float* identity, int B, int C, int Kc, int h, int w, int H, int W,
+                               int metric, void* stream);
 /* Same, for an evaluation size different from the padded batch size (pixel_grouping_model.py:139-160,
  * proposal_generation_model.py:139-155): feat (C, h, w) -> bilinear -> (Hp, Wp) -> crop (Hi, Wi) -> bilinear -> (Ho, Wo)
  * (detectron2 sem_seg_postprocess), both passes composed per output pixel; mask and labels are (Ho, Wo). */

@@ -49,6 +49,7 @@ SIGNATURES = {
     "pdb_group_norm_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _l, _i, _i, _f, _i, _p]),
     "pdb_group_norm_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _l, _i, _i, _i, _p]),
     "pdb_group_affinity": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "pdb_group_affinity_batched": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "pdb_group_scores": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "pdb_group_affinity_resized": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "pdb_grad_sumsq": (_i, [_p, _l, _f, _p, _p]),

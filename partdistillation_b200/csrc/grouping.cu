@@ -19,9 +19,13 @@ constexpr int kMaxCentroids = 16;
 
 __global__ void __launch_bounds__(256)
 group_affinity_kernel(const float* __restrict__ feat, const float* __restrict__ centroids, const uint8_t* __restrict__ mask,
-                      int32_t* __restrict__ labels, int C, int Kc, int h, int w, int H, int W, int l2) {
+                      int32_t* __restrict__ labels, int C, int Kc, int h, int w, int H, int W, int l2, int64_t cent_stride) {
     extern __shared__ float s_cent[];       // [C][Kc] + |c_k|^2 [Kc]
     float* s_norm = s_cent + C * Kc;
+    feat += (int64_t)blockIdx.z * C * h * w;                // blockIdx.z = image of the batch (cent_stride 0: shared centroids)
+    centroids += (int64_t)blockIdx.z * cent_stride;
+    mask += (int64_t)blockIdx.z * H * W;
+    labels += (int64_t)blockIdx.z * H * W;
     for (int i = threadIdx.x; i < C * Kc; i += blockDim.x) {
         const int c = i / Kc, k = i - c * Kc;
         s_cent[i] = __ldg(centroids + k * C + c);
@@ -91,7 +95,26 @@ extern "C" int pdb_group_affinity(const float* feat, const float* centroids, con
         attr_smem = smem;
     }
     dim3 grid((unsigned)((W + 31) / 32), (unsigned)((H + 7) / 8));
-    group_affinity_kernel<<<grid, 256, smem, as_stream(stream)>>>(feat, centroids, mask, labels, C, Kc, h, w, H, W, metric);
+    group_affinity_kernel<<<grid, 256, smem, as_stream(stream)>>>(feat, centroids, mask, labels, C, Kc, h, w, H, W, metric, 0);
+    return launched("group_affinity");
+}
+
+// B images of one geometry in two launches: score maps at feature resolution (pdb_group_scores per image, grid.y = B), then
+// the per-pixel interpolation + argmax on the Kc score maps (identity centroids).  scores: workspace (B, Kc, h, w) floats.
+extern "C" int pdb_group_affinity_batched(const float* feat, const float* centroids, const uint8_t* mask, int32_t* labels,
+                                          float* scores, const float* identity, int B, int C, int Kc, int h, int w, int H, int W,
+                                          int metric, void* stream) {
+    PDB_REQUIRE(feat && centroids && mask && labels && scores && identity, "group_affinity_batched: null pointer");
+    PDB_REQUIRE(B > 0 && B <= 65535 && C > 0 && Kc > 0 && Kc <= kMaxCentroids && h > 0 && w > 0 && H > 0 && W > 0,
+                "group_affinity_batched: bad sizes (1 <= Kc <= %d, B <= 65535)", kMaxCentroids);
+    PDB_REQUIRE(metric == 0 || metric == 1, "group_affinity_batched: metric %d (0 = dot, 1 = l2)", metric);
+    const int hw = h * w;
+    group_scores_kernel<<<dim3((unsigned)((hw + 31) / 32), (unsigned)B), 256, 0, as_stream(stream)>>>(feat, centroids, scores, C, Kc,
+                                                                                                     hw, metric);
+    PDB_TRY(launched("group_scores"));
+    const size_t smem = sizeof(float) * ((size_t)Kc * Kc + Kc);
+    dim3 grid((unsigned)((W + 31) / 32), (unsigned)((H + 7) / 8), (unsigned)B);
+    group_affinity_kernel<<<grid, 256, smem, as_stream(stream)>>>(scores, identity, mask, labels, Kc, Kc, h, w, H, W, 0, 0);
     return launched("group_affinity");
 }
 

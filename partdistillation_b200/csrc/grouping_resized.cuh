@@ -26,6 +26,9 @@ __global__ void __launch_bounds__(256)
 group_scores_kernel(const float* __restrict__ feat, const float* __restrict__ centroids, float* __restrict__ scores, int C,
                     int Kc, int hw, int l2) {
     __shared__ float s_part[8][kMaxGroupCentroids][33];
+    feat += (int64_t)blockIdx.y * C * hw;                  // blockIdx.y = image of the batch
+    centroids += (int64_t)blockIdx.y * Kc * C;
+    scores += (int64_t)blockIdx.y * Kc * hw;
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int p = blockIdx.x * 32 + lane;
     float acc[kMaxGroupCentroids], nrm[kMaxGroupCentroids];

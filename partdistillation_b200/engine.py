@@ -106,7 +106,12 @@ class DataParallelTrainer:
     ``all_reduce`` (world > 1), ``pdb_grad_sumsq`` and ``pdb_adamw_flat`` — two kernel launches instead of one
     fused-AdamW launch per parameter group (the reference builds one group per parameter, base_trainer.py:76-116).
     Parameters of other dtypes (PartDistillation's fp64 classifier) and CPU models (the gloo tests of the
-    sharding / all-reduce logic) are stepped by ``torch.optim.AdamW`` with the same clip coefficient."""
+    sharding / all-reduce logic) are stepped by ``torch.optim.AdamW`` with the same clip coefficient.
+
+    Differences from torch.optim.AdamW to know about: (1) the flat kernel updates EVERY segment each step, so a trainable
+    parameter that receives no gradient in a step still sees weight decay and moment decay (torch skips ``grad is None``);
+    every trainable parameter of the two meta-architectures is used in every training forward, so the hot path never hits
+    this.  (2) With world > 1 the constructor broadcasts rank 0's parameters and buffers (``broadcast_parameters``)."""
 
     def __init__(self, model, base_lr=1e-4, weight_decay=0.05, clip_norm=0.01, freeze_keys=("backbone", "encoder"),
                  backbone_multiplier=0.1, betas=(0.9, 0.999), eps=1e-8, cuda_graph=False):
@@ -166,6 +171,85 @@ class DataParallelTrainer:
         self.grad_bytes = sum(b.numel() * b.element_size() for b in self.flat.values())
         self.lr_schedule = None
         self.iteration = 0                  # optimizer steps taken through step() (graph replays included)
+        self.max_graphs = 8                 # captured steps kept alive (least recently used signature is dropped)
+        if self.world > 1:
+            self.broadcast_parameters()
+
+    def broadcast_parameters(self, src=0):
+        """What DistributedDataParallel does at construction (detectron2 wraps the reference's model in it,
+        train_net.py -> DefaultTrainer): every rank starts from rank `src`'s parameters and buffers, whatever seed it
+        initialised its own randomly-initialised decoder / head with.  Frozen parameters are included (a checkpoint loaded
+        on rank 0 only must reach every rank)."""
+        if self.flat_param is not None:
+            dist.broadcast(self.flat_param, src)
+        flat_ids = {id(p) for p in self.params if p.dtype == torch.float32 and p.is_cuda} if self.flat_param is not None else set()
+        with torch.no_grad():
+            for p in self.model.parameters():
+                if id(p) not in flat_ids:
+                    dist.broadcast(p.data, src)
+            for b in self.model.buffers():
+                dist.broadcast(b, src)
+
+    # ------------------------------------------------------------------------------------------ checkpointing
+    def state_dict(self):
+        """Optimizer / schedule state in torch.optim.AdamW's own layout — one param group per parameter, in the order
+        `build_param_groups` emits them (the reference's optimizer has the same structure, base_trainer.py:76-116), state[i] =
+        {"step", "exp_avg", "exp_avg_sq"} — so a checkpoint written by the reference's DefaultTrainer loads here and vice
+        versa, plus ``iteration`` (the LR-schedule position)."""
+        state, groups = {}, []
+        flat_i = 0
+        other = self.optimizer.state_dict() if self.optimizer is not None else None
+        other_i = 0
+        for i, p in enumerate(self.params):
+            if self.flat_param is not None and p.dtype == torch.float32 and p.is_cuda:
+                st, n = int(self.seg_start[flat_i]), p.numel()
+                base_lr = float(self.seg_lr_base[flat_i]) if hasattr(self, "seg_lr_base") else float(self.seg_lr[flat_i])
+                state[i] = {"step": self.step_dev.detach().to(torch.float32).reshape(()).clone(),
+                            "exp_avg": self.flat_m[st:st + n].view(p.shape).clone(),
+                            "exp_avg_sq": self.flat_v[st:st + n].view(p.shape).clone()}
+                groups.append({"lr": base_lr, "weight_decay": float(self.seg_wd[flat_i]), "betas": tuple(self.betas),
+                               "eps": self.eps, "params": [i]})
+                flat_i += 1
+            else:
+                g = other["param_groups"][other_i]
+                if other_i in other["state"]:
+                    state[i] = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in other["state"][other_i].items()}
+                groups.append({"lr": float(g.get("base_lr", g["lr"])), "weight_decay": g["weight_decay"], "betas": g["betas"],
+                               "eps": g["eps"], "params": [i]})
+                other_i += 1
+        return {"state": state, "param_groups": groups, "iteration": self.iteration}
+
+    def load_state_dict(self, sd):
+        """Inverse of ``state_dict`` (also accepts a plain torch.optim.AdamW state dict with one group per parameter)."""
+        if len(sd["param_groups"]) != len(self.params):
+            raise ValueError(f"optimizer state has {len(sd['param_groups'])} groups, the model {len(self.params)} parameters")
+        flat_i = other_i = 0
+        other_state = {}
+        steps = []
+        for i, p in enumerate(self.params):
+            st_i = sd["state"].get(i)
+            if self.flat_param is not None and p.dtype == torch.float32 and p.is_cuda:
+                st, n = int(self.seg_start[flat_i]), p.numel()
+                if st_i is not None:
+                    self.flat_m[st:st + n].copy_(st_i["exp_avg"].reshape(-1))
+                    self.flat_v[st:st + n].copy_(st_i["exp_avg_sq"].reshape(-1))
+                    steps.append(int(st_i["step"]))
+                flat_i += 1
+            else:
+                if st_i is not None:           # copies: torch's load_state_dict aliases tensors of matching dtype / device
+                    other_state[other_i] = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st_i.items()}
+                other_i += 1
+        if steps:
+            if len(set(steps)) != 1:
+                raise ValueError("per-parameter step counts differ: the flat AdamW kernel keeps ONE step counter")
+            self.step_dev.fill_(steps[0])
+            self.step_count = steps[0]
+        if self.optimizer is not None and other_state:
+            cur = self.optimizer.state_dict()
+            cur["state"] = other_state
+            self.optimizer.load_state_dict(cur)
+        self.iteration = int(sd.get("iteration", steps[0] if steps else 0))
+        self._graphs.clear()                # captured steps hold the old python-side state
 
     def set_lr_schedule(self, schedule):
         """``schedule.factor(iteration)`` scales every group's learning rate before each step.  The rates live in device
@@ -291,7 +375,10 @@ class DataParallelTrainer:
             return out
         sig = tuple((tuple(d["image"].shape), tuple(d["instances"].gt_masks.tensor.shape),
                      d.get("gt_object_class")) for d in batched_inputs)
-        entry = self._graphs.setdefault(sig, {"warm": 0})
+        entry = self._graphs.pop(sig, None) or {"warm": 0}
+        self._graphs[sig] = entry                       # most recently used last
+        while len(self._graphs) > self.max_graphs:      # bounded: variable per-image mask counts re-capture, they must not leak
+            self._graphs.pop(next(iter(self._graphs)))
         if "graph" not in entry:
             if self._side is None:
                 self._side = torch.cuda.Stream()
@@ -323,6 +410,9 @@ class DataParallelTrainer:
             self._global_num_masks(batched_inputs)
         entry["graph"].replay()
         self.pdb_launches += entry["launches"]
+        if self.world == 1:
+            from . import functional as PF
+            PF.weights_epoch += 1          # the replayed AdamW changed the weights: cached pre-split low parts are stale
         if self.world > 1:
             n0 = _lib.launch_count()
             self.reduce_gradients()

@@ -721,6 +721,13 @@ def linear(x, weight, bias=None, relu=False, gelu=False):
                 return torch.nn.functional.gelu(LinearFunction.apply(x, weight, bias, False))
             return LinearFunction.apply(x, weight, bias, 2)
         return LinearFunction.apply(x, weight, bias, relu)
+    if (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and weight.shape[1] % 4 == 0
+            and weight.shape[0] % 4 != 0):
+        # ragged head (the 2-column class_embed of the proposal model): zero rows up to a multiple of 4, same tensor-core GEMM
+        n, pad = weight.shape[0], (-weight.shape[0]) % 4
+        w = torch.nn.functional.pad(weight, (0, 0, 0, pad))
+        b = None if bias is None else torch.nn.functional.pad(bias, (0, pad))
+        return linear(x, w, b, relu=relu, gelu=gelu)[..., :n]
     y = torch.nn.functional.linear(x, weight.to(x.dtype), None if bias is None else bias.to(x.dtype))
     if gelu:
         return torch.nn.functional.gelu(y)
@@ -764,6 +771,27 @@ def group_affinity(feat, centroids, mask, metric="dot", geometry=None, two_stage
     rc = _lib.load().pdb_group_affinity(feat.data_ptr(), centroids.data_ptr(), mask.data_ptr(), labels.data_ptr(), C, Kc, h, w,
                                         H, W, 0 if metric == "dot" else 1, _stream())
     _lib.check(rc, "pdb_group_affinity")
+    return labels
+
+
+def group_affinity_batched(feats, centroids, masks, metric="dot"):
+    """B images of one geometry in two launches: feats (B, C, h, w) f32, centroids (B, Kc, C), masks (B, H, W) bool/uint8 ->
+    labels (B, H, W) int32, image by image what ``group_affinity`` returns."""
+    _need_cuda(feats, centroids, masks)
+    if metric not in ("dot", "l2"):
+        raise ValueError(f"distance metric {metric!r} (dot / l2)")
+    feats, centroids = _c(feats.float()), _c(centroids.float())
+    masks = _c(masks).view(torch.uint8) if masks.dtype == torch.bool else _c(masks.to(torch.uint8))
+    B, C, h, w = feats.shape
+    Kc = centroids.shape[1]
+    H, W = masks.shape[1:]
+    labels = torch.empty((B, H, W), dtype=torch.int32, device=feats.device)
+    scores = torch.empty((B, Kc, h, w), dtype=torch.float32, device=feats.device)
+    eye = host_table(torch.eye(Kc).flatten().tolist(), torch.float32, feats.device)
+    rc = _lib.load().pdb_group_affinity_batched(feats.data_ptr(), centroids.data_ptr(), masks.data_ptr(), labels.data_ptr(),
+                                                scores.data_ptr(), eye.data_ptr(), B, C, Kc, h, w, H, W,
+                                                0 if metric == "dot" else 1, _stream())
+    _lib.check(rc, "pdb_group_affinity_batched")
     return labels
 
 

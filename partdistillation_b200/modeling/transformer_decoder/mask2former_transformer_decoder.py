@@ -67,10 +67,12 @@ class SelfAttentionLayer(nn.Module):
         x = self.norm(tgt) if self.normalize_before else tgt
         qk_in = x if query_pos is None else x + query_pos
         B, Q, E = x.shape
-        qk = a.project(qk_in, 0, 2).view(B, Q, 2, a.num_heads, a.head_dim)
-        v = a.project(x, 2, 3).view(B, Q, a.num_heads, a.head_dim)
-        o = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2), v.transpose(1, 2))
-        o = PF.linear(o.transpose(1, 2).reshape(B, Q, E), a.out_proj.weight, a.out_proj.bias)
+        qk = a.project(qk_in, 0, 2)                                    # (B, Q, 2E): one GEMM for the query and key projections
+        v = a.project(x, 2, 3)
+        # the attention core is the library's own kernel (csrc/xattn.cu) with no mask: softmax(q k^T / sqrt(d)) v per head
+        o = PF.masked_cross_attention((qk[..., :E] * (1.0 / math.sqrt(a.head_dim))).float(), qk[..., E:].float(), v.float(),
+                                      None, None, a.num_heads)
+        o = PF.linear(o.to(x.dtype), a.out_proj.weight, a.out_proj.bias)
         return tgt + o if self.normalize_before else PF.layer_norm(tgt, self.norm.weight, self.norm.bias, self.norm.eps, residual=o)
 
 
@@ -204,7 +206,7 @@ class MultiScaleMaskedTransformerDecoder(nn.Module):
         return mem, mem_pos, sizes
 
     def _classify(self, decoder_output, targets):
-        return self.class_embed(decoder_output)
+        return PF.linear(decoder_output, self.class_embed.weight, self.class_embed.bias)
 
     def forward(self, x, mask_features, mask=None):
         assert len(x) == self.num_feature_levels

@@ -42,7 +42,7 @@ extern "C" int host_group_affinity(const float* feat, const float* centroids, co
     if (!(C > 0 && Kc > 0 && Kc <= kMaxCentroids)) return -1;
     const size_t smem = sizeof(float) * ((size_t)C * Kc + Kc);
     launch(dim3((unsigned)((W + 31) / 32), (unsigned)((H + 7) / 8)), dim3(256), smem,
-           [&] { group_affinity_kernel(feat, centroids, mask, labels, C, Kc, h, w, H, W, metric); });
+           [&] { group_affinity_kernel(feat, centroids, mask, labels, C, Kc, h, w, H, W, metric, 0); });
     return 0;
 }
 

@@ -38,9 +38,9 @@ def _worker(rank, world, port, out_path):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from partdistillation_b200.engine import DataParallelTrainer
-    torch.manual_seed(0)
+    torch.manual_seed(rank)                 # every rank initialises differently (the reference seeds with seed + rank) ...
     model = _Tiny()
-    tr = DataParallelTrainer(model, base_lr=1e-2, weight_decay=0.05, clip_norm=0.5, freeze_keys=())
+    tr = DataParallelTrainer(model, base_lr=1e-2, weight_decay=0.05, clip_norm=0.5, freeze_keys=())   # ... rank 0 is broadcast
     for step in range(3):
         tr.step(_data(100 * step + rank))
     torch.save({k: v.clone() for k, v in model.state_dict().items()}, f"{out_path}.{rank}")
@@ -159,3 +159,46 @@ def test_trainer_applies_lr_schedule_cpu():
     assert tr.iteration == 4
     for (k, va), vb in zip(a.state_dict().items(), b.state_dict().values()):
         assert torch.allclose(va, vb, rtol=1e-5, atol=1e-7), k
+
+
+def test_trainer_state_dict_round_trip_cpu():
+    """Checkpoint / resume (the reference's DefaultTrainer saves optimizer, scheduler and iteration): a trainer restored from
+    model + trainer state continues exactly like the one that kept running, and the state loads into a plain
+    torch.optim.AdamW with the reference's one-group-per-parameter layout."""
+    from partdistillation_b200.engine import DataParallelTrainer, WarmupMultiStepLR, build_param_groups
+    sched = WarmupMultiStepLR([3], gamma=0.1, warmup_factor=0.1, warmup_iters=2)
+    torch.manual_seed(0)
+    a = _Tiny()
+    ta = DataParallelTrainer(a, base_lr=1e-2, weight_decay=0.05, clip_norm=0.5, freeze_keys=())
+    ta.set_lr_schedule(sched)
+    for step in range(2):
+        ta.step(_data(step))
+    ckpt = {"model": {k: v.clone() for k, v in a.state_dict().items()}, "trainer": ta.state_dict()}
+    assert ckpt["trainer"]["iteration"] == 2 and len(ckpt["trainer"]["param_groups"]) == len(ta.params)
+    b = _Tiny()
+    b.load_state_dict(ckpt["model"])
+    tb = DataParallelTrainer(b, base_lr=1e-2, weight_decay=0.05, clip_norm=0.5, freeze_keys=())
+    tb.set_lr_schedule(sched)
+    tb.load_state_dict(ckpt["trainer"])
+    assert tb.iteration == 2
+    # the same state in a plain torch optimizer
+    c = _Tiny()
+    c.load_state_dict(ckpt["model"])
+    groups = build_param_groups(c, 1e-2, 0.05, freeze_keys=())
+    opt = torch.optim.AdamW(groups, lr=1e-2)
+    tsd = {"state": ckpt["trainer"]["state"], "param_groups": [dict(g, **{k: v for k, v in og.items() if k not in g})
+                                                               for g, og in zip(ckpt["trainer"]["param_groups"],
+                                                                                opt.state_dict()["param_groups"])]}
+    opt.load_state_dict(tsd)
+    for step in range(2, 5):
+        ta.step(_data(step))
+        tb.step(_data(step))
+        for g in opt.param_groups:
+            g["lr"] = 1e-2 * sched.factor(step)
+        opt.zero_grad()
+        sum(c(_data(step)).values()).backward()
+        torch.nn.utils.clip_grad_norm_([p for g in groups for p in g["params"]], 0.5)
+        opt.step()
+    for (k, va), vb, vc in zip(a.state_dict().items(), b.state_dict().values(), c.state_dict().values()):
+        assert torch.equal(va, vb), k
+        assert torch.allclose(va, vc, rtol=1e-5, atol=1e-7), k

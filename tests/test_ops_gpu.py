@@ -765,3 +765,17 @@ def test_msda_half_staged_value(fn, shapes, N, spread):
     vg2 = vc.clone().requires_grad_()
     (gv2,) = torch.autograd.grad(fn.ms_deform_attn(vg2, shapes, None, lc, ac), vg2, torch.ones_like(out))
     assert torch.allclose(gv, gv2, rtol=1e-5, atol=1e-6)          # backward is the fp32 one
+
+
+def test_group_affinity_batched_equals_per_image(fn):
+    """pdb_group_affinity_batched (two launches for the whole batch) labels every image as the per-image call does."""
+    g = torch.Generator().manual_seed(21)
+    B, C, Kc = 5, 96, 4
+    feats = torch.randn(B, C, 20, 24, generator=g).cuda()
+    cents = torch.randn(B, Kc, C, generator=g).cuda()
+    masks = (torch.rand(B, 160, 192, generator=g) > 0.3).cuda()
+    for metric in ("dot", "l2"):
+        got = fn.group_affinity_batched(feats, cents, masks, metric)
+        exp = torch.stack([fn.group_affinity(feats[b], cents[b], masks[b], metric) for b in range(B)])
+        assert torch.equal(got, exp)
+        assert (got[~masks] == 0).all() and (got[masks] >= 1).all()
