@@ -190,11 +190,12 @@ def test_trainer_state_dict_round_trip_cpu():
                                                                for g, og in zip(ckpt["trainer"]["param_groups"],
                                                                                 opt.state_dict()["param_groups"])]}
     opt.load_state_dict(tsd)
+    base = [g["lr"] for g in opt.param_groups]              # the state dict carries the un-scheduled per-group rates
     for step in range(2, 5):
         ta.step(_data(step))
         tb.step(_data(step))
-        for g in opt.param_groups:
-            g["lr"] = 1e-2 * sched.factor(step)
+        for g, lr in zip(opt.param_groups, base):
+            g["lr"] = lr * sched.factor(step)
         opt.zero_grad()
         sum(c(_data(step)).values()).backward()
         torch.nn.utils.clip_grad_norm_([p for g in groups for p in g["params"]], 0.5)
