@@ -115,6 +115,14 @@ PDB_API int pdb_gemm_tf32x3(const float* A, const float* B, const float* B_lo, f
                     int K, int batch,
                     int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc, int a_mn, int b_mn,
                     int c_trans, int relu, int accumulate, int ksplit, void* stream);
+/* bf16 contraction on the tensor cores (tcgen05 kind::f16, fp32 accumulation) for the autocast path (BASELINE configs[2]; the
+ * reference trains under AMP: Base-COCO-InstanceSegmentation.yaml:34-35) — replaces the cuBLAS bf16 GEMM behind nn.Linear of the
+ * Swin backbone and the transformer decoder under torch.autocast:
+ *   C[m][n] = sum_k A[m*lda + k] * B[n*ldb + k]  (+ bias[n]) (act: 0 none, 1 ReLU, 2 GELU)
+ * A (M x K), B (N x K): bf16, K contiguous, 16-byte aligned, K / lda / ldb multiples of 8; bias fp32 or NULL;
+ * C row-major with pitch ldc, fp32 (out_bf16 = 0) or bf16 (out_bf16 = 1). */
+PDB_API int pdb_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int64_t lda, int64_t ldb,
+                  int64_t ldc, int act, int out_bf16, void* stream);
 /* Convolution-shaped variant: K = taps * Ck, and the k range of tap t reads the A rows shifted by tap_off[t]:
  *   C_b[m][n] = sum_t sum_c A_b[m + tap_off[t]][c] * B[n][t * Ck + c]  (+ bias[n]) (ReLU)
  * A_b = A + b*sa is (a_rows x Ck), K-major, rows beyond a_rows read as 0; B is (N x taps*Ck), K-major, shared by all batch

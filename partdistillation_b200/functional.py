@@ -209,7 +209,14 @@ class MaskEinsumFunction(Function):
 
 def mask_einsum(mask_embed, mask_features, embed_lo=None, presplit=True):
     """torch.einsum("bqc,bchw->bqhw") (mask2former_transformer_decoder.py:449).  The tiny embed operand is pre-split into its
-    tf32 hi / lo parts by one extra launch (presplit) unless the caller hands in embed_lo = split_lo(mask_embed) itself."""
+    tf32 hi / lo parts by one extra launch (presplit) unless the caller hands in embed_lo = split_lo(mask_embed) itself.
+    Under bf16 autocast the embed arrives as bf16 (output of the mask MLP); the contraction itself stays on the fp32-accurate
+    kernel (the reference's autocast einsum rounds operands AND the mask logits to bf16; keeping fp32 here is the more precise
+    side of the documented tolerance)."""
+    if mask_embed.dtype != torch.float32:
+        mask_embed = mask_embed.float()
+    if mask_features.dtype != torch.float32:
+        mask_features = mask_features.float()
     if embed_lo is None and presplit and mask_embed.is_cuda and mask_embed.dtype == torch.float32 \
             and mask_embed.numel() % 4 == 0:
         embed_lo = split_lo(_c(mask_embed.detach()))
@@ -438,6 +445,7 @@ class ClassRowsFunction(Function):
         _lib.check(rc, "pdb_class_rows_forward")
         ctx.save_for_backward(x, weight, obj)
         ctx.num_parts = num_parts
+        ctx.bias_ref = bias
         return out
 
     @staticmethod
@@ -448,13 +456,18 @@ class ClassRowsFunction(Function):
         Ncls = weight.shape[0]
         grad_out = _c(grad_out.double())
         gx = torch.empty_like(x)
-        gw = torch.zeros_like(weight)                     # dense zero rows: AdamW parity with the reference
-        gb = torch.zeros((Ncls,), dtype=torch.float64, device=x.device)
+        # The kernel ADDS the <= B*(P+1) touched rows into its gradient buffers.  When the trainer has pre-allocated the
+        # (zero-filled, flat) fp64 gradients, the rows go straight into them and autograd gets None — no dense 360 MB zero
+        # tensor + accumulation per decoder layer (O = 22 000 x P = 8 classes: part_distillation_transformer_decoder.py:107).
+        direct = (weight.grad is not None and weight.grad.dtype == torch.float64 and weight.grad.is_contiguous()
+                  and ctx.bias_ref.grad is not None and ctx.bias_ref.grad.dtype == torch.float64)
+        gw = weight.grad if direct else torch.zeros_like(weight)       # dense zero rows otherwise: AdamW parity with the reference
+        gb = ctx.bias_ref.grad if direct else torch.zeros((Ncls,), dtype=torch.float64, device=x.device)
         rc = _lib.load().pdb_class_rows_backward(x.data_ptr(), weight.data_ptr(), obj.data_ptr(), grad_out.data_ptr(),
                                                  gx.data_ptr(), gw.data_ptr(), gb.data_ptr(), B, Q, C, ctx.num_parts, Ncls,
                                                  _stream())
         _lib.check(rc, "pdb_class_rows_backward")
-        return gx, gw, gb, None, None
+        return (gx, None, None, None, None) if direct else (gx, gw, gb, None, None)
 
 
 def class_rows(x, weight, bias, obj, num_parts):
@@ -698,6 +711,91 @@ class Conv3x3Function(Function):
         return gx, gw, gb
 
 
+# --------------------------------------------------------------------------------------------------
+# bf16 autocast path: nn.Linear on tcgen05 kind::f16 (csrc/gemm_bf16.cu)
+# --------------------------------------------------------------------------------------------------
+def gemm_bf16(a, b, bias=None, act=0, out_dtype=torch.bfloat16):
+    """a (M, K), b (N, K) bf16 with contiguous rows -> a @ b^T (+ bias) (act) as (M, N) bf16 or fp32."""
+    _need_cuda(a, b)
+    M, K = a.shape
+    N = b.shape[0]
+    out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    if M and N:
+        rc = _lib.load().pdb_gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), None if bias is None else bias.data_ptr(), M, N, K,
+                                       a.stride(0), b.stride(0), N, int(act), 1 if out_dtype == torch.bfloat16 else 0, _stream())
+        _lib.check(rc, "pdb_gemm_bf16")
+    return out
+
+
+_bf16_weights = {}
+
+
+def weight_bf16(weight, transposed=False):
+    """bf16 copy of a weight (optionally transposed), cached until the weight changes (optimizer step / load)."""
+    key = (weight.data_ptr(), tuple(weight.shape), transposed)
+    tag = (weight._version, weights_epoch)
+    hit = _bf16_weights.get(key)
+    if hit is None or hit[0] != tag:
+        if len(_bf16_weights) > 4096:
+            _bf16_weights.clear()
+        w = weight.detach()
+        hit = _bf16_weights[key] = (tag, (w.t() if transposed else w).to(torch.bfloat16).contiguous())
+    return hit[1]
+
+
+def _rows8(t):
+    """(R, M) bf16 with contiguous rows and M padded to a multiple of 8 with zeros (the contraction length of a GEMM)."""
+    R, M = t.shape
+    if M % 8 == 0:
+        return _c(t)
+    out = torch.zeros((R, (M + 7) // 8 * 8), dtype=t.dtype, device=t.device)
+    out[:, :M] = t
+    return out
+
+
+class LinearBF16Function(Function):
+    """nn.Linear under bf16 autocast: y = x W^T + b (optionally ReLU / GELU in the epilogue), operands bf16, accumulation fp32,
+    output bf16 — what torch.autocast makes of F.linear; the bias stays fp32 inside the epilogue.  Backward: dx = dy W and
+    dW = dy^T x on the same kernel (bf16 operands, dW accumulated and returned in fp32), db = column sums in fp32."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        _need_cuda(x, weight)
+        N, K = weight.shape
+        x2 = _c(x.reshape(-1, K).to(torch.bfloat16))
+        if x2.data_ptr() % 16:
+            x2 = x2.clone()
+        # torch.autocast casts the bias to bf16 as well; the epilogue adds its fp32 image to the fp32 accumulator
+        y = gemm_bf16(x2, weight_bf16(weight), None if bias is None else _c(bias.to(torch.bfloat16).float()), act)
+        ctx.save_for_backward(x2, weight, y if act == 1 else None)
+        ctx.meta = (tuple(x.shape), x.dtype, bias is not None, act)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x2, weight, y = ctx.saved_tensors
+        shape, xdtype, has_bias, act = ctx.meta
+        N, K = weight.shape
+        gy = gy.reshape(-1, N).to(torch.bfloat16)
+        if act == 1:
+            gy = gy * (y > 0)
+        gy = _c(gy)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm_bf16(gy, weight_bf16(weight, transposed=True)).view(shape).to(xdtype)
+        if ctx.needs_input_grad[1]:
+            gw = gemm_bf16(_rows8(gy.t()), _rows8(x2.t()), out_dtype=torch.float32).to(weight.dtype)
+        if has_bias and ctx.needs_input_grad[2]:
+            gb = gy.float().sum(0)
+        return gx, gw, gb, None
+
+
+def _autocast_bf16(x, weight):
+    return (x.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16
+            and weight.dtype in (torch.float32, torch.bfloat16) and weight.shape[1] % 8 == 0)
+
+
 def conv3x3(x, weight, bias=None):
     """F.conv2d(kernel 3, stride 1, padding 1) on the tensor cores for fp32 CUDA tensors with channel counts that are
     multiples of 32; returns the logical NCHW result in channels-last memory."""
@@ -712,7 +810,15 @@ def linear(x, weight, bias=None, relu=False, gelu=False):
     """nn.Linear (optionally fused ReLU) on the tensor cores for fp32 CUDA tensors whose feature sizes are
     multiples of 4; other dtypes (autocast halves, the fp64 classifier) and tiny ragged heads go through
     the library GEMM.  gelu=True applies nn.GELU() (erf form); it is folded into the GEMM epilogue when nothing
-    on the path needs a gradient (the frozen backbone), otherwise it runs as a separate differentiable op."""
+    on the path needs a gradient (the frozen backbone), otherwise it runs as a separate differentiable op.
+    Under torch.autocast(bfloat16) (and for bf16 inputs) the product runs on the bf16 tensor-core kernel and returns bf16."""
+    if _autocast_bf16(x, weight) or (x.is_cuda and x.dtype == torch.bfloat16 and weight.shape[1] % 8 == 0
+                                     and weight.dtype in (torch.float32, torch.bfloat16)):
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or
+                                                  (bias is not None and bias.requires_grad))
+        if gelu and needs_grad:
+            return torch.nn.functional.gelu(LinearBF16Function.apply(x, weight, bias, 0))
+        return LinearBF16Function.apply(x, weight, bias, 2 if gelu else (1 if relu else 0))
     if linear_supported(x, weight):
         if gelu:
             needs_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or
@@ -1005,6 +1111,10 @@ def layer_norm(x, weight, bias, eps=1e-5, residual=None, return_sum=False):
     """F.layer_norm over the last dimension of ``x + residual`` (``residual`` optional).  With ``return_sum`` also
     returns the sum (pre-norm residual streams).  fp32 CUDA tensors with C % 4 == 0 use the kernel; anything else goes
     through torch."""
+    if x.is_cuda and (x.dtype == torch.bfloat16 or (residual is not None and residual.dtype == torch.bfloat16)):
+        # autocast: LayerNorm runs (and returns) fp32, the residual stream stays fp32
+        x = x.float()
+        residual = None if residual is None else residual.float()
     ok = (x.is_cuda and x.dtype == torch.float32 and weight is not None and bias is not None and weight.dtype == torch.float32
           and x.shape[-1] % 4 == 0 and x.shape[-1] <= 2048 and (residual is None or residual.shape == x.shape))
     if not ok:

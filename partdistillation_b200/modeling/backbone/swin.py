@@ -125,7 +125,8 @@ class SwinTransformerBlock(nn.Module):
         qkv = PF.linear(PF.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps), a.qkv.weight, a.qkv.bias)
         N = self.window_size * self.window_size
         bias = a.relative_position_bias_table[a.relative_position_index.view(-1)].view(N, N, -1).permute(2, 0, 1)
-        o = PF.swin_window_attention(qkv.view(B, H, W, 3 * C), a.qkv.bias, bias, a.num_heads, self.window_size,
+        # under bf16 autocast the qkv Linear returns bf16; the attention core (scores, softmax, PV) runs in fp32 either way
+        o = PF.swin_window_attention(qkv.float().view(B, H, W, 3 * C), a.qkv.bias, bias, a.num_heads, self.window_size,
                                      self.shift_size, a.scale)
         return PF.linear(o.view(B, L, C), a.proj.weight, a.proj.bias)
 
@@ -134,8 +135,7 @@ class SwinTransformerBlock(nn.Module):
         frozen = not (torch.is_grad_enabled() and (x.requires_grad or a.qkv.weight.requires_grad
                                                    or a.relative_position_bias_table.requires_grad))
         return (x.is_cuda and x.dtype == torch.float32 and frozen and self.dim // a.num_heads == 32
-                and self.window_size * self.window_size <= 256 and a.attn_drop.p == 0 and a.proj_drop.p == 0
-                and not torch.is_autocast_enabled())
+                and self.window_size * self.window_size <= 256 and a.attn_drop.p == 0 and a.proj_drop.p == 0)
 
     def forward(self, x, H, W, mask_matrix):
         B, L, C = x.shape

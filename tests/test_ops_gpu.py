@@ -779,3 +779,40 @@ def test_group_affinity_batched_equals_per_image(fn):
         exp = torch.stack([fn.group_affinity(feats[b], cents[b], masks[b], metric) for b in range(B)])
         assert torch.equal(got, exp)
         assert (got[~masks] == 0).all() and (got[masks] >= 1).all()
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 256), (200, 2048, 256), (3200, 256, 2048), (130, 72, 136), (5, 3, 8)])
+def test_gemm_bf16_vs_fp64(fn, M, N, K):
+    """tcgen05 kind::f16 GEMM (bf16 operands, fp32 accumulation) against the fp64 product of the SAME bf16 operands: only the
+    fp32 accumulation order and the output rounding differ (tolerance 2^-8 of the row scale for bf16 outputs)."""
+    g = torch.Generator().manual_seed(31)
+    a = torch.randn(M, K, generator=g).cuda().to(torch.bfloat16)
+    b = torch.randn(N, K, generator=g).cuda().to(torch.bfloat16)
+    bias = torch.randn(N, generator=g).cuda()
+    ref = a.double() @ b.double().t() + bias.double()
+    out32 = fn.gemm_bf16(a, b, bias, 0, torch.float32)
+    assert _rel(out32.double(), ref) < 1e-5            # fp32 accumulation over up to 2048 terms (measured 2.5e-6 at K = 2048)
+    out16 = fn.gemm_bf16(a, b, bias, 1, torch.bfloat16)
+    assert out16.dtype == torch.bfloat16
+    assert _rel(out16.double(), ref.clamp_min(0)) < 2 ** -8
+    gel = fn.gemm_bf16(a, b, None, 2, torch.float32)
+    assert _rel(gel.double(), torch.nn.functional.gelu(a.double() @ b.double().t())) < 1e-5
+
+
+def test_linear_bf16_autocast_matches_torch(fn):
+    """functional.linear under torch.autocast(bfloat16): forward and all three gradients against torch's own autocast F.linear
+    (cuBLAS bf16) on the same inputs — both round operands to bf16 and accumulate in fp32."""
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(4, 50, 256, generator=g).cuda().requires_grad_()
+    w = (torch.randn(512, 256, generator=g) * 0.05).cuda().requires_grad_()
+    b = torch.randn(512, generator=g).cuda().requires_grad_()
+    go = torch.randn(4, 50, 512, generator=g).cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = fn.linear(x, w, b, relu=True)
+        yr = torch.relu(torch.nn.functional.linear(x, w, b))
+    assert y.dtype == torch.bfloat16 and yr.dtype == torch.bfloat16
+    assert _rel(y.float(), yr.float()) < 2 ** -7
+    gs = torch.autograd.grad(y, (x, w, b), go.to(y.dtype))
+    gr = torch.autograd.grad(yr, (x, w, b), go.to(yr.dtype))
+    for a_, r_ in zip(gs, gr):
+        assert a_.dtype == r_.dtype and _rel(a_.float(), r_.float()) < 2 ** -6
