@@ -33,6 +33,17 @@ QUERIES = 100
 POINTS = 12544
 
 
+# BASELINE configs[1] (default; the driver's line) and configs[2] (--workload c3)
+SPECS = {
+    "c2": dict(arch="ProposalModel", size=1024, batch=2, kmasks=(K_MASKS, K_MASKS), amp=False, dtype="f32", metric=METRIC,
+               workload="proposal_learning Swin-B 100q 1024x1024 bs=2/GPU fwd+bwd (BASELINE configs[1])", cfg={}),
+    "c3": dict(arch="PartDistillationModel", size=640, batch=32, kmasks=(2, 8), amp=True, dtype="bf16",
+               metric="train images/sec PartDistillation Swin-B 100q 640^2 bf16 autocast (fwd+loss+bwd+allreduce+AdamW)",
+               workload="part_distillation_model Swin-B 100q bf16 autocast, 640x640, bs=32/GPU, 22 000 object x 8 part classes "
+                        "(BASELINE configs[2])", cfg=dict(num_object_classes=22000, num_part_classes=8)),
+}
+
+
 # ------------------------------------------------------------------------------------------------
 # synthetic data: uint8 images, block label maps -> K disjoint bool masks
 # ------------------------------------------------------------------------------------------------
@@ -45,9 +56,13 @@ def synth_image_and_masks(seed, h=H, w=W, k=K_MASKS, block=16):
     return img, m[m.flatten(1).any(1)]
 
 
-def make_batch(rank, n, device=None, pin=False, packed=False):
-    """``packed``: hand the masks over as PackedBitMasks (1 bit / pixel) instead of BitMasks bools."""
+def make_batch(rank, n, device=None, pin=False, packed=False, spec=None):
+    """``packed``: hand the masks over as PackedBitMasks (1 bit / pixel) instead of BitMasks bools.
+    ``spec``: a SPECS entry (default configs[1]); configs[2] draws K ~ U{2..8} parts per image, part labels arange(K) % 8 and
+    an object class ~ U[0, 22000)."""
     from partdistillation_b200.compat import BitMasks, Instances, PackedBitMasks
+    if spec is not None and spec["arch"] == "PartDistillationModel":
+        return _make_pd_batch(rank, n, device, pin, spec)
     out = []
     for i in range(n):
         img, m = synth_image_and_masks(rank * 1000 + i)
@@ -61,6 +76,26 @@ def make_batch(rank, n, device=None, pin=False, packed=False):
         inst.gt_masks = PackedBitMasks(m, W) if packed else BitMasks(m)
         inst.gt_classes = torch.zeros(m.shape[0], dtype=torch.long, device=m.device)
         out.append({"image": img, "instances": inst, "height": H, "width": W})
+    return out
+
+
+def _make_pd_batch(rank, n, device, pin, spec):
+    from partdistillation_b200.compat import BitMasks, Instances
+    size = spec["size"]
+    out = []
+    for i in range(n):
+        g = torch.Generator().manual_seed(7000 + rank * 1000 + i)
+        k = int(torch.randint(spec["kmasks"][0], spec["kmasks"][1] + 1, (1,), generator=g))
+        img, m = synth_image_and_masks(rank * 1000 + i, size, size, k)
+        if pin:
+            img, m = img.pin_memory(), m.pin_memory()
+        if device is not None:
+            img, m = img.to(device), m.to(device)
+        inst = Instances((size, size))
+        inst.gt_masks = BitMasks(m)
+        inst.gt_classes = (torch.arange(m.shape[0]) % 8).to(m.device)
+        out.append({"image": img, "instances": inst, "height": size, "width": size,
+                    "gt_object_class": int(torch.randint(0, spec["cfg"]["num_object_classes"], (1,), generator=g))})
     return out
 
 
@@ -372,6 +407,29 @@ def kernel_rooflines(device):
     return out
 
 
+def c3_rooflines(device, per_gpu):
+    """configs[2]'s dominant kernel class: the bf16 tcgen05 GEMM (csrc/gemm_bf16.cu) at the Swin-B stage-3 MLP shape of a
+    640^2 batch (tokens = per_gpu * 40 * 40, 512 -> 2048, GELU in the epilogue), tensor-bound; measured live."""
+    from partdistillation_b200 import functional as fn
+    g = torch.Generator().manual_seed(0)
+    peak, how = measured_peak()
+    try:
+        tf_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        tf_peak = 1590.0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    rows = per_gpu * 40 * 40
+    xs = [torch.randn(rows, 512, generator=g).to(device).to(torch.bfloat16) for _ in range(4)]
+    w = torch.randn(2048, 512, generator=g).to(device).to(torch.bfloat16)
+    bias = torch.randn(2048, generator=g).to(device)
+    t = _time_kernel([(lambda x=x: fn.gemm_bf16(x, w, bias, 2)) for x in xs], flush)
+    flops = 2.0 * rows * 2048 * 512
+    ach = flops / t / 1e12
+    return [{"kernel": f"gemm_bf16_kernel (Swin-B stage-3 MLP fc1 {rows}x512->2048 + GELU, bf16 in / bf16 out)", "bound": "tensor",
+             "achieved": round(ach, 1), "peak": tf_peak, "peak_source": how + " bf16 burst", "unit": "TFLOP/s",
+             "frac": round(ach / tf_peak, 4), "traffic": None, "algorithmic_flops": flops, "avg_launch_us": round(t * 1e6, 2)}]
+
+
 # ------------------------------------------------------------------------------------------------
 def run_reference(args, rank):
     """The reference arm: rank 0 alone times the reference's CPU implementation of the same step (same batch of
@@ -476,8 +534,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
-                    help="c2 (default): the training step of BASELINE configs[1]; c4: the pixel-grouping throughput sweep of configs[3]")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
+                    help="c2 (default): the training step of BASELINE configs[1]; c3: PartDistillation under bf16 autocast "
+                         "(configs[2]); c4: the pixel-grouping throughput sweep of configs[3]")
+    ap.add_argument("--per-gpu-batch", type=int, default=0, help="images per GPU per step (default: the workload's own)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="run the step eagerly instead of replaying its CUDA graph")
     ap.add_argument("--packed-masks", action="store_true",
@@ -503,16 +563,20 @@ def main():
         return
     from partdistillation_b200 import _lib, compat, presets
     from partdistillation_b200.engine import DataParallelTrainer
-    cfg = presets.make_cfg("ProposalModel", "swin_b", QUERIES, 10, POINTS, 0.0, device=str(device))
+    spec = SPECS[args.workload]
+    per_gpu = args.per_gpu_batch or spec["batch"]
+    cfg = presets.make_cfg(spec["arch"], "swin_b", QUERIES, 10, POINTS, 0.0, device=str(device), **spec["cfg"])
     torch.manual_seed(0)                                   # identical random-init weights on every rank
     model = compat.build_model(cfg)
     model.train()
     trainer = DataParallelTrainer(model, base_lr=1e-4, weight_decay=0.05, clip_norm=0.01,
                                   freeze_keys=("backbone", "encoder"), cuda_graph=not args.no_cuda_graph)
-    cpu_sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()} if rank == 0 else None
+    cpu_sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()} if rank == 0 and args.workload == "c2" else None
 
-    dev_batch = make_batch(rank, PER_GPU_BATCH, device=device)
-    host_batch = make_batch(rank, PER_GPU_BATCH, pin=True, packed=args.packed_masks)
+    dev_batch = make_batch(rank, per_gpu, device=device, spec=spec)
+    host_batch = make_batch(rank, per_gpu, pin=True, packed=args.packed_masks, spec=spec)
+    import contextlib
+    amp = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if spec["amp"] else contextlib.nullcontext
 
     def barrier():
         if world > 1:
@@ -521,7 +585,8 @@ def main():
 
     def timed(batch, steps, warmup, read_loss):
         for _ in range(warmup):
-            total, _ = trainer.step(batch)
+            with amp():
+                total, _ = trainer.step(batch)
             if read_loss:
                 total.item()
         barrier()
@@ -534,7 +599,8 @@ def main():
         s.record()
         last = None
         for _ in range(steps):
-            total, _ = trainer.step(batch)
+            with amp():
+                total, _ = trainer.step(batch)
             if read_loss:
                 last = total.item()
         e.record()
@@ -555,16 +621,16 @@ def main():
     ms_e2e, wall_e2e, _, last_loss = timed(host_batch, args.steps, 4 if args.packed_masks else 1, read_loss=True)
     e2e_ms = max(ms_e2e, wall_e2e)          # the loss read-back makes wall clock the honest end-to-end time
 
-    images = PER_GPU_BATCH * world * args.steps
+    images = per_gpu * world * args.steps
     line = None
     if rank == 0:
-        roofs = kernel_rooflines(device)
+        roofs = kernel_rooflines(device) if args.workload == "c2" else c3_rooflines(device, per_gpu)
         roof = roofs[0]
-        line = {"metric": METRIC, "value": round(images / (ms * 1e-3), 3), "unit": "images/s", "n_gpus": world,
+        line = {"metric": spec["metric"], "value": round(images / (ms * 1e-3), 3), "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "proposal_learning Swin-B 100q 1024x1024 bs=2/GPU fwd+bwd (BASELINE configs[1])",
-                           "global_batch": PER_GPU_BATCH * world, "queries": QUERIES, "dec_layers": 10,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": spec["dtype"], "data": "synthetic",
+                "config": {"workload": spec["workload"],
+                           "global_batch": per_gpu * world, "queries": QUERIES, "dec_layers": 10,
                            "train_num_points": POINTS, "importance_sample_ratio": 0.0,
                            "freeze_keys": ["backbone", "encoder"], "optimizer": "AdamW + full-model clip 0.01", "cuda_graph": not args.no_cuda_graph,
                            "parallelism": f"dp{world}", "grad_allreduce_bytes": trainer.grad_bytes,
@@ -581,7 +647,7 @@ def main():
     if world > 1:
         dist.barrier()
     if rank == 0:
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "c2":
             step, kind, cores, what = make_cpu_reference_step(PER_GPU_BATCH, cpu_sd)
             t, _, _ = time_cpu_reference(step, steps=1, warmup=0)
             line["cpu_baseline"] = {"value": round(PER_GPU_BATCH / t, 5), "unit": "images/s", "cores": cores, "kind": kind,

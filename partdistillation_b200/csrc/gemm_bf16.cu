@@ -10,10 +10,12 @@
 // instructions, against 48-64 KB and twelve for the 3xTF32 kernel of gemm_tc.cu.
 //
 // Persistent kernel, one CTA per SM, 6 warps:
-//   warp 0      TMA producer: A / B k-blocks (128 rows x 128 bytes, SWIZZLE_128B) into a 6-deep ring
+//   warp 0      TMA producer: A / B k-blocks (128 rows x 128 bytes, SWIZZLE_128B) into a 5-deep ring
 //   warp 1      TMEM allocator + tcgen05.mma issuer (one elected lane)
-//   warps 2..5  epilogue, one per TMEM lane quarter: tcgen05.ld -> (+bias, activation) -> global stores, overlapped with the
-//               next tile's main loop through a double-buffered accumulator (2 x 128 columns)
+//   warps 2..9  epilogue, two per TMEM lane quarter (64 columns each): four tcgen05.ld in flight -> (+bias, activation) ->
+//               shared-memory transpose -> coalesced 128-byte row segments (a thread holds 64 outputs of ONE row; storing them
+//               directly costs one L1 wavefront per lane), overlapped with the next tile's main loop through a double-buffered
+//               accumulator (2 x 128 columns)
 // TMA zero-fills out-of-range rows / k, so ragged M, N, K need no masking on the operand side (K % 8 == 0: 16-byte row pitch).
 #include <cuda_bf16.h>
 
@@ -23,10 +25,12 @@
 namespace pdb {
 
 constexpr int H_BM = 128, H_BN = 128, H_BK = 64;       // bf16 elements: one k-block row = 128 bytes
-constexpr int H_STAGES = 6;
-constexpr int H_THREADS = 6 * 32;
+constexpr int H_STAGES = 5;
+constexpr int H_EPI_WARPS = 8;                         // two per TMEM lane quarter, each takes 64 of the 128 columns
+constexpr int H_THREADS = (2 + H_EPI_WARPS) * 32;
 constexpr int H_STAGE_BYTES = (H_BM + H_BN) * H_BK * 2;      // 32 KB
-constexpr int H_SMEM = H_STAGES * H_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int H_STG_WORDS = 32 * 36;                    // per epilogue warp: 32 rows x (32 + 4 pad) words
+constexpr int H_SMEM = H_STAGES * H_STAGE_BYTES + 256 /*barriers*/ + H_EPI_WARPS * H_STG_WORDS * 4 + 1024 /*align*/;
 
 struct HParams {
     void* C;
@@ -49,9 +53,21 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint6
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// GELU (erf form) for a bf16 result: erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below the 2^-9 of the output
+// rounding) on the fast exp / reciprocal units — erff() alone would make the epilogue longer than the tile's MMAs.
+__device__ __forceinline__ float fast_erf(float x) {
+    const float ax = fabsf(x);
+    const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float r = 1.f - poly * t * __expf(-ax * ax);
+    return copysignf(r, x);
+}
 __device__ __forceinline__ float h_act(float x, int mode) {
     if (mode == 1) return fmaxf(x, 0.f);
-    if (mode == 2) return x * 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+    if (mode == 2) return x * 0.5f * (1.f + fast_erf(x * 0.70710678118654752440f));
     return x;
 }
 
@@ -76,7 +92,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&acc_full[s], 1);
-            tc::mbar_init(&acc_empty[s], 4 * 32);
+            tc::mbar_init(&acc_empty[s], H_EPI_WARPS * 32);
         }
         tc::fence_barrier_init();
     }
@@ -127,8 +143,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
         }
     } else {
-        // epilogue: this warp may touch TMEM lanes 32 * (warp % 4) .. + 31 = rows of the tile
-        const int quarter = warp & 3;
+        // epilogue: this warp may touch TMEM lanes 32 * (warp % 4) .. + 31 = rows of the tile; it takes columns 64 * half .. + 63
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
         uint32_t t = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
             const int m0 = (tile / p.nt) * H_BM, n0 = (tile % p.nt) * H_BN;
@@ -136,47 +152,107 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             tc::mbar_wait(&acc_full[ab], (t >> 1) & 1);
             tc::tc_fence_after();
             const int row = m0 + quarter * 32 + lane;
-            const uint32_t taddr = tmem_base + ab * H_BN + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-            for (int c = 0; c < H_BN / 16; ++c) {
-                const int col0 = n0 + c * 16;
-                if (col0 >= p.N) break;                          // warp-uniform
-                float v[16];
-                tc::tmem_ld16(taddr + c * 16, v);
-                if (row < p.M) {
+            const int col0 = n0 + half * 64;
+            const uint32_t taddr = tmem_base + ab * H_BN + half * 64 + ((uint32_t)(quarter * 32) << 16);
+            uint32_t r[4][16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float bj = (p.bias && col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f;
-                        v[j] = h_act(v[j] + bj, p.act);
+            for (int c = 0; c < 4; ++c) tc::tmem_ld16_nowait(taddr + c * 16, r[c]);
+            tc::tmem_ld_wait();
+            tc::tc_fence_before();
+            tc::mbar_arrive(&acc_empty[ab]);                     // the accumulator is in registers: the MMA warp may reuse it
+            const bool full64 = col0 + 64 <= p.N;
+            const bool fast = full64 && (p.out_bf16 ? (p.ldc & 7) == 0 : (p.ldc & 3) == 0) && ((uintptr_t)p.C & 15) == 0;
+            if (col0 < p.N) {
+                // bias + activation in registers (thread = one row of the tile, 64 columns)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int cc = col0 + c * 16;
+                    if (p.bias) {
+                        if (full64) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cc) + j);
+                                r[c][4 * j] = __float_as_uint(__uint_as_float(r[c][4 * j]) + b4.x);
+                                r[c][4 * j + 1] = __float_as_uint(__uint_as_float(r[c][4 * j + 1]) + b4.y);
+                                r[c][4 * j + 2] = __float_as_uint(__uint_as_float(r[c][4 * j + 2]) + b4.z);
+                                r[c][4 * j + 3] = __float_as_uint(__uint_as_float(r[c][4 * j + 3]) + b4.w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                r[c][j] = __float_as_uint(__uint_as_float(r[c][j]) + ((cc + j < p.N) ? __ldg(p.bias + cc + j) : 0.f));
+                        }
                     }
-                    const bool full16 = col0 + 16 <= p.N;
+                    if (p.act) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) r[c][j] = __float_as_uint(h_act(__uint_as_float(r[c][j]), p.act));
+                    }
+                }
+                if (fast) {
+                    uint32_t* stg = reinterpret_cast<uint32_t*>(smem + H_STAGES * H_STAGE_BYTES + 256) + (warp - 2) * H_STG_WORDS;
+                    const int rr = lane >> 3, seg = lane & 7;
                     if (p.out_bf16) {
-                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + col0;
-                        if (full16 && (p.ldc & 7) == 0) {
+                        // 64 bf16 = 32 words per row: stage, then every warp instruction writes 4 rows x 128 contiguous bytes
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
                             uint32_t w[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[c][2 * j]), __uint_as_float(r[c][2 * j + 1]));
                                 w[j] = *reinterpret_cast<uint32_t*>(&h2);
                             }
-                            reinterpret_cast<uint4*>(o)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                            reinterpret_cast<uint4*>(o)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                        } else {
-                            for (int j = 0; j < 16 && col0 + j < p.N; ++j) o[j] = __float2bfloat16_rn(v[j]);
+                            *reinterpret_cast<uint4*>(stg + lane * 36 + c * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                            *reinterpret_cast<uint4*>(stg + lane * 36 + c * 8 + 4) = make_uint4(w[4], w[5], w[6], w[7]);
                         }
-                    } else {
-                        float* o = reinterpret_cast<float*>(p.C) + (int64_t)row * p.ldc + col0;
-                        if (full16 && (p.ldc & 3) == 0) {
+                        __syncwarp();
+                        __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(p.C) + col0 + seg * 8;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        } else {
-                            for (int j = 0; j < 16 && col0 + j < p.N; ++j) o[j] = v[j];
+                        for (int it = 0; it < 8; ++it) {
+                            const int lr = it * 4 + rr;
+                            const int gr = m0 + quarter * 32 + lr;
+                            const uint4 val = *reinterpret_cast<const uint4*>(stg + lr * 36 + seg * 4);
+                            if (gr < p.M) *reinterpret_cast<uint4*>(base + (int64_t)gr * p.ldc) = val;
+                        }
+                        __syncwarp();
+                    } else {
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {             // 32 fp32 columns = 32 words per row and pass
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    *reinterpret_cast<uint4*>(stg + lane * 36 + c * 16 + j * 4) =
+                                        make_uint4(r[h2 * 2 + c][4 * j], r[h2 * 2 + c][4 * j + 1], r[h2 * 2 + c][4 * j + 2], r[h2 * 2 + c][4 * j + 3]);
+                            __syncwarp();
+                            float* base = reinterpret_cast<float*>(p.C) + col0 + h2 * 32 + seg * 4;
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                const int lr = it * 4 + rr;
+                                const int gr = m0 + quarter * 32 + lr;
+                                const uint4 val = *reinterpret_cast<const uint4*>(stg + lr * 36 + seg * 4);
+                                if (gr < p.M) *reinterpret_cast<uint4*>(base + (int64_t)gr * p.ldc) = val;
+                            }
+                            __syncwarp();
+                        }
+                    }
+                } else if (row < p.M) {
+                    // ragged column tile / unaligned rows: element-wise stores
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        const int cc = col0 + c * 16;
+                        for (int j = 0; j < 16 && cc + j < p.N; ++j) {
+                            float val = 0.f;
+#pragma unroll
+                            for (int c2 = 0; c2 < 4; ++c2)
+#pragma unroll
+                                for (int j2 = 0; j2 < 16; ++j2)
+                                    if (c2 == c && j2 == j) val = __uint_as_float(r[c2][j2]);
+                            if (p.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.C)[(int64_t)row * p.ldc + cc + j] = __float2bfloat16_rn(val);
+                            else reinterpret_cast<float*>(p.C)[(int64_t)row * p.ldc + cc + j] = val;
                         }
                     }
                 }
             }
-            tc::tc_fence_before();
-            tc::mbar_arrive(&acc_empty[ab]);
         }
     }
     tc::tc_fence_before();
