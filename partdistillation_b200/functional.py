@@ -759,14 +759,17 @@ class LinearBF16Function(Function):
     dW = dy^T x on the same kernel (bf16 operands, dW accumulated and returned in fp32), db = column sums in fp32."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act):
+    def forward(ctx, x, weight, bias, act, out_fp32=False):
         _need_cuda(x, weight)
         N, K = weight.shape
         x2 = _c(x.reshape(-1, K).to(torch.bfloat16))
         if x2.data_ptr() % 16:
             x2 = x2.clone()
-        # torch.autocast casts the bias to bf16 as well; the epilogue adds its fp32 image to the fp32 accumulator
-        y = gemm_bf16(x2, weight_bf16(weight), None if bias is None else _c(bias.to(torch.bfloat16).float()), act)
+        # torch.autocast casts the bias to bf16 as well; the epilogue adds its fp32 image to the fp32 accumulator.
+        # out_fp32: the consumer is one of this library's fp32 kernels (attention cores, mask einsum): the epilogue writes the
+        # fp32 accumulator instead of rounding to bf16 and converting back in a separate pass.
+        y = gemm_bf16(x2, weight_bf16(weight), None if bias is None else _c(bias.to(torch.bfloat16).float()), act,
+                      torch.float32 if out_fp32 else torch.bfloat16)
         ctx.save_for_backward(x2, weight, y if act == 1 else None)
         ctx.meta = (tuple(x.shape), x.dtype, bias is not None, act)
         return y.view(*x.shape[:-1], N)
@@ -788,7 +791,7 @@ class LinearBF16Function(Function):
             gw = gemm_bf16(_rows8(gy.t()), _rows8(x2.t()), out_dtype=torch.float32).to(weight.dtype)
         if has_bias and ctx.needs_input_grad[2]:
             gb = gy.float().sum(0)
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None
 
 
 def _autocast_bf16(x, weight):
@@ -806,19 +809,21 @@ def conv3x3(x, weight, bias=None):
     return Conv3x3Function.apply(x, weight, bias)
 
 
-def linear(x, weight, bias=None, relu=False, gelu=False):
+def linear(x, weight, bias=None, relu=False, gelu=False, out_fp32=False):
     """nn.Linear (optionally fused ReLU) on the tensor cores for fp32 CUDA tensors whose feature sizes are
     multiples of 4; other dtypes (autocast halves, the fp64 classifier) and tiny ragged heads go through
     the library GEMM.  gelu=True applies nn.GELU() (erf form); it is folded into the GEMM epilogue when nothing
     on the path needs a gradient (the frozen backbone), otherwise it runs as a separate differentiable op.
-    Under torch.autocast(bfloat16) (and for bf16 inputs) the product runs on the bf16 tensor-core kernel and returns bf16."""
+    Under torch.autocast(bfloat16) (and for bf16 inputs) the product runs on the bf16 tensor-core kernel and returns bf16
+    (``out_fp32``: fp32, for consumers that are fp32 kernels of this library; no effect outside autocast, where the result is
+    fp32 anyway)."""
     if _autocast_bf16(x, weight) or (x.is_cuda and x.dtype == torch.bfloat16 and weight.shape[1] % 8 == 0
                                      and weight.dtype in (torch.float32, torch.bfloat16)):
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or
                                                   (bias is not None and bias.requires_grad))
         if gelu and needs_grad:
             return torch.nn.functional.gelu(LinearBF16Function.apply(x, weight, bias, 0))
-        return LinearBF16Function.apply(x, weight, bias, 2 if gelu else (1 if relu else 0))
+        return LinearBF16Function.apply(x, weight, bias, 2 if gelu else (1 if relu else 0), out_fp32)
     if linear_supported(x, weight):
         if gelu:
             needs_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or

@@ -122,7 +122,8 @@ class SwinTransformerBlock(nn.Module):
         shift mask / attention / window reverse / roll back / crop (functional.swin_window_attention)."""
         a = self.attn
         B, L, C = x.shape
-        qkv = PF.linear(PF.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps), a.qkv.weight, a.qkv.bias)
+        qkv = PF.linear(PF.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps), a.qkv.weight, a.qkv.bias,
+                        out_fp32=True)
         N = self.window_size * self.window_size
         bias = a.relative_position_bias_table[a.relative_position_index.view(-1)].view(N, N, -1).permute(2, 0, 1)
         # under bf16 autocast the qkv Linear returns bf16; the attention core (scores, softmax, PV) runs in fp32 either way
@@ -214,7 +215,12 @@ class BasicLayer(nn.Module):
         for blk in self.blocks:
             x = blk(x, H, W, mask)
         if self.downsample is not None:
-            return x, H, W, self.downsample(x, H, W), (H + 1) // 2, (W + 1) // 2
+            down = self.downsample(x, H, W)
+            if down.dtype != x.dtype and x.dtype == torch.float32:
+                # bf16 autocast: the reduction Linear returns bf16; the residual stream of the next stage stays fp32 (the fused
+                # LayerNorm / window-attention kernels read fp32; the more precise side of the autocast tolerance)
+                down = down.float()
+            return x, H, W, down, (H + 1) // 2, (W + 1) // 2
         return x, H, W, x, H, W
 
 

@@ -44,8 +44,9 @@ class _AttentionParams(nn.Module):
         nn.init.constant_(self.out_proj.bias, 0.0)
 
     def project(self, x, lo, hi):
+        """Rows lo*E .. hi*E of the packed q / k / v projection; fp32 out (the attention cores are fp32 kernels)."""
         E = self.embed_dim
-        return PF.linear(x, self.in_proj_weight[lo * E:hi * E], self.in_proj_bias[lo * E:hi * E])
+        return PF.linear(x, self.in_proj_weight[lo * E:hi * E], self.in_proj_bias[lo * E:hi * E], out_fp32=True)
 
 
 def _xavier(module):
@@ -124,8 +125,8 @@ class MLP(nn.Module):
         self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:]))
 
     def forward(self, x):
-        for i, layer in enumerate(self.layers):
-            x = PF.linear(x, layer.weight, layer.bias, relu=i < self.num_layers - 1)
+        for i, layer in enumerate(self.layers):          # the last layer feeds the fp32 mask einsum
+            x = PF.linear(x, layer.weight, layer.bias, relu=i < self.num_layers - 1, out_fp32=i == self.num_layers - 1)
         return x
 
 

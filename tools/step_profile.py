@@ -12,17 +12,26 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 
-def main(out_path):
+def main(out_path, workload="c2"):
+    import contextlib
     from partdistillation_b200 import compat, presets
     from partdistillation_b200.engine import DataParallelTrainer
     device = torch.device("cuda", 0)
     torch.cuda.set_device(0)
-    cfg = presets.make_cfg("ProposalModel", "swin_b", bench.QUERIES, 10, bench.POINTS, 0.0, device=str(device))
+    spec = bench.SPECS[workload]
+    cfg = presets.make_cfg(spec["arch"], "swin_b", bench.QUERIES, 10, bench.POINTS, 0.0, device=str(device), **spec["cfg"])
     torch.manual_seed(0)
     model = compat.build_model(cfg)
     model.train()
-    trainer = DataParallelTrainer(model, freeze_keys=("backbone", "encoder"))
-    batch = bench.make_batch(0, bench.PER_GPU_BATCH, device=device)
+    real = DataParallelTrainer(model, freeze_keys=("backbone", "encoder"))
+    batch = bench.make_batch(0, spec["batch"], device=device, spec=spec)
+    amp = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if spec["amp"] else contextlib.nullcontext
+
+    class T:                                    # the trainer's step under the workload's autocast context
+        def step(self, b):
+            with amp():
+                return real.step(b)
+    trainer = T()
     for _ in range(3):
         trainer.step(batch)
     torch.cuda.synchronize()
@@ -48,7 +57,7 @@ def main(out_path):
             total += t / 2
     rows.sort(reverse=True)
     with open(out_path, "w") as w:
-        w.write(f"# one training step (Swin-B 1024^2, bs=2, 100q): wall {wall:.2f} ms/step; summed kernel time "
+        w.write(f"# one training step ({spec['workload']}): wall {wall:.2f} ms/step; summed kernel time "
                 f"{total / 1e3:.2f} ms/step over {sum(r[1] for r in rows)} launches (torch.profiler, warm)\n")
         w.write(f"{'us/step':>10} {'share':>7} {'count':>6}  kernel\n")
         for t, c, k in rows[:70]:
@@ -67,4 +76,4 @@ def main(out_path):
 
 if __name__ == "__main__":
     os.makedirs("gpurun_out", exist_ok=True)
-    main(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/step_profile.txt")
+    main(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/step_profile.txt", sys.argv[2] if len(sys.argv) > 2 else "c2")
