@@ -268,6 +268,11 @@ PDB_API int pdb_adamw_flat(float* param, const float* grad, float* exp_avg, floa
  *   out (B, H, W, heads*32).  ws*ws <= 256, 0 <= shift < ws, head dim 32. */
 PDB_API int pdb_swin_window_attention_forward(const float* qkv, const float* qkv_bias, const float* bias, float* out, int B,
                                       int H, int W, int heads, int d, int ws, int shift, float scale, void* stream);
+/* Same contract on the tensor cores (warp-level mma.sync m16n8k8 TF32; csrc/window_attn_mma.cu): passes = 3 is fp32-accurate
+ * (hi / lo operand split), passes = 1 a single TF32 pass for the bf16-autocast path.  Window sizes 12, 8, 4; d = 32. */
+PDB_API int pdb_swin_window_attention_forward_tc(const float* qkv, const float* qkv_bias, const float* bias, float* out, int B,
+                                         int H, int W, int heads, int d, int ws, int shift, float scale, int passes,
+                                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Pixel grouping affinity — replaces, inside PixelGroupingModel.generate_part_segments

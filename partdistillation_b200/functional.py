@@ -1047,6 +1047,9 @@ def window_attention(qkv, bias, mask, heads, scale):
     return out
 
 
+swin_attention_tensor_cores = os.environ.get("PDB_SWIN_ATTN", "mma") != "ffma"     # A/B switch: the FFMA kernel of round 1
+
+
 def swin_window_attention(qkv, qkv_bias, bias, heads, window_size, shift, scale):
     """qkv (B, H, W, 3*heads*32) f32 in token order -> (B, H, W, heads*32): the whole shifted-window attention of a Swin
     block (pad, roll, partition, mask, attention, reverse, roll back, crop) in one kernel.  No autograd."""
@@ -1056,9 +1059,18 @@ def swin_window_attention(qkv, qkv_bias, bias, heads, window_size, shift, scale)
     d = C3 // (3 * heads)
     out = torch.empty((B, H, W, heads * d), dtype=torch.float32, device=qkv.device)
     qb = _c(qkv_bias.float()) if qkv_bias is not None else None
-    rc = _lib.load().pdb_swin_window_attention_forward(qkv.data_ptr(), qb.data_ptr() if qb is not None else None, bias.data_ptr(),
-                                                       out.data_ptr(), B, H, W, heads, d, int(window_size), int(shift),
-                                                       float(scale), _stream())
+    lib = _lib.load()
+    tc = getattr(lib, "pdb_swin_window_attention_forward_tc", None)     # absent only in the CPU-tier host builds of the tests
+    if swin_attention_tensor_cores and tc is not None and d == 32 and int(window_size) in (12, 8, 4):
+        # tensor-core kernel (csrc/window_attn_mma.cu): 3xTF32 = fp32-accurate; a single TF32 pass under bf16 autocast
+        passes = 1 if (torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16) else 3
+        rc = tc(qkv.data_ptr(), qb.data_ptr() if qb is not None else None, bias.data_ptr(), out.data_ptr(), B, H, W, heads, d,
+                int(window_size), int(shift), float(scale), passes, _stream())
+        _lib.check(rc, "pdb_swin_window_attention_forward_tc")
+        return out
+    rc = lib.pdb_swin_window_attention_forward(qkv.data_ptr(), qb.data_ptr() if qb is not None else None, bias.data_ptr(),
+                                               out.data_ptr(), B, H, W, heads, d, int(window_size), int(shift),
+                                               float(scale), _stream())
     _lib.check(rc, "pdb_swin_window_attention_forward")
     return out
 

@@ -28,6 +28,10 @@ def _load(golden_dir, name):
     return torch.load(os.path.join(golden_dir, name), weights_only=False)
 
 
+def DEV_IS_CUDA(t):
+    return t.is_cuda
+
+
 def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
@@ -636,7 +640,18 @@ def test_swin_window_attention_block(fn, H, W, ws, shift, heads):
     ref = o[:, :H, :W]
     qkv_tok = (x @ qkv_w.t() + qkv_b).float().cuda()
     out = fn.swin_window_attention(qkv_tok, qkv_b.float().cuda(), bias.cuda(), heads, ws, shift, scale)
-    assert _rel(out.double().cpu(), ref) < 1e-5
+    assert _rel(out.double().cpu(), ref) < 1e-5                  # tensor-core kernel, 3xTF32 (fp32-accurate)
+    if getattr(fn, "swin_attention_tensor_cores", False) and DEV_IS_CUDA(out):
+        old = fn.swin_attention_tensor_cores
+        try:
+            fn.swin_attention_tensor_cores = False               # the FFMA kernel of round 1 stays covered
+            out2 = fn.swin_window_attention(qkv_tok, qkv_b.float().cuda(), bias.cuda(), heads, ws, shift, scale)
+        finally:
+            fn.swin_attention_tensor_cores = old
+        assert _rel(out2.double().cpu(), ref) < 1e-5
+        with torch.autocast("cuda", dtype=torch.bfloat16):        # single TF32 pass: 10-bit operands
+            out3 = fn.swin_window_attention(qkv_tok, qkv_b.float().cuda(), bias.cuda(), heads, ws, shift, scale)
+        assert _rel(out3.double().cpu(), ref) < 3e-3
 
 
 def test_swin_backbone_frozen_path_vs_golden(fn, golden_dir):
