@@ -14,6 +14,7 @@
 // Backward: one pass with a thread per query (dq) and one with a thread per key (dk, dv).
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace pdb {
 
@@ -354,6 +355,24 @@ xattn_bwd_dkv(const float* __restrict__ q, const float* __restrict__ k, const fl
 
 }  // namespace pdb
 
+// xattn_mma.cu: the same three passes on the tensor cores (mma.sync TF32, 3-pass split); PDB_XATTN=simt keeps the kernels above
+namespace pdb {
+int xattn_fwd_partial_mma_launch(const float* q, const float* k, const float* v, const uint8_t* mask, const int32_t* row_any,
+                                 float* ws_acc, float* ws_ml, int B, int heads, int Q, int Lk, int ns, int tiles_per, int qtiles,
+                                 cudaStream_t st);
+int xattn_bwd_mma_launch(const float* q, const float* k, const float* v, const uint8_t* mask, const int32_t* row_any, const float* out,
+                         const float* lse, const float* gout, float* gq, float* gk, float* gv, int B, int heads, int Q, int Lk, int ns,
+                         int tiles_per, int qtiles, cudaStream_t st);
+static bool xattn_use_mma() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("PDB_XATTN");
+        mode = (e && e[0] == 's') ? 0 : 1;
+    }
+    return mode == 1;
+}
+}
+
 using namespace pdb;
 
 extern "C" int64_t pdb_masked_xattn_workspace_bytes(int B, int heads, int Q, int Lk, int d) {
@@ -375,10 +394,14 @@ extern "C" int pdb_masked_xattn_forward(const float* q, const float* k, const fl
     int qtiles = (Q + XTHREADS - 1) / XTHREADS;
     float* ws_acc = (float*)workspace;
     float* ws_ml = ws_acc + (int64_t)B * heads * ns * Q * XD;
-    dim3 grid((unsigned)(ns * qtiles), (unsigned)heads, (unsigned)B);
-    xattn_fwd_partial<<<grid, XTHREADS, 0, st>>>(q, k, v, mask, row_any, ws_acc, ws_ml, heads, Q, Lk, ns, tiles_per,
-                                                 qtiles);
-    PDB_TRY(launched("xattn_fwd_partial"));
+    if (xattn_use_mma()) {
+        PDB_TRY(xattn_fwd_partial_mma_launch(q, k, v, mask, row_any, ws_acc, ws_ml, B, heads, Q, Lk, ns, tiles_per, qtiles, st));
+    } else {
+        dim3 grid((unsigned)(ns * qtiles), (unsigned)heads, (unsigned)B);
+        xattn_fwd_partial<<<grid, XTHREADS, 0, st>>>(q, k, v, mask, row_any, ws_acc, ws_ml, heads, Q, Lk, ns, tiles_per,
+                                                     qtiles);
+        PDB_TRY(launched("xattn_fwd_partial"));
+    }
     int64_t warps = (int64_t)B * heads * Q;
     xattn_fwd_combine<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(ws_acc, ws_ml, out, lse, B, heads, Q, ns);
     return launched("xattn_fwd_combine");
@@ -397,6 +420,9 @@ extern "C" int pdb_masked_xattn_backward(const float* q, const float* k, const f
     int tiles_per = (tiles + ns - 1) / ns;
     int qtiles = (Q + XTHREADS - 1) / XTHREADS;
     cudaMemsetAsync(grad_q, 0, sizeof(float) * (size_t)B * Q * heads * XD, st);
+    if (xattn_use_mma())
+        return xattn_bwd_mma_launch(q, k, v, mask, row_any, out, lse, grad_out, grad_q, grad_k, grad_v, B, heads, Q, Lk, ns, tiles_per,
+                                    qtiles, st);
     dim3 grid((unsigned)(ns * qtiles), (unsigned)heads, (unsigned)B);
     xattn_bwd_dq<<<grid, XTHREADS, 0, st>>>(q, k, v, mask, row_any, out, lse, grad_out, grad_q, heads, Q, Lk, ns,
                                             tiles_per);
