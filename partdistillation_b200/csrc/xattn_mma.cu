@@ -49,6 +49,39 @@ __device__ __forceinline__ void xm_load_a(float (&a)[4][4], const float* __restr
         a[ks][3] = r1 ? __ldg(r1 + ks * 8 + t + 4) : 0.f;
     }
 }
+constexpr float kXmLog2e = 1.4426950408889634f, kXmLn2 = 0.6931471805599453f;
+__device__ __forceinline__ void xm_scale_a(float (&a)[4][4], float f) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[ks][i] *= f;
+}
+// 256-thread CTAs: a 64 x 32 tile is 512 float4 = 2 per thread.  Register stage of the NEXT tile (global loads in flight while
+// the current tile is computed), then a store into the other shared buffer.
+struct XmStage {
+    float4 k[2], v[2];
+};
+__device__ __forceinline__ void xm_prefetch(XmStage& st, const float* __restrict__ k, const float* __restrict__ v, int64_t rowbase, int row0,
+                                            int nrows, int ld, int hoff) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int e = threadIdx.x + i * 256, jj = e >> 3, c = e & 7;
+        st.k[i] = st.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + jj < nrows) {
+            const int64_t off = (rowbase + row0 + jj) * ld + hoff + c * 4;
+            st.k[i] = __ldg(reinterpret_cast<const float4*>(k + off));
+            st.v[i] = __ldg(reinterpret_cast<const float4*>(v + off));
+        }
+    }
+}
+__device__ __forceinline__ void xm_commit(const XmStage& st, float* __restrict__ sK, float* __restrict__ sV) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int e = threadIdx.x + i * 256, jj = e >> 3, c = e & 7;
+        *reinterpret_cast<float4*>(sK + jj * MXS + c * 4) = st.k[i];
+        *reinterpret_cast<float4*>(sV + jj * MXS + c * 4) = st.v[i];
+    }
+}
 // rows [row0, row0 + 64) of a (rows x heads*32) matrix -> shared tile [64][36] (rows >= nrows: zeros)
 __device__ __forceinline__ void xm_load_tile(float* __restrict__ dst, const float* __restrict__ src, int64_t rowbase, int row0, int nrows,
                                              int ld, int hoff) {
@@ -60,17 +93,19 @@ __device__ __forceinline__ void xm_load_tile(float* __restrict__ dst, const floa
     }
 }
 // acc[j] (j = 0..7) += A (16 x 32, fragments a) x T^T for the 64 rows of the shared tile T ([row][36])
-__device__ __forceinline__ void xm_scores(float (&acc)[8][4], const float (&a)[4][4], const float* __restrict__ tile, int g, int t) {
+template <int NF = 8>
+__device__ __forceinline__ void xm_scores(float (&acc)[NF][4], const float (&a)[4][4], const float* __restrict__ tile, int g, int t) {
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < NF; ++j)
             xm_mma3(acc[j], a[ks], tile[(j * 8 + g) * MXS + ks * 8 + t], tile[(j * 8 + g) * MXS + ks * 8 + t + 4]);
 }
 // out[n] (n = 0..3) += P (16 x 64, as the C fragments p[j] of a previous product) x T for the 64 rows of the shared tile T
-__device__ __forceinline__ void xm_chain(float (&out)[4][4], const float (&p)[8][4], const float* __restrict__ tile, int g, int t) {
+template <int NF = 8>
+__device__ __forceinline__ void xm_chain(float (&out)[4][4], const float (&p)[NF][4], const float* __restrict__ tile, int g, int t) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NF; ++j) {
         const float a[4] = {p[j][0], p[j][2], p[j][1], p[j][3]};
 #pragma unroll
         for (int n = 0; n < 4; ++n)
@@ -122,8 +157,8 @@ __global__ void __launch_bounds__(256)
 xattn_fwd_partial_mma(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                       const uint8_t* __restrict__ mask, const int32_t* __restrict__ row_any, float* __restrict__ ws_acc,
                       float* __restrict__ ws_ml, int heads, int Q, int Lk, int nsplit, int tiles_per) {
-    __shared__ __align__(16) float sK[MXT * MXS];
-    __shared__ __align__(16) float sV[MXT * MXS];
+    __shared__ __align__(16) float sKb[2][MXT * MXS];          // double-buffered: tile t + 1 lands while tile t is computed
+    __shared__ __align__(16) float sVb[2][MXT * MXS];
     const int split = blockIdx.x % nsplit, qt = blockIdx.x / nsplit;
     const int h = blockIdx.y, b = blockIdx.z;
     const int ld = heads * MXD, hoff = h * MXD;
@@ -131,23 +166,33 @@ xattn_fwd_partial_mma(const float* __restrict__ q, const float* __restrict__ k, 
     const XmRow R = xm_rows(qt, warp, g, Q, b, Lk, mask, row_any);
     float qf[4][4];
     xm_load_a(qf, R.act0 ? q + ((int64_t)b * Q + R.qi0) * ld + hoff : nullptr, R.act1 ? q + ((int64_t)b * Q + R.qi1) * ld + hoff : nullptr, t);
+    xm_scale_a(qf, kXmLog2e);                  // base-2 softmax inside the kernel: exp2 is one MUFU; (m, l) leave in natural units
     float o[4][4];
 #pragma unroll
     for (int n = 0; n < 4; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     const int tile_begin = split * tiles_per;
     const int tile_end = min(tile_begin + tiles_per, (Lk + MXT - 1) / MXT);
+    XmStage stg;
+    if (tile_begin < tile_end) {
+        xm_prefetch(stg, k, v, (int64_t)b * Lk, tile_begin * MXT, Lk, ld, hoff);
+        xm_commit(stg, sKb[0], sVb[0]);
+    }
+    __syncthreads();
     for (int tl = tile_begin; tl < tile_end; ++tl) {
         const int j0 = tl * MXT;
-        __syncthreads();
-        xm_load_tile(sK, k, (int64_t)b * Lk, j0, Lk, ld, hoff);
-        xm_load_tile(sV, v, (int64_t)b * Lk, j0, Lk, ld, hoff);
-        __syncthreads();
+        const float* sK = sKb[(tl - tile_begin) & 1];
+        const float* sV = sVb[(tl - tile_begin) & 1];
+        const bool more = tl + 1 < tile_end;
+        if (more) xm_prefetch(stg, k, v, (int64_t)b * Lk, j0 + MXT, Lk, ld, hoff);
+        // the barrier at the end of the iteration publishes the next tile; every path below must reach it
+        bool skip;
         unsigned k0, k1;
         xm_mask_rows(R.mr0, R.mr1, j0, Lk, t, k0, k1);
         if (!R.act0) k0 = 0xffffu;
         if (!R.act1) k1 = 0xffffu;
-        if (__all_sync(0xffffffffu, (k0 & k1) == 0xffffu)) continue;         // nothing attended in this warp's 16 x 64 block
+        skip = __all_sync(0xffffffffu, (k0 & k1) == 0xffffu);                // nothing attended in this warp's 16 x 64 block
+        if (!skip) {
         float s[8][4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
@@ -165,14 +210,14 @@ xattn_fwd_partial_mma(const float* __restrict__ q, const float* __restrict__ k, 
         t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 1)); t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 2));
         t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 1)); t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
         const float n0 = fmaxf(m0, t0), n1 = fmaxf(m1, t1);
-        const float c0 = (m0 == -INFINITY) ? 0.f : expf(m0 - n0), c1 = (m1 == -INFINITY) ? 0.f : expf(m1 - n1);
+        const float c0 = (m0 == -INFINITY) ? 0.f : exp2f(m0 - n0), c1 = (m1 == -INFINITY) ? 0.f : exp2f(m1 - n1);
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            s[j][0] = (s[j][0] == -INFINITY) ? 0.f : expf(s[j][0] - n0);
-            s[j][1] = (s[j][1] == -INFINITY) ? 0.f : expf(s[j][1] - n0);
-            s[j][2] = (s[j][2] == -INFINITY) ? 0.f : expf(s[j][2] - n1);
-            s[j][3] = (s[j][3] == -INFINITY) ? 0.f : expf(s[j][3] - n1);
+            s[j][0] = (s[j][0] == -INFINITY) ? 0.f : exp2f(s[j][0] - n0);
+            s[j][1] = (s[j][1] == -INFINITY) ? 0.f : exp2f(s[j][1] - n0);
+            s[j][2] = (s[j][2] == -INFINITY) ? 0.f : exp2f(s[j][2] - n1);
+            s[j][3] = (s[j][3] == -INFINITY) ? 0.f : exp2f(s[j][3] - n1);
             a0 += s[j][0] + s[j][1];
             a1 += s[j][2] + s[j][3];
         }
@@ -182,6 +227,9 @@ xattn_fwd_partial_mma(const float* __restrict__ q, const float* __restrict__ k, 
         for (int n = 0; n < 4; ++n) { o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1; }
         m0 = n0; m1 = n1;
         xm_chain(o, s, sV, g, t);
+        }
+        if (more) xm_commit(stg, sKb[(tl + 1 - tile_begin) & 1], sVb[(tl + 1 - tile_begin) & 1]);
+        __syncthreads();
     }
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
@@ -190,13 +238,13 @@ xattn_fwd_partial_mma(const float* __restrict__ q, const float* __restrict__ k, 
         float* oa = ws_acc + (base + R.qi0) * MXD;
 #pragma unroll
         for (int n = 0; n < 4; ++n) *reinterpret_cast<float2*>(oa + n * 8 + 2 * t) = make_float2(o[n][0], o[n][1]);
-        if (t == 0) { ws_ml[(base + R.qi0) * 2] = m0; ws_ml[(base + R.qi0) * 2 + 1] = l0; }
+        if (t == 0) { ws_ml[(base + R.qi0) * 2] = m0 * kXmLn2; ws_ml[(base + R.qi0) * 2 + 1] = l0; }
     }
     if (R.act1) {
         float* oa = ws_acc + (base + R.qi1) * MXD;
 #pragma unroll
         for (int n = 0; n < 4; ++n) *reinterpret_cast<float2*>(oa + n * 8 + 2 * t) = make_float2(o[n][2], o[n][3]);
-        if (t == 0) { ws_ml[(base + R.qi1) * 2] = m1; ws_ml[(base + R.qi1) * 2 + 1] = l1; }
+        if (t == 0) { ws_ml[(base + R.qi1) * 2] = m1 * kXmLn2; ws_ml[(base + R.qi1) * 2 + 1] = l1; }
     }
 }
 
@@ -206,8 +254,8 @@ xattn_bwd_dq_mma(const float* __restrict__ q, const float* __restrict__ k, const
                  const uint8_t* __restrict__ mask, const int32_t* __restrict__ row_any, const float* __restrict__ out,
                  const float* __restrict__ lse, const float* __restrict__ gout, float* __restrict__ gq, int heads, int Q, int Lk,
                  int nsplit, int tiles_per) {
-    __shared__ __align__(16) float sK[MXT * MXS];
-    __shared__ __align__(16) float sV[MXT * MXS];
+    __shared__ __align__(16) float sKb[2][MXT * MXS];
+    __shared__ __align__(16) float sVb[2][MXT * MXS];
     const int split = blockIdx.x % nsplit, qt = blockIdx.x / nsplit;
     const int h = blockIdx.y, b = blockIdx.z;
     const int ld = heads * MXD, hoff = h * MXD;
@@ -226,24 +274,31 @@ xattn_bwd_dq_mma(const float* __restrict__ q, const float* __restrict__ k, const
     }
     d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
     d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
-    const float e0 = R.act0 ? lse[((int64_t)b * heads + h) * Q + R.qi0] : 0.f;
-    const float e1 = R.act1 ? lse[((int64_t)b * heads + h) * Q + R.qi1] : 0.f;
+    xm_scale_a(qf, kXmLog2e);                  // P = exp(S - lse) = exp2(S log2e - lse log2e)
+    const float e0 = R.act0 ? lse[((int64_t)b * heads + h) * Q + R.qi0] * kXmLog2e : 0.f;
+    const float e1 = R.act1 ? lse[((int64_t)b * heads + h) * Q + R.qi1] * kXmLog2e : 0.f;
     float dq[4][4];
 #pragma unroll
     for (int n = 0; n < 4; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
     const int tile_begin = split * tiles_per;
     const int tile_end = min(tile_begin + tiles_per, (Lk + MXT - 1) / MXT);
+    XmStage stg;
+    if (tile_begin < tile_end) {
+        xm_prefetch(stg, k, v, (int64_t)b * Lk, tile_begin * MXT, Lk, ld, hoff);
+        xm_commit(stg, sKb[0], sVb[0]);
+    }
+    __syncthreads();
     for (int tl = tile_begin; tl < tile_end; ++tl) {
         const int j0 = tl * MXT;
-        __syncthreads();
-        xm_load_tile(sK, k, (int64_t)b * Lk, j0, Lk, ld, hoff);
-        xm_load_tile(sV, v, (int64_t)b * Lk, j0, Lk, ld, hoff);
-        __syncthreads();
+        const float* sK = sKb[(tl - tile_begin) & 1];
+        const float* sV = sVb[(tl - tile_begin) & 1];
+        const bool more = tl + 1 < tile_end;
+        if (more) xm_prefetch(stg, k, v, (int64_t)b * Lk, j0 + MXT, Lk, ld, hoff);
         unsigned k0, k1;
         xm_mask_rows(R.mr0, R.mr1, j0, Lk, t, k0, k1);
         if (!R.act0) k0 = 0xffffu;
         if (!R.act1) k1 = 0xffffu;
-        if (__all_sync(0xffffffffu, (k0 & k1) == 0xffffu)) continue;
+        if (!__all_sync(0xffffffffu, (k0 & k1) == 0xffffu)) {
         float s[8][4], dp[8][4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -254,12 +309,15 @@ xattn_bwd_dq_mma(const float* __restrict__ q, const float* __restrict__ k, const
         xm_scores(dp, df, sV, g, t);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {           // dS = P (dP - delta), P = exp(S - lse) on the attended keys
-            s[j][0] = ((k0 >> (2 * j)) & 1u) ? 0.f : expf(s[j][0] - e0) * (dp[j][0] - d0);
-            s[j][1] = ((k0 >> (2 * j + 1)) & 1u) ? 0.f : expf(s[j][1] - e0) * (dp[j][1] - d0);
-            s[j][2] = ((k1 >> (2 * j)) & 1u) ? 0.f : expf(s[j][2] - e1) * (dp[j][2] - d1);
-            s[j][3] = ((k1 >> (2 * j + 1)) & 1u) ? 0.f : expf(s[j][3] - e1) * (dp[j][3] - d1);
+            s[j][0] = ((k0 >> (2 * j)) & 1u) ? 0.f : exp2f(s[j][0] - e0) * (dp[j][0] - d0);
+            s[j][1] = ((k0 >> (2 * j + 1)) & 1u) ? 0.f : exp2f(s[j][1] - e0) * (dp[j][1] - d0);
+            s[j][2] = ((k1 >> (2 * j)) & 1u) ? 0.f : exp2f(s[j][2] - e1) * (dp[j][2] - d1);
+            s[j][3] = ((k1 >> (2 * j + 1)) & 1u) ? 0.f : exp2f(s[j][3] - e1) * (dp[j][3] - d1);
         }
         xm_chain(dq, s, sK, g, t);
+        }
+        if (more) xm_commit(stg, sKb[(tl + 1 - tile_begin) & 1], sVb[(tl + 1 - tile_begin) & 1]);
+        __syncthreads();
     }
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
@@ -269,100 +327,122 @@ xattn_bwd_dq_mma(const float* __restrict__ q, const float* __restrict__ k, const
 }
 
 // ------------------------------------------------------------------------------------------------ grad_k / grad_v
-// CTA = 64 keys of one (b, h): warp w owns keys j0 + 16w + g (+ 8); queries are staged 64 at a time.
+// CTA = KT consecutive 64-key tiles of one (b, h); warp w owns keys 16w + g (+ 8) of the current tile.  ALL queries of the (b, h)
+// (Q, dO, lse, delta = dO . O, mask-use flags; QP = Q rounded up to 32 rows) are staged in shared memory once, after which the
+// warps run without any block barrier: per key tile and per 32 queries, S^T = K Q^T and dP^T = V dO^T, then the two chained
+// products dV += P^T dO and dK += dS^T Q.
 __global__ void __launch_bounds__(128)
 xattn_bwd_dkv_mma(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                   const uint8_t* __restrict__ mask, const int32_t* __restrict__ row_any, const float* __restrict__ out,
                   const float* __restrict__ lse, const float* __restrict__ gout, float* __restrict__ gk, float* __restrict__ gv,
-                  int heads, int Q, int Lk) {
-    __shared__ __align__(16) float sQ[MXT * MXS];
-    __shared__ __align__(16) float sDO[MXT * MXS];
-    __shared__ float sLse[MXT], sDelta[MXT];
-    __shared__ int sUse[MXT];                   // 1: masked row, 0: unmasked row (no mask / reset row), -1: beyond Q
+                  int heads, int Q, int Lk, int QP, int KT) {
+    extern __shared__ __align__(16) float xm_smem[];
+    float* sQ = xm_smem;
+    float* sDO = sQ + QP * MXS;
+    float* sLse = sDO + QP * MXS;              // lse * log2(e)
+    float* sDelta = sLse + QP;
+    int* sUse = reinterpret_cast<int*>(sDelta + QP);     // 1: masked row, 0: unmasked row (no mask / reset row), -1: beyond Q
     const int h = blockIdx.y, b = blockIdx.z;
     const int ld = heads * MXD, hoff = h * MXD;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int key0 = blockIdx.x * MXT + warp * 16 + g, key1 = key0 + 8;
-    const bool a0 = key0 < Lk, a1 = key1 < Lk;
-    const int64_t o0 = ((int64_t)b * Lk + key0) * ld + hoff, o1 = ((int64_t)b * Lk + key1) * ld + hoff;
-    float kf[4][4], vf[4][4];
-    xm_load_a(kf, a0 ? k + o0 : nullptr, a1 ? k + o1 : nullptr, t);
-    xm_load_a(vf, a0 ? v + o0 : nullptr, a1 ? v + o1 : nullptr, t);
-    float dk[4][4], dv[4][4];
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-        dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f;
-        dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
-    }
-    for (int i0 = 0; i0 < Q; i0 += MXT) {
-        __syncthreads();
-        xm_load_tile(sQ, q, (int64_t)b * Q, i0, Q, ld, hoff);
-        xm_load_tile(sDO, gout, (int64_t)b * Q, i0, Q, ld, hoff);
-        for (int ii = warp; ii < MXT; ii += 4) {          // one warp per staged query: delta = dO . O, lse, mask use
-            float pr = 0.f;
-            if (i0 + ii < Q) {
-                const int64_t ro = ((int64_t)b * Q + i0 + ii) * ld + hoff + lane;
-                pr = __ldg(gout + ro) * __ldg(out + ro);
-            }
-            pr = warp_sum(pr);
-            if (lane == 0) {
-                sDelta[ii] = pr;
-                sLse[ii] = (i0 + ii < Q) ? lse[((int64_t)b * heads + h) * Q + i0 + ii] : 0.f;
-                sUse[ii] = (i0 + ii < Q) ? ((mask != nullptr && (row_any == nullptr || row_any[(int64_t)b * Q + i0 + ii] != 0)) ? 1 : 0) : -1;
-            }
+    for (int e = threadIdx.x; e < QP * (MXD / 4); e += 128) {
+        const int jj = e >> 3, c = e & 7;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
+        if (jj < Q) {
+            const int64_t off = ((int64_t)b * Q + jj) * ld + hoff + c * 4;
+            x = __ldg(reinterpret_cast<const float4*>(q + off));
+            y = __ldg(reinterpret_cast<const float4*>(gout + off));
         }
-        __syncthreads();
-        // masked flags of this thread's entries: bit (2j + c) of f0 / f1 = (key0 / key1, query i0 + 8j + 2t + c)
-        unsigned f0 = 0u, f1 = 0u;
+        *reinterpret_cast<float4*>(sQ + jj * MXS + c * 4) = x;
+        *reinterpret_cast<float4*>(sDO + jj * MXS + c * 4) = y;
+    }
+    for (int ii = warp; ii < QP; ii += 4) {               // one warp per query: delta = dO . O, lse, mask use
+        float pr = 0.f;
+        if (ii < Q) {
+            const int64_t ro = ((int64_t)b * Q + ii) * ld + hoff + lane;
+            pr = __ldg(gout + ro) * __ldg(out + ro);
+        }
+        pr = warp_sum(pr);
+        if (lane == 0) {
+            sDelta[ii] = pr;
+            sLse[ii] = (ii < Q) ? lse[((int64_t)b * heads + h) * Q + ii] * kXmLog2e : 0.f;
+            sUse[ii] = (ii < Q) ? ((mask != nullptr && (row_any == nullptr || row_any[(int64_t)b * Q + ii] != 0)) ? 1 : 0) : -1;
+        }
+    }
+    __syncthreads();
+    for (int kt = 0; kt < KT; ++kt) {
+        const int tile = blockIdx.x * KT + kt;
+        if (tile * MXT >= Lk) break;
+        const int key0 = tile * MXT + warp * 16 + g, key1 = key0 + 8;
+        const bool a0 = key0 < Lk, a1 = key1 < Lk;
+        const int64_t o0 = ((int64_t)b * Lk + key0) * ld + hoff, o1 = ((int64_t)b * Lk + key1) * ld + hoff;
+        float kf[4][4], vf[4][4];
+        xm_load_a(kf, a0 ? k + o0 : nullptr, a1 ? k + o1 : nullptr, t);
+        xm_load_a(vf, a0 ? v + o0 : nullptr, a1 ? v + o1 : nullptr, t);
+        xm_scale_a(kf, kXmLog2e);              // S^T in log2 units (kf is only used for the scores)
+        float dk[4][4], dv[4][4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int n = 0; n < 4; ++n) {
+            dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f;
+            dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
+        }
+#pragma unroll 1
+        for (int i0 = 0; i0 < QP; i0 += 32) {
+            // masked flags of this thread's entries: bit (2j + c) of f0 / f1 = (key0 / key1, query i0 + 8j + 2t + c)
+            unsigned f0 = 0u, f1 = 0u;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int qq = j * 8 + 2 * t + c;
-                const int use = sUse[qq];
-                bool x0 = use < 0 || !a0, x1 = use < 0 || !a1;
-                if (use == 1) {
-                    const uint8_t* mrow = mask + ((int64_t)b * Q + i0 + qq) * Lk;
-                    if (a0 && __ldg(mrow + key0)) x0 = true;
-                    if (a1 && __ldg(mrow + key1)) x1 = true;
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int qq = i0 + j * 8 + 2 * t + c;
+                    const int use = sUse[qq];
+                    bool x0 = use < 0 || !a0, x1 = use < 0 || !a1;
+                    if (use == 1) {
+                        const uint8_t* mrow = mask + ((int64_t)b * Q + qq) * Lk;
+                        if (a0 && __ldg(mrow + key0)) x0 = true;
+                        if (a1 && __ldg(mrow + key1)) x1 = true;
+                    }
+                    f0 |= (x0 ? 1u : 0u) << (2 * j + c);
+                    f1 |= (x1 ? 1u : 0u) << (2 * j + c);
                 }
-                f0 |= (x0 ? 1u : 0u) << (2 * j + c);
-                f1 |= (x1 ? 1u : 0u) << (2 * j + c);
+            if (__all_sync(0xffffffffu, (f0 & f1) == 0xffu)) continue;
+            const float* tq = sQ + i0 * MXS;
+            const float* td = sDO + i0 * MXS;
+            float st[4][4], dp[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
+                dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
             }
-        if (__all_sync(0xffffffffu, (f0 & f1) == 0xffffu)) continue;
-        float st[8][4], dp[8][4];
+            xm_scores<4>(st, kf, tq, g, t);          // S^T = K Q^T
+            xm_scores<4>(dp, vf, td, g, t);          // dP^T = V dO^T
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
-            dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
+            for (int j = 0; j < 4; ++j) {
+                const int qa = i0 + j * 8 + 2 * t;
+                const float la = sLse[qa], lb = sLse[qa + 1];
+                const float da = sDelta[qa], db = sDelta[qa + 1];
+                st[j][0] = ((f0 >> (2 * j)) & 1u) ? 0.f : exp2f(st[j][0] - la);
+                st[j][1] = ((f0 >> (2 * j + 1)) & 1u) ? 0.f : exp2f(st[j][1] - lb);
+                st[j][2] = ((f1 >> (2 * j)) & 1u) ? 0.f : exp2f(st[j][2] - la);
+                st[j][3] = ((f1 >> (2 * j + 1)) & 1u) ? 0.f : exp2f(st[j][3] - lb);
+                dp[j][0] = st[j][0] * (dp[j][0] - da);
+                dp[j][1] = st[j][1] * (dp[j][1] - db);
+                dp[j][2] = st[j][2] * (dp[j][2] - da);
+                dp[j][3] = st[j][3] * (dp[j][3] - db);
+            }
+            xm_chain<4>(dv, st, td, g, t);           // dV += P^T dO
+            xm_chain<4>(dk, dp, tq, g, t);           // dK += dS^T Q
         }
-        xm_scores(st, kf, sQ, g, t);            // S^T = K Q^T
-        xm_scores(dp, vf, sDO, g, t);           // dP^T = V dO^T
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float la = sLse[j * 8 + 2 * t], lb = sLse[j * 8 + 2 * t + 1];
-            const float da = sDelta[j * 8 + 2 * t], db = sDelta[j * 8 + 2 * t + 1];
-            st[j][0] = ((f0 >> (2 * j)) & 1u) ? 0.f : expf(st[j][0] - la);
-            st[j][1] = ((f0 >> (2 * j + 1)) & 1u) ? 0.f : expf(st[j][1] - lb);
-            st[j][2] = ((f1 >> (2 * j)) & 1u) ? 0.f : expf(st[j][2] - la);
-            st[j][3] = ((f1 >> (2 * j + 1)) & 1u) ? 0.f : expf(st[j][3] - lb);
-            dp[j][0] = st[j][0] * (dp[j][0] - da);
-            dp[j][1] = st[j][1] * (dp[j][1] - db);
-            dp[j][2] = st[j][2] * (dp[j][2] - da);
-            dp[j][3] = st[j][3] * (dp[j][3] - db);
-        }
-        xm_chain(dv, st, sDO, g, t);            // dV += P^T dO
-        xm_chain(dk, dp, sQ, g, t);             // dK += dS^T Q
-    }
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-        if (a0) {
-            *reinterpret_cast<float2*>(gk + o0 + n * 8 + 2 * t) = make_float2(dk[n][0], dk[n][1]);
-            *reinterpret_cast<float2*>(gv + o0 + n * 8 + 2 * t) = make_float2(dv[n][0], dv[n][1]);
-        }
-        if (a1) {
-            *reinterpret_cast<float2*>(gk + o1 + n * 8 + 2 * t) = make_float2(dk[n][2], dk[n][3]);
-            *reinterpret_cast<float2*>(gv + o1 + n * 8 + 2 * t) = make_float2(dv[n][2], dv[n][3]);
+        for (int n = 0; n < 4; ++n) {
+            if (a0) {
+                *reinterpret_cast<float2*>(gk + o0 + n * 8 + 2 * t) = make_float2(dk[n][0], dk[n][1]);
+                *reinterpret_cast<float2*>(gv + o0 + n * 8 + 2 * t) = make_float2(dv[n][0], dv[n][1]);
+            }
+            if (a1) {
+                *reinterpret_cast<float2*>(gk + o1 + n * 8 + 2 * t) = make_float2(dk[n][2], dk[n][3]);
+                *reinterpret_cast<float2*>(gv + o1 + n * 8 + 2 * t) = make_float2(dv[n][2], dv[n][3]);
+            }
         }
     }
 }
@@ -381,8 +461,20 @@ int xattn_bwd_mma_launch(const float* q, const float* k, const float* v, const u
     dim3 grid((unsigned)(ns * qtiles), (unsigned)heads, (unsigned)B);
     xattn_bwd_dq_mma<<<grid, 256, 0, st>>>(q, k, v, mask, row_any, out, lse, gout, gq, heads, Q, Lk, ns, tiles_per);
     PDB_TRY(launched("xattn_bwd_dq_mma"));
-    dim3 grid2((unsigned)((Lk + MXT - 1) / MXT), (unsigned)heads, (unsigned)B);
-    xattn_bwd_dkv_mma<<<grid2, 128, 0, st>>>(q, k, v, mask, row_any, out, lse, gout, gk, gv, heads, Q, Lk);
+    const int tiles = (Lk + MXT - 1) / MXT;
+    const int QP = (Q + 31) / 32 * 32;
+    int KT = (int)(((int64_t)tiles * heads * B) / (4 * kNumSMs));       // key tiles per CTA: keep >= ~600 CTAs in flight
+    KT = KT < 1 ? 1 : (KT > 8 ? 8 : KT);
+    const size_t smem = sizeof(float) * ((size_t)2 * QP * MXS + 3 * QP);
+    PDB_REQUIRE(smem <= 200 * 1024, "masked_xattn_backward: %d queries do not fit shared memory", Q);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(xattn_bwd_dkv_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(PDB_ERR_LAUNCH, "xattn_bwd_dkv_mma: smem attribute: %s", cudaGetErrorString(e));
+        attr = smem;
+    }
+    dim3 grid2((unsigned)((tiles + KT - 1) / KT), (unsigned)heads, (unsigned)B);
+    xattn_bwd_dkv_mma<<<grid2, 128, smem, st>>>(q, k, v, mask, row_any, out, lse, gout, gk, gv, heads, Q, Lk, QP, KT);
     return launched("xattn_bwd_dkv_mma");
 }
 
