@@ -520,6 +520,18 @@ def _split_k(M, N, K):
     return max(1, min((K + 31) // 32, (2 * 148 + tiles - 1) // tiles))
 
 
+def col_sum(x2):
+    """Sum over the rows of a contiguous fp32 (rows, N) matrix: the bias gradient of a Linear layer.  Short matrices (the
+    decoder's 200 rows) use the library's one-line-per-warp kernel; long ones ATen's two-stage reduction."""
+    f = getattr(_lib.load(), "pdb_col_sum", None)             # absent only in the CPU-tier host builds of the tests
+    if f is None or not x2.is_cuda or x2.dtype != torch.float32 or x2.shape[0] > 4096 or x2.shape[0] == 0:
+        return x2.sum(0)
+    x2 = _c(x2)
+    out = torch.empty((x2.shape[1],), dtype=torch.float32, device=x2.device)
+    _lib.check(f(x2.data_ptr(), out.data_ptr(), x2.shape[0], x2.shape[1], _stream()), "pdb_col_sum")
+    return out
+
+
 def linear_supported(x, weight):
     return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32
             and weight.shape[0] % 4 == 0 and weight.shape[1] % 4 == 0 and weight.is_contiguous())
@@ -571,7 +583,7 @@ class LinearFunction(Function):
             gemm_tf32x3(gy2, x2, gw, N, K, M, lda=N, ldb=K, ldc=K, a_mn=True, b_mn=True, accumulate=True,
                         ksplit=_split_k(N, K, M))
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gy2.sum(0)
+            gb = col_sum(gy2)
         return gx, gw, gb, None
 
 

@@ -831,3 +831,11 @@ def test_linear_bf16_autocast_matches_torch(fn):
     gr = torch.autograd.grad(yr, (x, w, b), go.to(yr.dtype))
     for a_, r_ in zip(gs, gr):
         assert a_.dtype == r_.dtype and _rel(a_.float(), r_.float()) < 2 ** -6
+
+
+@pytest.mark.parametrize("rows,N", [(200, 256), (200, 2048), (37, 100), (4096, 512), (1, 4)])
+def test_col_sum(fn, rows, N):
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(rows, N, generator=g).cuda()
+    # fp32 running sums of rows / 8 terms per lane: error ~ rows / 8 * 2^-24 of the partial sums
+    assert torch.allclose(fn.col_sum(x).double(), x.double().sum(0), rtol=1e-4, atol=2e-4)
