@@ -382,12 +382,14 @@ def kernel_rooflines(device):
     del sets, outs
 
     # ---- BASELINE configs[3] = C4: pixel grouping, res3 + res4 features (768 ch at 64^2) of a 512^2 image, 4 centroids
-    feats = [torch.randn(768, 64, 64, generator=g).to(device) for _ in range(16)]        # 16 x 12.6 MB > L2
-    cent = torch.randn(4, 768, generator=g).to(device)
+    GB = 16                                                                               # images per batched call
+    feats = [torch.randn(GB, 768, 64, 64, generator=g).to(device) for _ in range(2)]      # 2 x 201 MB > L2
+    cent = torch.randn(GB, 4, 768, generator=g).to(device)
     yy, xx = torch.meshgrid(torch.arange(512), torch.arange(512), indexing="ij")
-    gmask = (((yy - 256) ** 2 + (xx - 256) ** 2) < 200 ** 2).to(device)
-    t = _time_kernel([(lambda f=f: fn.group_affinity(f, cent, gmask, "dot")) for f in feats], flush, per_event=16)
-    out.append(hbm_entry("group_affinity_kernel (C4: 768 ch 64^2 -> 512^2 labels, 4 centroids)", 4 * 768 * 64 * 64 + 512 * 512 * 5, t))
+    gmask = (((yy - 256) ** 2 + (xx - 256) ** 2) < 200 ** 2).to(device)[None].repeat(GB, 1, 1)
+    t = _time_kernel([(lambda f=f: fn.group_affinity_batched(f, cent, gmask, "dot")) for f in feats], flush, per_event=4) / GB
+    out.append(hbm_entry("group_scores_kernel + group_affinity_kernel (C4: 768 ch 64^2 -> 512^2 labels, 4 centroids; per image of a "
+                         "16-image batched call)", 4 * 768 * 64 * 64 + 512 * 512 * 5, t))
     out[-1]["images_per_s"] = round(1.0 / t, 1)
     del feats
 
