@@ -123,8 +123,9 @@ PDB_API int pdb_gemm_tf32x3(const float* A, const float* B, const float* B_lo, f
  * C row-major with pitch ldc, fp32 (out_bf16 = 0) or bf16 (out_bf16 = 1). */
 PDB_API int pdb_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int64_t lda, int64_t ldb,
                   int64_t ldc, int act, int out_bf16, void* stream);
-/* out[n] = sum_r x[r*N + n]: bias gradient of a Linear layer over few rows (the decoder's B*Q = 200 rows; autograd's db). */
-PDB_API int pdb_col_sum(const float* x, float* out, int rows, int N, void* stream);
+/* out[n] (+)= sum_r x[r*N + n]: bias gradient of a Linear layer over few rows (the decoder's B*Q = 200 rows; autograd's db);
+ * accumulate != 0 adds into out (a preallocated parameter gradient). */
+PDB_API int pdb_col_sum(const float* x, float* out, int rows, int N, int accumulate, void* stream);
 /* Convolution-shaped variant: K = taps * Ck, and the k range of tap t reads the A rows shifted by tap_off[t]:
  *   C_b[m][n] = sum_t sum_c A_b[m + tap_off[t]][c] * B[n][t * Ck + c]  (+ bias[n]) (ReLU)
  * A_b = A + b*sa is (a_rows x Ck), K-major, rows beyond a_rows read as 0; B is (N x taps*Ck), K-major, shared by all batch

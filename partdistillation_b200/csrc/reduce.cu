@@ -7,7 +7,7 @@
 namespace pdb {
 
 __global__ void __launch_bounds__(256)
-col_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, int N) {
+col_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, int N, int accumulate) {
     __shared__ float part[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), r0 = threadIdx.x >> 5;
     float a0 = 0.f, a1 = 0.f;
@@ -25,7 +25,7 @@ col_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, i
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) s += part[i][threadIdx.x];
-        out[c] = s;
+        out[c] = accumulate ? out[c] + s : s;
     }
 }
 
@@ -33,9 +33,9 @@ col_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, i
 
 using namespace pdb;
 
-extern "C" int pdb_col_sum(const float* x, float* out, int rows, int N, void* stream) {
+extern "C" int pdb_col_sum(const float* x, float* out, int rows, int N, int accumulate, void* stream) {
     PDB_REQUIRE(x && out, "col_sum: null pointer");
     PDB_REQUIRE(rows > 0 && N > 0, "col_sum: non-positive size");
-    col_sum_kernel<<<(unsigned)((N + 31) / 32), 256, 0, as_stream(stream)>>>(x, out, rows, N);
+    col_sum_kernel<<<(unsigned)((N + 31) / 32), 256, 0, as_stream(stream)>>>(x, out, rows, N, accumulate);
     return launched("col_sum");
 }

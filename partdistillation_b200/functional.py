@@ -520,16 +520,42 @@ def _split_k(M, N, K):
     return max(1, min((K + 31) // 32, (2 * 148 + tiles - 1) // tiles))
 
 
-def col_sum(x2):
+def col_sum(x2, into=None):
     """Sum over the rows of a contiguous fp32 (rows, N) matrix: the bias gradient of a Linear layer.  Short matrices (the
-    decoder's 200 rows) use the library's one-line-per-warp kernel; long ones ATen's two-stage reduction."""
+    decoder's 200 rows) use the library's one-line-per-warp kernel; long ones ATen's two-stage reduction.  ``into``: a
+    preallocated fp32 (N,) gradient to ADD the sums to (returns None then)."""
     f = getattr(_lib.load(), "pdb_col_sum", None)             # absent only in the CPU-tier host builds of the tests
     if f is None or not x2.is_cuda or x2.dtype != torch.float32 or x2.shape[0] > 4096 or x2.shape[0] == 0:
+        if into is not None:
+            into.add_(x2.sum(0))
+            return None
         return x2.sum(0)
     x2 = _c(x2)
-    out = torch.empty((x2.shape[1],), dtype=torch.float32, device=x2.device)
-    _lib.check(f(x2.data_ptr(), out.data_ptr(), x2.shape[0], x2.shape[1], _stream()), "pdb_col_sum")
-    return out
+    out = into if into is not None else torch.empty((x2.shape[1],), dtype=torch.float32, device=x2.device)
+    _lib.check(f(x2.data_ptr(), out.data_ptr(), x2.shape[0], x2.shape[1], 1 if into is not None else 0, _stream()), "pdb_col_sum")
+    return None if into is not None else out
+
+
+# Weight / bias gradients of LinearFunction go STRAIGHT into the parameter's preallocated gradient when there is one (the trainer
+# keeps every trainable parameter's .grad as a view of its zero-filled flat buffer): the weight-gradient GEMM accumulates into it
+# (it is a split-K red.add product anyway) and autograd receives None — no zero-filled (N, K) temporary, no AccumulateGrad add,
+# and for row slices of a packed parameter (the q / k / v blocks of in_proj_weight) no SliceBackward (zeros + copy of the whole
+# parameter per use).  Without a preallocated gradient (plain autograd use, the parity tests) nothing changes.
+direct_param_grads = True
+
+
+def _direct_grad(t, shape):
+    if not direct_param_grads or t is None or not t.requires_grad or not t.is_contiguous():
+        return None
+    p = t if t.is_leaf else t._base
+    if p is None or not p.is_leaf or p.grad is None or p.grad.dtype != torch.float32 or not p.grad.is_contiguous() \
+            or p.grad.shape != p.shape:
+        return None
+    off = t.storage_offset() - p.storage_offset()
+    if off < 0 or off + t.numel() > p.numel():
+        return None
+    g = p.grad.view(-1)[off:off + t.numel()].view(shape)
+    return g if g.data_ptr() % 16 == 0 else None
 
 
 def linear_supported(x, weight):
@@ -555,6 +581,7 @@ class LinearFunction(Function):
         ctx.w_lo = w_lo
         ctx.relu = int(relu)            # epilogue activation: 0 none, 1 ReLU, 2 GELU (forward-only: see linear())
         ctx.has_bias = bias is not None
+        ctx.wref, ctx.bref = weight, bias       # the caller's tensors (leaf parameters or row slices of one): see _direct_grad
         ctx.save_for_backward(x2, weight, out if ctx.relu == 1 else None)
         return out.view(*x.shape[:-1], N)
 
@@ -578,12 +605,15 @@ class LinearFunction(Function):
             gemm_tf32x3(gy2, weight, gx, M, K, N, lda=N, ldb=K, ldc=K, b_mn=True, B_lo=ctx.w_lo)
             gx = gx.view(*gy.shape[:-1], K)
         if ctx.needs_input_grad[1]:
-            gw = torch.zeros((N, K), dtype=torch.float32, device=gy.device)
+            tgt = _direct_grad(ctx.wref, (N, K))
+            gw = tgt if tgt is not None else torch.zeros((N, K), dtype=torch.float32, device=gy.device)
             # dW[o,i] = sum_m gy[m,o] x[m,i]:  A(m'=o,k=m) = gy[m*N+o], B(n'=i,k=m) = x[m*K+i]  (both MN-major)
             gemm_tf32x3(gy2, x2, gw, N, K, M, lda=N, ldb=K, ldc=K, a_mn=True, b_mn=True, accumulate=True,
                         ksplit=_split_k(N, K, M))
+            if tgt is not None:
+                gw = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = col_sum(gy2)
+            gb = col_sum(gy2, into=_direct_grad(ctx.bref, (N,)))
         return gx, gw, gb, None
 
 

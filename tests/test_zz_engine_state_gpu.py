@@ -62,3 +62,49 @@ def test_graph_replay_advances_weights_epoch():
     tr.cuda_graph = False
     tr.step(batch)
     assert PF.weights_epoch == e0 + 1
+
+
+def test_direct_param_grads_match_autograd_accumulation():
+    """functional.LinearFunction writes weight / bias gradients straight into the trainer's preallocated flat gradients (row
+    slices of a packed parameter included); the training trajectory equals the one with autograd's own accumulation."""
+    from partdistillation_b200 import functional as PF
+    from partdistillation_b200.engine import DataParallelTrainer
+
+    class Packed(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            E = 64
+            self.E = E
+            self.in_proj_weight = torch.nn.Parameter(torch.randn(3 * E, E) * 0.1)
+            self.in_proj_bias = torch.nn.Parameter(torch.randn(3 * E) * 0.1)
+            self.lin = torch.nn.Linear(E, 2 * E)
+            self.out = torch.nn.Linear(2 * E, 8)
+
+        def forward(self, batch):
+            x, y = batch
+            E = self.E
+            q = PF.linear(x, self.in_proj_weight[:E], self.in_proj_bias[:E])
+            k = PF.linear(x + 1.0, self.in_proj_weight[E:2 * E], self.in_proj_bias[E:2 * E])
+            v = PF.linear(x, self.in_proj_weight[2 * E:], self.in_proj_bias[2 * E:])
+            h = PF.linear(q * k + v, self.lin.weight, self.lin.bias, relu=True)
+            h = h + PF.linear(v, self.lin.weight, self.lin.bias)              # the same weight used twice
+            o = PF.linear(h, self.out.weight, self.out.bias)
+            return {"loss": (o - y).pow(2).mean()}
+
+    g = torch.Generator().manual_seed(5)
+    batches = [(torch.randn(3, 50, 64, generator=g).cuda(), torch.randn(3, 50, 8, generator=g).cuda()) for _ in range(3)]
+    finals = []
+    for flag in (True, False):
+        torch.manual_seed(1)
+        m = Packed().cuda()
+        tr = DataParallelTrainer(m, base_lr=1e-2, weight_decay=0.05, clip_norm=0.5, freeze_keys=())
+        old = PF.direct_param_grads
+        try:
+            PF.direct_param_grads = flag
+            for b in batches:
+                tr.step(b)
+        finally:
+            PF.direct_param_grads = old
+        finals.append({k: v.clone() for k, v in m.state_dict().items()})
+    for k in finals[0]:       # split-K weight gradients are red.add sums (order not fixed run to run) and Adam normalises: 1e-4
+        assert torch.allclose(finals[0][k], finals[1][k], rtol=1e-4, atol=1e-5), k
