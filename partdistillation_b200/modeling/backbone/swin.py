@@ -242,6 +242,22 @@ class PatchEmbed(nn.Module):
             x = self.norm(x.flatten(2).transpose(1, 2)).transpose(1, 2).reshape(x.shape[0], -1, Wh, Ww)
         return x
 
+    def forward_tokens(self, x):
+        """Same result as ``forward`` in token order, (B, Wh * Ww, C) + (Wh, Ww): the stride-p p x p convolution is a GEMM over
+        the non-overlapping patches (one im2col copy of the image, then the tensor-core Linear + the library's LayerNorm), so the
+        NCHW <-> token transposes around the reference's conv + norm (swin.py:418-447) disappear."""
+        p = self.patch_size
+        _, _, H, W = x.shape
+        if W % p or H % p:
+            x = F.pad(x, (0, (p - W % p) % p, 0, (p - H % p) % p))
+        B, C, H, W = x.shape
+        Wh, Ww = H // p, W // p
+        patches = x.view(B, C, Wh, p, Ww, p).permute(0, 2, 4, 1, 3, 5).reshape(B, Wh * Ww, C * p * p)
+        t = PF.linear(patches, self.proj.weight.view(self.proj.weight.shape[0], -1), self.proj.bias)
+        if self.norm is not None:
+            t = PF.layer_norm(t, self.norm.weight, self.norm.bias, self.norm.eps)
+        return t, Wh, Ww
+
 
 class SwinTransformer(nn.Module):
     def __init__(self, pretrain_img_size=224, patch_size=4, in_chans=3, embed_dim=96, depths=(2, 2, 6, 2),
@@ -278,14 +294,14 @@ class SwinTransformer(nn.Module):
             nn.init.constant_(m.weight, 1.0)
 
     def forward(self, x):
-        x = self.patch_embed(x)
-        Wh, Ww = x.shape[2:]
-        x = self.pos_drop(x.flatten(2).transpose(1, 2))
+        x, Wh, Ww = self.patch_embed.forward_tokens(x)
+        x = self.pos_drop(x)
         outs = {}
         for i, layer in enumerate(self.layers):
             x_out, H, W, x, Wh, Ww = layer(x, Wh, Ww)
             if i in self.out_indices:
-                o = getattr(self, f"norm{i}")(x_out)
+                n = getattr(self, f"norm{i}")
+                o = PF.layer_norm(x_out, n.weight, n.bias, n.eps)
                 outs[f"res{i + 2}"] = o.view(-1, H, W, self.num_features[i]).permute(0, 3, 1, 2).contiguous()
         return outs
 
