@@ -174,7 +174,9 @@ PDB_API int pdb_masked_xattn_backward(const float* q, const float* k, const floa
 /* ------------------------------------------------------------------------------------------------
  * Point sampling — replaces detectron2 point_sample == F.grid_sample(input, 2*coords-1,
  * bilinear, zeros, align_corners=False) at its call sites criterion.py:178-196, matcher.py:130-140.
- *   src: R_src maps of (H, W), f32 (src_dtype 0) or uint8 0/1 (src_dtype 1);
+ *   src: R_src maps of (H, W), f32 (src_dtype 0), uint8 0/1 (src_dtype 1) or bit-packed (src_dtype 2: int32 words
+ *   (H, ceil(W / 32)) per map, bit x % 32 of word x / 32, the layout of pdb_pack_bits — ground-truth masks sampled straight
+ *   from the words they arrived in);
  *   map_index (R) int32 or NULL (identity): which map row r samples from;
  *   coords (Rc, P, 2) f32 (x, y) in [0,1]; coord_index (R) int32 or NULL (identity; a constant 0
  *   table shares one point set across rows as matcher.py:128 does);
@@ -216,19 +218,20 @@ PDB_API int pdb_lsap_batched(const float* cost, const int32_t* tgt_offset, int64
  * Point-sampled mask loss — replaces point_sample x2 + sigmoid_ce_loss + dice_loss
  * (criterion.py:25-69,188-206) fused over all matched pairs.
  *   pred (Rp, H, W) f32 mask logits; pred_index (Nm) int64 (-1 entries are skipped);
- *   gt (Rg, Hg, Wg) uint8; gt_index (Nm) int64; coords (Nm, P, 2) f32;
+ *   gt (Rg, Hg, Wg) uint8 (gt_bits 0) or bit-packed int32 words (Rg, Hg, ceil(Wg / 32)) (gt_bits 1); gt_index (Nm) int64;
+ *   coords (Nm, P, 2) f32;
  *   sums (Nm, 4) f32 out: [sum BCE, sum s*t, sum s, sum t] per pair (loss assembly is host-side:
  *   loss_mask = sum_i BCE_i/P / num_masks, loss_dice = sum_i (1-(2 st+1)/(s+t+1)) / num_masks).
  * backward: g_bce, g_dice (Nm) f32 = d loss / d (BCE_i/P), d loss / d dice_i; grad_pred (Rp, H, W)
  * must be zero-filled by the caller; accumulated.
  * ---------------------------------------------------------------------------------------------- */
-PDB_API int pdb_point_loss_forward(const float* pred, const int64_t* pred_index, const uint8_t* gt,
+PDB_API int pdb_point_loss_forward(const float* pred, const int64_t* pred_index, const void* gt,
                            const int64_t* gt_index, const float* coords, float* sums,
-                           int Nm, int P, int H, int W, int Hg, int Wg, void* stream);
-PDB_API int pdb_point_loss_backward(const float* pred, const int64_t* pred_index, const uint8_t* gt,
+                           int Nm, int P, int H, int W, int Hg, int Wg, int gt_bits, void* stream);
+PDB_API int pdb_point_loss_backward(const float* pred, const int64_t* pred_index, const void* gt,
                             const int64_t* gt_index, const float* coords, const float* sums,
                             const float* g_bce, const float* g_dice, float* grad_pred,
-                            int Nm, int P, int H, int W, int Hg, int Wg, void* stream);
+                            int Nm, int P, int H, int W, int Hg, int Wg, int gt_bits, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * PartDistillation classifier rows — replaces the float64 Linear(256, P*O+1) followed by

@@ -15,6 +15,7 @@ struct Offsets { int v[kMaxBatch + 1]; };
 struct Bilin {
     int off[4];
     float w[4];   // 0 when the corner is outside the map
+    int px[4], py[4];   // clamped corner coordinates (the bit-packed sources address words, not bytes)
 };
 __device__ __forceinline__ Bilin bilin_setup(float cx, float cy, int H, int W) {
     float gx = __fsub_rn(__fmul_rn(2.f, cx), 1.f);
@@ -31,7 +32,9 @@ __device__ __forceinline__ Bilin bilin_setup(float cx, float cy, int H, int W) {
     for (int c = 0; c < 4; ++c) {
         int xi = x0 + (c & 1), yi = y0 + (c >> 1);
         bool ok = xi >= 0 && xi < W && yi >= 0 && yi < H;
-        r.off[c] = min(max(yi, 0), H - 1) * W + min(max(xi, 0), W - 1);
+        r.px[c] = min(max(xi, 0), W - 1);
+        r.py[c] = min(max(yi, 0), H - 1);
+        r.off[c] = r.py[c] * W + r.px[c];
         r.w[c] = ok ? ((c & 1) ? wx1 : wx0) * ((c >> 1) ? wy1 : wy0) : 0.f;
     }
     return r;
@@ -52,6 +55,23 @@ __device__ __forceinline__ float sample_u8(const uint8_t* __restrict__ m, const 
     return s;
 }
 
+// maps at one bit per pixel: int32 words (rows x ceil(W / 32)), bit x % 32 of word x / 32 (the layout of pdb_pack_bits): the
+// ground-truth masks are sampled straight from the words they arrived in
+__device__ __forceinline__ float sample_bits(const uint32_t* __restrict__ m, const Bilin& t, int Ww) {
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (t.w[c] != 0.f) s += (float)((__ldg(m + t.py[c] * Ww + (t.px[c] >> 5)) >> (t.px[c] & 31)) & 1u) * t.w[c];
+    return s;
+}
+__device__ __forceinline__ float sample_gt(const void* __restrict__ gt, int64_t gi, const Bilin& t, int Hg, int Wg, int bits) {
+    if (bits) {
+        const int Ww = (Wg + 31) >> 5;
+        return sample_bits((const uint32_t*)gt + gi * Hg * Ww, t, Ww);
+    }
+    return sample_u8((const uint8_t*)gt + gi * Hg * Wg, t);
+}
+
 __global__ void point_sample_fwd(const void* __restrict__ src, int src_u8, const int32_t* __restrict__ map_index,
                                  const float* __restrict__ coords, const int32_t* __restrict__ coord_index,
                                  float* __restrict__ out, int R, int P, int H, int W) {
@@ -64,7 +84,7 @@ __global__ void point_sample_fwd(const void* __restrict__ src, int src_u8, const
     if (mp >= 0) {
         const float* c = coords + ((int64_t)cr * P + p) * 2;
         Bilin t = bilin_setup(__ldg(c), __ldg(c + 1), H, W);
-        v = src_u8 ? sample_u8((const uint8_t*)src + (int64_t)mp * H * W, t)
+        v = src_u8 ? sample_gt(src, mp, t, H, W, src_u8 == 2)       // src_u8: 0 = f32, 1 = uint8, 2 = bit-packed words
                    : sample_f32((const float*)src + (int64_t)mp * H * W, t);
     }
     out[idx] = v;
@@ -276,9 +296,9 @@ lsap_kernel(const float* __restrict__ cost, Offsets off, int64_t* __restrict__ p
 // one CTA of 1024 threads per matched pair: there are only a handful of pairs per layer, so the block is as wide as it
 // can be (12544 points -> 12 per thread)
 __global__ void __launch_bounds__(1024)
-point_loss_fwd(const float* __restrict__ pred, const int64_t* __restrict__ pred_index, const uint8_t* __restrict__ gt,
+point_loss_fwd(const float* __restrict__ pred, const int64_t* __restrict__ pred_index, const void* __restrict__ gt,
                const int64_t* __restrict__ gt_index, const float* __restrict__ coords, float* __restrict__ sums, int P,
-               int H, int W, int Hg, int Wg) {
+               int H, int W, int Hg, int Wg, int gt_bits) {
     __shared__ float red[32];
     const int i = blockIdx.x;
     const int64_t pi = pred_index[i], gi = gt_index[i];
@@ -287,13 +307,12 @@ point_loss_fwd(const float* __restrict__ pred, const int64_t* __restrict__ pred_
         return;
     }
     const float* pm = pred + pi * H * W;
-    const uint8_t* gm = gt + gi * Hg * Wg;
     float a_bce = 0.f, a_st = 0.f, a_s = 0.f, a_t = 0.f;
     for (int p = threadIdx.x; p < P; p += blockDim.x) {
         const float* c = coords + ((int64_t)i * P + p) * 2;
         float cx = __ldg(c), cy = __ldg(c + 1);
         float x = sample_f32(pm, bilin_setup(cx, cy, H, W));
-        float t = sample_u8(gm, bilin_setup(cx, cy, Hg, Wg));
+        float t = sample_gt(gt, gi, bilin_setup(cx, cy, Hg, Wg), Hg, Wg, gt_bits);
         // ATen binary_cross_entropy_with_logits: (1-t)*x + max(-x,0) + log(1+exp(-|x|))
         a_bce += (1.f - t) * x + fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)));
         float s = sigmoid_f(x);
@@ -308,16 +327,15 @@ point_loss_fwd(const float* __restrict__ pred, const int64_t* __restrict__ pred_
 }
 
 __global__ void __launch_bounds__(1024)
-point_loss_bwd(const float* __restrict__ pred, const int64_t* __restrict__ pred_index, const uint8_t* __restrict__ gt,
+point_loss_bwd(const float* __restrict__ pred, const int64_t* __restrict__ pred_index, const void* __restrict__ gt,
                const int64_t* __restrict__ gt_index, const float* __restrict__ coords, const float* __restrict__ sums,
                const float* __restrict__ g_bce, const float* __restrict__ g_dice, float* __restrict__ gpred, int P,
-               int H, int W, int Hg, int Wg) {
+               int H, int W, int Hg, int Wg, int gt_bits) {
     const int i = blockIdx.x;
     const int64_t pi = pred_index[i], gi = gt_index[i];
     if (pi < 0 || gi < 0) return;
     const float* pm = pred + pi * H * W;
     float* gp = gpred + pi * H * W;
-    const uint8_t* gm = gt + gi * Hg * Wg;
     const float st = sums[i * 4 + 1], S = sums[i * 4 + 2], T = sums[i * 4 + 3];
     const float den = S + T + 1.f, num = 2.f * st + 1.f;
     const float gb = g_bce[i] / (float)P, gd = g_dice[i];
@@ -326,7 +344,7 @@ point_loss_bwd(const float* __restrict__ pred, const int64_t* __restrict__ pred_
         float cx = __ldg(c), cy = __ldg(c + 1);
         Bilin tp = bilin_setup(cx, cy, H, W);
         float x = sample_f32(pm, tp);
-        float t = sample_u8(gm, bilin_setup(cx, cy, Hg, Wg));
+        float t = sample_gt(gt, gi, bilin_setup(cx, cy, Hg, Wg), Hg, Wg, gt_bits);
         float s = sigmoid_f(x);
         // d dice / d s_p = -(2 t den - num) / den^2 ; d s / d x = s (1 - s)
         float dx = gb * (s - t) + gd * (-(2.f * t * den - num) / (den * den)) * s * (1.f - s);
@@ -416,7 +434,7 @@ extern "C" int pdb_point_sample_forward(const void* src, int src_dtype, const in
                                         void* stream) {
     PDB_REQUIRE(src && coords && out, "point_sample_forward: null pointer");
     PDB_REQUIRE(R >= 0 && P > 0 && H > 0 && W > 0, "point_sample_forward: bad shape");
-    PDB_REQUIRE(src_dtype == 0 || src_dtype == 1, "point_sample_forward: src_dtype %d", src_dtype);
+    PDB_REQUIRE(src_dtype >= 0 && src_dtype <= 2, "point_sample_forward: src_dtype %d (0 f32, 1 uint8, 2 bit-packed)", src_dtype);
     if (R == 0) return PDB_OK;
     int64_t total = (int64_t)R * P;
     point_sample_fwd<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(src, src_dtype, map_index, coords,
@@ -467,27 +485,27 @@ extern "C" int pdb_lsap_batched(const float* cost, const int32_t* tgt_offset, in
     return launched("lsap_batched");
 }
 
-extern "C" int pdb_point_loss_forward(const float* pred, const int64_t* pred_index, const uint8_t* gt,
+extern "C" int pdb_point_loss_forward(const float* pred, const int64_t* pred_index, const void* gt,
                                       const int64_t* gt_index, const float* coords, float* sums, int Nm, int P, int H,
-                                      int W, int Hg, int Wg, void* stream) {
+                                      int W, int Hg, int Wg, int gt_bits, void* stream) {
     PDB_REQUIRE(pred && pred_index && gt && gt_index && coords && sums, "point_loss_forward: null pointer");
     PDB_REQUIRE(Nm >= 0 && P > 0 && H > 0 && W > 0 && Hg > 0 && Wg > 0, "point_loss_forward: bad shape");
     if (Nm == 0) return PDB_OK;
     point_loss_fwd<<<(unsigned)Nm, 1024, 0, as_stream(stream)>>>(pred, pred_index, gt, gt_index, coords, sums, P, H, W,
-                                                                Hg, Wg);
+                                                                Hg, Wg, gt_bits);
     return launched("point_loss_forward");
 }
 
-extern "C" int pdb_point_loss_backward(const float* pred, const int64_t* pred_index, const uint8_t* gt,
+extern "C" int pdb_point_loss_backward(const float* pred, const int64_t* pred_index, const void* gt,
                                        const int64_t* gt_index, const float* coords, const float* sums,
                                        const float* g_bce, const float* g_dice, float* grad_pred, int Nm, int P, int H,
-                                       int W, int Hg, int Wg, void* stream) {
+                                       int W, int Hg, int Wg, int gt_bits, void* stream) {
     PDB_REQUIRE(pred && pred_index && gt && gt_index && coords && sums && g_bce && g_dice && grad_pred,
                 "point_loss_backward: null pointer");
     PDB_REQUIRE(Nm >= 0 && P > 0 && H > 0 && W > 0 && Hg > 0 && Wg > 0, "point_loss_backward: bad shape");
     if (Nm == 0) return PDB_OK;
     point_loss_bwd<<<(unsigned)Nm, 1024, 0, as_stream(stream)>>>(pred, pred_index, gt, gt_index, coords, sums, g_bce,
-                                                                g_dice, grad_pred, P, H, W, Hg, Wg);
+                                                                g_dice, grad_pred, P, H, W, Hg, Wg, gt_bits);
     return launched("point_loss_backward");
 }
 

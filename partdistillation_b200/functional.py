@@ -321,8 +321,11 @@ class PointSampleFunction(Function):
             sd = 0
         elif src.dtype in (torch.uint8, torch.bool):
             sd = 1
+        elif src.dtype == torch.int32:               # bit-packed maps: (R, H, W / 32) words of 32 pixels
+            sd = 2
+            W *= 32
         else:
-            raise RuntimeError("point_sample: maps must be float32 or uint8/bool")
+            raise RuntimeError("point_sample: maps must be float32, uint8/bool or bit-packed int32 words")
         out = torch.empty((R, P), dtype=torch.float32, device=src.device)
         if R:       # nothing to sample for an empty row set (a batch without targets): empty tensors have null pointers
             rc = _lib.load().pdb_point_sample_forward(src.data_ptr(), sd, map_index.data_ptr() if map_index is not None else None,
@@ -390,15 +393,18 @@ class PointLossFunction(Function):
     def forward(ctx, pred, pred_index, gt, gt_index, coords):
         _need_cuda(pred, pred_index, gt, gt_index, coords)
         pred, gt, coords = _c(pred), _c(gt), _c(coords)
-        if pred.dtype != torch.float32 or gt.dtype not in (torch.uint8, torch.bool):
-            raise RuntimeError("point_loss: pred float32, gt uint8/bool")
+        if pred.dtype != torch.float32 or gt.dtype not in (torch.uint8, torch.bool, torch.int32):
+            raise RuntimeError("point_loss: pred float32, gt uint8/bool or bit-packed int32 words")
         Rp, H, W = pred.shape
+        bits = int(gt.dtype == torch.int32)          # (Rg, Hg, Wg / 32) words of 32 pixels (padded widths are multiples of 32)
         _, Hg, Wg = gt.shape
+        if bits:
+            Wg *= 32
         Nm, P = coords.shape[0], coords.shape[1]
         sums = torch.empty((Nm, 4), dtype=torch.float32, device=pred.device)
         if Nm:      # no matched pair (a batch without targets): the losses are empty sums, as in the reference
             rc = _lib.load().pdb_point_loss_forward(pred.data_ptr(), pred_index.data_ptr(), gt.data_ptr(), gt_index.data_ptr(),
-                                                    coords.data_ptr(), sums.data_ptr(), Nm, P, H, W, Hg, Wg, _stream())
+                                                    coords.data_ptr(), sums.data_ptr(), Nm, P, H, W, Hg, Wg, bits, _stream())
             _lib.check(rc, "pdb_point_loss_forward")
         ctx.save_for_backward(pred, pred_index, gt, gt_index, coords, sums)
         bce = sums[:, 0] / P
@@ -410,14 +416,17 @@ class PointLossFunction(Function):
     def backward(ctx, g_bce, g_dice):
         pred, pred_index, gt, gt_index, coords, sums = ctx.saved_tensors
         Rp, H, W = pred.shape
+        bits = int(gt.dtype == torch.int32)
         _, Hg, Wg = gt.shape
+        if bits:
+            Wg *= 32
         Nm, P = coords.shape[0], coords.shape[1]
         g_bce, g_dice = _c(g_bce.float()), _c(g_dice.float())
         gp = torch.zeros_like(pred)
         if Nm:
             rc = _lib.load().pdb_point_loss_backward(pred.data_ptr(), pred_index.data_ptr(), gt.data_ptr(), gt_index.data_ptr(),
                                                      coords.data_ptr(), sums.data_ptr(), g_bce.data_ptr(), g_dice.data_ptr(),
-                                                     gp.data_ptr(), Nm, P, H, W, Hg, Wg, _stream())
+                                                     gp.data_ptr(), Nm, P, H, W, Hg, Wg, bits, _stream())
             _lib.check(rc, "pdb_point_loss_backward")
         return gp, None, None, None, None
 

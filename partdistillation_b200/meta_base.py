@@ -16,6 +16,8 @@ class Mask2FormerTrainingArch(nn.Module):
 
     part_distillation = False
 
+    keep_packed_targets = True      # f3: bit-packed targets stay packed and are sampled from the words (False: expand to bytes)
+
     def _init_common(self, backbone, sem_seg_head, criterion, num_queries, num_classes, size_divisibility,
                      pixel_mean: Tuple[float], pixel_std: Tuple[float], test_topk_per_image, use_wandb):
         self.backbone = backbone
@@ -71,12 +73,24 @@ class Mask2FormerTrainingArch(nn.Module):
         offs = [0]
         for c in counts:
             offs.append(offs[-1] + c)
-        packed = torch.zeros((offs[-1], h_pad, w_pad), dtype=torch.uint8, device=dev)
+        # f3: when every image's masks arrive bit-packed (and the padded width is a whole number of 32-pixel words, which
+        # size_divisibility = 32 guarantees) the targets STAY packed — (Ktot, h_pad, w_pad / 32) int32 words, 1/8 of the bytes on
+        # the wire and in HBM — and the matcher / criterion kernels sample the ground truth straight from the words.
+        keep_bits = self.keep_packed_targets and w_pad % 32 == 0 and all(isinstance(i.gt_masks, PackedBitMasks) for i in inst) \
+            and not self.use_wandb
+        if keep_bits:
+            packed = torch.zeros((offs[-1], h_pad, w_pad // 32), dtype=torch.int32, device=dev)
+        else:
+            packed = torch.zeros((offs[-1], h_pad, w_pad), dtype=torch.uint8, device=dev)
         out = TargetList()
         labels = []
         for b, (x, i) in enumerate(zip(inputs, inst)):
             view = packed[offs[b]:offs[b + 1]]
-            if isinstance(i.gt_masks, PackedBitMasks):      # 1 bit / pixel over the wire, expanded on the device (f3)
+            if keep_bits:
+                if counts[b]:
+                    words = i.gt_masks.tensor.to(dev, non_blocking=True)      # bits beyond the image width are zero by construction
+                    view[:, :words.shape[1], :words.shape[2]] = words
+            elif isinstance(i.gt_masks, PackedBitMasks):    # 1 bit / pixel over the wire, expanded on the device
                 if counts[b]:
                     from .functional import unpack_bits
                     m = unpack_bits(i.gt_masks.tensor.to(dev, non_blocking=True), i.gt_masks.width)
@@ -86,12 +100,13 @@ class Mask2FormerTrainingArch(nn.Module):
                 view[:, :m.shape[1], :m.shape[2]] = m
             if self.part_distillation:
                 lab = i.gt_classes.to(dev, non_blocking=True).long()
-                t = {"labels": lab, "masks": view.view(torch.bool), "gt_object_class": x["gt_object_class"]}
+                t = {"labels": lab, "masks": PackedBitMasks(view, w_pad) if keep_bits else view.view(torch.bool),
+                     "gt_object_class": x["gt_object_class"]}
                 if self.use_wandb:
                     t["object_mask"] = view.sum(dim=0, keepdim=True)
             else:
                 lab = torch.zeros(counts[b], dtype=torch.long, device=dev)
-                t = {"labels": lab, "masks": view.view(torch.bool)}
+                t = {"labels": lab, "masks": PackedBitMasks(view, w_pad) if keep_bits else view.view(torch.bool)}
                 if self.use_wandb:
                     t["object_masks"] = view.sum(0, keepdim=True)
             labels.append(lab)

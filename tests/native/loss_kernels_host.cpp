@@ -48,19 +48,20 @@ extern "C" int host_lsap_batched(const float* cost, const int32_t* tgt_offset, i
     return 0;
 }
 
-extern "C" int host_point_loss_forward(const float* pred, const int64_t* pred_index, const uint8_t* gt, const int64_t* gt_index,
-                                       const float* coords, float* sums, int Nm, int P, int H, int W, int Hg, int Wg) {
+extern "C" int host_point_loss_forward(const float* pred, const int64_t* pred_index, const void* gt, const int64_t* gt_index,
+                                       const float* coords, float* sums, int Nm, int P, int H, int W, int Hg, int Wg, int gt_bits) {
     if (Nm == 0) return 0;
-    launch(dim3((unsigned)Nm), dim3(1024), [&] { point_loss_fwd(pred, pred_index, gt, gt_index, coords, sums, P, H, W, Hg, Wg); });
+    launch(dim3((unsigned)Nm), dim3(1024), [&] { point_loss_fwd(pred, pred_index, gt, gt_index, coords, sums, P, H, W, Hg, Wg, gt_bits); });
     return 0;
 }
 
-extern "C" int host_point_loss_backward(const float* pred, const int64_t* pred_index, const uint8_t* gt,
+extern "C" int host_point_loss_backward(const float* pred, const int64_t* pred_index, const void* gt,
                                         const int64_t* gt_index, const float* coords, const float* sums, const float* g_bce,
-                                        const float* g_dice, float* grad_pred, int Nm, int P, int H, int W, int Hg, int Wg) {
+                                        const float* g_dice, float* grad_pred, int Nm, int P, int H, int W, int Hg, int Wg,
+                                        int gt_bits) {
     if (Nm == 0) return 0;
     launch(dim3((unsigned)Nm), dim3(1024),
-           [&] { point_loss_bwd(pred, pred_index, gt, gt_index, coords, sums, g_bce, g_dice, grad_pred, P, H, W, Hg, Wg); });
+           [&] { point_loss_bwd(pred, pred_index, gt, gt_index, coords, sums, g_bce, g_dice, grad_pred, P, H, W, Hg, Wg, gt_bits); });
     return 0;
 }
 

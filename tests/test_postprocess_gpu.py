@@ -293,4 +293,24 @@ def test_packed_bit_masks_ingestion(fn):
     ta, tb = arch._prepare_pseudo_targets(plain, images), arch._prepare_pseudo_targets(packed, images)
     assert ta.offsets == tb.offsets == [0, 3, 3, 5]
     assert str(tb.packed_masks.device).startswith(DEV)
-    assert torch.equal(ta.packed_masks, tb.packed_masks) and torch.equal(ta.packed_labels, tb.packed_labels)
+    # f3: the packed targets STAY packed (int32 words, 1/8 of the bytes) ...
+    assert tb.packed_masks.dtype == torch.int32 and tuple(tb.packed_masks.shape) == (5, 96, 3)
+    assert torch.equal(fn.unpack_bits(tb.packed_masks, 96).to(torch.uint8), ta.packed_masks)
+    assert torch.equal(ta.packed_labels, tb.packed_labels)
+    # ... and sampling from the words gives the same values as sampling from the bytes, bit for bit
+    g2 = torch.Generator().manual_seed(9)
+    coords = (torch.rand(5, 700, 2, generator=g2) * 1.1 - 0.05).to(DEV)
+    assert torch.equal(fn.point_sample(ta.packed_masks, coords), fn.point_sample(tb.packed_masks, coords))
+    pred = torch.randn(7, 24, 24, generator=g2).to(DEV).requires_grad_()
+    pi = torch.tensor([0, 3, 6, 2, 5], device=DEV)
+    gi = torch.tensor([4, 0, 2, 1, 3], device=DEV)
+    la = fn.point_loss(pred, pi, ta.packed_masks, gi, coords)
+    lb = fn.point_loss(pred, pi, tb.packed_masks, gi, coords)
+    assert torch.equal(la[0], lb[0]) and torch.equal(la[1], lb[1])
+    ga = torch.autograd.grad(la[0].sum() + la[1].sum(), pred)[0]
+    gb = torch.autograd.grad(lb[0].sum() + lb[1].sum(), pred)[0]
+    assert torch.allclose(ga, gb, rtol=1e-6, atol=1e-7)            # same values; atomics order only
+    # the expanded layout is still available
+    arch.keep_packed_targets = False
+    tc = arch._prepare_pseudo_targets(packed, images)
+    assert tc.packed_masks.dtype == torch.uint8 and torch.equal(tc.packed_masks, ta.packed_masks)
