@@ -126,6 +126,13 @@ PDB_API int pdb_gemm_bf16(const void* A, const void* B, void* C, const float* bi
 /* out[n] (+)= sum_r x[r*N + n]: bias gradient of a Linear layer over few rows (the decoder's B*Q = 200 rows; autograd's db);
  * accumulate != 0 adds into out (a preallocated parameter gradient). */
 PDB_API int pdb_col_sum(const float* x, float* out, int rows, int N, int accumulate, void* stream);
+/* Short-A variant of pdb_gemm_tf32x3 for the transformer decoder's B*Q = 200-row products (nn.Linear forward and input gradient,
+ * mask2former_transformer_decoder.py:148-208): C[m][n] = sum_k A[m*lda + k] * B(n,k) (+ bias[n]) (ReLU), same 3xTF32 arithmetic
+ * on mma.sync 32 x 64 tiles with no TMEM / TMA set-up.  b_mn = 0: B(n,k) = B[n*ldb + k];  b_mn = 1: B(n,k) = B[k*ldb + n].
+ * K, lda, ldb multiples of 4 (N too when b_mn); A, B 16-byte aligned.  ksplit > 1 splits K over blockIdx.z and red.adds into C,
+ * which the caller must have zero-filled; it excludes relu. */
+PDB_API int pdb_gemm_small_tf32x3(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int64_t lda,
+                          int64_t ldb, int64_t ldc, int b_mn, int relu, int ksplit, void* stream);
 /* Convolution-shaped variant: K = taps * Ck, and the k range of tap t reads the A rows shifted by tap_off[t]:
  *   C_b[m][n] = sum_t sum_c A_b[m + tap_off[t]][c] * B[n][t * Ck + c]  (+ bias[n]) (ReLU)
  * A_b = A + b*sa is (a_rows x Ck), K-major, rows beyond a_rows read as 0; B is (N x taps*Ck), K-major, shared by all batch

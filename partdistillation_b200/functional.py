@@ -523,6 +523,28 @@ def gemm_tf32x3(A, B, C, M, N, K, *, batch=1, lda, ldb, ldc, sa=0, sb=0, sc=0, a
     return C
 
 
+small_gemm_rows = 512      # row count up to which Linear forward / input-gradient products take the mma.sync kernel (0 disables)
+
+
+def _small_gemm(M, relu):
+    return 0 < M <= small_gemm_rows and relu in (0, 1, False, True) and getattr(_lib.load(), "pdb_gemm_small_tf32x3", None) is not None
+
+
+def gemm_small(A, B, M, N, K, *, lda, ldb, b_mn=False, bias=None, relu=False):
+    """C[m][n] = sum_k A[m][k] B(n, k) (+ bias) (ReLU) for short A (csrc/gemm_small.cu); returns a new (M, N) fp32 tensor.
+    Long contractions are split over K (red.add into a zero-filled C) until ~2 CTAs per SM are in flight."""
+    ctas = ((N + 63) // 64) * ((M + 31) // 32)
+    chunks = (K + 31) // 32
+    ksplit = 1
+    if not relu and chunks >= 16 and ctas < 148:
+        ksplit = max(1, min(chunks // 4, (296 + ctas - 1) // ctas))
+    C = (torch.zeros if ksplit > 1 else torch.empty)((M, N), dtype=torch.float32, device=A.device)
+    rc = _lib.load().pdb_gemm_small_tf32x3(A.data_ptr(), B.data_ptr(), C.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                           M, N, K, lda, ldb, N, int(b_mn), int(bool(relu)), ksplit, _stream())
+    _lib.check(rc, "pdb_gemm_small_tf32x3")
+    return C
+
+
 def _split_k(M, N, K):
     """K slices so that a weight-gradient / reduction-shaped GEMM fills the 148 SMs."""
     tiles = ((M + 127) // 128) * ((N + 127) // 128)
@@ -583,10 +605,13 @@ class LinearFunction(Function):
         if x2.data_ptr() % 16:
             x2 = x2.clone()
         M = x2.shape[0]
-        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
         w_lo = weight_lo(weight, M)
-        if M > 0:
-            gemm_tf32x3(x2, weight, out, M, N, K, lda=K, ldb=K, ldc=N, bias=bias, relu=relu, B_lo=w_lo)
+        if _small_gemm(M, relu) and weight.data_ptr() % 16 == 0:
+            out = gemm_small(x2, weight, M, N, K, lda=K, ldb=K, bias=bias, relu=relu)
+        else:
+            out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+            if M > 0:
+                gemm_tf32x3(x2, weight, out, M, N, K, lda=K, ldb=K, ldc=N, bias=bias, relu=relu, B_lo=w_lo)
         ctx.w_lo = w_lo
         ctx.relu = int(relu)            # epilogue activation: 0 none, 1 ReLU, 2 GELU (forward-only: see linear())
         ctx.has_bias = bias is not None
@@ -609,9 +634,12 @@ class LinearFunction(Function):
             gy2 = gy2.clone()
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = torch.empty((M, K), dtype=torch.float32, device=gy.device)
             # dx[m,i] = sum_o gy[m,o] W[o,i]:  A = gy (K-major), B(n=i,k=o) = W[o*K+i] (MN-major)
-            gemm_tf32x3(gy2, weight, gx, M, K, N, lda=N, ldb=K, ldc=K, b_mn=True, B_lo=ctx.w_lo)
+            if _small_gemm(M, 0) and weight.data_ptr() % 16 == 0:
+                gx = gemm_small(gy2, weight, M, K, N, lda=N, ldb=K, b_mn=True)
+            else:
+                gx = torch.empty((M, K), dtype=torch.float32, device=gy.device)
+                gemm_tf32x3(gy2, weight, gx, M, K, N, lda=N, ldb=K, ldc=K, b_mn=True, B_lo=ctx.w_lo)
             gx = gx.view(*gy.shape[:-1], K)
         if ctx.needs_input_grad[1]:
             tgt = _direct_grad(ctx.wref, (N, K))

@@ -30,6 +30,15 @@ def test_head_and_loss_vs_reference_golden(on_host, golden_dir, name):
     head_tests.test_head_and_loss_vs_reference_golden(golden_dir, name)
 
 
+def test_gpu_body_packed_bit_masks_ingestion(monkeypatch, host_lib):
+    """tests/test_postprocess_gpu.py::test_packed_bit_masks_ingestion on the host builds: packed targets stay packed and the
+    sampling / point-loss kernels read the words bit-identically to the byte layout."""
+    import test_postprocess_gpu as gpu_pp
+    fn = patch_functional(monkeypatch, host_lib)
+    monkeypatch.setattr(gpu_pp, "DEV", "cpu")
+    gpu_pp.test_packed_bit_masks_ingestion(fn)
+
+
 def _eval_inputs(H, W, out, seed=0):
     from partdistillation_b200.compat import BitMasks, Instances
     g = torch.Generator().manual_seed(seed)

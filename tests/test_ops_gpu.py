@@ -839,3 +839,41 @@ def test_col_sum(fn, rows, N):
     x = torch.randn(rows, N, generator=g).cuda()
     # fp32 running sums of rows / 8 terms per lane: error ~ rows / 8 * 2^-24 of the partial sums
     assert torch.allclose(fn.col_sum(x).double(), x.double().sum(0), rtol=1e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("M,N,K,b_mn,relu", [
+    (200, 256, 256, False, False), (200, 2048, 256, False, True), (200, 256, 2048, False, False),      # decoder forward shapes
+    (200, 256, 256, True, False), (200, 256, 2048, True, False), (200, 2048, 256, True, False),         # input gradients
+    (1, 4, 4, False, False), (33, 68, 36, False, True), (33, 68, 36, True, False), (512, 100, 260, False, False),
+])
+def test_gemm_small_vs_fp64(fn, M, N, K, b_mn, relu):
+    """Short-A mma.sync GEMM (csrc/gemm_small.cu): 3xTF32 within 1e-5 of the fp64 product, every tail (M, N, K) exercised,
+    both B layouts, the split-K path (K = 2048) and the fused bias / ReLU."""
+    g = torch.Generator().manual_seed(43)
+    A = torch.randn(M, K, generator=g).cuda()
+    B = (torch.randn(K, N, generator=g) if b_mn else torch.randn(N, K, generator=g)).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    C = fn.gemm_small(A, B, M, N, K, lda=K, ldb=N if b_mn else K, b_mn=b_mn, bias=bias, relu=relu)
+    ref = A.double() @ (B.double() if b_mn else B.double().t()) + bias.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    assert (C.double() - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_linear_small_rows_matches_tensor_core_path(fn):
+    """LinearFunction takes the mma.sync kernel for <= 512 rows; values and gradients agree with the tcgen05 path."""
+    g = torch.Generator().manual_seed(44)
+    x = torch.randn(2, 100, 256, generator=g).cuda().requires_grad_()
+    w = (torch.randn(2048, 256, generator=g) * 0.05).cuda().requires_grad_()
+    b = torch.randn(2048, generator=g).cuda().requires_grad_()
+    go = torch.randn(2, 100, 2048, generator=g).cuda()
+    res = []
+    for rows in (512, 0):
+        fn.small_gemm_rows = rows
+        try:
+            y = fn.linear(x, w, b)          # no ReLU here: a 1-ulp difference at y = 0 would flip gradient entries
+            res.append((y, *torch.autograd.grad(y, (x, w, b), go)))
+        finally:
+            fn.small_gemm_rows = 512
+    for a_, r_ in zip(*res):
+        assert (a_ - r_).abs().max().item() < 2e-5 * max(1.0, r_.abs().max().item())

@@ -589,10 +589,14 @@ def test_packed_bit_masks_ingestion(kernels_on_host):
     images = ImageList(torch.zeros(3, 3, 96, 96), sizes)
     ta, tb = arch._prepare_pseudo_targets(plain, images), arch._prepare_pseudo_targets(packed, images)
     assert ta.offsets == tb.offsets == [0, 3, 3, 5]
-    assert torch.equal(ta.packed_masks, tb.packed_masks) and ta.packed_masks.shape == (5, 96, 96)
+    # f3: packed targets stay packed (int32 words); expanded they are the BitMasks buffer
+    fn = kernels_on_host
+    assert tb.packed_masks.dtype == torch.int32 and tuple(tb.packed_masks.shape) == (5, 96, 3)
+    assert torch.equal(fn.unpack_bits(tb.packed_masks, 96).to(torch.uint8), ta.packed_masks) and ta.packed_masks.shape == (5, 96, 96)
     assert torch.equal(ta.packed_labels, tb.packed_labels)
     for a, b in zip(ta, tb):
-        assert torch.equal(a["masks"], b["masks"])
+        assert torch.equal(a["masks"], fn.unpack_bits(b["masks"].tensor, 96).bool())
+    arch.keep_packed_targets = False
     static = _clone_batch(packed, torch.device("cpu"))
     assert all(s["instances"].gt_masks.width == p["instances"].gt_masks.width for s, p in zip(static, packed))
     assert all(s["instances"].gt_masks.tensor.data_ptr() != p["instances"].gt_masks.tensor.data_ptr() or len(p["instances"].gt_masks) == 0
@@ -608,6 +612,5 @@ def test_packed_bit_masks_ingestion(kernels_on_host):
         PackedBitMasks(torch.zeros(1, 4, 2, dtype=torch.int32), width=20)
 
 
-def test_gpu_body_packed_bit_masks_ingestion(gpu_bodies):
-    gpu_pp, fn = gpu_bodies
-    gpu_pp.test_packed_bit_masks_ingestion(fn)
+# test_packed_bit_masks_ingestion's GPU body also samples the packed words (point_sample / point_loss): its twin lives in
+# tests/test_head_host_cpu.py, which builds the loss kernels too
