@@ -166,9 +166,40 @@ def _pixel_major(t):
     return t if t.is_contiguous(memory_format=torch.channels_last) else t.contiguous(memory_format=torch.channels_last)
 
 
+class GradFanOut(Function):
+    """Identity on a tensor that feeds several mask_einsum calls (mask_features: the 10 prediction heads of the decoder).  Their
+    backward GEMMs accumulate into ONE gradient buffer kept in ``holder`` (first one stores, the rest red.add) and hand autograd
+    None; this node runs after all of them (autograd orders a node behind every consumer of its output, whether or not the
+    consumer returned a gradient) and delivers the buffer — instead of 10 full-size gradients and 9 ATen add_ passes."""
+
+    @staticmethod
+    def forward(ctx, x, holder):
+        ctx.holder = holder
+        ctx.set_materialize_grads(False)
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        buf = ctx.holder.pop("buf", None)
+        if buf is None:
+            return g, None
+        if g is not None:                  # consumers that went through plain autograd
+            buf = buf.add_(g)
+        return buf, None
+
+
+def grad_fan_out(x):
+    """-> (x', holder) for mask_einsum(..., grad_acc=holder); a no-op pair (x, None) when x needs no gradient."""
+    if not (torch.is_grad_enabled() and x.requires_grad):
+        return x, None
+    holder = {}
+    return GradFanOut.apply(x, holder), holder
+
+
 class MaskEinsumFunction(Function):
     @staticmethod
-    def forward(ctx, mask_embed, mask_features, embed_lo=None):
+    def forward(ctx, mask_embed, mask_features, embed_lo=None, grad_acc=None):
+        ctx.grad_acc = grad_acc
         _need_cuda(mask_embed, mask_features)
         if mask_embed.dtype != torch.float32 or mask_features.dtype != torch.float32:
             raise RuntimeError("mask_einsum: float32 only")
@@ -197,22 +228,30 @@ class MaskEinsumFunction(Function):
         H, W = mask_features.shape[-2:]
         grad_out = _c(grad_out)
         ge = torch.empty_like(mask_embed) if ctx.needs_input_grad[0] else None
-        gf = (torch.empty_like(mask_features, memory_format=torch.channels_last)
-              if ctx.needs_input_grad[1] else None)
+        acc, holder = 0, ctx.grad_acc
+        gf = None
+        if ctx.needs_input_grad[1]:
+            if holder is not None and "buf" in holder:
+                gf, acc = holder["buf"], 1
+            else:
+                gf = torch.empty_like(mask_features, memory_format=torch.channels_last)
+                if holder is not None:
+                    holder["buf"] = gf
         rc = _lib.load().pdb_mask_einsum_backward(mask_embed.data_ptr(), mask_features.data_ptr(), grad_out.data_ptr(),
                                                   ge.data_ptr() if ge is not None else None,
-                                                  gf.data_ptr() if gf is not None else None, 0,
+                                                  gf.data_ptr() if gf is not None else None, acc,
                                                   B, Q, C, H * W, _stream())
         _lib.check(rc, "pdb_mask_einsum_backward")
-        return ge, gf, None
+        return ge, (None if holder is not None else gf), None, None
 
 
-def mask_einsum(mask_embed, mask_features, embed_lo=None, presplit=True):
+def mask_einsum(mask_embed, mask_features, embed_lo=None, presplit=True, grad_acc=None):
     """torch.einsum("bqc,bchw->bqhw") (mask2former_transformer_decoder.py:449).  The tiny embed operand is pre-split into its
     tf32 hi / lo parts by one extra launch (presplit) unless the caller hands in embed_lo = split_lo(mask_embed) itself.
     Under bf16 autocast the embed arrives as bf16 (output of the mask MLP); the contraction itself stays on the fp32-accurate
     kernel (the reference's autocast einsum rounds operands AND the mask logits to bf16; keeping fp32 here is the more precise
-    side of the documented tolerance)."""
+    side of the documented tolerance).  grad_acc: the holder of grad_fan_out(mask_features) when several calls share the
+    features (mask_features must then be that call's first result)."""
     if mask_embed.dtype != torch.float32:
         mask_embed = mask_embed.float()
     if mask_features.dtype != torch.float32:
@@ -220,7 +259,7 @@ def mask_einsum(mask_embed, mask_features, embed_lo=None, presplit=True):
     if embed_lo is None and presplit and mask_embed.is_cuda and mask_embed.dtype == torch.float32 \
             and mask_embed.numel() % 4 == 0:
         embed_lo = split_lo(_c(mask_embed.detach()))
-    return MaskEinsumFunction.apply(mask_embed, mask_features, embed_lo)
+    return MaskEinsumFunction.apply(mask_embed, mask_features, embed_lo, grad_acc)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -526,8 +565,15 @@ def gemm_tf32x3(A, B, C, M, N, K, *, batch=1, lda, ldb, ldc, sa=0, sb=0, sc=0, a
 small_gemm_rows = 512      # row count up to which Linear forward / input-gradient products take the mma.sync kernel (0 disables)
 
 
-def _small_gemm(M, relu):
-    return 0 < M <= small_gemm_rows and relu in (0, 1, False, True) and getattr(_lib.load(), "pdb_gemm_small_tf32x3", None) is not None
+def _small_gemm(M, N, K, relu):
+    """Measured on B200 inside a replayed graph (tools/bench_small_gemm.py, profiles/r02_small_gemm.txt): the mma.sync kernel wins
+    while its 32 x 64 tiles do not fill the SMs (5.1 vs 8.0 us at 200 x 256 x 256) and for long contractions, which it splits
+    over K (10.4 vs 35.4 us at K = 2048); the tcgen05 kernel wins from ~150 tiles on (200 x 2048 x 256: 9.6 vs 9.5 us)."""
+    if not (0 < M <= small_gemm_rows and relu in (0, 1, False, True)):
+        return False
+    if getattr(_lib.load(), "pdb_gemm_small_tf32x3", None) is None:       # absent only in the CPU-tier host builds of the tests
+        return False
+    return ((N + 63) // 64) * ((M + 31) // 32) < 148 or (K >= 1024 and not relu)
 
 
 def gemm_small(A, B, M, N, K, *, lda, ldb, b_mn=False, bias=None, relu=False):
@@ -553,10 +599,10 @@ def _split_k(M, N, K):
 
 def col_sum(x2, into=None):
     """Sum over the rows of a contiguous fp32 (rows, N) matrix: the bias gradient of a Linear layer.  Short matrices (the
-    decoder's 200 rows) use the library's one-line-per-warp kernel; long ones ATen's two-stage reduction.  ``into``: a
+    decoder's 200 rows) take one CTA per 32 columns, tall ones row blocks that meet through red.add.  ``into``: a
     preallocated fp32 (N,) gradient to ADD the sums to (returns None then)."""
     f = getattr(_lib.load(), "pdb_col_sum", None)             # absent only in the CPU-tier host builds of the tests
-    if f is None or not x2.is_cuda or x2.dtype != torch.float32 or x2.shape[0] > 4096 or x2.shape[0] == 0:
+    if f is None or not x2.is_cuda or x2.dtype != torch.float32 or x2.shape[0] == 0:
         if into is not None:
             into.add_(x2.sum(0))
             return None
@@ -606,7 +652,7 @@ class LinearFunction(Function):
             x2 = x2.clone()
         M = x2.shape[0]
         w_lo = weight_lo(weight, M)
-        if _small_gemm(M, relu) and weight.data_ptr() % 16 == 0:
+        if _small_gemm(M, N, K, relu) and weight.data_ptr() % 16 == 0:
             out = gemm_small(x2, weight, M, N, K, lda=K, ldb=K, bias=bias, relu=relu)
         else:
             out = torch.empty((M, N), dtype=torch.float32, device=x.device)
@@ -635,7 +681,7 @@ class LinearFunction(Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             # dx[m,i] = sum_o gy[m,o] W[o,i]:  A = gy (K-major), B(n=i,k=o) = W[o*K+i] (MN-major)
-            if _small_gemm(M, 0) and weight.data_ptr() % 16 == 0:
+            if _small_gemm(M, K, N, 0) and weight.data_ptr() % 16 == 0:
                 gx = gemm_small(gy2, weight, M, K, N, lda=N, ldb=K, b_mn=True)
             else:
                 gx = torch.empty((M, K), dtype=torch.float32, device=gy.device)
@@ -705,7 +751,7 @@ class Conv1x1Function(Function):
                             a_mn=True, accumulate=True, ksplit=ks)
             gw = gw.view_as(weight)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gy_pm.sum((0, 1))
+            gb = col_sum(gy_pm.reshape(-1, gy_pm.shape[-1]))
         return gx, gw, gb
 
 
@@ -786,7 +832,7 @@ class Conv3x3Function(Function):
                             sa=K * O, sb=rows * C, sc=0, a_mn=True, b_mn=True, accumulate=True, ksplit=ks)
             gw = gw9.view(O, 3, 3, C).permute(0, 3, 1, 2)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gy_nhwc.sum((0, 1, 2))
+            gb = col_sum(gy_nhwc.reshape(-1, gy_nhwc.shape[-1]))
         return gx, gw, gb
 
 

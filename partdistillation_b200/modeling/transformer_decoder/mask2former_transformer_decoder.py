@@ -216,7 +216,8 @@ class MultiScaleMaskedTransformerDecoder(nn.Module):
         bs = mem[0].shape[0]
         query_embed = self.query_embed.weight.unsqueeze(0).expand(bs, -1, -1)
         output = self.query_feat.weight.unsqueeze(0).expand(bs, -1, -1)
-        mask_features = mask_features.float()
+        # the num_layers + 1 prediction heads share mask_features: their einsum backwards accumulate into one gradient buffer
+        mask_features, self._mask_grad_acc = PF.grad_fan_out(mask_features.float())
         classes, masks = [], []
         c, m, attn_mask, decoder_output = self.forward_prediction_heads(output, mask_features, sizes[0], targets)
         classes.append(c)
@@ -233,6 +234,7 @@ class MultiScaleMaskedTransformerDecoder(nn.Module):
                 output, mask_features, sizes[(i + 1) % self.num_feature_levels], targets)
             classes.append(c)
             masks.append(m)
+        self._mask_grad_acc = None
         out = {"pred_logits": classes[-1], "pred_masks": masks[-1], "decoder_output": decoder_output,
                "aux_outputs": self._set_aux_loss(classes if self.mask_classification else None, masks)}
         self._extra_outputs(out, output)
@@ -249,7 +251,8 @@ class MultiScaleMaskedTransformerDecoder(nn.Module):
         mask_embed = self.mask_embed(decoder_output)
         if self.query_feature_normalize:
             mask_embed = F.normalize(mask_embed, p=2, dim=-1)
-        outputs_mask = PF.mask_einsum(mask_embed.float(), mask_features)
+        # grad_acc only inside forward() (a direct caller hands in its own mask_features, not the fan-out's)
+        outputs_mask = PF.mask_einsum(mask_embed.float(), mask_features, grad_acc=getattr(self, "_mask_grad_acc", None))
         mask, row_any = PF.build_attention_mask(outputs_mask, attn_mask_target_size)
         return outputs_class, outputs_mask, AttnMask(mask, row_any), decoder_output
 

@@ -271,8 +271,12 @@ def test_linear_gelu_epilogue(fn, rows, K, N):
         y = fn.linear(x, w, b, gelu=True)
     assert _rel(y.double(), ref) < 1e-5
     # same association as ATen's kernel on the same fp32 pre-activation: identical up to the last bit or two
-    with torch.no_grad():
-        pre = fn.linear(x, w, b)
+    rows_limit, fn.small_gemm_rows = fn.small_gemm_rows, 0          # the pre-activation of the SAME (tcgen05) kernel
+    try:
+        with torch.no_grad():
+            pre = fn.linear(x, w, b)
+    finally:
+        fn.small_gemm_rows = rows_limit
     assert (y - F.gelu(pre)).abs().max() <= 2e-7 * max(1.0, float(pre.abs().max()))
     xg = x.clone().requires_grad_()
     yg = fn.linear(xg, w, b, gelu=True)
@@ -833,7 +837,7 @@ def test_linear_bf16_autocast_matches_torch(fn):
         assert a_.dtype == r_.dtype and _rel(a_.float(), r_.float()) < 2 ** -6
 
 
-@pytest.mark.parametrize("rows,N", [(200, 256), (200, 2048), (37, 100), (4096, 512), (1, 4)])
+@pytest.mark.parametrize("rows,N", [(200, 256), (200, 2048), (37, 100), (4096, 512), (1, 4), (32768, 256), (1025, 36), (43008, 1024)])
 def test_col_sum(fn, rows, N):
     g = torch.Generator().manual_seed(41)
     x = torch.randn(rows, N, generator=g).cuda()
@@ -864,9 +868,9 @@ def test_linear_small_rows_matches_tensor_core_path(fn):
     """LinearFunction takes the mma.sync kernel for <= 512 rows; values and gradients agree with the tcgen05 path."""
     g = torch.Generator().manual_seed(44)
     x = torch.randn(2, 100, 256, generator=g).cuda().requires_grad_()
-    w = (torch.randn(2048, 256, generator=g) * 0.05).cuda().requires_grad_()
-    b = torch.randn(2048, generator=g).cuda().requires_grad_()
-    go = torch.randn(2, 100, 2048, generator=g).cuda()
+    w = (torch.randn(768, 256, generator=g) * 0.05).cuda().requires_grad_()
+    b = torch.randn(768, generator=g).cuda().requires_grad_()
+    go = torch.randn(2, 100, 768, generator=g).cuda()
     res = []
     for rows in (512, 0):
         fn.small_gemm_rows = rows

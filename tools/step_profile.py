@@ -43,7 +43,8 @@ def main(out_path, workload="c2"):
     wall = (time.perf_counter() - t0) / n * 1e3
     # stage split with events
     from torch.profiler import ProfilerActivity, profile
-    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
+    stacks = bool(os.environ.get("PROFILE_STACK"))
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True, with_stack=stacks) as prof:
         for _ in range(2):
             trainer.step(batch)
         torch.cuda.synchronize()
@@ -71,6 +72,28 @@ def main(out_path, workload="c2"):
         ops.sort(reverse=True)
         for t, c, k, sh in ops[:60]:
             w.write(f"{t:10.1f} {c:6d}  {k[:40]:40s} {sh}\n")
+        w.write("\n# ops by SELF device time (kernels the op launched itself), all shapes together\n")
+        selfs = []
+        for e in prof.key_averages():
+            t = getattr(e, "self_device_time_total", 0.0) or 0.0
+            if t > 0 and e.device_type == torch.autograd.DeviceType.CPU:
+                selfs.append((t / 2, e.count // 2, e.key))
+        selfs.sort(reverse=True)
+        for t, c, k in selfs[:50]:
+            w.write(f"{t:10.1f} {c:6d}  {k[:80]}\n")
+        if stacks:
+            w.write("\n# python call sites of the element-wise / copy ATen ops (PROFILE_STACK=1)\n")
+            glue = ("aten::copy_", "aten::add", "aten::add_", "aten::cat", "aten::div", "aten::mul", "aten::fill_", "aten::zero_",
+                    "aten::sum", "aten::index", "aten::gather", "aten::clone", "aten::sub", "aten::where", "aten::addcmul")
+            sites = []
+            for e in prof.key_averages(group_by_stack_n=12):
+                t = getattr(e, "self_device_time_total", 0.0) or 0.0
+                if t > 0 and e.key in glue:
+                    here = [f for f in e.stack if "/partdistillation_b200/" in f or "/bench.py" in f][:3]
+                    sites.append((t / 2, e.count // 2, e.key, " <- ".join(h.split("/partdistillation_b200/")[-1] for h in here)))
+            sites.sort(reverse=True)
+            for t, c, k, st in sites[:70]:
+                w.write(f"{t:10.1f} {c:6d}  {k:14s} {st[:260]}\n")
     print(open(out_path).read()[:6000])
 
 
