@@ -56,7 +56,7 @@ def synth_image_and_masks(seed, h=H, w=W, k=K_MASKS, block=16):
     return img, m[m.flatten(1).any(1)]
 
 
-def make_batch(rank, n, device=None, pin=False, packed=False, spec=None):
+def make_batch(rank, n, device=None, pin=False, packed=False, spec=None, k_masks=None):
     """``packed``: hand the masks over as PackedBitMasks (1 bit / pixel) instead of BitMasks bools.
     ``spec``: a SPECS entry (default configs[1]); configs[2] draws K ~ U{2..8} parts per image, part labels arange(K) % 8 and
     an object class ~ U[0, 22000)."""
@@ -65,7 +65,7 @@ def make_batch(rank, n, device=None, pin=False, packed=False, spec=None):
         return _make_pd_batch(rank, n, device, pin, spec)
     out = []
     for i in range(n):
-        img, m = synth_image_and_masks(rank * 1000 + i)
+        img, m = synth_image_and_masks(rank * 1000 + i) if k_masks is None else synth_image_and_masks(rank * 1000 + i, k=k_masks)
         if packed:
             m = PackedBitMasks.from_bool(m).tensor
         if pin:
@@ -542,6 +542,11 @@ def main():
     ap.add_argument("--per-gpu-batch", type=int, default=0, help="images per GPU per step (default: the workload's own)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="run the step eagerly instead of replaying its CUDA graph")
+    ap.add_argument("--target-bucket", type=int, default=0,
+                    help="pad every image's targets to a multiple of this (engine.DataParallelTrainer target_bucket): batches with "
+                         "different target counts / object classes replay one CUDA graph")
+    ap.add_argument("--distinct-batches", type=int, default=1,
+                    help="cycle the steps over this many batches with different target counts (default 1: the fixed BASELINE batch)")
     ap.add_argument("--packed-masks", action="store_true",
                     help="e2e leg: feed the target masks bit-packed (PackedBitMasks, 1 bit/pixel over PCIe) instead of bools")
     args = ap.parse_args()
@@ -572,11 +577,21 @@ def main():
     model = compat.build_model(cfg)
     model.train()
     trainer = DataParallelTrainer(model, base_lr=1e-4, weight_decay=0.05, clip_norm=0.01,
-                                  freeze_keys=("backbone", "encoder"), cuda_graph=not args.no_cuda_graph)
+                                  freeze_keys=("backbone", "encoder"), cuda_graph=not args.no_cuda_graph,
+                                  target_bucket=args.target_bucket)
     cpu_sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()} if rank == 0 and args.workload == "c2" else None
 
     dev_batch = make_batch(rank, per_gpu, device=device, spec=spec)
     host_batch = make_batch(rank, per_gpu, pin=True, packed=args.packed_masks, spec=spec)
+    if args.distinct_batches > 1:
+        # the steps cycle over batches with different numbers of pseudo masks per image (and, configs[2], other object classes):
+        # what a real loader delivers.  Without --target-bucket every distinct batch is its own step signature / CUDA graph.
+        def variant(j, **kw):
+            if spec["arch"] == "PartDistillationModel":
+                return make_batch(rank + 101 * j, per_gpu, spec=spec, **kw)
+            return make_batch(rank, per_gpu, spec=spec, k_masks=max(1, K_MASKS - j), **kw)
+        dev_batch = [variant(j, device=device) for j in range(args.distinct_batches)]
+        host_batch = [variant(j, pin=True, packed=args.packed_masks) for j in range(args.distinct_batches)]
     import contextlib
     amp = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if spec["amp"] else contextlib.nullcontext
 
@@ -585,10 +600,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(batch, steps, warmup, read_loss):
-        for _ in range(warmup):
+    def timed(batches, steps, warmup, read_loss):
+        if not isinstance(batches[0], list):
+            batches = [batches]
+        for i in range(warmup * len(batches)):
             with amp():
-                total, _ = trainer.step(batch)
+                total, _ = trainer.step(batches[i % len(batches)])
             if read_loss:
                 total.item()
         barrier()
@@ -600,9 +617,9 @@ def main():
         t0 = time.perf_counter()
         s.record()
         last = None
-        for _ in range(steps):
+        for i in range(steps):
             with amp():
-                total, _ = trainer.step(batch)
+                total, _ = trainer.step(batches[i % len(batches)])
             if read_loss:
                 last = total.item()
         e.record()
@@ -635,13 +652,17 @@ def main():
                            "global_batch": per_gpu * world, "queries": QUERIES, "dec_layers": 10,
                            "train_num_points": POINTS, "importance_sample_ratio": 0.0,
                            "freeze_keys": ["backbone", "encoder"], "optimizer": "AdamW + full-model clip 0.01", "cuda_graph": not args.no_cuda_graph,
+                           **({"target_bucket": args.target_bucket} if args.target_bucket else {}),
+                           **({"distinct_batches": args.distinct_batches, "step_signatures": len(trainer._graphs)}
+                              if args.distinct_batches > 1 else {}),
                            "parallelism": f"dp{world}", "grad_allreduce_bytes": trainer.grad_bytes,
                            "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; kernel roofline "
                                  "run: 8 back-to-back launches per CUDA-event pair rotating over 4 buffer sets (inputs larger than L2), "
                                  "L2 flushed ahead of each group"},
                 "clocks": clocks,
                 "e2e": {"value": round(images / (e2e_ms * 1e-3), 3), "unit": "images/s",
-                        "h2d_bytes_per_step": batch_bytes(host_batch), "d2h_bytes_per_step": 4,
+                        "h2d_bytes_per_step": batch_bytes(host_batch[0] if isinstance(host_batch[0], list) else host_batch),
+                        "d2h_bytes_per_step": 4,
                         **({"packed_masks": True} if args.packed_masks else {}),
                         "ms_per_step": round(e2e_ms / args.steps, 3), "last_loss": last_loss},
                 "gpu_launches": int(launches),

@@ -166,8 +166,12 @@ matcher_cost_kernel(const float* __restrict__ pred_pts, const float* __restrict_
             if (threadIdx.x == 0) {
                 float cmask = m / (float)P;
                 float cdice = 1.f - (2.f * st + 1.f) / (S + T + 1.f);
-                float ccls = -__ldg(cls_prob + ((int64_t)b * Q + q) * Kc + tgt_label[k0 + kb + k]);
-                crow[kb + k] = w_mask * cmask + w_class * ccls + w_dice * cdice;
+                // label < 0: a padding slot (the trainer pads every image's targets to a multiple of its bucket so that batches with
+                // different target counts replay one CUDA graph).  Its column costs the same for every query, so the optimal
+                // assignment of the real targets is the one of the unpadded problem (K_padded <= Q: a free query always exists).
+                const int lab = tgt_label[k0 + kb + k];
+                float ccls = lab < 0 ? 0.f : -__ldg(cls_prob + ((int64_t)b * Q + q) * Kc + lab);
+                crow[kb + k] = lab < 0 ? 0.f : w_mask * cmask + w_class * ccls + w_dice * cdice;
             }
         }
     }

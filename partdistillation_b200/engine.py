@@ -114,9 +114,20 @@ class DataParallelTrainer:
     this.  (2) With world > 1 the constructor broadcasts rank 0's parameters and buffers (``broadcast_parameters``)."""
 
     def __init__(self, model, base_lr=1e-4, weight_decay=0.05, clip_norm=0.01, freeze_keys=("backbone", "encoder"),
-                 backbone_multiplier=0.1, betas=(0.9, 0.999), eps=1e-8, cuda_graph=False):
+                 backbone_multiplier=0.1, betas=(0.9, 0.999), eps=1e-8, cuda_graph=False, target_bucket=0):
         self.model = model
         self.cuda_graph = bool(cuda_graph)
+        # target_bucket = m > 0: every image's K pseudo masks are padded (on the device) to the next multiple of m with empty masks
+        # marked gt_classes = -1, and PartDistillation's object class travels as a device scalar, so that batches with different
+        # target counts / object classes share ONE step signature (hence one captured graph) per bucket.  The padding slots cost
+        # the same for every query in the matcher (the real targets' assignment is unchanged), are "no object" in the class loss,
+        # carry zero mask loss and are not counted in num_masks (criterion.py, loss.cu matcher_cost_kernel).  The random point
+        # coordinates are drawn per matched pair, padding included, so the draws differ from an unpadded run's (same law).
+        self.target_bucket = int(target_bucket)
+        if self.target_bucket > 0:
+            if not hasattr(model, "target_padding"):
+                raise ValueError("target_bucket needs a Mask2FormerTrainingArch model (meta_base.py)")
+            model.target_padding = True
         self._graphs = {}
         self._side = None
         self._num_masks = None
@@ -344,6 +355,18 @@ class DataParallelTrainer:
         total.backward()
         return total, losses
 
+    def _padded_counts(self, batched_inputs):
+        """Target slots per image: K rounded up to the bucket, never beyond the number of queries (a padding slot must always
+        find a free query, or it would compete with the real targets), and 0 stays 0 (an image without targets has no matcher
+        problem at all)."""
+        m = self.target_bucket
+        q = int(getattr(self.model, "num_queries", 0)) or (1 << 30)
+        out = []
+        for d in batched_inputs:
+            k = int(d["instances"].gt_masks.tensor.shape[0])
+            out.append(k if k == 0 or k >= q else min(q, (k + m - 1) // m * m))
+        return out
+
     def _global_num_masks(self, batched_inputs):
         """mean over ranks of the per-rank number of target masks, clamped to >= 1 (criterion.py:248-254), all-reduced
         here, ahead of the step, so that the captured forward/backward holds no collective."""
@@ -368,13 +391,23 @@ class DataParallelTrainer:
         if self.lr_schedule is not None:
             self._apply_lr_factor(self.lr_schedule.factor(self.iteration))
         self.iteration += 1
+        raw_inputs = batched_inputs                     # the real target counts (num_masks all-reduce)
+        dev = next(self.model.parameters()).device
         if not self.cuda_graph:
+            if self.target_bucket > 0:
+                batched_inputs = _padded_batch(batched_inputs, dev, self._padded_counts(batched_inputs))
             n0 = _lib.launch_count()
             out = self._eager_step(batched_inputs)
             self.pdb_launches += _lib.launch_count() - n0
             return out
-        sig = tuple((tuple(d["image"].shape), tuple(d["instances"].gt_masks.tensor.shape),
-                     d.get("gt_object_class")) for d in batched_inputs)
+        if self.target_bucket > 0:
+            counts = self._padded_counts(batched_inputs)
+            sig = tuple((tuple(d["image"].shape), (k,) + tuple(d["instances"].gt_masks.tensor.shape[1:]),
+                         "gt_object_class" in d) for d, k in zip(batched_inputs, counts))
+        else:
+            counts = None
+            sig = tuple((tuple(d["image"].shape), tuple(d["instances"].gt_masks.tensor.shape),
+                         d.get("gt_object_class")) for d in batched_inputs)
         entry = self._graphs.pop(sig, None) or {"warm": 0}
         self._graphs[sig] = entry                       # most recently used last
         while len(self._graphs) > self.max_graphs:      # bounded: variable per-image mask counts re-capture, they must not leak
@@ -387,7 +420,9 @@ class DataParallelTrainer:
                 # created on, and a node living on the default stream would invalidate the capture
                 entry["warm"] += 1
                 if self.world > 1:
-                    self._global_num_masks(batched_inputs)
+                    self._global_num_masks(raw_inputs)
+                if counts is not None:
+                    batched_inputs = _padded_batch(batched_inputs, dev, counts)
                 n0 = _lib.launch_count()
                 cur = torch.cuda.current_stream()
                 self._side.wait_stream(cur)
@@ -396,7 +431,7 @@ class DataParallelTrainer:
                 cur.wait_stream(self._side)
                 self.pdb_launches += _lib.launch_count() - n0
                 return out
-            static = _clone_batch(batched_inputs, next(self.model.parameters()).device)
+            static = _padded_batch(batched_inputs, dev, counts) if counts is not None else _clone_batch(batched_inputs, dev)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
@@ -405,9 +440,12 @@ class DataParallelTrainer:
                 # the flat-gradient all-reduce after) and the two optimizer kernels stay outside the graph
                 total, losses = self._eager_step(static) if self.world == 1 else self._forward_backward(static)
             entry.update(graph=graph, static=static, total=total, losses=losses, launches=_lib.launch_count() - n0)
-        _copy_batch(entry["static"], batched_inputs)
+        if counts is not None:
+            _padded_batch(batched_inputs, dev, counts, out=entry["static"])
+        else:
+            _copy_batch(entry["static"], batched_inputs)
         if self.world > 1:
-            self._global_num_masks(batched_inputs)
+            self._global_num_masks(raw_inputs)
         entry["graph"].replay()
         self.pdb_launches += entry["launches"]
         if self.world == 1:
@@ -419,6 +457,41 @@ class DataParallelTrainer:
             self.clip_and_step()
             self.pdb_launches += _lib.launch_count() - n0
         return entry["total"], entry["losses"]
+
+
+def _padded_batch(batch, device, counts, out=None):
+    """Device-resident copy of a batch whose i-th image carries counts[i] >= K_i target slots: the K_i real masks / classes, then
+    empty masks with class -1 (see DataParallelTrainer's target_bucket).  PartDistillation's object class is added as an int32
+    device scalar ("gt_object_class_dev").  ``out``: a previous result of the same shapes to refill in place (the static inputs
+    of a captured step); otherwise new tensors are allocated."""
+    res = out if out is not None else []
+    for n, (d, kp) in enumerate(zip(batch, counts)):
+        src = d["instances"]
+        k = int(src.gt_masks.tensor.shape[0])
+        if out is None:
+            e = dict(d)
+            e["image"] = d["image"].to(device, copy=True)
+            inst = type(src)(src.image_size)
+            t = torch.zeros((kp,) + tuple(src.gt_masks.tensor.shape[1:]), dtype=src.gt_masks.tensor.dtype, device=device)
+            inst.gt_masks = src.gt_masks.like(t) if hasattr(src.gt_masks, "like") else type(src.gt_masks)(t)
+            inst.gt_classes = torch.full((kp,), -1, dtype=src.gt_classes.dtype, device=device)
+            e["instances"] = inst
+            if "gt_object_class" in d:
+                e["gt_object_class_dev"] = torch.zeros((), dtype=torch.int32, device=device)
+            res.append(e)
+        else:
+            e = res[n]
+            e["image"].copy_(d["image"], non_blocking=True)
+            if kp > k:
+                e["instances"].gt_masks.tensor[k:].zero_()
+                e["instances"].gt_classes[k:].fill_(-1)
+        if k:
+            e["instances"].gt_masks.tensor[:k].copy_(src.gt_masks.tensor, non_blocking=True)
+            e["instances"].gt_classes[:k].copy_(src.gt_classes, non_blocking=True)
+        if "gt_object_class" in d:
+            e["gt_object_class"] = d["gt_object_class"]                 # the reference-format dicts keep the host value
+            e["gt_object_class_dev"].fill_(int(d["gt_object_class"]))   # a kernel argument, not a host-to-device copy
+    return res
 
 
 def _clone_batch(batch, device):

@@ -16,6 +16,7 @@ class Mask2FormerTrainingArch(nn.Module):
 
     part_distillation = False
 
+    target_padding = False          # set by the trainer's target bucketing: gt_classes == -1 marks a padding slot (engine.py)
     keep_packed_targets = True      # f3: bit-packed targets stay packed and are sampled from the words (False: expand to bytes)
 
     def _init_common(self, backbone, sem_seg_head, criterion, num_queries, num_classes, size_divisibility,
@@ -106,6 +107,8 @@ class Mask2FormerTrainingArch(nn.Module):
                     t["object_mask"] = view.sum(dim=0, keepdim=True)
             else:
                 lab = torch.zeros(counts[b], dtype=torch.long, device=dev)
+                if self.target_padding:         # class-agnostic labels, but the padding slots (gt_classes == -1) keep their mark
+                    lab = torch.where(i.gt_classes.to(dev, non_blocking=True) < 0, -1, lab)
                 t = {"labels": lab, "masks": PackedBitMasks(view, w_pad) if keep_bits else view.view(torch.bool)}
                 if self.use_wandb:
                     t["object_masks"] = view.sum(0, keepdim=True)
@@ -114,8 +117,12 @@ class Mask2FormerTrainingArch(nn.Module):
         out.offsets = offs
         out.packed_masks = packed
         out.packed_labels = torch.cat(labels).to(torch.int32) if offs[-1] else torch.zeros((0,), dtype=torch.int32, device=dev)
+        out.has_dummies = bool(self.target_padding)
         if self.part_distillation:
-            out.object_classes = host_table([int(x["gt_object_class"]) for x in inputs], torch.int32, dev)
+            if all("gt_object_class_dev" in x for x in inputs):     # device scalars of a static (graph) batch: data, not constants
+                out.object_classes = torch.stack([x["gt_object_class_dev"].reshape(()) for x in inputs]).to(torch.int32)
+            else:
+                out.object_classes = host_table([int(x["gt_object_class"]) for x in inputs], torch.int32, dev)
         return out
 
     def run_head(self, features, targets):

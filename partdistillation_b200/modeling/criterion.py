@@ -74,7 +74,10 @@ class SetCriterion(nn.Module):
         B, Q, _ = logits.shape
         src, tgt = self._flat_indices(targets, match, B, Q)
         target_classes = torch.full((B * Q,), self.num_classes, dtype=torch.int64, device=logits.device)
-        target_classes[src] = targets.packed_labels[tgt].long()
+        lab = targets.packed_labels[tgt].long()
+        if getattr(targets, "has_dummies", False):          # padding slots (label -1) are "no object", like unmatched queries
+            lab = torch.where(lab < 0, self.num_classes, lab)
+        target_classes[src] = lab
         loss_ce = F.cross_entropy(logits.view(B * Q, -1), target_classes, self.empty_weight)
         return {"loss_ce": loss_ce}
 
@@ -88,6 +91,9 @@ class SetCriterion(nn.Module):
         with torch.no_grad():
             coords = self._uncertain_point_coords(flat, src, Nm)
         bce, dice = PF.point_loss(flat, src, targets.packed_masks, tgt, coords)
+        if getattr(targets, "has_dummies", False):          # pairs matched to padding slots carry no loss
+            w = (targets.packed_labels[tgt] >= 0).to(bce.dtype)
+            bce, dice = bce * w, dice * w
         return {"loss_mask": bce.sum() / num_masks, "loss_dice": dice.sum() / num_masks}
 
     def _uncertain_point_coords(self, flat, src, Nm):
@@ -121,7 +127,11 @@ class SetCriterion(nn.Module):
         if self.external_num_masks is not None:
             num_masks = self.external_num_masks.reshape(-1)[0]
         else:
-            num_masks = torch.full((1,), float(targets.total), dtype=torch.float, device=dev)
+            if getattr(targets, "has_dummies", False):
+                # padded targets: the real count is data, not shape — counted on the device so that a captured step stays valid
+                num_masks = (targets.packed_labels >= 0).sum().float().reshape(1)
+            else:
+                num_masks = torch.full((1,), float(targets.total), dtype=torch.float, device=dev)
             if dist.is_available() and dist.is_initialized():
                 dist.all_reduce(num_masks)
                 num_masks = num_masks / dist.get_world_size()

@@ -17,6 +17,7 @@ class TargetList(list):
     packed_labels = None     # (Ktot,) int32
     offsets = None           # python list, len B+1
     object_classes = None    # (B,) int32 or None
+    has_dummies = False      # packed_labels may hold -1: padding slots added by the trainer's target bucketing (engine.py)
 
     @property
     def total(self):

@@ -203,3 +203,49 @@ def test_trainer_state_dict_round_trip_cpu():
     for (k, va), vb, vc in zip(a.state_dict().items(), b.state_dict().values(), c.state_dict().values()):
         assert torch.equal(va, vb), k
         assert torch.allclose(va, vc, rtol=1e-5, atol=1e-7), k
+
+
+def test_padded_counts_rules():
+    from partdistillation_b200.engine import DataParallelTrainer
+
+    class Arch(torch.nn.Module):
+        target_padding = False
+        num_queries = 10
+
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(4))
+    tr = DataParallelTrainer(Arch(), freeze_keys=(), target_bucket=4)
+    assert tr.model.target_padding is True
+
+    class I:
+        def __init__(self, k):
+            self.gt_masks = type("M", (), {"tensor": torch.zeros(k, 2, 2)})()
+    counts = tr._padded_counts([{"instances": I(k)} for k in (0, 1, 4, 5, 9, 10, 13)])
+    assert counts == [0, 4, 4, 8, 10, 10, 13]                     # 0 stays, capped at the query count, K >= Q untouched
+
+
+def test_padded_batch_allocates_then_refills_in_place():
+    """engine._padded_batch: K real rows + empty slots marked class -1; a second call refills the same tensors (the static inputs
+    of a captured step) and clears what the previous, larger batch left in the tail; the object class travels as a device
+    scalar next to the host value."""
+    from partdistillation_b200.compat import BitMasks, Instances
+    from partdistillation_b200.engine import _padded_batch
+
+    def item(k, obj, fill):
+        inst = Instances((4, 4))
+        inst.gt_masks = BitMasks(torch.full((k, 4, 4), fill, dtype=torch.bool))
+        inst.gt_classes = torch.arange(k)
+        return {"image": torch.full((3, 4, 4), k, dtype=torch.uint8), "instances": inst, "gt_object_class": obj}
+    dev = torch.device("cpu")
+    static = _padded_batch([item(3, 7, True)], dev, [4])
+    s = static[0]
+    assert s["instances"].gt_masks.tensor.shape == (4, 4, 4) and s["instances"].gt_masks.tensor[:3].all()
+    assert not s["instances"].gt_masks.tensor[3].any() and s["instances"].gt_classes.tolist() == [0, 1, 2, -1]
+    assert int(s["gt_object_class_dev"]) == 7 and s["gt_object_class"] == 7
+    ptr = s["instances"].gt_masks.tensor.data_ptr()
+    again = _padded_batch([item(1, 2, True)], dev, [4], out=static)
+    assert again is static and s["instances"].gt_masks.tensor.data_ptr() == ptr
+    assert s["instances"].gt_masks.tensor[:1].all() and not s["instances"].gt_masks.tensor[1:].any()
+    assert s["instances"].gt_classes.tolist() == [0, -1, -1, -1] and int(s["gt_object_class_dev"]) == 2
+    assert int(s["image"][0, 0, 0]) == 1

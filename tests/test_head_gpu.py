@@ -35,7 +35,7 @@ def _build(g, device=None):
     return model, c
 
 
-def _inputs(model, c):
+def _inputs(model, c, pad=0):
     from partdistillation_b200.compat import BitMasks, ImageList, Instances
     pd = c["arch"] == "PartDistillationModel"
     feats = {k: v.cuda() for k, v in synth.synth_features(c["B"], c["H"], c["W"], c["channels"], seed=c["feature_seed"]).items()}
@@ -49,6 +49,9 @@ def _inputs(model, c):
         if pd:
             e["gt_object_class"] = d["gt_object_class"]
         bi.append(e)
+    if pad:         # the trainer's target bucketing (engine._padded_batch): `pad` extra empty slots per image, class -1
+        from partdistillation_b200.engine import _padded_batch
+        bi = _padded_batch(bi, torch.device(DEV), [len(d["instances"].gt_classes) + pad for d in bi])
     il = ImageList(torch.zeros(c["B"], 3, c["H"], c["W"], device=DEV), [(c["H"], c["W"])] * c["B"])
     return feats, model.prepare_targets(bi, il)
 
@@ -139,6 +142,59 @@ def test_head_and_loss_vs_reference_golden(golden_dir, name):
     for k, n in g["grad_norms"].items():
         mine = named[k].grad.double().norm().item()
         assert abs(mine - n) <= 1e-2 * max(n, 1e-6), k
+
+
+class _SharedRowsRand:
+    """Point provider whose rows all share one pattern per call shape, so that adding rows (padding slots) does not shift the
+    coordinates of the others."""
+
+    def __call__(self, *size, device=None, dtype=None, **kw):
+        base = torch.rand(1, size[-2], 2, generator=torch.Generator().manual_seed(size[-2]))
+        return base.expand(size[0], -1, -1).contiguous().to(device=device, dtype=dtype or torch.float32)
+
+
+@pytest.mark.parametrize("name", ["proposal_micro", "pd_micro"])
+def test_padded_targets_are_loss_neutral(golden_dir, name):
+    """Target bucketing (DataParallelTrainer(target_bucket=...)): padding every image's targets with empty slots marked
+    class -1 changes neither the Hungarian assignment of the real targets, nor any loss term, nor the gradients."""
+    if DEV == "cuda" and not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    g = torch.load(os.path.join(golden_dir, f"head_{name}.pt"), weights_only=False)
+    res = []
+    for pad in (0, 3):
+        model, c = _build(g)
+        model.target_padding = bool(pad)
+        feats, targets = _inputs(model, c, pad)
+        assert targets.offsets[-1] == sum(c["K"]) + pad * c["B"] if isinstance(c["K"], (list, tuple)) else True
+        model.criterion.rand = model.criterion.matcher.rand = _SharedRowsRand()
+        matches = []
+        mp = model.criterion.matcher.match_packed
+
+        def rec_match(o, t, mp=mp, matches=matches):
+            r = mp(o, t)
+            matches.append(r)
+            return r
+        model.criterion.matcher.match_packed = rec_match
+        losses = model.losses_from_features(feats, targets)
+        sum(losses.values()).backward()
+        real = []
+        for pi, ti in matches:
+            per = []
+            for b in range(c["B"]):
+                s, e = targets.offsets[b], targets.offsets[b + 1]
+                k_real = e - s - pad
+                per.append(sorted((int(j), int(i)) for i, j in zip(pi[s:e].tolist(), ti[s:e].tolist()) if j < k_real))
+            real.append(per)
+        grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+        res.append(({k: float(v.detach()) for k, v in losses.items()}, real, grads))
+    (la, ma, ga), (lb, mb, gb) = res
+    assert ma == mb                                             # same query for every real target, every decoder output
+    assert set(la) == set(lb)
+    for k in la:
+        assert abs(la[k] - lb[k]) <= 2e-6 * max(1.0, abs(la[k])), (k, la[k], lb[k])
+    assert set(ga) == set(gb)
+    for k in ga:
+        assert float((ga[k] - gb[k]).abs().max()) <= 1e-4 * max(float(ga[k].abs().max()), 1e-8), k
 
 
 def test_matcher_public_api(golden_dir):
