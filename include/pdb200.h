@@ -335,6 +335,11 @@ PDB_API int pdb_window_attention_forward(const float* qkv, const float* bias, co
  * ---------------------------------------------------------------------------------------------- */
 PDB_API int pdb_layer_norm_forward(const float* x, const float* residual, const float* weight, const float* bias, float* y,
                            float* sum_out, float* mean, float* rstd, int64_t rows, int C, float eps, void* stream);
+/* Same with stochastic depth on the residual branch (swin_transformer.py:131-134, x = shortcut + drop_path(branch)):
+ * y = LayerNorm(x + res_scale[row / rows_per_sample] * residual); res_scale: one f32 factor per sample (keep / (1 - p)), NULL = 1. */
+PDB_API int pdb_layer_norm_forward_scaled(const float* x, const float* residual, const float* res_scale, int64_t rows_per_sample,
+                                  const float* weight, const float* bias, float* y, float* sum_out, float* mean, float* rstd,
+                                  int64_t rows, int C, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm (+ ReLU) over channels-last maps — replaces nn.GroupNorm(32, C) and the F.relu behind it on the pixel decoder's

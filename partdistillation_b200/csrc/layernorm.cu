@@ -15,10 +15,14 @@ template <int VEC>      // float4 per lane: C <= VEC * 128
 __global__ void __launch_bounds__(256)
 layer_norm_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ res, const float4* __restrict__ w,
                       const float4* __restrict__ b, float4* __restrict__ y, float4* __restrict__ sum_out,
-                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int C4, float inv_c, float eps) {
+                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int C4, float inv_c, float eps,
+                      const float* __restrict__ res_scale, int64_t rows_per_sample) {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
+    // stochastic depth (swin_transformer.py:131-134: x = shortcut + drop_path(branch)): the branch of sample b enters scaled by
+    // res_scale[b] = keep_b / (1 - p)
+    const float sc = res_scale ? __ldg(res_scale + row / rows_per_sample) : 1.f;
     const float4* xr = x + row * C4;
     float4 v[VEC];
     float s = 0.f;
@@ -29,7 +33,8 @@ layer_norm_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ r
             v[i] = __ldg(xr + c);
             if (res) {
                 const float4 r = __ldg(res + row * C4 + c);
-                v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
+                v[i].x = fmaf(sc, r.x, v[i].x); v[i].y = fmaf(sc, r.y, v[i].y);
+                v[i].z = fmaf(sc, r.z, v[i].z); v[i].w = fmaf(sc, r.w, v[i].w);
             }
             if (sum_out) sum_out[row * C4 + c] = v[i];
             s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
@@ -70,9 +75,11 @@ layer_norm_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ r
 
 using namespace pdb;
 
-extern "C" int pdb_layer_norm_forward(const float* x, const float* residual, const float* weight, const float* bias, float* y,
-                                      float* sum_out, float* mean, float* rstd, int64_t rows, int C, float eps, void* stream) {
+extern "C" int pdb_layer_norm_forward_scaled(const float* x, const float* residual, const float* res_scale, int64_t rows_per_sample,
+                                             const float* weight, const float* bias, float* y, float* sum_out, float* mean,
+                                             float* rstd, int64_t rows, int C, float eps, void* stream) {
     PDB_REQUIRE(x && weight && bias && y && mean && rstd, "layer_norm: null pointer");
+    PDB_REQUIRE(!res_scale || (residual && rows_per_sample > 0), "layer_norm: res_scale needs a residual and rows_per_sample > 0");
     PDB_REQUIRE(rows >= 0 && C > 0 && C % 4 == 0 && C <= 2048, "layer_norm: C=%d must be a multiple of 4, at most 2048", C);
     uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(weight) |
                    reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(sum_out);
@@ -86,7 +93,7 @@ extern "C" int pdb_layer_norm_forward(const float* x, const float* residual, con
     layer_norm_fwd_kernel<V><<<(unsigned)blocks, 256, 0, st>>>(                                                             \
         reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(residual), reinterpret_cast<const float4*>(weight), \
         reinterpret_cast<const float4*>(bias), reinterpret_cast<float4*>(y), reinterpret_cast<float4*>(sum_out), mean, rstd, rows, \
-        C4, 1.f / (float)C, eps)
+        C4, 1.f / (float)C, eps, res_scale, rows_per_sample)
     if (C4 <= 32) PDB_LN_LAUNCH(1);
     else if (C4 <= 64) PDB_LN_LAUNCH(2);
     else if (C4 <= 128) PDB_LN_LAUNCH(4);
@@ -94,4 +101,9 @@ extern "C" int pdb_layer_norm_forward(const float* x, const float* residual, con
     else PDB_LN_LAUNCH(16);
 #undef PDB_LN_LAUNCH
     return launched("layer_norm_forward");
+}
+
+extern "C" int pdb_layer_norm_forward(const float* x, const float* residual, const float* weight, const float* bias, float* y,
+                                      float* sum_out, float* mean, float* rstd, int64_t rows, int C, float eps, void* stream) {
+    return pdb_layer_norm_forward_scaled(x, residual, nullptr, 0, weight, bias, y, sum_out, mean, rstd, rows, C, eps, stream);
 }

@@ -1249,14 +1249,39 @@ class LayerNormFunction(Function):
                 gw, gb, None, None)
 
 
-def layer_norm(x, weight, bias, eps=1e-5, residual=None, return_sum=False):
+def layer_norm(x, weight, bias, eps=1e-5, residual=None, return_sum=False, residual_scale=None):
     """F.layer_norm over the last dimension of ``x + residual`` (``residual`` optional).  With ``return_sum`` also
     returns the sum (pre-norm residual streams).  fp32 CUDA tensors with C % 4 == 0 use the kernel; anything else goes
-    through torch."""
+    through torch.  ``residual_scale``: one factor per sample (numel == x.shape[0]) applied to ``residual`` — stochastic
+    depth's keep / (1 - p) — folded into the same pass when nothing needs a gradient (the frozen backbone)."""
     if x.is_cuda and (x.dtype == torch.bfloat16 or (residual is not None and residual.dtype == torch.bfloat16)):
         # autocast: LayerNorm runs (and returns) fp32, the residual stream stays fp32
         x = x.float()
         residual = None if residual is None else residual.float()
+    if residual_scale is not None:
+        grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, residual, weight, bias))
+        fused = (not grad and residual is not None and x.is_cuda and x.dtype == torch.float32 and residual.dtype == torch.float32
+                 and residual.shape == x.shape and x.dim() >= 2 and weight is not None and bias is not None
+                 and weight.dtype == torch.float32 and x.shape[-1] % 4 == 0 and x.shape[-1] <= 2048
+                 and residual_scale.numel() == x.shape[0]
+                 and getattr(_lib.load(), "pdb_layer_norm_forward_scaled", None) is not None)
+        if not fused:
+            residual = residual * residual_scale.view((x.shape[0],) + (1,) * (x.dim() - 1)).to(residual.dtype)
+        else:
+            C = x.shape[-1]
+            x2, r2 = _c(x).view(-1, C), _c(residual).view(-1, C)
+            sc = _c(residual_scale.reshape(-1).float())
+            rows = x2.shape[0]
+            y = torch.empty_like(x2)
+            z = torch.empty_like(x2) if return_sum else None
+            mean = torch.empty((rows,), dtype=torch.float32, device=x.device)
+            rstd = torch.empty((rows,), dtype=torch.float32, device=x.device)
+            rc = _lib.load().pdb_layer_norm_forward_scaled(x2.data_ptr(), r2.data_ptr(), sc.data_ptr(), rows // x.shape[0],
+                                                           weight.data_ptr(), bias.data_ptr(), y.data_ptr(),
+                                                           z.data_ptr() if z is not None else None, mean.data_ptr(),
+                                                           rstd.data_ptr(), rows, C, float(eps), _stream())
+            _lib.check(rc, "pdb_layer_norm_forward_scaled")
+            return (y.view(x.shape), z.view(x.shape)) if return_sum else y.view(x.shape)
     ok = (x.is_cuda and x.dtype == torch.float32 and weight is not None and bias is not None and weight.dtype == torch.float32
           and x.shape[-1] % 4 == 0 and x.shape[-1] <= 2048 and (residual is None or residual.shape == x.shape))
     if not ok:

@@ -117,13 +117,15 @@ class SwinTransformerBlock(nn.Module):
         self.norm2 = nn.LayerNorm(dim)
         self.mlp = Mlp(dim, int(dim * mlp_ratio), drop)
 
-    def _fused_attention(self, x, H, W):
+    def _fused_attention(self, x, H, W, normed=None):
         """Frozen-backbone path: qkv Linear on the token grid, then ONE kernel for pad / roll / window partition /
-        shift mask / attention / window reverse / roll back / crop (functional.swin_window_attention)."""
+        shift mask / attention / window reverse / roll back / crop (functional.swin_window_attention).  ``normed``: norm1(x)
+        when the caller already has it."""
         a = self.attn
         B, L, C = x.shape
-        qkv = PF.linear(PF.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps), a.qkv.weight, a.qkv.bias,
-                        out_fp32=True)
+        if normed is None:
+            normed = PF.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        qkv = PF.linear(normed, a.qkv.weight, a.qkv.bias, out_fp32=True)
         N = self.window_size * self.window_size
         bias = a.relative_position_bias_table[a.relative_position_index.view(-1)].view(N, N, -1).permute(2, 0, 1)
         # under bf16 autocast the qkv Linear returns bf16; the attention core (scores, softmax, PV) runs in fp32 either way
@@ -138,14 +140,31 @@ class SwinTransformerBlock(nn.Module):
         return (x.is_cuda and x.dtype == torch.float32 and frozen and self.dim // a.num_heads == 32
                 and self.window_size * self.window_size <= 256 and a.attn_drop.p == 0 and a.proj_drop.p == 0)
 
+    def _branch_scale(self, x):
+        dp = self.drop_path
+        return dp.sample_scale(x) if isinstance(dp, DropPath) and dp.p > 0.0 and dp.training else None
+
+    def forward_fused(self, x, H, W, pending=None):
+        """The block on the frozen-backbone path with every residual add (and its stochastic-depth factor) folded into the
+        LayerNorm behind it.  ``pending`` = (branch, scale) of the previous block's MLP, still to be added to ``x``; returns
+        (x, pending) in the same form — BasicLayer adds the last one.  Draw order of the stochastic-depth masks = the
+        reference's (attention branch, then MLP branch)."""
+        if pending is not None:
+            h, x = PF.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, residual=pending[0],
+                                 residual_scale=pending[1], return_sum=True)
+        else:
+            h = None
+        attn = self._fused_attention(x, H, W, normed=h)
+        h, x = PF.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=attn,
+                             residual_scale=self._branch_scale(x), return_sum=True)
+        return x, (self.mlp(h), self._branch_scale(x))
+
     def forward(self, x, H, W, mask_matrix):
         B, L, C = x.shape
         ws = self.window_size
         if self._can_fuse(x):
-            # residual add fused into norm2: one pass writes both the new residual stream and its normalised copy
-            h, x = PF.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps,
-                                 residual=self.drop_path(self._fused_attention(x, H, W)), return_sum=True)
-            return self._add_drop_path(x, self.mlp(h))
+            x, (m, scale) = self.forward_fused(x, H, W)
+            return x + m if scale is None else torch.addcmul(x, m, scale)
         h = self.norm1(x).view(B, H, W, C)
         pr, pb = (ws - W % ws) % ws, (ws - H % ws) % ws
         h = F.pad(h, (0, 0, 0, pr, 0, pb))
@@ -165,6 +184,11 @@ class SwinTransformerBlock(nn.Module):
     def _add_drop_path(self, residual, x):
         dp = self.drop_path
         return dp.add_to(residual, x) if isinstance(dp, DropPath) else residual + dp(x)
+
+
+def _add_branch(x, pending):
+    m, scale = pending
+    return x + m if scale is None else torch.addcmul(x, m, scale)
 
 
 class PatchMerging(nn.Module):
@@ -212,8 +236,16 @@ class BasicLayer(nn.Module):
 
     def forward(self, x, H, W):
         mask = self._shift_mask(H, W, x.device)
+        pending = None
         for blk in self.blocks:
+            if blk._can_fuse(x):
+                x, pending = blk.forward_fused(x, H, W, pending)
+                continue
+            if pending is not None:
+                x, pending = _add_branch(x, pending), None
             x = blk(x, H, W, mask)
+        if pending is not None:
+            x = _add_branch(x, pending)
         if self.downsample is not None:
             down = self.downsample(x, H, W)
             if down.dtype != x.dtype and x.dtype == torch.float32:

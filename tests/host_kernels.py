@@ -85,7 +85,7 @@ HARNESSES = [
     ("xattn.cu", "xattn_section.inc", "xattn_kernels_host.cpp",
      ("masked_xattn_workspace_bytes", "masked_xattn_forward", "masked_xattn_backward"), [], False),
     ("groupnorm.cu", "groupnorm_section.inc", "norm_kernels_host.cpp",
-     ("layer_norm_forward", "group_norm_forward", "group_norm_backward"), [("layernorm.cu", "layernorm_section.inc")], False),
+     ("layer_norm_forward", "layer_norm_forward_scaled", "group_norm_forward", "group_norm_backward"), [("layernorm.cu", "layernorm_section.inc")], False),
     ("window_attn.cu", "window_attn_section.inc", "window_attn_kernels_host.cpp",
      ("window_attention_forward", "swin_window_attention_forward"), [], True),
     ("optim.cu", "optim_section.inc", "misc_kernels_host.cpp",

@@ -19,7 +19,7 @@ def host_lib(tmp_path_factory):
     src = open(os.path.join(ROOT, "partdistillation_b200", "csrc", "layernorm.cu")).read()
     (tmp / "layernorm_section.inc").write_text(re.search(NAMESPACE_BLOCK, src, re.S).group(1))
     return build_host_library(tmp, "groupnorm.cu", "groupnorm_section.inc", "norm_kernels_host.cpp",
-                              ("layer_norm_forward", "group_norm_forward", "group_norm_backward"))
+                              ("layer_norm_forward", "layer_norm_forward_scaled", "group_norm_forward", "group_norm_backward"))
 
 
 @pytest.fixture
@@ -33,6 +33,11 @@ def fn(monkeypatch, host_lib):
                                                   ((3, 5), 512, True, True), ((9,), 2048, True, True), ((4, 11), 36, False, True)])
 def test_layer_norm_fused(fn, rows, C, res, want_sum):
     gpu_tests.test_layer_norm_fused(fn, rows, C, res, want_sum)
+
+
+@pytest.mark.parametrize("B,L,C", [(2, 30, 128), (3, 5, 512)])
+def test_layer_norm_with_stochastic_depth_scale(fn, B, L, C):
+    gpu_tests.test_layer_norm_with_stochastic_depth_scale(fn, B, L, C)
 
 
 @pytest.mark.parametrize("B,C,H,W,G,relu", [(2, 256, 8, 8, 32, True), (1, 128, 9, 7, 32, True), (3, 64, 6, 6, 8, False),

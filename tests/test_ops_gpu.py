@@ -881,3 +881,45 @@ def test_linear_small_rows_matches_tensor_core_path(fn):
             fn.small_gemm_rows = 512
     for a_, r_ in zip(*res):
         assert (a_ - r_).abs().max().item() < 2e-5 * max(1.0, r_.abs().max().item())
+
+
+@pytest.mark.parametrize("B,L,C", [(2, 300, 128), (3, 64, 512), (1, 7, 1024)])
+def test_layer_norm_with_stochastic_depth_scale(fn, B, L, C):
+    """y = LayerNorm(x + s_b * branch), z = x + s_b * branch in one pass (Swin's x = shortcut + drop_path(branch) folded into
+    the next norm) against the two-step torch expression."""
+    g = torch.Generator().manual_seed(50)
+    x, r = torch.randn(B, L, C, generator=g).cuda(), torch.randn(B, L, C, generator=g).cuda()
+    w, b = torch.randn(C, generator=g).cuda(), torch.randn(C, generator=g).cuda()
+    s = (torch.rand(B, 1, 1, generator=g) > 0.4).float().div(0.6).cuda()
+    y, z = fn.layer_norm(x, w, b, 1e-5, residual=r, residual_scale=s, return_sum=True)
+    zr = torch.addcmul(x, r, s)
+    assert torch.allclose(z, zr, rtol=0, atol=1e-6)
+    assert torch.allclose(y, F.layer_norm(zr, (C,), w, b, 1e-5), rtol=1e-5, atol=1e-5)
+    # with gradients in play the scale is applied explicitly and autograd sees the plain fused-residual LayerNorm
+    xg = x.clone().requires_grad_()
+    y2 = fn.layer_norm(xg, w, b, 1e-5, residual=r, residual_scale=s)
+    assert torch.allclose(y2, y, rtol=1e-5, atol=1e-5)
+    torch.autograd.grad(y2.sum(), xg)
+
+
+def test_swin_layer_fused_stochastic_depth_matches_plain_path(fn):
+    """A frozen Swin stage in TRAINING mode (stochastic depth active, as in the recipe): the path that folds every
+    `x = shortcut + drop_path(branch)` into the following LayerNorm against the block-by-block path of the reference
+    (swin.py:239-300), same random draws."""
+    from partdistillation_b200.modeling.backbone.swin import BasicLayer, SwinTransformerBlock
+    torch.manual_seed(3)
+    layer = BasicLayer(64, 3, 2, 4, 4.0, True, None, 0.0, 0.0, [0.3, 0.5, 0.4], downsample=True).cuda().train()
+    for p in layer.parameters():
+        p.requires_grad_(False)
+    x = torch.randn(4, 12 * 20, 64, device="cuda")
+    torch.manual_seed(11)
+    fused = layer(x, 12, 20)
+    plain_fuse = SwinTransformerBlock._can_fuse
+    SwinTransformerBlock._can_fuse = lambda self, x: False
+    try:
+        torch.manual_seed(11)
+        plain = layer(x, 12, 20)
+    finally:
+        SwinTransformerBlock._can_fuse = plain_fuse
+    assert torch.allclose(fused[0], plain[0], rtol=1e-4, atol=1e-4) and torch.allclose(fused[3], plain[3], rtol=1e-4, atol=1e-4)
+    assert (fused[0] - x).abs().max() > 0.1          # the stage did something
