@@ -282,10 +282,11 @@ PDB_API int pdb_adamw_flat(float* param, const float* grad, float* exp_avg, floa
 PDB_API int pdb_swin_window_attention_forward(const float* qkv, const float* qkv_bias, const float* bias, float* out, int B,
                                       int H, int W, int heads, int d, int ws, int shift, float scale, void* stream);
 /* Same contract on the tensor cores (warp-level mma.sync m16n8k8 TF32; csrc/window_attn_mma.cu): passes = 3 is fp32-accurate
- * (hi / lo operand split), passes = 1 a single TF32 pass for the bf16-autocast path.  Window sizes 12, 8, 4; d = 32. */
-PDB_API int pdb_swin_window_attention_forward_tc(const float* qkv, const float* qkv_bias, const float* bias, float* out, int B,
+ * (hi / lo operand split), passes = 1 a single TF32 pass for the bf16-autocast path.  Window sizes 12, 8, 4; d = 32.
+ * out_bf16 != 0: out is bf16 (the input of the bf16 projection GEMM under autocast), else f32. */
+PDB_API int pdb_swin_window_attention_forward_tc(const float* qkv, const float* qkv_bias, const float* bias, void* out, int B,
                                          int H, int W, int heads, int d, int ws, int shift, float scale, int passes,
-                                         void* stream);
+                                         int out_bf16, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Pixel grouping affinity — replaces, inside PixelGroupingModel.generate_part_segments
@@ -336,10 +337,12 @@ PDB_API int pdb_window_attention_forward(const float* qkv, const float* bias, co
 PDB_API int pdb_layer_norm_forward(const float* x, const float* residual, const float* weight, const float* bias, float* y,
                            float* sum_out, float* mean, float* rstd, int64_t rows, int C, float eps, void* stream);
 /* Same with stochastic depth on the residual branch (swin_transformer.py:131-134, x = shortcut + drop_path(branch)):
- * y = LayerNorm(x + res_scale[row / rows_per_sample] * residual); res_scale: one f32 factor per sample (keep / (1 - p)), NULL = 1. */
+ * y = LayerNorm(x + res_scale[row / rows_per_sample] * residual); res_scale: one f32 factor per sample (keep / (1 - p)), NULL = 1.
+ * y_bf16 != 0: y is (rows, C) bf16 (round to nearest even) — the input of a bf16 GEMM under torch.autocast, without the separate
+ * conversion pass; sum_out, mean, rstd stay f32. */
 PDB_API int pdb_layer_norm_forward_scaled(const float* x, const float* residual, const float* res_scale, int64_t rows_per_sample,
-                                  const float* weight, const float* bias, float* y, float* sum_out, float* mean, float* rstd,
-                                  int64_t rows, int C, float eps, void* stream);
+                                  const float* weight, const float* bias, void* y, float* sum_out, float* mean, float* rstd,
+                                  int64_t rows, int C, float eps, int y_bf16, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm (+ ReLU) over channels-last maps — replaces nn.GroupNorm(32, C) and the F.relu behind it on the pixel decoder's

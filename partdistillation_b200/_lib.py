@@ -48,9 +48,9 @@ SIGNATURES = {
     "pdb_class_rows_forward": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _l, _p]),
     "pdb_window_attention_forward": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p]),
     "pdb_swin_window_attention_forward": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p]),
-    "pdb_swin_window_attention_forward_tc": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
+    "pdb_swin_window_attention_forward_tc": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _p]),
     "pdb_layer_norm_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _f, _p]),
-    "pdb_layer_norm_forward_scaled": (_i, [_p, _p, _p, _l, _p, _p, _p, _p, _p, _p, _l, _i, _f, _p]),
+    "pdb_layer_norm_forward_scaled": (_i, [_p, _p, _p, _l, _p, _p, _p, _p, _p, _p, _l, _i, _f, _i, _p]),
     "pdb_group_norm_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _l, _i, _i, _f, _i, _p]),
     "pdb_group_norm_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _l, _i, _i, _i, _p]),
     "pdb_group_affinity": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),

@@ -7,6 +7,7 @@
 //   x, residual, y, sum_out: (rows, C) f32;  mean, rstd: (rows) f32 (saved for backward, as native_layer_norm)
 //   sum_out (optional): z itself, for pre-norm residual streams that keep using the sum.
 // C % 4 == 0 and C <= 2048.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace pdb {
@@ -16,7 +17,7 @@ __global__ void __launch_bounds__(256)
 layer_norm_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ res, const float4* __restrict__ w,
                       const float4* __restrict__ b, float4* __restrict__ y, float4* __restrict__ sum_out,
                       float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int C4, float inv_c, float eps,
-                      const float* __restrict__ res_scale, int64_t rows_per_sample) {
+                      const float* __restrict__ res_scale, int64_t rows_per_sample, int y_bf16) {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -66,7 +67,15 @@ layer_norm_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ r
             o.y = (v[i].y - mean) * rstd * ww.y + bv.y;
             o.z = (v[i].z - mean) * rstd * ww.z + bv.z;
             o.w = (v[i].w - mean) * rstd * ww.w + bv.w;
-            y[row * C4 + c] = o;
+            if (y_bf16) {       // autocast: the consumer is a bf16 GEMM; same rounding as the cast it replaces
+                const __nv_bfloat162 lo2 = __floats2bfloat162_rn(o.x, o.y), hi2 = __floats2bfloat162_rn(o.z, o.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&lo2);
+                pk.y = *reinterpret_cast<const uint32_t*>(&hi2);
+                reinterpret_cast<uint2*>(y)[row * C4 + c] = pk;
+            } else {
+                y[row * C4 + c] = o;
+            }
         }
     }
 }
@@ -76,8 +85,8 @@ layer_norm_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ r
 using namespace pdb;
 
 extern "C" int pdb_layer_norm_forward_scaled(const float* x, const float* residual, const float* res_scale, int64_t rows_per_sample,
-                                             const float* weight, const float* bias, float* y, float* sum_out, float* mean,
-                                             float* rstd, int64_t rows, int C, float eps, void* stream) {
+                                             const float* weight, const float* bias, void* y, float* sum_out, float* mean,
+                                             float* rstd, int64_t rows, int C, float eps, int y_bf16, void* stream) {
     PDB_REQUIRE(x && weight && bias && y && mean && rstd, "layer_norm: null pointer");
     PDB_REQUIRE(!res_scale || (residual && rows_per_sample > 0), "layer_norm: res_scale needs a residual and rows_per_sample > 0");
     PDB_REQUIRE(rows >= 0 && C > 0 && C % 4 == 0 && C <= 2048, "layer_norm: C=%d must be a multiple of 4, at most 2048", C);
@@ -93,7 +102,7 @@ extern "C" int pdb_layer_norm_forward_scaled(const float* x, const float* residu
     layer_norm_fwd_kernel<V><<<(unsigned)blocks, 256, 0, st>>>(                                                             \
         reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(residual), reinterpret_cast<const float4*>(weight), \
         reinterpret_cast<const float4*>(bias), reinterpret_cast<float4*>(y), reinterpret_cast<float4*>(sum_out), mean, rstd, rows, \
-        C4, 1.f / (float)C, eps, res_scale, rows_per_sample)
+        C4, 1.f / (float)C, eps, res_scale, rows_per_sample, y_bf16)
     if (C4 <= 32) PDB_LN_LAUNCH(1);
     else if (C4 <= 64) PDB_LN_LAUNCH(2);
     else if (C4 <= 128) PDB_LN_LAUNCH(4);
@@ -105,5 +114,5 @@ extern "C" int pdb_layer_norm_forward_scaled(const float* x, const float* residu
 
 extern "C" int pdb_layer_norm_forward(const float* x, const float* residual, const float* weight, const float* bias, float* y,
                                       float* sum_out, float* mean, float* rstd, int64_t rows, int C, float eps, void* stream) {
-    return pdb_layer_norm_forward_scaled(x, residual, nullptr, 0, weight, bias, y, sum_out, mean, rstd, rows, C, eps, stream);
+    return pdb_layer_norm_forward_scaled(x, residual, nullptr, 0, weight, bias, y, sum_out, mean, rstd, rows, C, eps, 0, stream);
 }

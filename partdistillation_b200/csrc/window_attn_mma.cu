@@ -15,6 +15,7 @@
 // 16 x 32 output fragments stay in registers.  The C-fragment of S (thread holds columns 2t, 2t+1 of every 8-wide key tile)
 // feeds the A-fragment of the second product directly by permuting the contraction index: "k = t" is key 8j + 2t and
 // "k = t + 4" is key 8j + 2t + 1, and the V rows of the B-fragment are read in the same order — no shuffles, no smem round trip.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace pdb {
@@ -34,7 +35,8 @@ __device__ __forceinline__ uint32_t lo_bits(float x) {          // x - trunc_tf3
 template <int PASSES, int NT>      // NT = N / 8 key tiles (18 for ws = 12)
 __global__ void __launch_bounds__(NT * 16, NT * 16 <= 288 ? 2 : 1)
 swin_window_attention_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias, const float* __restrict__ bias,
-                                 float* __restrict__ out, int H, int W, int heads, int ws, int shift, int Hp, int Wp, float scale) {
+                                 float* __restrict__ out, int H, int W, int heads, int ws, int shift, int Hp, int Wp, float scale,
+                                 int out_bf16) {
     constexpr int N = NT * 8;
     extern __shared__ __align__(16) float s_kv[];      // K [N][36] | V [N][36] | region id [N]
     float* s_k = s_kv;
@@ -184,14 +186,21 @@ swin_window_attention_mma_kernel(const float* __restrict__ qkv, const float* __r
     const float i0 = 1.f / l0, i1 = 1.f / l1;
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
-        if (src0 >= 0) *reinterpret_cast<float2*>(out + src0 * C + h * kMD + n * 8 + 2 * t) = make_float2(o[n][0] * i0, o[n][1] * i0);
-        if (src1 >= 0) *reinterpret_cast<float2*>(out + src1 * C + h * kMD + n * 8 + 2 * t) = make_float2(o[n][2] * i1, o[n][3] * i1);
+        const int64_t col = h * kMD + n * 8 + 2 * t;
+        if (out_bf16) {         // the consumer is the bf16 projection GEMM of the autocast path: no separate conversion pass
+            __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out);
+            if (src0 >= 0) *reinterpret_cast<__nv_bfloat162*>(ob + src0 * C + col) = __floats2bfloat162_rn(o[n][0] * i0, o[n][1] * i0);
+            if (src1 >= 0) *reinterpret_cast<__nv_bfloat162*>(ob + src1 * C + col) = __floats2bfloat162_rn(o[n][2] * i1, o[n][3] * i1);
+        } else {
+            if (src0 >= 0) *reinterpret_cast<float2*>(out + src0 * C + col) = make_float2(o[n][0] * i0, o[n][1] * i0);
+            if (src1 >= 0) *reinterpret_cast<float2*>(out + src1 * C + col) = make_float2(o[n][2] * i1, o[n][3] * i1);
+        }
     }
 }
 
 template <int PASSES, int NT>
 static int launch_mma(const float* qkv, const float* qkv_bias, const float* bias, float* out, int B, int H, int W, int heads, int ws,
-                      int shift, float scale, cudaStream_t st) {
+                      int shift, float scale, int out_bf16, cudaStream_t st) {
     const int Hp = (H + ws - 1) / ws * ws, Wp = (W + ws - 1) / ws * ws;
     const int64_t ctas = (int64_t)B * (Hp / ws) * (Wp / ws) * heads;
     PDB_REQUIRE(ctas < (1ll << 31), "swin_window_attention: too many windows");
@@ -204,7 +213,7 @@ static int launch_mma(const float* qkv, const float* qkv_bias, const float* bias
         attr = true;
     }
     swin_window_attention_mma_kernel<PASSES, NT><<<(unsigned)ctas, NT * 16, smem, st>>>(qkv, qkv_bias, bias, out, H, W, heads, ws, shift,
-                                                                                      Hp, Wp, scale);
+                                                                                      Hp, Wp, scale, out_bf16);
     return launched("swin_window_attention_mma");
 }
 
@@ -214,9 +223,9 @@ using namespace pdb;
 
 // passes: 3 = fp32-accurate (3xTF32), 1 = single TF32 pass (bf16-autocast path).  Window sizes 12 (N = 144), 8 (N = 64) and 4
 // (N = 16: the micro trunks of the tests); other sizes: PDB_ERR_UNSUPPORTED (callers use pdb_swin_window_attention_forward).
-extern "C" int pdb_swin_window_attention_forward_tc(const float* qkv, const float* qkv_bias, const float* bias, float* out, int B,
+extern "C" int pdb_swin_window_attention_forward_tc(const float* qkv, const float* qkv_bias, const float* bias, void* out, int B,
                                                     int H, int W, int heads, int d, int ws, int shift, float scale, int passes,
-                                                    void* stream) {
+                                                    int out_bf16, void* stream) {
     PDB_REQUIRE(qkv && bias && out, "swin_window_attention_tc: null pointer");
     PDB_REQUIRE(d == kMD, "swin_window_attention_tc: head dim %d (only 32)", d);
     PDB_REQUIRE(B > 0 && H > 0 && W > 0 && heads > 0 && shift >= 0 && shift < ws, "swin_window_attention_tc: bad sizes");
@@ -224,8 +233,8 @@ extern "C" int pdb_swin_window_attention_forward_tc(const float* qkv, const floa
     cudaStream_t st = as_stream(stream);
 #define PDB_WIN_CASE(WS, NT_)                                                                                              \
     if (ws == WS)                                                                                                          \
-        return passes == 3 ? launch_mma<3, NT_>(qkv, qkv_bias, bias, out, B, H, W, heads, ws, shift, scale, st)            \
-                           : launch_mma<1, NT_>(qkv, qkv_bias, bias, out, B, H, W, heads, ws, shift, scale, st);
+        return passes == 3 ? launch_mma<3, NT_>(qkv, qkv_bias, bias, (float*)out, B, H, W, heads, ws, shift, scale, out_bf16, st) \
+                           : launch_mma<1, NT_>(qkv, qkv_bias, bias, (float*)out, B, H, W, heads, ws, shift, scale, out_bf16, st);
     PDB_WIN_CASE(12, 18)
     PDB_WIN_CASE(8, 8)
     PDB_WIN_CASE(4, 2)

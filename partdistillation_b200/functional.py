@@ -536,11 +536,22 @@ _weight_lo = {}          # frozen weights: (data_ptr, shape) -> lo tensor (compu
 weights_epoch = 0        # bumped by the trainer after every optimizer step (trainable weights change in place)
 
 
+def forget_weight(weight):
+    """Drops the cached low part of a derived frozen weight that is about to be released (its address may be reused)."""
+    _weight_lo.pop((weight.data_ptr(), tuple(weight.shape)), None)
+    for transposed in (False, True):
+        _bf16_weights.pop((weight.data_ptr(), tuple(weight.shape), transposed), None)
+
+
 def weight_lo(weight, rows):
     """Pre-split low parts of a Linear weight for GEMMs with many row tiles (every 128-row tile would otherwise
     re-split the same weight tile).  Frozen weights are split once; trainable ones once per optimizer step."""
     if rows < 2048 or weight.numel() % 4 or weight.data_ptr() % 16 or not weight.is_contiguous():
         return None
+    if not (weight.is_leaf or (weight._base is not None and weight._base.is_leaf)):
+        # a temporary (e.g. a scaled / concatenated weight rebuilt inside autograd on every call): its address says nothing about
+        # its contents, so nothing is cached
+        return split_lo(weight.detach())
     key = (weight.data_ptr(), tuple(weight.shape))
     epoch = weights_epoch if weight.requires_grad or weight._base is not None and weight._base.requires_grad else -1
     hit = _weight_lo.get(key)
@@ -560,6 +571,34 @@ def gemm_tf32x3(A, B, C, M, N, K, *, batch=1, lda, ldb, ldc, sa=0, sb=0, sc=0, a
                                      int(relu), int(accumulate), int(ksplit), _stream())
     _lib.check(rc, "pdb_gemm_tf32x3")
     return C
+
+
+class SplitColumns(Function):
+    """x[..., :n], x[..., n:] as views; backward writes the two gradients into the column ranges of ONE new tensor (autograd's own
+    slice backward builds a zero-filled full-size tensor per slice and adds them)."""
+
+    @staticmethod
+    def forward(ctx, x, n):
+        ctx.n, ctx.shape = n, x.shape
+        ctx.set_materialize_grads(False)
+        return x[..., :n], x[..., n:]
+
+    @staticmethod
+    def backward(ctx, ga, gb):
+        if ga is None and gb is None:
+            return None, None
+        ref = ga if ga is not None else gb
+        g = torch.empty(ctx.shape, dtype=ref.dtype, device=ref.device)
+        for part, grad in ((g[..., :ctx.n], ga), (g[..., ctx.n:], gb)):
+            if grad is None:
+                part.zero_()
+            else:
+                part.copy_(grad)
+        return g, None
+
+
+def split_columns(x, n):
+    return SplitColumns.apply(x, n) if torch.is_grad_enabled() and x.requires_grad else (x[..., :n], x[..., n:])
 
 
 small_gemm_rows = 512      # row count up to which Linear forward / input-gradient products take the mma.sync kernel (0 disables)
@@ -857,6 +896,9 @@ _bf16_weights = {}
 
 def weight_bf16(weight, transposed=False):
     """bf16 copy of a weight (optionally transposed), cached until the weight changes (optimizer step / load)."""
+    if not (weight.is_leaf or (weight._base is not None and weight._base.is_leaf)):     # a temporary: see weight_lo
+        w = weight.detach()
+        return (w.t() if transposed else w).to(torch.bfloat16).contiguous()
     key = (weight.data_ptr(), tuple(weight.shape), transposed)
     tag = (weight._version, weights_epoch)
     hit = _bf16_weights.get(key)
@@ -1175,29 +1217,32 @@ def window_attention(qkv, bias, mask, heads, scale):
 swin_attention_tensor_cores = os.environ.get("PDB_SWIN_ATTN", "mma") != "ffma"     # A/B switch: the FFMA kernel of round 1
 
 
-def swin_window_attention(qkv, qkv_bias, bias, heads, window_size, shift, scale):
+def swin_window_attention(qkv, qkv_bias, bias, heads, window_size, shift, scale, out_dtype=torch.float32):
     """qkv (B, H, W, 3*heads*32) f32 in token order -> (B, H, W, heads*32): the whole shifted-window attention of a Swin
-    block (pad, roll, partition, mask, attention, reverse, roll back, crop) in one kernel.  No autograd."""
+    block (pad, roll, partition, mask, attention, reverse, roll back, crop) in one kernel.  No autograd.
+    out_dtype = torch.bfloat16 (autocast: the consumer is the bf16 projection GEMM) is written by the tensor-core kernel itself."""
     _need_cuda(qkv, bias)
     qkv, bias = _c(qkv), _c(bias.float())
     B, H, W, C3 = qkv.shape
     d = C3 // (3 * heads)
-    out = torch.empty((B, H, W, heads * d), dtype=torch.float32, device=qkv.device)
     qb = _c(qkv_bias.float()) if qkv_bias is not None else None
     lib = _lib.load()
     tc = getattr(lib, "pdb_swin_window_attention_forward_tc", None)     # absent only in the CPU-tier host builds of the tests
     if swin_attention_tensor_cores and tc is not None and d == 32 and int(window_size) in (12, 8, 4):
         # tensor-core kernel (csrc/window_attn_mma.cu): 3xTF32 = fp32-accurate; a single TF32 pass under bf16 autocast
         passes = 1 if (torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16) else 3
+        half = out_dtype == torch.bfloat16
+        out = torch.empty((B, H, W, heads * d), dtype=torch.bfloat16 if half else torch.float32, device=qkv.device)
         rc = tc(qkv.data_ptr(), qb.data_ptr() if qb is not None else None, bias.data_ptr(), out.data_ptr(), B, H, W, heads, d,
-                int(window_size), int(shift), float(scale), passes, _stream())
+                int(window_size), int(shift), float(scale), passes, int(half), _stream())
         _lib.check(rc, "pdb_swin_window_attention_forward_tc")
         return out
+    out = torch.empty((B, H, W, heads * d), dtype=torch.float32, device=qkv.device)
     rc = lib.pdb_swin_window_attention_forward(qkv.data_ptr(), qb.data_ptr() if qb is not None else None, bias.data_ptr(),
                                                out.data_ptr(), B, H, W, heads, d, int(window_size), int(shift),
                                                float(scale), _stream())
     _lib.check(rc, "pdb_swin_window_attention_forward")
-    return out
+    return out if out_dtype == torch.float32 else out.to(out_dtype)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -1249,39 +1294,61 @@ class LayerNormFunction(Function):
                 gw, gb, None, None)
 
 
-def layer_norm(x, weight, bias, eps=1e-5, residual=None, return_sum=False, residual_scale=None):
+def _layer_norm_nograd(x, weight, bias, eps, residual, return_sum, residual_scale, out_dtype):
+    """The forward-only variants of the LayerNorm kernel (per-sample residual scale, bf16 output); None when they do not apply."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, residual, weight, bias)):
+        return None
+    f = getattr(_lib.load(), "pdb_layer_norm_forward_scaled", None)
+    if f is None or out_dtype not in (torch.float32, torch.bfloat16):
+        return None
+    if x.is_cuda and residual is not None and residual.dtype == torch.bfloat16:
+        residual = residual.float()
+    ok = (x.is_cuda and x.dtype == torch.float32 and x.dim() >= 2 and weight is not None and bias is not None
+          and weight.dtype == torch.float32 and bias.dtype == torch.float32 and x.shape[-1] % 4 == 0 and x.shape[-1] <= 2048
+          and (residual is None or (residual.dtype == torch.float32 and residual.shape == x.shape))
+          and (residual_scale is None or (residual is not None and residual_scale.numel() == x.shape[0])))
+    if not ok:
+        return None
+    C = x.shape[-1]
+    x2 = _c(x).view(-1, C)
+    r2 = _c(residual).view(-1, C) if residual is not None else None
+    sc = _c(residual_scale.reshape(-1).float()) if residual_scale is not None else None
+    rows = x2.shape[0]
+    y = torch.empty((rows, C), dtype=out_dtype, device=x.device)
+    z = torch.empty_like(x2) if (return_sum and r2 is not None) else None
+    mean = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    rstd = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    rc = f(x2.data_ptr(), r2.data_ptr() if r2 is not None else None, sc.data_ptr() if sc is not None else None,
+           rows // max(1, x.shape[0]), _c(weight).data_ptr(), _c(bias).data_ptr(), y.data_ptr(), z.data_ptr() if z is not None else None,
+           mean.data_ptr(), rstd.data_ptr(), rows, C, float(eps), int(out_dtype == torch.bfloat16), _stream())
+    _lib.check(rc, "pdb_layer_norm_forward_scaled")
+    if return_sum:
+        return y.view(x.shape), (z if z is not None else x2).view(x.shape)
+    return y.view(x.shape)
+
+
+def layer_norm(x, weight, bias, eps=1e-5, residual=None, return_sum=False, residual_scale=None, out_dtype=None):
     """F.layer_norm over the last dimension of ``x + residual`` (``residual`` optional).  With ``return_sum`` also
     returns the sum (pre-norm residual streams).  fp32 CUDA tensors with C % 4 == 0 use the kernel; anything else goes
     through torch.  ``residual_scale``: one factor per sample (numel == x.shape[0]) applied to ``residual`` — stochastic
-    depth's keep / (1 - p) — folded into the same pass when nothing needs a gradient (the frozen backbone)."""
+    depth's keep / (1 - p) — folded into the same pass when nothing needs a gradient (the frozen backbone).
+    ``out_dtype`` = torch.bfloat16: the normalised output is written as bf16 by the kernel (autocast: it feeds a bf16 GEMM; the
+    sum stays fp32) — also only on the no-gradient path; otherwise the result is converted afterwards."""
+    if out_dtype is not None and out_dtype != torch.float32:
+        r = _layer_norm_nograd(x, weight, bias, eps, residual, return_sum, residual_scale, out_dtype)
+        if r is not None:
+            return r
+        r = layer_norm(x, weight, bias, eps, residual, return_sum, residual_scale)
+        return (r[0].to(out_dtype), r[1]) if return_sum else r.to(out_dtype)
     if x.is_cuda and (x.dtype == torch.bfloat16 or (residual is not None and residual.dtype == torch.bfloat16)):
         # autocast: LayerNorm runs (and returns) fp32, the residual stream stays fp32
         x = x.float()
         residual = None if residual is None else residual.float()
     if residual_scale is not None:
-        grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, residual, weight, bias))
-        fused = (not grad and residual is not None and x.is_cuda and x.dtype == torch.float32 and residual.dtype == torch.float32
-                 and residual.shape == x.shape and x.dim() >= 2 and weight is not None and bias is not None
-                 and weight.dtype == torch.float32 and x.shape[-1] % 4 == 0 and x.shape[-1] <= 2048
-                 and residual_scale.numel() == x.shape[0]
-                 and getattr(_lib.load(), "pdb_layer_norm_forward_scaled", None) is not None)
-        if not fused:
-            residual = residual * residual_scale.view((x.shape[0],) + (1,) * (x.dim() - 1)).to(residual.dtype)
-        else:
-            C = x.shape[-1]
-            x2, r2 = _c(x).view(-1, C), _c(residual).view(-1, C)
-            sc = _c(residual_scale.reshape(-1).float())
-            rows = x2.shape[0]
-            y = torch.empty_like(x2)
-            z = torch.empty_like(x2) if return_sum else None
-            mean = torch.empty((rows,), dtype=torch.float32, device=x.device)
-            rstd = torch.empty((rows,), dtype=torch.float32, device=x.device)
-            rc = _lib.load().pdb_layer_norm_forward_scaled(x2.data_ptr(), r2.data_ptr(), sc.data_ptr(), rows // x.shape[0],
-                                                           weight.data_ptr(), bias.data_ptr(), y.data_ptr(),
-                                                           z.data_ptr() if z is not None else None, mean.data_ptr(),
-                                                           rstd.data_ptr(), rows, C, float(eps), _stream())
-            _lib.check(rc, "pdb_layer_norm_forward_scaled")
-            return (y.view(x.shape), z.view(x.shape)) if return_sum else y.view(x.shape)
+        r = _layer_norm_nograd(x, weight, bias, eps, residual, return_sum, residual_scale, torch.float32)
+        if r is not None:
+            return r
+        residual = residual * residual_scale.view((x.shape[0],) + (1,) * (x.dim() - 1)).to(residual.dtype)
     ok = (x.is_cuda and x.dtype == torch.float32 and weight is not None and bias is not None and weight.dtype == torch.float32
           and x.shape[-1] % 4 == 0 and x.shape[-1] <= 2048 and (residual is None or residual.shape == x.shape))
     if not ok:

@@ -12,6 +12,13 @@ from ... import functional as PF
 from ...compat import BACKBONE_REGISTRY, Backbone, ShapeSpec
 
 
+def _autocast_half():
+    """torch.bfloat16 under torch.autocast("cuda", bfloat16), else None."""
+    if torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+        return torch.bfloat16
+    return None
+
+
 class DropPath(nn.Module):
     """Per-sample stochastic depth (timm semantics)."""
 
@@ -49,12 +56,13 @@ class Mlp(nn.Module):
         self.fc2 = nn.Linear(hidden, dim)
         self.drop = nn.Dropout(drop)
 
-    def forward(self, x):
+    def forward(self, x, out_fp32=False):
+        """out_fp32: under bf16 autocast the second Linear writes fp32 (the residual stream's dtype) from its accumulator."""
         if isinstance(self.act, nn.GELU) and getattr(self.act, "approximate", "none") == "none":
             h = PF.linear(x, self.fc1.weight, self.fc1.bias, gelu=True)       # GELU in the GEMM epilogue when frozen
         else:
             h = self.act(PF.linear(x, self.fc1.weight, self.fc1.bias))
-        return self.drop(PF.linear(self.drop(h), self.fc2.weight, self.fc2.bias))
+        return self.drop(PF.linear(self.drop(h), self.fc2.weight, self.fc2.bias, out_fp32=out_fp32))
 
 
 def window_partition(x, ws):
@@ -123,15 +131,16 @@ class SwinTransformerBlock(nn.Module):
         when the caller already has it."""
         a = self.attn
         B, L, C = x.shape
+        half = _autocast_half()        # bf16 autocast: every hand-over between kernels already has the consumer's dtype
         if normed is None:
-            normed = PF.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+            normed = PF.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, out_dtype=half)
         qkv = PF.linear(normed, a.qkv.weight, a.qkv.bias, out_fp32=True)
         N = self.window_size * self.window_size
         bias = a.relative_position_bias_table[a.relative_position_index.view(-1)].view(N, N, -1).permute(2, 0, 1)
-        # under bf16 autocast the qkv Linear returns bf16; the attention core (scores, softmax, PV) runs in fp32 either way
+        # the attention core (scores, softmax, PV) reads fp32 q / k / v (written by the qkv GEMM's epilogue) either way
         o = PF.swin_window_attention(qkv.float().view(B, H, W, 3 * C), a.qkv.bias, bias, a.num_heads, self.window_size,
-                                     self.shift_size, a.scale)
-        return PF.linear(o.view(B, L, C), a.proj.weight, a.proj.bias)
+                                     self.shift_size, a.scale, out_dtype=half or torch.float32)
+        return PF.linear(o.view(B, L, C), a.proj.weight, a.proj.bias, out_fp32=True)
 
     def _can_fuse(self, x):
         a = self.attn
@@ -149,15 +158,16 @@ class SwinTransformerBlock(nn.Module):
         LayerNorm behind it.  ``pending`` = (branch, scale) of the previous block's MLP, still to be added to ``x``; returns
         (x, pending) in the same form — BasicLayer adds the last one.  Draw order of the stochastic-depth masks = the
         reference's (attention branch, then MLP branch)."""
+        half = _autocast_half()
         if pending is not None:
             h, x = PF.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, residual=pending[0],
-                                 residual_scale=pending[1], return_sum=True)
+                                 residual_scale=pending[1], return_sum=True, out_dtype=half)
         else:
             h = None
         attn = self._fused_attention(x, H, W, normed=h)
         h, x = PF.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=attn,
-                             residual_scale=self._branch_scale(x), return_sum=True)
-        return x, (self.mlp(h), self._branch_scale(x))
+                             residual_scale=self._branch_scale(x), return_sum=True, out_dtype=half)
+        return x, (self.mlp(h, out_fp32=True), self._branch_scale(x))
 
     def forward(self, x, H, W, mask_matrix):
         B, L, C = x.shape

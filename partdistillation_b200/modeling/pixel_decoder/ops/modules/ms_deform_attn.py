@@ -41,6 +41,37 @@ class MSDeformAttn(nn.Module):
             nn.init.xavier_uniform_(self.output_proj.weight)
             self.output_proj.bias.zero_()
 
+    fold_normalizer = True      # False: the reference's expression, two projections and a division pass
+
+    def _merged_projection(self, spatial_shapes, normalizer, query):
+        """[sampling_offsets / (W_l, H_l) ; attention_weights] as one (M*L*P*3, C) weight and bias.  Frozen weights (the recipe
+        freezes the encoder) and python shapes: built once per (shapes, weight versions) and kept; otherwise rebuilt inside
+        autograd on every call (four element-wise launches on 288 x 256 numbers)."""
+        M, L, P = self.n_heads, self.n_levels, self.n_points
+        so, aw = self.sampling_offsets, self.attention_weights
+        frozen = not (torch.is_grad_enabled() and any(t.requires_grad for t in (so.weight, so.bias, aw.weight, aw.bias)))
+        key = None
+        if frozen and not isinstance(spatial_shapes, torch.Tensor):
+            key = (tuple((int(h), int(w)) for h, w in spatial_shapes), query.device, query.dtype,
+                   so.weight._version, so.bias._version, aw.weight._version, aw.bias._version,
+                   so.weight.data_ptr(), aw.weight.data_ptr())
+            hit = self.__dict__.get("_merged")
+            if hit is not None and hit[0] == key:
+                return hit[1], hit[2]
+            normalizer = torch.tensor([[w, h] for h, w in spatial_shapes], dtype=torch.float32, device=query.device)
+        elif normalizer is None:
+            normalizer = torch.tensor([[w, h] for h, w in spatial_shapes], dtype=torch.float32, device=query.device)
+        inv = (1.0 / normalizer.to(torch.float32)).view(1, L, 1, 2).expand(M, L, P, 2).reshape(-1)
+        W = torch.cat([so.weight * inv[:, None], aw.weight])
+        b = torch.cat([so.bias * inv, aw.bias])
+        if key is not None:
+            old = self.__dict__.get("_merged")
+            if old is not None:
+                PF.forget_weight(old[1])        # its address may be handed to the next tensor of this shape
+            W, b = W.detach(), b.detach()
+            self.__dict__["_merged"] = (key, W, b)
+        return W, b
+
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
                 input_padding_mask=None, offset_normalizer=None):
         """query (N, Lq, C); reference_points (N, Lq, L, 2|4) in [0, 1]; input_flatten (N, S, C);
@@ -52,6 +83,19 @@ class MSDeformAttn(nn.Module):
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], 0.0)
         value = value.view(N, S, M, self.d_model // M)
+        if reference_points.shape[-1] == 2 and self.fold_normalizer and query.is_cuda:
+            # ONE projection for offsets and attention logits (the query is read once), with the division by (W_l, H_l) of
+            # `offsets / offset_normalizer` (ms_deform_attn.py:107-109) folded into the offset rows of the weight and bias
+            if offset_normalizer is None and isinstance(input_spatial_shapes, torch.Tensor):
+                offset_normalizer = torch.stack([input_spatial_shapes[..., 1], input_spatial_shapes[..., 0]], -1)
+            W, b = self._merged_projection(input_spatial_shapes, offset_normalizer, query)
+            off, logits = PF.split_columns(PF.linear(query, W, b), M * L * P * 2)
+            offsets = off.view(N, Lq, M, L, P, 2)
+            weights = F.softmax(logits.reshape(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
+            loc = reference_points[:, :, None, :, None, :] + offsets
+            out = PF.ms_deform_attn(value, input_spatial_shapes, input_level_start_index, loc.contiguous(),
+                                    weights, self.im2col_step)
+            return PF.linear(out, self.output_proj.weight, self.output_proj.bias)
         offsets = PF.linear(query, self.sampling_offsets.weight, self.sampling_offsets.bias).view(N, Lq, M, L, P, 2)
         weights = F.softmax(PF.linear(query, self.attention_weights.weight, self.attention_weights.bias).view(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
         if reference_points.shape[-1] == 2:

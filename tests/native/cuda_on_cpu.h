@@ -29,6 +29,15 @@ struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+// bf16 pairs as the kernels store them (round to nearest even; NaN payloads are not needed by the tests)
+struct alignas(4) __nv_bfloat162 { unsigned short x, y; };
+inline unsigned short host_f2bf16_rn(float f) {
+    unsigned u;
+    __builtin_memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (unsigned short)((u >> 16) | 0x40);
+    return (unsigned short)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { return __nv_bfloat162{host_f2bf16_rn(a), host_f2bf16_rn(b)}; }
 
 #define __global__
 #define __grid_constant__

@@ -10,8 +10,8 @@ using namespace pdb;
 using cpu_cuda::launch;
 
 extern "C" int host_layer_norm_forward_scaled(const float* x, const float* residual, const float* res_scale, int64_t rows_per_sample,
-                                              const float* weight, const float* bias, float* y, float* sum_out, float* mean,
-                                              float* rstd, int64_t rows, int C, float eps) {
+                                              const float* weight, const float* bias, void* y, float* sum_out, float* mean,
+                                              float* rstd, int64_t rows, int C, float eps, int y_bf16) {
     if (!(rows >= 0 && C > 0 && C % 4 == 0 && C <= 2048)) return -1;
     if (res_scale && !(residual && rows_per_sample > 0)) return -1;
     if (rows == 0) return 0;
@@ -22,7 +22,7 @@ extern "C" int host_layer_norm_forward_scaled(const float* x, const float* resid
         layer_norm_fwd_kernel<V>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(residual),             \
                                  reinterpret_cast<const float4*>(weight), reinterpret_cast<const float4*>(bias),            \
                                  reinterpret_cast<float4*>(y), reinterpret_cast<float4*>(sum_out), mean, rstd, rows, C4,    \
-                                 1.f / (float)C, eps, res_scale, rows_per_sample);                                          \
+                                 1.f / (float)C, eps, res_scale, rows_per_sample, y_bf16);                                          \
     })
     if (C4 <= 32) HOST_LN_LAUNCH(1);
     else if (C4 <= 64) HOST_LN_LAUNCH(2);
@@ -35,7 +35,7 @@ extern "C" int host_layer_norm_forward_scaled(const float* x, const float* resid
 
 extern "C" int host_layer_norm_forward(const float* x, const float* residual, const float* weight, const float* bias, float* y,
                                        float* sum_out, float* mean, float* rstd, int64_t rows, int C, float eps) {
-    return host_layer_norm_forward_scaled(x, residual, nullptr, 0, weight, bias, y, sum_out, mean, rstd, rows, C, eps);
+    return host_layer_norm_forward_scaled(x, residual, nullptr, 0, weight, bias, y, sum_out, mean, rstd, rows, C, eps, 0);
 }
 
 extern "C" int host_group_norm_forward(const float* x, const float* weight, const float* bias, float* y, double* stats,

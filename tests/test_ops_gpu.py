@@ -923,3 +923,29 @@ def test_swin_layer_fused_stochastic_depth_matches_plain_path(fn):
         SwinTransformerBlock._can_fuse = plain_fuse
     assert torch.allclose(fused[0], plain[0], rtol=1e-4, atol=1e-4) and torch.allclose(fused[3], plain[3], rtol=1e-4, atol=1e-4)
     assert (fused[0] - x).abs().max() > 0.1          # the stage did something
+
+
+def test_bf16_hand_overs_equal_the_conversion_they_replace(fn):
+    """Under bf16 autocast LayerNorm and the window-attention kernel write bf16 for the GEMM behind them: bit-identical to
+    converting their own fp32 result (round to nearest even), sums / statistics untouched."""
+    g = torch.Generator().manual_seed(51)
+    x, r = torch.randn(3, 200, 256, generator=g).cuda(), torch.randn(3, 200, 256, generator=g).cuda()
+    w, b = torch.randn(256, generator=g).cuda(), torch.randn(256, generator=g).cuda()
+    s = torch.tensor([0.0, 1.25, 1.25]).cuda()
+    y32, z32 = fn.layer_norm(x, w, b, 1e-5, residual=r, residual_scale=s, return_sum=True)
+    y16, z16 = fn.layer_norm(x, w, b, 1e-5, residual=r, residual_scale=s, return_sum=True, out_dtype=torch.bfloat16)
+    assert y16.dtype == torch.bfloat16 and torch.equal(y16, y32.to(torch.bfloat16)) and torch.equal(z16, z32)
+    y16 = fn.layer_norm(x, w, b, 1e-5, out_dtype=torch.bfloat16)
+    assert torch.equal(y16, fn.layer_norm(x, w, b, 1e-5).to(torch.bfloat16))
+    # with a gradient in play: converted afterwards, still differentiable
+    xg = x.clone().requires_grad_()
+    yg = fn.layer_norm(xg, w, b, 1e-5, out_dtype=torch.bfloat16)
+    assert yg.dtype == torch.bfloat16 and torch.equal(yg.detach(), y16)
+    torch.autograd.grad(yg.float().sum(), xg)
+    heads, ws = 4, 8
+    qkv = torch.randn(2, 20, 28, 3 * heads * 32, generator=g).cuda()
+    bias = torch.randn(heads, ws * ws, ws * ws, generator=g).cuda()
+    qb = torch.randn(3 * heads * 32, generator=g).cuda()
+    o32 = fn.swin_window_attention(qkv, qb, bias, heads, ws, 4, 32 ** -0.5)
+    o16 = fn.swin_window_attention(qkv, qb, bias, heads, ws, 4, 32 ** -0.5, out_dtype=torch.bfloat16)
+    assert o16.dtype == torch.bfloat16 and torch.equal(o16, o32.to(torch.bfloat16))
