@@ -120,12 +120,17 @@ PDB_API int pdb_gemm_tf32x3(const float* A, const float* B, const float* B_lo, f
  * Swin backbone and the transformer decoder under torch.autocast:
  *   C[m][n] = sum_k A[m*lda + k] * B[n*ldb + k]  (+ bias[n]) (act: 0 none, 1 ReLU, 2 GELU)
  * A (M x K), B (N x K): bf16, K contiguous, 16-byte aligned, K / lda / ldb multiples of 8; bias fp32 or NULL;
- * C row-major with pitch ldc, fp32 (out_bf16 = 0) or bf16 (out_bf16 = 1). */
+ * C row-major with pitch ldc, fp32 (out_bf16 = 0) or bf16 (out_bf16 = 1).
+ * accumulate != 0: C += product (red.add; C fp32, act = 0) — e.g. straight into a parameter's gradient.  ksplit > 1 (weight
+ * gradients: a few output tiles over a very long K) cuts K into that many slices whose partial sums meet in C the same way; it
+ * implies accumulate, so the caller zero-fills C when it wants the plain product. */
 PDB_API int pdb_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int64_t lda, int64_t ldb,
-                  int64_t ldc, int act, int out_bf16, void* stream);
+                  int64_t ldc, int act, int out_bf16, int ksplit, int accumulate, void* stream);
 /* out[n] (+)= sum_r x[r*N + n]: bias gradient of a Linear layer over few rows (the decoder's B*Q = 200 rows; autograd's db);
  * accumulate != 0 adds into out (a preallocated parameter gradient). */
 PDB_API int pdb_col_sum(const float* x, float* out, int rows, int N, int accumulate, void* stream);
+/* Same for a bf16 matrix (output gradients under torch.autocast), fp32 sums; N even. */
+PDB_API int pdb_col_sum_bf16(const void* x, float* out, int rows, int N, int accumulate, void* stream);
 /* Short-A variant of pdb_gemm_tf32x3 for the transformer decoder's B*Q = 200-row products (nn.Linear forward and input gradient,
  * mask2former_transformer_decoder.py:148-208): C[m][n] = sum_k A[m*lda + k] * B(n,k) (+ bias[n]) (ReLU), same 3xTF32 arithmetic
  * on mma.sync 32 x 64 tiles with no TMEM / TMA set-up.  b_mn = 0: B(n,k) = B[n*ldb + k];  b_mn = 1: B(n,k) = B[k*ldb + n].

@@ -39,6 +39,9 @@ struct HParams {
     int64_t ldc;
     int out_bf16, act;
     int nt, total_tiles, num_kb;
+    int accumulate;                         // C += instead of C = (red.add); implied by ksplit > 1
+    int mn_tiles, ksplit, kb_per_split;     // split-K (weight gradients: few output tiles, very long K): tile = split * mn_tiles + mn,
+                                            // fp32 partial sums meet in a zero-filled C through red.add
 };
 
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, dense
@@ -107,8 +110,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             int s = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int m0 = (tile / p.nt) * H_BM, n0 = (tile % p.nt) * H_BN;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int mn = tile % p.mn_tiles, kb0 = (tile / p.mn_tiles) * p.kb_per_split;
+                const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+                const int m0 = (mn / p.nt) * H_BM, n0 = (mn % p.nt) * H_BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
                     tc::mbar_wait(&empty[s], ph ^ 1);
                     tc::mbar_expect_tx(&full[s], H_STAGE_BYTES);
                     uint8_t* a = smem + s * H_STAGE_BYTES;
@@ -128,14 +133,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 tc::mbar_wait(&acc_empty[ab], ((t >> 1) & 1) ^ 1);
                 tc::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + ab * H_BN;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int kb0 = (tile / p.mn_tiles) * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     tc::mbar_wait(&full[s], ph);
                     tc::tc_fence_after();
                     const uint8_t* a = smem + s * H_STAGE_BYTES;
                     const uint8_t* b = a + H_BM * H_BK * 2;
 #pragma unroll
                     for (int k = 0; k < H_BK / 16; ++k)          // UMMA_K = 16 bf16 = 32 bytes along the swizzled row
-                        mma_bf16(tmem_d, tc::umma_desc_k_sw128(a, k * 32), tc::umma_desc_k_sw128(b, k * 32), idesc, (kb | k) != 0);
+                        mma_bf16(tmem_d, tc::umma_desc_k_sw128(a, k * 32), tc::umma_desc_k_sw128(b, k * 32), idesc, ((kb - kb0) | k) != 0);
                     tc::tc_commit(&empty[s]);
                     if (++s == H_STAGES) { s = 0; ph ^= 1u; }
                 }
@@ -147,7 +153,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int quarter = warp & 3, half = (warp - 2) >> 2;
         uint32_t t = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
-            const int m0 = (tile / p.nt) * H_BM, n0 = (tile % p.nt) * H_BN;
+            const int mn = tile % p.mn_tiles;
+            const int m0 = (mn / p.nt) * H_BM, n0 = (mn % p.nt) * H_BN;
+            const bool split = p.accumulate != 0, first_split = tile < p.mn_tiles;
             const uint32_t ab = t & 1;
             tc::mbar_wait(&acc_full[ab], (t >> 1) & 1);
             tc::tc_fence_after();
@@ -167,7 +175,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int cc = col0 + c * 16;
-                    if (p.bias) {
+                    if (p.bias && first_split) {
                         if (full64) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -230,7 +238,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                 const int lr = it * 4 + rr;
                                 const int gr = m0 + quarter * 32 + lr;
                                 const uint4 val = *reinterpret_cast<const uint4*>(stg + lr * 36 + seg * 4);
-                                if (gr < p.M) *reinterpret_cast<uint4*>(base + (int64_t)gr * p.ldc) = val;
+                                if (gr < p.M) {
+                                    float* dst = base + (int64_t)gr * p.ldc;
+                                    if (split)
+                                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(val.x)),
+                                                     "f"(__uint_as_float(val.y)), "f"(__uint_as_float(val.z)), "f"(__uint_as_float(val.w)) : "memory");
+                                    else
+                                        *reinterpret_cast<uint4*>(dst) = val;
+                                }
                             }
                             __syncwarp();
                         }
@@ -248,6 +263,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                 for (int j2 = 0; j2 < 16; ++j2)
                                     if (c2 == c && j2 == j) val = __uint_as_float(r[c2][j2]);
                             if (p.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.C)[(int64_t)row * p.ldc + cc + j] = __float2bfloat16_rn(val);
+                            else if (split) atomicAdd(reinterpret_cast<float*>(p.C) + (int64_t)row * p.ldc + cc + j, val);
                             else reinterpret_cast<float*>(p.C)[(int64_t)row * p.ldc + cc + j] = val;
                         }
                     }
@@ -292,7 +308,7 @@ static int make_map_bf16(CUtensorMap* map, const void* base, int rows, int K, in
 using namespace pdb;
 
 extern "C" int pdb_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int64_t lda,
-                             int64_t ldb, int64_t ldc, int act, int out_bf16, void* stream) {
+                             int64_t ldb, int64_t ldc, int act, int out_bf16, int ksplit, int accumulate, void* stream) {
     PDB_REQUIRE(A && B && C, "gemm_bf16: null pointer");
     PDB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_bf16: non-positive dimension");
     PDB_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "gemm_bf16: K, lda, ldb must be multiples of 8 (16-byte rows)");
@@ -304,8 +320,16 @@ extern "C" int pdb_gemm_bf16(const void* A, const void* B, void* C, const float*
     HParams p;
     p.C = C; p.bias = bias; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.out_bf16 = out_bf16; p.act = act;
     p.nt = (N + H_BN - 1) / H_BN;
-    p.total_tiles = ((M + H_BM - 1) / H_BM) * p.nt;
+    p.mn_tiles = ((M + H_BM - 1) / H_BM) * p.nt;
     p.num_kb = (K + H_BK - 1) / H_BK;
+    if (ksplit < 1) ksplit = 1;
+    if (ksplit > p.num_kb) ksplit = p.num_kb;
+    if (ksplit > 1) accumulate = 1;
+    PDB_REQUIRE(!accumulate || (!out_bf16 && act == 0), "gemm_bf16: split-K / accumulation needs an fp32 C and no activation");
+    p.accumulate = accumulate;
+    p.kb_per_split = (p.num_kb + ksplit - 1) / ksplit;
+    p.ksplit = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+    p.total_tiles = p.mn_tiles * p.ksplit;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);

@@ -640,6 +640,15 @@ def col_sum(x2, into=None):
     """Sum over the rows of a contiguous fp32 (rows, N) matrix: the bias gradient of a Linear layer.  Short matrices (the
     decoder's 200 rows) take one CTA per 32 columns, tall ones row blocks that meet through red.add.  ``into``: a
     preallocated fp32 (N,) gradient to ADD the sums to (returns None then)."""
+    if x2.is_cuda and x2.dtype == torch.bfloat16 and x2.shape[0] > 0 and x2.shape[1] % 2 == 0:
+        fb = getattr(_lib.load(), "pdb_col_sum_bf16", None)
+        if fb is not None:
+            x2 = _c(x2)
+            out = into if into is not None else torch.empty((x2.shape[1],), dtype=torch.float32, device=x2.device)
+            _lib.check(fb(x2.data_ptr(), out.data_ptr(), x2.shape[0], x2.shape[1], 1 if into is not None else 0, _stream()),
+                       "pdb_col_sum_bf16")
+            return None if into is not None else out
+        x2 = x2.float()
     f = getattr(_lib.load(), "pdb_col_sum", None)             # absent only in the CPU-tier host builds of the tests
     if f is None or not x2.is_cuda or x2.dtype != torch.float32 or x2.shape[0] == 0:
         if into is not None:
@@ -878,17 +887,31 @@ class Conv3x3Function(Function):
 # --------------------------------------------------------------------------------------------------
 # bf16 autocast path: nn.Linear on tcgen05 kind::f16 (csrc/gemm_bf16.cu)
 # --------------------------------------------------------------------------------------------------
-def gemm_bf16(a, b, bias=None, act=0, out_dtype=torch.bfloat16):
-    """a (M, K), b (N, K) bf16 with contiguous rows -> a @ b^T (+ bias) (act) as (M, N) bf16 or fp32."""
+def gemm_bf16(a, b, bias=None, act=0, out_dtype=torch.bfloat16, ksplit=1, into=None):
+    """a (M, K), b (N, K) bf16 with contiguous rows -> a @ b^T (+ bias) (act) as (M, N) bf16 or fp32.  ksplit > 1 (fp32 result
+    only): K is cut into slices that run on different SMs and meet through red.add.  ``into``: an existing contiguous fp32
+    (M, N) tensor to ADD the product to (returns it)."""
     _need_cuda(a, b)
     M, K = a.shape
     N = b.shape[0]
-    out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    if into is not None:
+        out = into
+    elif ksplit > 1:
+        out = torch.zeros((M, N), dtype=out_dtype, device=a.device)
+    else:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
     if M and N:
         rc = _lib.load().pdb_gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), None if bias is None else bias.data_ptr(), M, N, K,
-                                       a.stride(0), b.stride(0), N, int(act), 1 if out_dtype == torch.bfloat16 else 0, _stream())
+                                       a.stride(0), b.stride(0), N, int(act), 1 if out_dtype == torch.bfloat16 else 0,
+                                       int(ksplit), int(into is not None), _stream())
         _lib.check(rc, "pdb_gemm_bf16")
     return out
+
+
+def _split_k_bf16(M, N, K):
+    """K slices of a bf16 weight-gradient product (128 x 128 output tiles, 64-wide k-blocks): ~2 tiles per SM, >= 8 k-blocks each."""
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    return max(1, min((K + 511) // 512, (2 * 148 + tiles - 1) // tiles))
 
 
 _bf16_weights = {}
@@ -938,6 +961,7 @@ class LinearBF16Function(Function):
         y = gemm_bf16(x2, weight_bf16(weight), None if bias is None else _c(bias.to(torch.bfloat16).float()), act,
                       torch.float32 if out_fp32 else torch.bfloat16)
         ctx.save_for_backward(x2, weight, y if act == 1 else None)
+        ctx.wref, ctx.bref = weight, bias       # the caller's tensors (leaves or row slices of one): see _direct_grad
         ctx.meta = (tuple(x.shape), x.dtype, bias is not None, act)
         return y.view(*x.shape[:-1], N)
 
@@ -955,9 +979,17 @@ class LinearBF16Function(Function):
         if ctx.needs_input_grad[0]:
             gx = gemm_bf16(gy, weight_bf16(weight, transposed=True)).view(shape).to(xdtype)
         if ctx.needs_input_grad[1]:
-            gw = gemm_bf16(_rows8(gy.t()), _rows8(x2.t()), out_dtype=torch.float32).to(weight.dtype)
+            # dW = dy^T x: a handful of output tiles over a contraction as long as the token count -> split over K; straight
+            # into the parameter's preallocated fp32 gradient when there is one (see _direct_grad)
+            gyt, xt = _rows8(gy.t()), _rows8(x2.t())
+            tgt = _direct_grad(ctx.wref, (N, K)) if weight.dtype == torch.float32 else None
+            ks = _split_k_bf16(N, K, gyt.shape[1])
+            if tgt is not None:
+                gemm_bf16(gyt, xt, out_dtype=torch.float32, ksplit=ks, into=tgt)
+            else:
+                gw = gemm_bf16(gyt, xt, out_dtype=torch.float32, ksplit=ks).to(weight.dtype)
         if has_bias and ctx.needs_input_grad[2]:
-            gb = gy.float().sum(0)
+            gb = col_sum(gy, into=_direct_grad(ctx.bref, (N,)))
         return gx, gw, gb, None, None
 
 

@@ -949,3 +949,35 @@ def test_bf16_hand_overs_equal_the_conversion_they_replace(fn):
     o32 = fn.swin_window_attention(qkv, qb, bias, heads, ws, 4, 32 ** -0.5)
     o16 = fn.swin_window_attention(qkv, qb, bias, heads, ws, 4, 32 ** -0.5, out_dtype=torch.bfloat16)
     assert o16.dtype == torch.bfloat16 and torch.equal(o16, o32.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("M,N,K,ks", [(256, 256, 20480, 74), (130, 72, 4104, 5), (512, 100, 1024, 64)])
+def test_gemm_bf16_split_k_and_accumulate(fn, M, N, K, ks):
+    """Weight-gradient shape: a few output tiles over a very long K, cut into slices that meet through red.add; and the product
+    added straight into an existing fp32 tensor (a parameter's gradient)."""
+    g = torch.Generator().manual_seed(32)
+    a = torch.randn(M, K, generator=g).cuda().to(torch.bfloat16)
+    b = torch.randn(N, K, generator=g).cuda().to(torch.bfloat16)
+    ref = a.double() @ b.double().t()
+    out = fn.gemm_bf16(a, b, None, 0, torch.float32, ksplit=ks)
+    assert _rel(out.double(), ref) < 1e-5
+    base = torch.randn(M, N, generator=g).cuda()
+    acc = base.clone()
+    assert fn.gemm_bf16(a, b, None, 0, torch.float32, ksplit=ks, into=acc) is acc
+    assert _rel(acc.double(), ref + base.double()) < 1e-5
+    acc = base.clone()
+    fn.gemm_bf16(a, b, None, 0, torch.float32, ksplit=1, into=acc)
+    # one accumulator over all of K: the tensor core truncates when it aligns addends (measured 1.9e-5 at K = 20480; the
+    # split product above, whose slices are summed in fp32 by red.add, is the more accurate one)
+    assert _rel(acc.double(), ref + base.double()) < 1e-4
+
+
+@pytest.mark.parametrize("rows,N", [(200, 256), (3200, 2048), (204800, 256), (37, 6)])
+def test_col_sum_bf16(fn, rows, N):
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(rows, N, generator=g).cuda().to(torch.bfloat16)
+    ref = x.double().sum(0)
+    assert torch.allclose(fn.col_sum(x).double(), ref, rtol=1e-4, atol=2e-3 * (rows / 200) ** 0.5)
+    into = torch.ones(N, device="cuda")
+    assert fn.col_sum(x, into=into) is None
+    assert torch.allclose(into.double(), ref + 1, rtol=1e-4, atol=2e-3 * (rows / 200) ** 0.5)
