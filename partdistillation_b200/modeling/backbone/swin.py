@@ -135,12 +135,27 @@ class SwinTransformerBlock(nn.Module):
         if normed is None:
             normed = PF.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, out_dtype=half)
         qkv = PF.linear(normed, a.qkv.weight, a.qkv.bias, out_fp32=True)
-        N = self.window_size * self.window_size
-        bias = a.relative_position_bias_table[a.relative_position_index.view(-1)].view(N, N, -1).permute(2, 0, 1)
+        bias = self._relative_bias()
         # the attention core (scores, softmax, PV) reads fp32 q / k / v (written by the qkv GEMM's epilogue) either way
         o = PF.swin_window_attention(qkv.float().view(B, H, W, 3 * C), a.qkv.bias, bias, a.num_heads, self.window_size,
                                      self.shift_size, a.scale, out_dtype=half or torch.float32)
         return PF.linear(o.view(B, L, C), a.proj.weight, a.proj.bias, out_fp32=True)
+
+    def _relative_bias(self):
+        """(heads, N, N) relative position bias of this block (swin_transformer.py:91-96: a gather from the (2ws-1)^2 table),
+        contiguous fp32.  A frozen table is gathered once per table version instead of once per forward."""
+        a = self.attn
+        t = a.relative_position_bias_table
+        N = self.window_size * self.window_size
+        if torch.is_grad_enabled() and t.requires_grad:
+            return t[a.relative_position_index.view(-1)].view(N, N, -1).permute(2, 0, 1)
+        key = (t._version, t.data_ptr(), t.device, t.dtype)
+        hit = self.__dict__.get("_rel_bias")
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                b = t[a.relative_position_index.view(-1)].view(N, N, -1).permute(2, 0, 1).float().contiguous()
+            hit = self.__dict__["_rel_bias"] = (key, b)
+        return hit[1]
 
     def _can_fuse(self, x):
         a = self.attn
