@@ -182,6 +182,10 @@ PDB_API int pdb_masked_xattn_backward(const float* q, const float* k, const floa
                               const int32_t* row_any, const float* out, const float* lse,
                               const float* grad_out, float* grad_q, float* grad_k, float* grad_v,
                               int B, int heads, int Q, int Lk, int d, void* stream);
+/* Arithmetic of the tensor-core attention kernels for the calls that follow (process-wide; a captured CUDA graph keeps what was
+ * set at capture): 3 = 3xTF32 products, fp32-accurate (default); 1 = one TF32 product per MMA — for torch.autocast(bfloat16)
+ * regions, where the reference's SDPA rounds q, k, p and v to bf16 (8-bit mantissas; TF32 keeps 10).  Returns the previous value. */
+PDB_API int pdb_set_xattn_passes(int passes);
 
 /* ------------------------------------------------------------------------------------------------
  * Point sampling — replaces detectron2 point_sample == F.grid_sample(input, 2*coords-1,

@@ -359,10 +359,12 @@ xattn_bwd_dkv(const float* __restrict__ q, const float* __restrict__ k, const fl
 namespace pdb {
 int xattn_fwd_partial_mma_launch(const float* q, const float* k, const float* v, const uint8_t* mask, const int32_t* row_any,
                                  float* ws_acc, float* ws_ml, int B, int heads, int Q, int Lk, int ns, int tiles_per, int qtiles,
-                                 cudaStream_t st);
+                                 int one_pass, cudaStream_t st);
 int xattn_bwd_mma_launch(const float* q, const float* k, const float* v, const uint8_t* mask, const int32_t* row_any, const float* out,
                          const float* lse, const float* gout, float* gq, float* gk, float* gv, int B, int heads, int Q, int Lk, int ns,
-                         int tiles_per, int qtiles, cudaStream_t st);
+                         int tiles_per, int qtiles, int one_pass, cudaStream_t st);
+// 3 = fp32-accurate 3xTF32 products (default), 1 = one TF32 product (pdb_set_xattn_passes; the bf16-autocast path)
+static int g_xattn_passes = 3;
 static bool xattn_use_mma() {
     static int mode = -1;
     if (mode < 0) {
@@ -395,7 +397,8 @@ extern "C" int pdb_masked_xattn_forward(const float* q, const float* k, const fl
     float* ws_acc = (float*)workspace;
     float* ws_ml = ws_acc + (int64_t)B * heads * ns * Q * XD;
     if (xattn_use_mma()) {
-        PDB_TRY(xattn_fwd_partial_mma_launch(q, k, v, mask, row_any, ws_acc, ws_ml, B, heads, Q, Lk, ns, tiles_per, qtiles, st));
+        PDB_TRY(xattn_fwd_partial_mma_launch(q, k, v, mask, row_any, ws_acc, ws_ml, B, heads, Q, Lk, ns, tiles_per, qtiles,
+                                             g_xattn_passes == 1, st));
     } else {
         dim3 grid((unsigned)(ns * qtiles), (unsigned)heads, (unsigned)B);
         xattn_fwd_partial<<<grid, XTHREADS, 0, st>>>(q, k, v, mask, row_any, ws_acc, ws_ml, heads, Q, Lk, ns, tiles_per,
@@ -422,7 +425,7 @@ extern "C" int pdb_masked_xattn_backward(const float* q, const float* k, const f
     cudaMemsetAsync(grad_q, 0, sizeof(float) * (size_t)B * Q * heads * XD, st);
     if (xattn_use_mma())
         return xattn_bwd_mma_launch(q, k, v, mask, row_any, out, lse, grad_out, grad_q, grad_k, grad_v, B, heads, Q, Lk, ns, tiles_per,
-                                    qtiles, st);
+                                    qtiles, g_xattn_passes == 1, st);
     dim3 grid((unsigned)(ns * qtiles), (unsigned)heads, (unsigned)B);
     xattn_bwd_dq<<<grid, XTHREADS, 0, st>>>(q, k, v, mask, row_any, out, lse, grad_out, grad_q, heads, Q, Lk, ns,
                                             tiles_per);
@@ -430,4 +433,13 @@ extern "C" int pdb_masked_xattn_backward(const float* q, const float* k, const f
     dim3 grid2((unsigned)((Lk + XTHREADS - 1) / XTHREADS), (unsigned)heads, (unsigned)B);
     xattn_bwd_dkv<<<grid2, XTHREADS, 0, st>>>(q, k, v, mask, row_any, out, lse, grad_out, grad_k, grad_v, heads, Q, Lk);
     return launched("xattn_bwd_dkv");
+}
+
+// Arithmetic of the tensor-core attention kernels for the calls that follow (process-wide; a captured CUDA graph keeps what was
+// set when it was captured): 3 = 3xTF32, fp32-accurate (default); 1 = one TF32 product per MMA, for torch.autocast(bfloat16)
+// regions, whose reference rounds q, k, softmax(p) and v to bf16.  Returns the previous value.
+extern "C" int pdb_set_xattn_passes(int passes) {
+    const int prev = pdb::g_xattn_passes;
+    if (passes == 1 || passes == 3) pdb::g_xattn_passes = passes;
+    return prev;
 }

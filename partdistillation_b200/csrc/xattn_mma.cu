@@ -27,8 +27,16 @@ __device__ __forceinline__ void xm_mma(float (&d)[4], const uint32_t (&a)[4], co
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ float xm_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-// d += A B with fp32 accuracy: a_hi b_hi + a_lo b_hi + a_hi b_lo (the tensor core reads the top 19 bits of each operand)
+// d += A B with fp32 accuracy: a_hi b_hi + a_lo b_hi + a_hi b_lo (the tensor core reads the top 19 bits of each operand).
+// ONE: a single TF32 product (10-bit mantissas, fp32 accumulation) — the bf16-autocast path, whose reference rounds q, k, p, v to
+// 8-bit mantissas.
+template <bool ONE>
 __device__ __forceinline__ void xm_mma3(float (&d)[4], const float (&a)[4], const float b0, const float b1) {
+    if (ONE) {
+        const uint32_t ar[4] = {__float_as_uint(a[0]), __float_as_uint(a[1]), __float_as_uint(a[2]), __float_as_uint(a[3])};
+        xm_mma(d, ar, __float_as_uint(b0), __float_as_uint(b1));
+        return;
+    }
     uint32_t ah[4], al[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -93,23 +101,23 @@ __device__ __forceinline__ void xm_load_tile(float* __restrict__ dst, const floa
     }
 }
 // acc[j] (j = 0..7) += A (16 x 32, fragments a) x T^T for the 64 rows of the shared tile T ([row][36])
-template <int NF = 8>
+template <int NF = 8, bool ONE = false>
 __device__ __forceinline__ void xm_scores(float (&acc)[NF][4], const float (&a)[4][4], const float* __restrict__ tile, int g, int t) {
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
         for (int j = 0; j < NF; ++j)
-            xm_mma3(acc[j], a[ks], tile[(j * 8 + g) * MXS + ks * 8 + t], tile[(j * 8 + g) * MXS + ks * 8 + t + 4]);
+            xm_mma3<ONE>(acc[j], a[ks], tile[(j * 8 + g) * MXS + ks * 8 + t], tile[(j * 8 + g) * MXS + ks * 8 + t + 4]);
 }
 // out[n] (n = 0..3) += P (16 x 64, as the C fragments p[j] of a previous product) x T for the 64 rows of the shared tile T
-template <int NF = 8>
+template <int NF = 8, bool ONE = false>
 __device__ __forceinline__ void xm_chain(float (&out)[4][4], const float (&p)[NF][4], const float* __restrict__ tile, int g, int t) {
 #pragma unroll
     for (int j = 0; j < NF; ++j) {
         const float a[4] = {p[j][0], p[j][2], p[j][1], p[j][3]};
 #pragma unroll
         for (int n = 0; n < 4; ++n)
-            xm_mma3(out[n], a, tile[(j * 8 + 2 * t) * MXS + n * 8 + g], tile[(j * 8 + 2 * t + 1) * MXS + n * 8 + g]);
+            xm_mma3<ONE>(out[n], a, tile[(j * 8 + 2 * t) * MXS + n * 8 + g], tile[(j * 8 + 2 * t + 1) * MXS + n * 8 + g]);
     }
 }
 
@@ -153,6 +161,7 @@ __device__ __forceinline__ XmRow xm_rows(int qt, int warp, int g, int Q, int b, 
 }
 
 // ------------------------------------------------------------------------------------------------ forward (partial over a key split)
+template <bool ONE>
 __global__ void __launch_bounds__(256)
 xattn_fwd_partial_mma(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                       const uint8_t* __restrict__ mask, const int32_t* __restrict__ row_any, float* __restrict__ ws_acc,
@@ -196,7 +205,7 @@ xattn_fwd_partial_mma(const float* __restrict__ q, const float* __restrict__ k, 
         float s[8][4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-        xm_scores(s, qf, sK, g, t);
+        xm_scores<8, ONE>(s, qf, sK, g, t);
         float t0 = -INFINITY, t1 = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -226,7 +235,7 @@ xattn_fwd_partial_mma(const float* __restrict__ q, const float* __restrict__ k, 
 #pragma unroll
         for (int n = 0; n < 4; ++n) { o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1; }
         m0 = n0; m1 = n1;
-        xm_chain(o, s, sV, g, t);
+        xm_chain<8, ONE>(o, s, sV, g, t);
         }
         if (more) xm_commit(stg, sKb[(tl + 1 - tile_begin) & 1], sVb[(tl + 1 - tile_begin) & 1]);
         __syncthreads();
@@ -249,6 +258,7 @@ xattn_fwd_partial_mma(const float* __restrict__ q, const float* __restrict__ k, 
 }
 
 // ------------------------------------------------------------------------------------------------ grad_q (partial over a key split)
+template <bool ONE>
 __global__ void __launch_bounds__(256)
 xattn_bwd_dq_mma(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                  const uint8_t* __restrict__ mask, const int32_t* __restrict__ row_any, const float* __restrict__ out,
@@ -305,8 +315,8 @@ xattn_bwd_dq_mma(const float* __restrict__ q, const float* __restrict__ k, const
             s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
             dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
         }
-        xm_scores(s, qf, sK, g, t);
-        xm_scores(dp, df, sV, g, t);
+        xm_scores<8, ONE>(s, qf, sK, g, t);
+        xm_scores<8, ONE>(dp, df, sV, g, t);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {           // dS = P (dP - delta), P = exp(S - lse) on the attended keys
             s[j][0] = ((k0 >> (2 * j)) & 1u) ? 0.f : exp2f(s[j][0] - e0) * (dp[j][0] - d0);
@@ -314,7 +324,7 @@ xattn_bwd_dq_mma(const float* __restrict__ q, const float* __restrict__ k, const
             s[j][2] = ((k1 >> (2 * j)) & 1u) ? 0.f : exp2f(s[j][2] - e1) * (dp[j][2] - d1);
             s[j][3] = ((k1 >> (2 * j + 1)) & 1u) ? 0.f : exp2f(s[j][3] - e1) * (dp[j][3] - d1);
         }
-        xm_chain(dq, s, sK, g, t);
+        xm_chain<8, ONE>(dq, s, sK, g, t);
         }
         if (more) xm_commit(stg, sKb[(tl + 1 - tile_begin) & 1], sVb[(tl + 1 - tile_begin) & 1]);
         __syncthreads();
@@ -331,6 +341,7 @@ xattn_bwd_dq_mma(const float* __restrict__ q, const float* __restrict__ k, const
 // (Q, dO, lse, delta = dO . O, mask-use flags; QP = Q rounded up to 32 rows) are staged in shared memory once, after which the
 // warps run without any block barrier: per key tile and per 32 queries, S^T = K Q^T and dP^T = V dO^T, then the two chained
 // products dV += P^T dO and dK += dS^T Q.
+template <bool ONE>
 __global__ void __launch_bounds__(128)
 xattn_bwd_dkv_mma(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                   const uint8_t* __restrict__ mask, const int32_t* __restrict__ row_any, const float* __restrict__ out,
@@ -414,8 +425,8 @@ xattn_bwd_dkv_mma(const float* __restrict__ q, const float* __restrict__ k, cons
                 st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
                 dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
             }
-            xm_scores<4>(st, kf, tq, g, t);          // S^T = K Q^T
-            xm_scores<4>(dp, vf, td, g, t);          // dP^T = V dO^T
+            xm_scores<4, ONE>(st, kf, tq, g, t);          // S^T = K Q^T
+            xm_scores<4, ONE>(dp, vf, td, g, t);          // dP^T = V dO^T
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int qa = i0 + j * 8 + 2 * t;
@@ -430,8 +441,8 @@ xattn_bwd_dkv_mma(const float* __restrict__ q, const float* __restrict__ k, cons
                 dp[j][2] = st[j][2] * (dp[j][2] - da);
                 dp[j][3] = st[j][3] * (dp[j][3] - db);
             }
-            xm_chain<4>(dv, st, td, g, t);           // dV += P^T dO
-            xm_chain<4>(dk, dp, tq, g, t);           // dK += dS^T Q
+            xm_chain<4, ONE>(dv, st, td, g, t);           // dV += P^T dO
+            xm_chain<4, ONE>(dk, dp, tq, g, t);           // dK += dS^T Q
         }
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
@@ -450,16 +461,18 @@ xattn_bwd_dkv_mma(const float* __restrict__ q, const float* __restrict__ k, cons
 // launchers used by xattn.cu's C ABI (same grids as the SIMT kernels: 128 queries per CTA in the forward / grad_q pass)
 int xattn_fwd_partial_mma_launch(const float* q, const float* k, const float* v, const uint8_t* mask, const int32_t* row_any,
                                  float* ws_acc, float* ws_ml, int B, int heads, int Q, int Lk, int ns, int tiles_per, int qtiles,
-                                 cudaStream_t st) {
+                                 int one_pass, cudaStream_t st) {
     dim3 grid((unsigned)(ns * qtiles), (unsigned)heads, (unsigned)B);
-    xattn_fwd_partial_mma<<<grid, 256, 0, st>>>(q, k, v, mask, row_any, ws_acc, ws_ml, heads, Q, Lk, ns, tiles_per);
+    if (one_pass) xattn_fwd_partial_mma<true><<<grid, 256, 0, st>>>(q, k, v, mask, row_any, ws_acc, ws_ml, heads, Q, Lk, ns, tiles_per);
+    else xattn_fwd_partial_mma<false><<<grid, 256, 0, st>>>(q, k, v, mask, row_any, ws_acc, ws_ml, heads, Q, Lk, ns, tiles_per);
     return launched("xattn_fwd_partial_mma");
 }
 int xattn_bwd_mma_launch(const float* q, const float* k, const float* v, const uint8_t* mask, const int32_t* row_any, const float* out,
                          const float* lse, const float* gout, float* gq, float* gk, float* gv, int B, int heads, int Q, int Lk, int ns,
-                         int tiles_per, int qtiles, cudaStream_t st) {
+                         int tiles_per, int qtiles, int one_pass, cudaStream_t st) {
     dim3 grid((unsigned)(ns * qtiles), (unsigned)heads, (unsigned)B);
-    xattn_bwd_dq_mma<<<grid, 256, 0, st>>>(q, k, v, mask, row_any, out, lse, gout, gq, heads, Q, Lk, ns, tiles_per);
+    if (one_pass) xattn_bwd_dq_mma<true><<<grid, 256, 0, st>>>(q, k, v, mask, row_any, out, lse, gout, gq, heads, Q, Lk, ns, tiles_per);
+    else xattn_bwd_dq_mma<false><<<grid, 256, 0, st>>>(q, k, v, mask, row_any, out, lse, gout, gq, heads, Q, Lk, ns, tiles_per);
     PDB_TRY(launched("xattn_bwd_dq_mma"));
     const int tiles = (Lk + MXT - 1) / MXT;
     const int QP = (Q + 31) / 32 * 32;
@@ -469,12 +482,14 @@ int xattn_bwd_mma_launch(const float* q, const float* k, const float* v, const u
     PDB_REQUIRE(smem <= 200 * 1024, "masked_xattn_backward: %d queries do not fit shared memory", Q);
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(xattn_bwd_dkv_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(xattn_bwd_dkv_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(xattn_bwd_dkv_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(PDB_ERR_LAUNCH, "xattn_bwd_dkv_mma: smem attribute: %s", cudaGetErrorString(e));
         attr = smem;
     }
     dim3 grid2((unsigned)((tiles + KT - 1) / KT), (unsigned)heads, (unsigned)B);
-    xattn_bwd_dkv_mma<<<grid2, 128, smem, st>>>(q, k, v, mask, row_any, out, lse, gout, gk, gv, heads, Q, Lk, QP, KT);
+    if (one_pass) xattn_bwd_dkv_mma<true><<<grid2, 128, smem, st>>>(q, k, v, mask, row_any, out, lse, gout, gk, gv, heads, Q, Lk, QP, KT);
+    else xattn_bwd_dkv_mma<false><<<grid2, 128, smem, st>>>(q, k, v, mask, row_any, out, lse, gout, gk, gv, heads, Q, Lk, QP, KT);
     return launched("xattn_bwd_dkv_mma");
 }
 

@@ -293,10 +293,27 @@ def reset_fully_masked_rows(mask, row_any):
 # --------------------------------------------------------------------------------------------------
 # masked cross-attention core  (nn.MultiheadAttention inside CrossAttentionLayer, :84,102-114)
 # --------------------------------------------------------------------------------------------------
+_xattn_passes_now = [3]
+
+
+def _set_xattn_passes(passes):
+    """3xTF32 (fp32-accurate) or a single TF32 product per MMA in the attention kernels; the library keeps the value until told
+    otherwise, so the setter is only called on a change."""
+    if _xattn_passes_now[0] != passes:
+        f = getattr(_lib.load(), "pdb_set_xattn_passes", None)       # absent only in the CPU-tier host builds of the tests
+        if f is not None:
+            f(passes)
+        _xattn_passes_now[0] = passes
+
+
 class MaskedCrossAttentionFunction(Function):
     @staticmethod
     def forward(ctx, q, k, v, mask, row_any, heads):
         _need_cuda(q, k, v, mask, row_any)
+        # under torch.autocast(bfloat16) the reference's attention rounds q, k, p, v to bf16 (2^-9): one TF32 product (operands
+        # truncated at 2^-10) stays inside that; the backward (which runs outside the autocast region) follows the forward
+        ctx.passes = 1 if (torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16) else 3
+        _set_xattn_passes(ctx.passes)
         q, k, v = _c(q), _c(k), _c(v)
         if q.dtype != torch.float32 or k.dtype != torch.float32 or v.dtype != torch.float32:
             raise RuntimeError("masked_cross_attention: float32 only")
@@ -332,6 +349,7 @@ class MaskedCrossAttentionFunction(Function):
         Lk = k.shape[1]
         grad_out = _c(grad_out)
         gq, gk, gv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        _set_xattn_passes(ctx.passes)
         rc = _lib.load().pdb_masked_xattn_backward(
             q.data_ptr(), k.data_ptr(), v.data_ptr(), mask.data_ptr() if mask is not None else None,
             row_any.data_ptr() if row_any is not None else None, out.data_ptr(), lse.data_ptr(), grad_out.data_ptr(),

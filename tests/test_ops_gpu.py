@@ -981,3 +981,31 @@ def test_col_sum_bf16(fn, rows, N):
     into = torch.ones(N, device="cuda")
     assert fn.col_sum(x, into=into) is None
     assert torch.allclose(into.double(), ref + 1, rtol=1e-4, atol=2e-3 * (rows / 200) ** 0.5)
+
+
+def test_masked_cross_attention_single_pass_under_autocast(fn):
+    """Inside torch.autocast(bfloat16) the attention kernels issue one TF32 product per MMA (the reference's SDPA rounds q, k,
+    p, v to bf16 there, 2^-9 per operand; TF32 truncates at 2^-10): within 2^-8 of the fp64 result (measured 2.3e-3: the
+    softmax amplifies score errors), forward and backward (the backward runs outside the autocast region and follows the
+    forward); and the fp32 contract is back afterwards."""
+    heads, E, B, Q, Lk = 8, 256, 2, 100, 1600
+    g = torch.Generator().manual_seed(6)
+    q = (torch.randn(B, Q, E, generator=g) * 0.3).double()
+    k, v = torch.randn(B, Lk, E, generator=g).double(), torch.randn(B, Lk, E, generator=g).double()
+    mask = (torch.rand(B, Q, Lk, generator=g) < 0.8).to(torch.uint8)
+    row_any = (~mask.bool().all(-1)).view(-1).to(torch.int32).cuda()
+    qr, kr, vr = (t.clone().requires_grad_() for t in (q, k, v))
+    ref = _ref_attention(qr, kr, vr, mask, heads)
+    go = torch.randn(ref.shape, generator=g).double()
+    rg = torch.autograd.grad(ref, (qr, kr, vr), go)
+    for amp, bar_o, bar_g in ((True, 2 ** -8, 2 ** -7), (False, 5e-6, 2e-5)):
+        qc, kc, vc = (t.float().cuda().requires_grad_() for t in (q, k, v))
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            out = fn.masked_cross_attention(qc, kc, vc, mask.cuda(), row_any, heads)
+        gs = torch.autograd.grad(out, (qc, kc, vc), go.float().cuda())
+        err = _rel(out.double().cpu(), ref.detach())
+        assert err < bar_o
+        if amp:
+            assert err > 5e-6           # it really is the single-pass arithmetic
+        for a_, r_ in zip(gs, rg):
+            assert _rel(a_.double().cpu(), r_) < bar_g
