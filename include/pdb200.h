@@ -123,9 +123,11 @@ PDB_API int pdb_gemm_tf32x3(const float* A, const float* B, const float* B_lo, f
  * C row-major with pitch ldc, fp32 (out_bf16 = 0) or bf16 (out_bf16 = 1).
  * accumulate != 0: C += product (red.add; C fp32, act = 0) — e.g. straight into a parameter's gradient.  ksplit > 1 (weight
  * gradients: a few output tiles over a very long K) cuts K into that many slices whose partial sums meet in C the same way; it
- * implies accumulate, so the caller zero-fills C when it wants the plain product. */
+ * implies accumulate, so the caller zero-fills C when it wants the plain product.
+ * layout = 3: both operands MN-major — A(m,k) = A[k*lda + m], B(n,k) = B[k*ldb + n] (the contraction index is the row index of
+ * the stored matrices): the weight gradient dW = dy^T x with dy and x read in place; K arbitrary.  layout = 0: as above. */
 PDB_API int pdb_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int64_t lda, int64_t ldb,
-                  int64_t ldc, int act, int out_bf16, int ksplit, int accumulate, void* stream);
+                  int64_t ldc, int act, int out_bf16, int ksplit, int accumulate, int layout, void* stream);
 /* out[n] (+)= sum_r x[r*N + n]: bias gradient of a Linear layer over few rows (the decoder's B*Q = 200 rows; autograd's db);
  * accumulate != 0 adds into out (a preallocated parameter gradient). */
 PDB_API int pdb_col_sum(const float* x, float* out, int rows, int N, int accumulate, void* stream);

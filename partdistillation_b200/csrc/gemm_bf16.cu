@@ -4,9 +4,10 @@
 // Swin backbone and of the transformer decoder run in the low-precision dtype through cuBLAS):
 //     C[m][n] = sum_k A[m][k] * B[n][k]  (+ bias[n]) (ReLU | GELU),   A (M x K) and B (N x K) bf16, K contiguous,
 //     C fp32 or bf16 row-major.
-// nn.Linear forward is A = x, B = W; the input gradient dx = dy W is A = dy, B = W^T; the weight gradient dW = dy^T x is
-// A = dy^T, B = x^T (functional.py materialises the transposes: decoder-sized operands, and the frozen backbone has no
-// backward).  No hi / lo split, 2-byte tiles: one 128 x 128 x 64 k-block is 32 KB of shared memory and four UMMA_K = 16
+// nn.Linear forward is A = x, B = W; the input gradient dx = dy W is A = dy, B = W^T (cached); the weight gradient
+// dW = dy^T x reads dy and x IN PLACE as MN-major operands (layout bit 1 / 2: A(m, k) = A[k][m], B(n, k) = B[k][n], i.e. the
+// contraction index is the row index of the stored matrices): TMA boxes of 64 mn-elements x 64 k-rows, UMMA descriptors with
+// the MN-major 128-byte-swizzle canonical layout (64-element mn blocks LBO = 8 KB apart, 8-row k groups SBO = 1 KB apart).  No hi / lo split, 2-byte tiles: one 128 x 128 x 64 k-block is 32 KB of shared memory and four UMMA_K = 16
 // instructions, against 48-64 KB and twelve for the 3xTF32 kernel of gemm_tc.cu.
 //
 // Persistent kernel, one CTA per SM, 6 warps:
@@ -74,6 +75,19 @@ __device__ __forceinline__ float h_act(float x, int mode) {
     return x;
 }
 
+// MN-major operand tile: [mn block j of 64][k row r of 64][64 mn elements = 128 bytes, swizzled]; one UMMA_K = 16 step = 2 KB
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_h(const void* smem_tile, uint32_t byte_offset) {
+    uint32_t addr = tc::smem_u32(smem_tile) + byte_offset;
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((8192 >> 4) & 0x3FFF) << 16;     // LBO: next 64-element block along MN
+    d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;     // SBO: next group of 8 k rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+
+template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(H_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const HParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -117,15 +131,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     tc::mbar_wait(&empty[s], ph ^ 1);
                     tc::mbar_expect_tx(&full[s], H_STAGE_BYTES);
                     uint8_t* a = smem + s * H_STAGE_BYTES;
-                    tc::tma_load_2d(a, &tm_a, &full[s], kb * H_BK, m0);
-                    tc::tma_load_2d(a + H_BM * H_BK * 2, &tm_b, &full[s], kb * H_BK, n0);
+                    uint8_t* b = a + H_BM * H_BK * 2;
+                    if (A_MN) {
+                        tc::tma_load_2d(a, &tm_a, &full[s], m0, kb * H_BK);
+                        tc::tma_load_2d(a + 8192, &tm_a, &full[s], m0 + 64, kb * H_BK);
+                    } else {
+                        tc::tma_load_2d(a, &tm_a, &full[s], kb * H_BK, m0);
+                    }
+                    if (B_MN) {
+                        tc::tma_load_2d(b, &tm_b, &full[s], n0, kb * H_BK);
+                        tc::tma_load_2d(b + 8192, &tm_b, &full[s], n0 + 64, kb * H_BK);
+                    } else {
+                        tc::tma_load_2d(b, &tm_b, &full[s], kb * H_BK, n0);
+                    }
                     if (++s == H_STAGES) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(H_BM, H_BN);
+            constexpr uint32_t idesc = umma_idesc_bf16(H_BM, H_BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
             int s = 0;
             uint32_t ph = 0, t = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
@@ -141,7 +166,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     const uint8_t* b = a + H_BM * H_BK * 2;
 #pragma unroll
                     for (int k = 0; k < H_BK / 16; ++k)          // UMMA_K = 16 bf16 = 32 bytes along the swizzled row
-                        mma_bf16(tmem_d, tc::umma_desc_k_sw128(a, k * 32), tc::umma_desc_k_sw128(b, k * 32), idesc, ((kb - kb0) | k) != 0);
+                        mma_bf16(tmem_d, A_MN ? umma_desc_mn_sw128_h(a, k * 2048) : tc::umma_desc_k_sw128(a, k * 32),
+                                 B_MN ? umma_desc_mn_sw128_h(b, k * 2048) : tc::umma_desc_k_sw128(b, k * 32), idesc, ((kb - kb0) | k) != 0);
                     tc::tc_commit(&empty[s]);
                     if (++s == H_STAGES) { s = 0; ph ^= 1u; }
                 }
@@ -281,16 +307,20 @@ typedef CUresult (*EncodeTiledFnH)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // (rows x K) bf16, K contiguous, row pitch ld elements: box (64, 128), 128-byte swizzle
-static int make_map_bf16(CUtensorMap* map, const void* base, int rows, int K, int64_t ld) {
+static EncodeTiledFnH encode_tiled_entry() {
     static EncodeTiledFnH encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
-            return fail(PDB_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
-        encode = reinterpret_cast<EncodeTiledFnH>(fn);
+        if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess && fn) encode = reinterpret_cast<EncodeTiledFnH>(fn);
     }
+    return encode;
+}
+
+static int make_map_bf16(CUtensorMap* map, const void* base, int rows, int K, int64_t ld) {
+    EncodeTiledFnH encode = encode_tiled_entry();
+    if (!encode) return fail(PDB_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
     cuuint32_t box[2] = {(cuuint32_t)H_BK, (cuuint32_t)H_BM};
@@ -303,20 +333,56 @@ static int make_map_bf16(CUtensorMap* map, const void* base, int rows, int K, in
     return PDB_OK;
 }
 
+// MN-major operand: the stored matrix is (K rows x mn), mn contiguous, row pitch ld elements: box (64 mn, 64 k rows)
+static int make_map_bf16_mn(CUtensorMap* map, const void* base, int mn, int K, int64_t ld) {
+    EncodeTiledFnH encode = encode_tiled_entry();
+    if (!encode) return fail(PDB_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)mn, (cuuint64_t)K};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)H_BK};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(PDB_ERR_INVALID, "gemm_bf16: cuTensorMapEncodeTiled (MN-major) failed (%d): %d x %d, ld %lld", (int)r, K, mn, (long long)ld);
+    return PDB_OK;
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_bf16(const CUtensorMap& ta, const CUtensorMap& tb, const HParams& p, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
+        if (e != cudaSuccess) return fail(PDB_ERR_LAUNCH, "gemm_bf16: smem attribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+    gemm_bf16_kernel<A_MN, B_MN><<<grid, H_THREADS, H_SMEM, st>>>(ta, tb, p);
+    return launched("gemm_bf16");
+}
+
 }  // namespace pdb
 
 using namespace pdb;
 
 extern "C" int pdb_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int64_t lda,
-                             int64_t ldb, int64_t ldc, int act, int out_bf16, int ksplit, int accumulate, void* stream) {
+                             int64_t ldb, int64_t ldc, int act, int out_bf16, int ksplit, int accumulate, int layout, void* stream) {
     PDB_REQUIRE(A && B && C, "gemm_bf16: null pointer");
     PDB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_bf16: non-positive dimension");
-    PDB_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "gemm_bf16: K, lda, ldb must be multiples of 8 (16-byte rows)");
+    PDB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm_bf16: lda, ldb must be multiples of 8 (16-byte rows)");
+    PDB_REQUIRE(layout == 0 || layout == 3, "gemm_bf16: layout %d (0: A, B K-major; 3: both MN-major)", layout);
+    PDB_REQUIRE(layout != 0 || K % 8 == 0, "gemm_bf16: K must be a multiple of 8 for K-major operands");
     PDB_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm_bf16: A and B must be 16-byte aligned");
     PDB_REQUIRE(act >= 0 && act <= 2, "gemm_bf16: activation %d (0 none, 1 ReLU, 2 GELU)", act);
     CUtensorMap ta, tb;
-    PDB_TRY(make_map_bf16(&ta, A, M, K, lda));
-    PDB_TRY(make_map_bf16(&tb, B, N, K, ldb));
+    if (layout == 3) {
+        PDB_TRY(make_map_bf16_mn(&ta, A, M, K, lda));
+        PDB_TRY(make_map_bf16_mn(&tb, B, N, K, ldb));
+    } else {
+        PDB_TRY(make_map_bf16(&ta, A, M, K, lda));
+        PDB_TRY(make_map_bf16(&tb, B, N, K, ldb));
+    }
     HParams p;
     p.C = C; p.bias = bias; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.out_bf16 = out_bf16; p.act = act;
     p.nt = (N + H_BN - 1) / H_BN;
@@ -330,13 +396,5 @@ extern "C" int pdb_gemm_bf16(const void* A, const void* B, void* C, const float*
     p.kb_per_split = (p.num_kb + ksplit - 1) / ksplit;
     p.ksplit = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
     p.total_tiles = p.mn_tiles * p.ksplit;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
-        if (e != cudaSuccess) return fail(PDB_ERR_LAUNCH, "gemm_bf16: smem attribute: %s", cudaGetErrorString(e));
-        attr_set = true;
-    }
-    const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-    gemm_bf16_kernel<<<grid, H_THREADS, H_SMEM, as_stream(stream)>>>(ta, tb, p);
-    return launched("gemm_bf16");
+    return layout == 3 ? launch_bf16<true, true>(ta, tb, p, as_stream(stream)) : launch_bf16<false, false>(ta, tb, p, as_stream(stream));
 }

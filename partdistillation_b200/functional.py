@@ -905,13 +905,18 @@ class Conv3x3Function(Function):
 # --------------------------------------------------------------------------------------------------
 # bf16 autocast path: nn.Linear on tcgen05 kind::f16 (csrc/gemm_bf16.cu)
 # --------------------------------------------------------------------------------------------------
-def gemm_bf16(a, b, bias=None, act=0, out_dtype=torch.bfloat16, ksplit=1, into=None):
+def gemm_bf16(a, b, bias=None, act=0, out_dtype=torch.bfloat16, ksplit=1, into=None, transposed=False):
     """a (M, K), b (N, K) bf16 with contiguous rows -> a @ b^T (+ bias) (act) as (M, N) bf16 or fp32.  ksplit > 1 (fp32 result
     only): K is cut into slices that run on different SMs and meet through red.add.  ``into``: an existing contiguous fp32
-    (M, N) tensor to ADD the product to (returns it)."""
+    (M, N) tensor to ADD the product to (returns it).  ``transposed``: a is (K, M) and b is (K, N) — a^T @ b with both read in
+    place as MN-major operands (the weight gradient dy^T x)."""
     _need_cuda(a, b)
-    M, K = a.shape
-    N = b.shape[0]
+    if transposed:
+        K, M = a.shape
+        N = b.shape[1]
+    else:
+        M, K = a.shape
+        N = b.shape[0]
     if into is not None:
         out = into
     elif ksplit > 1:
@@ -921,9 +926,12 @@ def gemm_bf16(a, b, bias=None, act=0, out_dtype=torch.bfloat16, ksplit=1, into=N
     if M and N:
         rc = _lib.load().pdb_gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), None if bias is None else bias.data_ptr(), M, N, K,
                                        a.stride(0), b.stride(0), N, int(act), 1 if out_dtype == torch.bfloat16 else 0,
-                                       int(ksplit), int(into is not None), _stream())
+                                       int(ksplit), int(into is not None), 3 if transposed else 0, _stream())
         _lib.check(rc, "pdb_gemm_bf16")
     return out
+
+
+bf16_wgrad_in_place = True     # A/B switch: False materialises dy^T and x^T in front of the weight-gradient GEMM (first version)
 
 
 def _split_k_bf16(M, N, K):
@@ -999,13 +1007,16 @@ class LinearBF16Function(Function):
         if ctx.needs_input_grad[1]:
             # dW = dy^T x: a handful of output tiles over a contraction as long as the token count -> split over K; straight
             # into the parameter's preallocated fp32 gradient when there is one (see _direct_grad)
-            gyt, xt = _rows8(gy.t()), _rows8(x2.t())
             tgt = _direct_grad(ctx.wref, (N, K)) if weight.dtype == torch.float32 else None
-            ks = _split_k_bf16(N, K, gyt.shape[1])
-            if tgt is not None:
-                gemm_bf16(gyt, xt, out_dtype=torch.float32, ksplit=ks, into=tgt)
+            ks = _split_k_bf16(N, K, gy.shape[0])
+            if bf16_wgrad_in_place and N % 8 == 0 and K % 8 == 0 and gy.data_ptr() % 16 == 0 and x2.data_ptr() % 16 == 0:
+                ops = dict(a=gy, b=x2, transposed=True)           # dy (rows, N) and x (rows, K) read in place, MN-major
             else:
-                gw = gemm_bf16(gyt, xt, out_dtype=torch.float32, ksplit=ks).to(weight.dtype)
+                ops = dict(a=_rows8(gy.t()), b=_rows8(x2.t()))
+            if tgt is not None:
+                gemm_bf16(out_dtype=torch.float32, ksplit=ks, into=tgt, **ops)
+            else:
+                gw = gemm_bf16(out_dtype=torch.float32, ksplit=ks, **ops).to(weight.dtype)
         if has_bias and ctx.needs_input_grad[2]:
             gb = col_sum(gy, into=_direct_grad(ctx.bref, (N,)))
         return gx, gw, gb, None, None

@@ -1009,3 +1009,18 @@ def test_masked_cross_attention_single_pass_under_autocast(fn):
             assert err > 5e-6           # it really is the single-pass arithmetic
         for a_, r_ in zip(gs, rg):
             assert _rel(a_.double().cpu(), r_) < bar_g
+
+
+@pytest.mark.parametrize("M,N,K,ks", [(256, 256, 4096, 8), (256, 256, 3200, 1), (136, 72, 1000, 3), (2048, 512, 204800, 2)])
+def test_gemm_bf16_mn_major_operands(fn, M, N, K, ks):
+    """dW = dy^T x with dy (K, M) and x (K, N) read in place (MN-major UMMA operands, TMA boxes of 64 x 64): same result as the
+    product of the materialised transposes, ragged M / N / K included."""
+    g = torch.Generator().manual_seed(33)
+    a = torch.randn(K, M, generator=g).cuda().to(torch.bfloat16)
+    b = torch.randn(K, N, generator=g).cuda().to(torch.bfloat16)
+    out = fn.gemm_bf16(a, b, None, 0, torch.float32, ksplit=ks, transposed=True)
+    if K <= 4096:
+        ref = a.double().t() @ b.double()
+        assert _rel(out.double(), ref) < 1e-5
+    ref2 = fn.gemm_bf16(fn._rows8(a.t()), fn._rows8(b.t()), None, 0, torch.float32, ksplit=ks)
+    assert _rel(out.double(), ref2.double()) < 1e-5
