@@ -115,6 +115,13 @@ PDB_API int pdb_gemm_tf32x3(const float* A, const float* B, const float* B_lo, f
                     int K, int batch,
                     int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc, int a_mn, int b_mn,
                     int c_trans, int relu, int accumulate, int ksplit, void* stream);
+/* pdb_gemm_tf32x3 with the backward of a ReLU fused into the store: C[m][n] = gate[m][n] > 0 ? sum_k A(m,k) B(n,k) : 0, gate laid
+ * out like C (row-major, pitch ldc, batch stride sc).  The input gradient of the Linear behind a ReLU, dh = (dy W) * (h > 0) with
+ * gate = h, in one pass instead of a GEMM and a threshold_backward pass (FFN of the encoder and decoder layers,
+ * msdeformattn.py:120-124, mask2former_transformer_decoder.py:167-171 via autograd). */
+PDB_API int pdb_gemm_tf32x3_gated(const float* A, const float* B, const float* B_lo, float* C, const float* gate, int M, int N, int K,
+                          int batch, int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc, int a_mn,
+                          int b_mn, void* stream);
 /* bf16 contraction on the tensor cores (tcgen05 kind::f16, fp32 accumulation) for the autocast path (BASELINE configs[2]; the
  * reference trains under AMP: Base-COCO-InstanceSegmentation.yaml:34-35) — replaces the cuBLAS bf16 GEMM behind nn.Linear of the
  * Swin backbone and the transformer decoder under torch.autocast:

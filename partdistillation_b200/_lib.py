@@ -30,6 +30,7 @@ SIGNATURES = {
     "pdb_mask_einsum_backward": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _l, _p]),
     "pdb_gemm_tf32x3": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _l, _l, _l, _l, _l, _l, _i, _i, _i, _i, _i, _i, _p]),
     "pdb_gemm_bf16": (_i, [_p, _p, _p, _p, _i, _i, _i, _l, _l, _l, _i, _i, _i, _i, _i, _p]),
+    "pdb_gemm_tf32x3_gated": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _l, _l, _l, _l, _l, _l, _i, _i, _p]),
     "pdb_col_sum": (_i, [_p, _p, _i, _i, _i, _p]),
     "pdb_col_sum_bf16": (_i, [_p, _p, _i, _i, _i, _p]),
     "pdb_set_xattn_passes": (_i, [_i]),

@@ -67,6 +67,8 @@ struct GemmParams {
     int b_box_rows;                   // rows of the K-major B box (BN, or the 16-multiple covering N when N < BN)
     long long* trace;                 // debug timeline of CTA 0 (pdb_debug_set_trace), normally NULL
     int stages, stage_bytes;          // raw ring: depth and bytes per stage (A raw/hi | B raw/hi | B lo)
+    const float* gate;                // ReLU backward fused into the store: C[m][n] = gate[m][n] > 0 ? value : 0 (same layout as C;
+                                      // row-major stores only) — the input gradient of the layer behind a ReLU
 };
 
 template <int BN>
@@ -197,7 +199,7 @@ __device__ __forceinline__ void b_layout(const GemmParams& p, int bn_eff, int& b
 // ALO: the A_lo k-blocks live in tensor memory instead of shared memory: the split warps write them with tcgen05.st (thread =
 // one row = one TMEM lane) and the correction MMA takes its A operand from TMEM, which removes 16 KB of shared-memory writes and
 // 16 KB of operand reads per k-block.  K-major A only, and the accumulators must leave 64 columns (see GemmSmem).
-template <int BN, bool A_MN, bool B_MN, bool ALO>
+template <int BN, bool A_MN, bool B_MN, bool ALO, bool GATE = false>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const __grid_constant__ CUtensorMap tm_blo, const GemmParams p) {
@@ -557,6 +559,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (p.bias && n_ok) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
                         float* dst = Cb + (int64_t)(mrow0 + sub_r) * p.ldc + n;
+                        // ReLU gate: all eight loads of this thread in flight at once (one at a time inside the store loop cost
+                        // eight L2 round trips per 32-column block: +140 us on the encoder's 43 008 x 1024 input gradient)
+                        float4 hg[GATE ? 8 : 1];
+                        if (GATE) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                hg[i] = (n_ok && mrow0 + i * 4 + sub_r < p.M)
+                                            ? __ldg(reinterpret_cast<const float4*>(p.gate + (dst - p.C) + (int64_t)i * 4 * p.ldc))
+                                            : make_float4(1.f, 1.f, 1.f, 1.f);
+                        }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int r = i * 4 + sub_r;
@@ -564,6 +576,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                             x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
                             if (p.relu) { x.x = epi_act(x.x, p.relu); x.y = epi_act(x.y, p.relu); x.z = epi_act(x.z, p.relu); x.w = epi_act(x.w, p.relu); }
                             if (n_ok && mrow0 + r < p.M) {
+                                if (GATE) {
+                                    const float4 h = hg[GATE ? i : 0];
+                                    x.x = h.x > 0.f ? x.x : 0.f; x.y = h.y > 0.f ? x.y : 0.f;
+                                    x.z = h.z > 0.f ? x.z : 0.f; x.w = h.w > 0.f ? x.w : 0.f;
+                                }
                                 if (p.atomic) red_add_v4(dst, x.x, x.y, x.z, x.w);
                                 else *reinterpret_cast<float4*>(dst) = x;
                             }
@@ -579,6 +596,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                             if (mrow0 + r < p.M && n_ok) {
                                 float x = tile_s[r * 36 + lane] + bv;
                                 x = epi_act(x, p.relu);
+                                if (GATE && !(__ldg(p.gate + (dst - p.C)) > 0.f)) x = 0.f;
                                 if (p.atomic) atomicAdd(dst, x); else *dst = x;
                             }
                             dst += p.ldc;
@@ -675,6 +693,28 @@ static int launch_gemm_alo(const CUtensorMap& ta, const CUtensorMap& tb, const C
     return launched("gemm_tf32x3");
 }
 
+// The gated store (ReLU backward fused into the input-gradient GEMM) exists for the one shape that uses it: 128-wide tiles, K-major
+// A (dy), MN-major B (W read in place).  Its own instantiation keeps the eight gate loads per thread out of every other GEMM.
+static int launch_gemm_gated(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbl, const GemmParams& p, cudaStream_t st) {
+    using S = GemmSmem<128>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<128, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) return fail(PDB_ERR_LAUNCH, "gemm_tf32x3: smem attribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    GemmParams q = p;
+    q.trace = g_trace_ptr;
+    q.stages = G_RS;
+    q.stage_bytes = S::RAW_STAGE;
+    q.mt = (p.M + G_BM - 1) / G_BM;
+    q.nt = (p.N + 127) / 128;
+    q.total_tiles = q.mt * q.nt * p.batch * p.ksplit;
+    const unsigned grid = (unsigned)std::min(q.total_tiles, kNumSMs);
+    gemm_tf32x3_kernel<128, false, true, false, true><<<grid, G_THREADS, S::TOTAL, st>>>(ta, tb, tbl, q);
+    return launched("gemm_tf32x3(gated)");
+}
+
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbl, const GemmParams& p, cudaStream_t st) {
     // A_lo in tensor memory: K-major A only (the split warps own whole rows), and the accumulators must leave 64 columns
@@ -695,8 +735,10 @@ static int dispatch_layout(const CUtensorMap& ta, const CUtensorMap& tb, const C
 static int gemm_impl(const float* A, const float* B, const float* B_lo, float* C, const float* bias, int M, int N, int K, int batch,
                      int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc, int a_mn, int b_mn,
                      int c_trans, int relu, int accumulate, int ksplit, int taps, const int32_t* tap_off, int a_rows,
-                     cudaStream_t st) {
+                     cudaStream_t st, const float* gate = nullptr) {
     PDB_REQUIRE(A && B && C, "gemm_tf32x3: null pointer");
+    PDB_REQUIRE(!gate || (!c_trans && ksplit == 1 && !accumulate && (reinterpret_cast<uintptr_t>(gate) & 15) == 0),
+                "gemm_tf32x3: the ReLU gate needs a plain row-major store (no transpose, split-K or accumulation), 16-byte aligned");
     PDB_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "gemm_tf32x3: non-positive dimension");
     PDB_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm_tf32x3: operands must be 16-byte aligned");
     PDB_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && sa % 4 == 0 && sb % 4 == 0,
@@ -704,6 +746,7 @@ static int gemm_impl(const float* A, const float* B, const float* B_lo, float* C
     PDB_REQUIRE(ksplit >= 1 && (ksplit == 1 || accumulate), "gemm_tf32x3: split-K needs accumulate mode");
     GemmParams p;
     p.C = C; p.bias = bias; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.sc = sc; p.batch = batch;
+    p.gate = gate;
     int kb_total = (K + G_BK - 1) / G_BK;
     if (ksplit > kb_total) ksplit = kb_total;
     p.ksplit = ksplit;
@@ -732,6 +775,11 @@ static int gemm_impl(const float* A, const float* B, const float* B_lo, float* C
     PDB_TRY(make_operand_map(&tb, B, b_mn != 0, N, K, batch, ldb, sb, p.b_box_rows));
     tbl = tb;
     if (B_lo) PDB_TRY(make_operand_map(&tbl, B_lo, b_mn != 0, N, K, batch, ldb, sb, p.b_box_rows));
+    if (gate) {
+        PDB_REQUIRE(BN == 128 && !a_mn && b_mn && N > 112 && N % 4 == 0,
+                    "gemm_tf32x3: the gated store needs 128-wide tiles (many rows, N > 112, N %% 4 == 0), K-major A and MN-major B");
+        return launch_gemm_gated(ta, tb, tbl, p, st);
+    }
     if (BN == 32) return dispatch_layout<32>(ta, tb, tbl, p, a_mn != 0, b_mn != 0, st);
     if (BN == 64) return dispatch_layout<64>(ta, tb, tbl, p, a_mn != 0, b_mn != 0, st);
     return dispatch_layout<128>(ta, tb, tbl, p, a_mn != 0, b_mn != 0, st);
@@ -763,6 +811,16 @@ extern "C" int pdb_gemm_tf32x3(const float* A, const float* B, const float* B_lo
                                int b_mn, int c_trans, int relu, int accumulate, int ksplit, void* stream) {
     return gemm_tf32x3(A, B, B_lo, C, bias, M, N, K, batch, lda, ldb, ldc, sa, sb, sc, a_mn, b_mn, c_trans, relu, accumulate,
                        ksplit, as_stream(stream));
+}
+
+// pdb_gemm_tf32x3 with the backward of a ReLU fused into the store: C[m][n] = gate[m][n] > 0 ? (A B^T)[m][n] : 0, gate laid out
+// like C.  The input gradient of a Linear whose INPUT was relu(.) : dh = (dy W) * (h > 0) in one pass (gate = h).
+extern "C" int pdb_gemm_tf32x3_gated(const float* A, const float* B, const float* B_lo, float* C, const float* gate, int M, int N,
+                                     int K, int batch, int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc,
+                                     int a_mn, int b_mn, void* stream) {
+    PDB_REQUIRE(gate, "gemm_tf32x3_gated: null gate");
+    return gemm_impl(A, B, B_lo, C, nullptr, M, N, K, batch, lda, ldb, ldc, sa, sb, sc, a_mn, b_mn, 0, 0, 0, 1, 1, nullptr, 0,
+                     as_stream(stream), gate);
 }
 
 namespace pdb {

@@ -766,6 +766,91 @@ class LinearFunction(Function):
         return gx, gw, gb, None
 
 
+class FFNFunction(Function):
+    """y = relu(x W1^T + b1) W2^T + b2 as ONE autograd node (the FFN of the encoder and decoder layers, msdeformattn.py:120-124,
+    mask2former_transformer_decoder.py:167-171).  Forward = two LinearFunction products; what the single node buys is the
+    backward: dh = (dy W2) * (h > 0) leaves the input-gradient GEMM already gated (pdb_gemm_tf32x3_gated, gate = h) instead of
+    a GEMM pass followed by a threshold_backward pass over the (rows, d_ffn) tensor.  Weight / bias gradients as in
+    LinearFunction (straight into preallocated parameter gradients when there are any)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        _need_cuda(x, w1, w2)
+        F1, K = w1.shape
+        N = w2.shape[0]
+        x2 = _c(x).view(-1, K)
+        if x2.data_ptr() % 16:
+            x2 = x2.clone()
+        M = x2.shape[0]
+        lo1, lo2 = weight_lo(w1, M), weight_lo(w2, M)
+        h = torch.empty((M, F1), dtype=torch.float32, device=x.device)
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        if M > 0:
+            gemm_tf32x3(x2, w1, h, M, F1, K, lda=K, ldb=K, ldc=F1, bias=b1, relu=True, B_lo=lo1)
+            gemm_tf32x3(h, w2, y, M, N, F1, lda=F1, ldb=F1, ldc=N, bias=b2, B_lo=lo2)
+        ctx.lo = (lo1, lo2)
+        ctx.refs = (w1, b1, w2, b2)
+        ctx.save_for_backward(x2, h, w1, w2)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x2, h, w1, w2 = ctx.saved_tensors
+        r1, rb1, r2, rb2 = ctx.refs
+        lo1, lo2 = ctx.lo
+        F1, K = w1.shape
+        N = w2.shape[0]
+        M = x2.shape[0]
+        gy2 = _c(gy).view(M, N)
+        if gy2.data_ptr() % 16:
+            gy2 = gy2.clone()
+        gx = gw1 = gb1 = gw2 = gb2 = None
+        need_h = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or (rb1 is not None and ctx.needs_input_grad[2])
+        if need_h:
+            # dh[m, f] = (sum_o gy[m, o] W2[o, f]) * (h[m, f] > 0): A = gy (K-major), B(n = f, k = o) = W2[o*F1 + f] (MN-major)
+            gh = torch.empty((M, F1), dtype=torch.float32, device=gy.device)
+            rc = _lib.load().pdb_gemm_tf32x3_gated(gy2.data_ptr(), w2.data_ptr(), lo2.data_ptr() if lo2 is not None else None,
+                                                   gh.data_ptr(), h.data_ptr(), M, F1, N, 1, N, F1, F1, 0, 0, 0, 0, 1, _stream())
+            _lib.check(rc, "pdb_gemm_tf32x3_gated")
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty((M, K), dtype=torch.float32, device=gy.device)
+                gemm_tf32x3(gh, w1, gx, M, K, F1, lda=F1, ldb=K, ldc=K, b_mn=True, B_lo=lo1)
+                gx = gx.view(*gy.shape[:-1], K)
+            if ctx.needs_input_grad[1]:
+                tgt = _direct_grad(r1, (F1, K))
+                gw1 = tgt if tgt is not None else torch.zeros((F1, K), dtype=torch.float32, device=gy.device)
+                gemm_tf32x3(gh, x2, gw1, F1, K, M, lda=F1, ldb=K, ldc=K, a_mn=True, b_mn=True, accumulate=True,
+                            ksplit=_split_k(F1, K, M))
+                gw1 = None if tgt is not None else gw1
+            if rb1 is not None and ctx.needs_input_grad[2]:
+                gb1 = col_sum(gh, into=_direct_grad(rb1, (F1,)))
+        if ctx.needs_input_grad[3]:
+            tgt = _direct_grad(r2, (N, F1))
+            gw2 = tgt if tgt is not None else torch.zeros((N, F1), dtype=torch.float32, device=gy.device)
+            gemm_tf32x3(gy2, h, gw2, N, F1, M, lda=N, ldb=F1, ldc=F1, a_mn=True, b_mn=True, accumulate=True,
+                        ksplit=_split_k(N, F1, M))
+            gw2 = None if tgt is not None else gw2
+        if rb2 is not None and ctx.needs_input_grad[4]:
+            gb2 = col_sum(gy2, into=_direct_grad(rb2, (N,)))
+        return gx, gw1, gb1, gw2, gb2
+
+
+ffn_fused_rows = 2048       # from this many rows on the two-Linear FFN runs as one node with the gated input-gradient GEMM
+
+
+def ffn(x, w1, b1, w2, b2):
+    """relu(x W1^T + b1) W2^T + b2.  Tall fp32 CUDA inputs (the encoder's 43 008 rows) take FFNFunction; short ones (the decoder's
+    200 rows, where a threshold_backward pass costs 2 us and the short-A GEMM kernels matter more), autocast and everything the
+    GEMM cannot take go through two ``linear`` calls."""
+    rows = x.numel() // max(1, x.shape[-1])
+    if (rows >= ffn_fused_rows and w1.shape[0] >= 256 and not _autocast_bf16(x, w1) and linear_supported(x, w1) and linear_supported(x, w2)
+            and b1 is not None and b2 is not None and w1.data_ptr() % 16 == 0 and w2.data_ptr() % 16 == 0
+            and getattr(_lib.load(), "pdb_gemm_tf32x3_gated", None) is not None):
+        return FFNFunction.apply(x, w1, b1, w2, b2)
+    return linear(linear(x, w1, b1, relu=True), w2, b2)
+
+
 class Conv1x1Function(Function):
     """1x1 convolution as a GEMM over pixels.  An NCHW-contiguous input is read in place as an MN-major operand
     (pixels contiguous), a channels-last one as a K-major operand; the result is the logical (B, O, H, W) tensor in

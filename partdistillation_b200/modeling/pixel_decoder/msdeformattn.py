@@ -51,11 +51,11 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         src2 = self.self_attn(q, reference_points, src, spatial_shapes, level_start_index, padding_mask,
                               offset_normalizer=offset_normalizer)
         src = PF.layer_norm(src, self.norm1.weight, self.norm1.bias, self.norm1.eps, residual=self.dropout1(src2))
-        if self.activation is F.relu:
-            hidden = PF.linear(src, self.linear1.weight, self.linear1.bias, relu=True)
+        if self.activation is F.relu and not (self.training and self.dropout2.p > 0):
+            src2 = PF.ffn(src, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias)
         else:
             hidden = self.activation(PF.linear(src, self.linear1.weight, self.linear1.bias))
-        src2 = PF.linear(self.dropout2(hidden), self.linear2.weight, self.linear2.bias)
+            src2 = PF.linear(self.dropout2(hidden), self.linear2.weight, self.linear2.bias)
         return PF.layer_norm(src, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=self.dropout3(src2))
 
 

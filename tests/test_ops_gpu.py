@@ -1024,3 +1024,32 @@ def test_gemm_bf16_mn_major_operands(fn, M, N, K, ks):
         assert _rel(out.double(), ref) < 1e-5
     ref2 = fn.gemm_bf16(fn._rows8(a.t()), fn._rows8(b.t()), None, 0, torch.float32, ksplit=ks)
     assert _rel(out.double(), ref2.double()) < 1e-5
+
+
+@pytest.mark.parametrize("rows,C,Fd", [((2, 2100), 256, 1024), ((4200,), 64, 132)])
+def test_ffn_fused_node_matches_two_linears(fn, rows, C, Fd):
+    """functional.ffn as one autograd node (ReLU backward fused into the input-gradient GEMM's store, pdb_gemm_tf32x3_gated)
+    against the fp64 two-Linear expression: output and all five gradients; and against the library's own two-node path."""
+    g = torch.Generator().manual_seed(60)
+    x = torch.randn(*rows, C, generator=g)
+    w1, b1 = torch.randn(Fd, C, generator=g) / C ** 0.5, torch.randn(Fd, generator=g) * 0.1
+    w2, b2 = torch.randn(C, Fd, generator=g) / Fd ** 0.5, torch.randn(C, generator=g) * 0.1
+    go = torch.randn(*rows, C, generator=g)
+    ts = [t.double().requires_grad_() for t in (x, w1, b1, w2, b2)]
+    ref = F.linear(F.relu(F.linear(ts[0], ts[1], ts[2])), ts[3], ts[4])
+    rg = torch.autograd.grad(ref, ts, go.double())
+    res = []
+    for fused in (2048, 1 << 30):
+        fn.ffn_fused_rows = fused
+        try:
+            tc = [t.cuda().requires_grad_() for t in (x, w1, b1, w2, b2)]
+            y = fn.ffn(*tc)
+            res.append((y, *torch.autograd.grad(y, tc, go.cuda())))
+        finally:
+            fn.ffn_fused_rows = 2048
+    for got in res:
+        assert _rel(got[0].double().cpu(), ref.detach()) < 1e-5
+        for a_, r_ in zip(got[1:], rg):
+            assert _rel(a_.double().cpu(), r_) < 2e-5
+    # the gate is exact: gradient entries behind inactive units are exactly zero in both paths' dh, hence identical dx patterns
+    assert torch.equal(res[0][1] == 0, res[1][1] == 0)
