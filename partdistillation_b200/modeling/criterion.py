@@ -118,24 +118,25 @@ class SetCriterion(nn.Module):
         assert loss in loss_map, f"do you really want to compute {loss} loss?"
         return loss_map[loss](outputs, targets, indices, num_masks)
 
+    def _num_masks(self, targets, dev):
+        """Average number of target masks across ranks, >= 1 (:248-254) — kept on the device.  It depends only on the target
+        counts, so a trainer may all-reduce it before the step and hand it over (external_num_masks): the forward / backward then
+        contains no collective and can be replayed as a CUDA graph on every rank.  With padded targets (the trainer's target
+        bucketing) the real count is data, not shape: it is counted on the device from the labels (-1 = padding slot)."""
+        if self.external_num_masks is not None:
+            return self.external_num_masks.reshape(-1)[0]
+        if getattr(targets, "has_dummies", False):
+            num_masks = (targets.packed_labels >= 0).sum().float().reshape(1)
+        else:
+            num_masks = torch.full((1,), float(targets.total), dtype=torch.float, device=dev)
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(num_masks)
+            num_masks = num_masks / dist.get_world_size()
+        return torch.clamp(num_masks, min=1)[0]
+
     def forward(self, outputs, targets):
         targets = pack_targets(targets)
-        dev = outputs["pred_masks"].device
-        # average number of target masks across ranks, >= 1 (:248-254) — kept on the device.  It depends only on the
-        # target counts, so a trainer may all-reduce it before the step and hand it over (external_num_masks): the
-        # forward/backward then contains no collective and can be replayed as a CUDA graph on every rank.
-        if self.external_num_masks is not None:
-            num_masks = self.external_num_masks.reshape(-1)[0]
-        else:
-            if getattr(targets, "has_dummies", False):
-                # padded targets: the real count is data, not shape — counted on the device so that a captured step stays valid
-                num_masks = (targets.packed_labels >= 0).sum().float().reshape(1)
-            else:
-                num_masks = torch.full((1,), float(targets.total), dtype=torch.float, device=dev)
-            if dist.is_available() and dist.is_initialized():
-                dist.all_reduce(num_masks)
-                num_masks = num_masks / dist.get_world_size()
-            num_masks = torch.clamp(num_masks, min=1)[0]
+        num_masks = self._num_masks(targets, outputs["pred_masks"].device)
 
         losses = {}
         main = {k: v for k, v in outputs.items() if k != "aux_outputs"}

@@ -249,3 +249,51 @@ def test_padded_batch_allocates_then_refills_in_place():
     assert s["instances"].gt_masks.tensor[:1].all() and not s["instances"].gt_masks.tensor[1:].any()
     assert s["instances"].gt_classes.tolist() == [0, -1, -1, -1] and int(s["gt_object_class_dev"]) == 2
     assert int(s["image"][0, 0, 0]) == 1
+
+
+def _num_masks_worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from partdistillation_b200.engine import DataParallelTrainer
+    from partdistillation_b200.modeling.criterion import SetCriterion
+    from partdistillation_b200.modeling.targets import TargetList
+    crit = SetCriterion.__new__(SetCriterion)            # only the normaliser logic is exercised
+    crit.external_num_masks = None
+    t = TargetList()
+    # rank 0: 3 real + 1 padding slot, rank 1: no real target at all (2 padding slots)
+    t.packed_labels = torch.tensor([0, 0, 0, -1] if rank == 0 else [-1, -1], dtype=torch.int32)
+    t.offsets = [0, len(t.packed_labels)]
+    t.has_dummies = True
+    padded = float(crit._num_masks(t, torch.device("cpu")))
+    t.has_dummies = False                                # shape-based count (the unpadded contract): (4 + 2) / 2
+    plain = float(crit._num_masks(t, torch.device("cpu")))
+
+    class Arch(torch.nn.Module):                         # the trainer's pre-step all-reduce uses the RAW (unpadded) counts
+        target_padding = False
+        num_queries = 10
+
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(4))
+            self.criterion = type("Crit", (), {"external_num_masks": None})()
+    arch = Arch()
+    tr = DataParallelTrainer(arch, freeze_keys=(), target_bucket=4)
+
+    class I:
+        def __init__(self, k):
+            self.gt_masks = type("M", (), {"tensor": torch.zeros(k, 2, 2)})()
+    tr._global_num_masks([{"instances": I(3 if rank == 0 else 0)}])
+    torch.save({"padded": padded, "plain": plain, "external": float(arch.criterion.external_num_masks)}, f"{out_path}.{rank}")
+    dist.destroy_process_group()
+
+
+def test_num_masks_counts_real_targets_gloo_world2(tmp_path):
+    """criterion.py:248-254 under target bucketing: the normaliser is the mean over ranks of the REAL target counts (padding slots
+    carry label -1), clamped to >= 1, whether the criterion computes it (eager) or the trainer hands it over (captured steps)."""
+    out = str(tmp_path / "nm")
+    mp.spawn(_num_masks_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for rank in range(2):
+        r = torch.load(f"{out}.{rank}")
+        assert r["padded"] == 1.5 and r["plain"] == 3.0 and r["external"] == 1.5
