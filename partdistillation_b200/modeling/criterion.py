@@ -39,6 +39,7 @@ class SetCriterion(nn.Module):
         self.importance_sample_ratio = importance_sample_ratio
         self.rand = torch.rand
         self.external_num_masks = None     # device float tensor set by the trainer (see forward)
+        self.batched_matching = True       # the Hungarian assignments of all decoder outputs in one cost + one LSAP launch
 
     # ------------------------------------------------------------------------------------------
     def _flat_indices(self, targets, match, B, Q):
@@ -81,42 +82,48 @@ class SetCriterion(nn.Module):
         loss_ce = F.cross_entropy(logits.view(B * Q, -1), target_classes, self.empty_weight)
         return {"loss_ce": loss_ce}
 
-    def loss_masks(self, outputs, targets, match, num_masks):
-        """Point-sampled sigmoid-CE + dice on the matched masks (:147-207)."""
+    def loss_masks(self, outputs, targets, match, num_masks, loss_points=None):
+        """Point-sampled sigmoid-CE + dice on the matched masks (:147-207).  ``loss_points``: the random draws of this call made
+        ahead of time by ``forward`` (_draw_loss_points)."""
         pred = outputs["pred_masks"]
         B, Q, H, W = pred.shape
         src, tgt = self._flat_indices(targets, match, B, Q)
         Nm = src.shape[0]
         flat = pred.float().flatten(0, 1)
         with torch.no_grad():
-            coords = self._uncertain_point_coords(flat, src, Nm)
+            coords = self._uncertain_point_coords(flat, src, Nm, loss_points)
         bce, dice = PF.point_loss(flat, src, targets.packed_masks, tgt, coords)
         if getattr(targets, "has_dummies", False):          # pairs matched to padding slots carry no loss
             w = (targets.packed_labels[tgt] >= 0).to(bce.dtype)
             bce, dice = bce * w, dice * w
         return {"loss_mask": bce.sum() / num_masks, "loss_dice": dice.sum() / num_masks}
 
-    def _uncertain_point_coords(self, flat, src, Nm):
-        """detectron2 get_uncertain_point_coords_with_randomness with uncertainty = -|logit|."""
-        dev = flat.device
+    def _draw_loss_points(self, Nm, dev):
+        """The random numbers of one get_uncertain_point_coords_with_randomness call, in its order: the over-sampled candidates,
+        then the uniformly random remainder (None when importance sampling takes every point)."""
         n_over = int(self.num_points * self.oversample_ratio)
+        n_rand = self.num_points - int(self.importance_sample_ratio * self.num_points)
+        over = self.rand(Nm, n_over, 2, device=dev, dtype=torch.float32)
+        return over, (self.rand(Nm, n_rand, 2, device=dev) if n_rand > 0 else None)
+
+    def _uncertain_point_coords(self, flat, src, Nm, drawn=None):
+        """detectron2 get_uncertain_point_coords_with_randomness with uncertainty = -|logit|."""
         n_unc = int(self.importance_sample_ratio * self.num_points)
-        n_rand = self.num_points - n_unc
-        over = self.rand(Nm, n_over, 2, device=dev, dtype=flat.dtype)
+        over, rnd = drawn if drawn is not None else self._draw_loss_points(Nm, flat.device)
         if n_unc > 0:
             unc = -PF.point_sample(flat.detach(), over, src.to(torch.int32), None).abs()
             idx = torch.topk(unc, k=n_unc, dim=1)[1]
             coords = torch.gather(over, 1, idx[:, :, None].expand(-1, -1, 2))
+            if rnd is not None:
+                coords = torch.cat([coords, rnd], dim=1)
         else:
-            coords = over[:, :0]
-        if n_rand > 0:
-            coords = torch.cat([coords, self.rand(Nm, n_rand, 2, device=dev)], dim=1)
+            coords = rnd            # every point is a uniformly random one: nothing to concatenate
         return coords.contiguous()
 
-    def get_loss(self, loss, outputs, targets, indices, num_masks):
+    def get_loss(self, loss, outputs, targets, indices, num_masks, **kw):
         loss_map = {"labels": self.loss_labels, "masks": self.loss_masks}
         assert loss in loss_map, f"do you really want to compute {loss} loss?"
-        return loss_map[loss](outputs, targets, indices, num_masks)
+        return loss_map[loss](outputs, targets, indices, num_masks, **kw)
 
     def _num_masks(self, targets, dev):
         """Average number of target masks across ranks, >= 1 (:248-254) — kept on the device.  It depends only on the target
@@ -140,13 +147,29 @@ class SetCriterion(nn.Module):
 
         losses = {}
         main = {k: v for k, v in outputs.items() if k != "aux_outputs"}
-        match = self.matcher.match_packed(main, targets)
-        for loss in self.losses:
-            losses.update(self.get_loss(loss, main, targets, match, num_masks))
-        for i, aux in enumerate(outputs.get("aux_outputs", [])):
-            match = self.matcher.match_packed(aux, targets)
+        outs = [main] + list(outputs.get("aux_outputs", []))
+        points = [None] * len(outs)
+        if self.batched_matching and len(outs) > 1 and hasattr(self.matcher, "match_all"):
+            # Every random number of the step first, in the reference's order (per output: the matcher's coordinates, then the
+            # loss points; none of the shapes depends on a matching result), then the assignments of ALL outputs in one cost
+            # launch and one LSAP launch (matcher.match_all), then the losses.
+            B, Q = main["pred_logits"].shape[:2]
+            dev = main["pred_masks"].device
+            Nm = sum(min(Q, targets.offsets[b + 1] - targets.offsets[b]) for b in range(B))
+            coords = []
+            for i in range(len(outs)):
+                coords.append(self.matcher.draw_coords(B, dev))
+                if "masks" in self.losses:
+                    points[i] = self._draw_loss_points(Nm, dev)
+            matches = self.matcher.match_all(outs, targets, coords)
+        else:
+            matches = None
+        for i, out in enumerate(outs):
+            match = matches[i] if matches is not None else self.matcher.match_packed(out, targets)
+            suffix = "" if i == 0 else f"_{i - 1}"
             for loss in self.losses:
-                losses.update({f"{k}_{i}": v for k, v in self.get_loss(loss, aux, targets, match, num_masks).items()})
+                kw = {"loss_points": points[i]} if (loss == "masks" and points[i] is not None) else {}
+                losses.update({k + suffix: v for k, v in self.get_loss(loss, out, targets, match, num_masks, **kw).items()})
         return losses
 
     def __repr__(self):

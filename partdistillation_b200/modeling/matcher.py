@@ -36,7 +36,7 @@ class HungarianMatcher(nn.Module):
         if targets.total == 0:
             e = torch.zeros((0,), dtype=torch.int64, device=dev)
             return e, e
-        coords = torch.cat([self.rand(1, self.num_points, 2, device=dev) for _ in range(B)], 0)
+        coords = self.draw_coords(B, dev)
         cache = _index_cache(targets, B, Q, dev)
         prob = logits.float().sigmoid() if logits.shape[-1] == 1 else logits.float().softmax(-1)
         pred_pts = PF.point_sample(masks.detach().float().flatten(0, 1), coords, None, cache["img_of_query"])
@@ -44,6 +44,50 @@ class HungarianMatcher(nn.Module):
         cost = PF.matcher_cost(pred_pts, tgt_pts, prob.reshape(B * Q, -1), targets.packed_labels, targets.offsets, Q,
                                self.cost_class, self.cost_mask, self.cost_dice)
         return PF.lsap_batched(cost, targets.offsets, Q)
+
+    @torch.no_grad()
+    def draw_coords(self, B, dev):
+        """The point coordinates of one matcher call: one (1, P, 2) draw per image, in image order (matcher.py:130-131)."""
+        return torch.cat([self.rand(1, self.num_points, 2, device=dev) for _ in range(B)], 0)
+
+    @torch.no_grad()
+    def match_all(self, outs, targets, coords_list=None):
+        """match_packed for several decoder outputs (the main one and the deep-supervision ones) at once: the cost matrices of
+        len(outs) * B (output, image) pairs in ONE cost launch and ONE LSAP launch — at B = 2 the per-output launches put 200
+        CTAs / 2 warps on 148 SMs, ten times in a row.  ``coords_list``: the matcher coordinates of every output, already drawn
+        (the criterion draws all random numbers of the step in the reference's order); drawn here otherwise.  Returns the list of
+        match_packed results.  Same arithmetic per (output, image, query, target) as match_packed: identical assignments."""
+        targets = pack_targets(targets)
+        n = len(outs)
+        B, Q = outs[0]["pred_logits"].shape[:2]
+        dev = outs[0]["pred_masks"].device
+        if coords_list is None:
+            coords_list = [self.draw_coords(B, dev) for _ in outs]
+        if targets.total == 0:
+            e = torch.zeros((0,), dtype=torch.int64, device=dev)
+            return [(e, e) for _ in outs]
+        cache = _index_cache(targets, B, Q, dev)
+        Ktot = targets.offsets[-1]
+        res = []
+        step = max(1, 255 // B)                     # the kernels take at most 255 cost matrices per launch
+        for s in range(0, n, step):
+            chunk, coords = outs[s:s + step], coords_list[s:s + step]
+            m = len(chunk)
+            pred = torch.cat([PF.point_sample(o["pred_masks"].detach().float().flatten(0, 1), c, None, cache["img_of_query"])
+                              for o, c in zip(chunk, coords)])
+            tgt = torch.cat([PF.point_sample(targets.packed_masks, c, None, cache["img_of_target"]) for c in coords])
+            prob = torch.cat([(o["pred_logits"].float().sigmoid() if o["pred_logits"].shape[-1] == 1
+                               else o["pred_logits"].float().softmax(-1)).reshape(B * Q, -1) for o in chunk])
+            key = ("all", m)
+            tiled = cache.get(key)
+            if tiled is None:
+                offs = [i * Ktot + o for i in range(m) for o in targets.offsets[:-1]] + [m * Ktot]
+                tiled = cache[key] = (offs, targets.packed_labels.repeat(m))
+            offs, labels = tiled
+            cost = PF.matcher_cost(pred, tgt, prob, labels, offs, Q, self.cost_class, self.cost_mask, self.cost_dice)
+            pi, ti = PF.lsap_batched(cost, offs, Q)
+            res += [(pi[i * Ktot:(i + 1) * Ktot], ti[i * Ktot:(i + 1) * Ktot]) for i in range(m)]
+        return res
 
     @torch.no_grad()
     def forward(self, outputs, targets):

@@ -84,6 +84,13 @@ def test_head_and_loss_vs_reference_golden(golden_dir, name):
         matches.append(r)
         return r
     model.criterion.matcher.match_packed = rec_match
+    ma = model.criterion.matcher.match_all
+
+    def rec_all(outs, t, coords=None):          # the criterion matches all decoder outputs in one call (matcher.match_all)
+        r = ma(outs, t, coords)
+        matches.extend(r)
+        return r
+    model.criterion.matcher.match_all = rec_all
 
     outputs = model.run_head(feats, targets)
     losses = model.criterion(outputs, targets)
@@ -175,6 +182,13 @@ def test_padded_targets_are_loss_neutral(golden_dir, name):
             matches.append(r)
             return r
         model.criterion.matcher.match_packed = rec_match
+        ma = model.criterion.matcher.match_all
+
+        def rec_all(outs, t, coords=None, ma=ma, matches=matches):
+            r = ma(outs, t, coords)
+            matches.extend(r)
+            return r
+        model.criterion.matcher.match_all = rec_all
         losses = model.losses_from_features(feats, targets)
         sum(losses.values()).backward()
         real = []
@@ -195,6 +209,43 @@ def test_padded_targets_are_loss_neutral(golden_dir, name):
     assert set(ga) == set(gb)
     for k in ga:
         assert float((ga[k] - gb[k]).abs().max()) <= 1e-4 * max(float(ga[k].abs().max()), 1e-8), k
+
+
+@pytest.mark.parametrize("name", ["proposal_micro", "pd_micro"])
+def test_batched_matching_equals_per_output(golden_dir, name):
+    """criterion.batched_matching (all decoder outputs' Hungarian assignments in one cost launch + one LSAP launch, every random
+    number of the step drawn first in the reference's order) against the output-by-output flow on the same replayed draws:
+    identical assignments, identical losses."""
+    if DEV == "cuda" and not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    g = torch.load(os.path.join(golden_dir, f"head_{name}.pt"), weights_only=False)
+    res = []
+    for batched in (True, False):
+        model, c = _build(g)
+        feats, targets = _inputs(model, c)
+        replay = synth.ReplayRand(g["rand_draws"], device=DEV)
+        model.criterion.rand = model.criterion.matcher.rand = replay
+        model.criterion.batched_matching = batched
+        matches = []
+        for attr in ("match_packed", "match_all"):
+            f = getattr(model.criterion.matcher, attr)
+
+            def rec(*a, f=f, many=attr == "match_all"):
+                r = f(*a)
+                matches.extend(r) if many else matches.append(r)
+                return r
+            setattr(model.criterion.matcher, attr, rec)
+        with torch.no_grad():
+            losses = model.losses_from_features(feats, targets)
+        assert replay.i == len(g["rand_draws"])
+        res.append((matches, {k: float(v) for k, v in losses.items()}))
+    (ma, la), (mb, lb) = res
+    assert len(ma) == len(mb) == c["dec_layers"]          # DEC_LAYERS counts the prediction heads (layers + 1)
+    for (pa, ta), (pb, tb) in zip(ma, mb):
+        assert torch.equal(pa, pb) and torch.equal(ta, tb)
+    assert la.keys() == lb.keys()
+    for k in la:        # the two runs are separate forward passes: split-K red.add orders differ in the last bit on the GPU
+        assert abs(la[k] - lb[k]) <= 2e-6 * max(1.0, abs(lb[k])), (k, la[k], lb[k])
 
 
 def test_matcher_public_api(golden_dir):

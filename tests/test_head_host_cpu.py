@@ -35,6 +35,10 @@ def test_padded_targets_are_loss_neutral(on_host, golden_dir, name):
     head_tests.test_padded_targets_are_loss_neutral(golden_dir, name)
 
 
+def test_batched_matching_equals_per_output(on_host, golden_dir):
+    head_tests.test_batched_matching_equals_per_output(golden_dir, "pd_micro")
+
+
 def test_gpu_body_packed_bit_masks_ingestion(monkeypatch, host_lib):
     """tests/test_postprocess_gpu.py::test_packed_bit_masks_ingestion on the host builds: packed targets stay packed and the
     sampling / point-loss kernels read the words bit-identically to the byte layout."""
