@@ -249,13 +249,16 @@ PDB_API int pdb_lsap_batched(const float* cost, const int32_t* tgt_offset, int64
  *   loss_mask = sum_i BCE_i/P / num_masks, loss_dice = sum_i (1-(2 st+1)/(s+t+1)) / num_masks).
  * backward: g_bce, g_dice (Nm) f32 = d loss / d (BCE_i/P), d loss / d dice_i; grad_pred (Rp, H, W)
  * must be zero-filled by the caller; accumulated.
+ * splits > 1 (few pairs: a dozen per decoder output at B = 2): the P points of a pair are cut into `splits` chunks handled by
+ * different CTAs; forward writes their sums to `partial` (Nm * splits * 4 f32) and a second launch adds them in split order
+ * (deterministic); backward only needs the count.  splits <= 1: one CTA of 1024 threads per pair, partial may be NULL.
  * ---------------------------------------------------------------------------------------------- */
 PDB_API int pdb_point_loss_forward(const float* pred, const int64_t* pred_index, const void* gt,
-                           const int64_t* gt_index, const float* coords, float* sums,
+                           const int64_t* gt_index, const float* coords, float* sums, float* partial, int splits,
                            int Nm, int P, int H, int W, int Hg, int Wg, int gt_bits, void* stream);
 PDB_API int pdb_point_loss_backward(const float* pred, const int64_t* pred_index, const void* gt,
                             const int64_t* gt_index, const float* coords, const float* sums,
-                            const float* g_bce, const float* g_dice, float* grad_pred,
+                            const float* g_bce, const float* g_dice, float* grad_pred, int splits,
                             int Nm, int P, int H, int W, int Hg, int Wg, int gt_bits, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -46,8 +46,8 @@ SIGNATURES = {
     "pdb_point_sample_backward": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "pdb_matcher_cost": (_i, [_p, _p, _p, _p, _hp32, _p, _i, _i, _i, _i, _f, _f, _f, _p]),
     "pdb_lsap_batched": (_i, [_p, _hp32, _p, _p, _i, _i, _p]),
-    "pdb_point_loss_forward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
-    "pdb_point_loss_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "pdb_point_loss_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "pdb_point_loss_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "pdb_class_rows_forward": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _l, _p]),
     "pdb_window_attention_forward": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p]),
     "pdb_swin_window_attention_forward": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p]),

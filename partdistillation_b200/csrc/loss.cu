@@ -299,20 +299,24 @@ lsap_kernel(const float* __restrict__ cost, Offsets off, int64_t* __restrict__ p
 // ------------------------------------------------------------------------------------------------
 // one CTA of 1024 threads per matched pair: there are only a handful of pairs per layer, so the block is as wide as it
 // can be (12544 points -> 12 per thread)
+// With few pairs (B = 2: 12 per decoder output) the points of a pair are additionally split over blockIdx.y (`chunk` points per
+// CTA); the partial sums go to sums[(i * gridDim.y + s) * 4 ..] and point_loss_fwd_final adds them in split order (deterministic).
 __global__ void __launch_bounds__(1024)
 point_loss_fwd(const float* __restrict__ pred, const int64_t* __restrict__ pred_index, const void* __restrict__ gt,
                const int64_t* __restrict__ gt_index, const float* __restrict__ coords, float* __restrict__ sums, int P,
-               int H, int W, int Hg, int Wg, int gt_bits) {
+               int H, int W, int Hg, int Wg, int gt_bits, int chunk) {
     __shared__ float red[32];
     const int i = blockIdx.x;
     const int64_t pi = pred_index[i], gi = gt_index[i];
+    float* out = sums + ((int64_t)i * gridDim.y + blockIdx.y) * 4;
     if (pi < 0 || gi < 0) {
-        if (threadIdx.x < 4) sums[i * 4 + threadIdx.x] = 0.f;
+        if (threadIdx.x < 4) out[threadIdx.x] = 0.f;
         return;
     }
     const float* pm = pred + pi * H * W;
     float a_bce = 0.f, a_st = 0.f, a_s = 0.f, a_t = 0.f;
-    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    const int p_end = min(P, (int)(blockIdx.y + 1) * chunk);
+    for (int p = blockIdx.y * chunk + threadIdx.x; p < p_end; p += blockDim.x) {
         const float* c = coords + ((int64_t)i * P + p) * 2;
         float cx = __ldg(c), cy = __ldg(c + 1);
         float x = sample_f32(pm, bilin_setup(cx, cy, H, W));
@@ -326,15 +330,24 @@ point_loss_fwd(const float* __restrict__ pred, const int64_t* __restrict__ pred_
     }
     float r0 = block_sum(a_bce, red), r1 = block_sum(a_st, red), r2 = block_sum(a_s, red), r3 = block_sum(a_t, red);
     if (threadIdx.x == 0) {
-        sums[i * 4 + 0] = r0; sums[i * 4 + 1] = r1; sums[i * 4 + 2] = r2; sums[i * 4 + 3] = r3;
+        out[0] = r0; out[1] = r1; out[2] = r2; out[3] = r3;
     }
+}
+
+__global__ void point_loss_fwd_final(const float* __restrict__ partial, float* __restrict__ sums, int n4, int S) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;       // (pair, component)
+    if (e >= n4) return;
+    const int i = e >> 2, k = e & 3;
+    float a = 0.f;
+    for (int s = 0; s < S; ++s) a += partial[((int64_t)i * S + s) * 4 + k];
+    sums[e] = a;
 }
 
 __global__ void __launch_bounds__(1024)
 point_loss_bwd(const float* __restrict__ pred, const int64_t* __restrict__ pred_index, const void* __restrict__ gt,
                const int64_t* __restrict__ gt_index, const float* __restrict__ coords, const float* __restrict__ sums,
                const float* __restrict__ g_bce, const float* __restrict__ g_dice, float* __restrict__ gpred, int P,
-               int H, int W, int Hg, int Wg, int gt_bits) {
+               int H, int W, int Hg, int Wg, int gt_bits, int chunk) {
     const int i = blockIdx.x;
     const int64_t pi = pred_index[i], gi = gt_index[i];
     if (pi < 0 || gi < 0) return;
@@ -343,7 +356,8 @@ point_loss_bwd(const float* __restrict__ pred, const int64_t* __restrict__ pred_
     const float st = sums[i * 4 + 1], S = sums[i * 4 + 2], T = sums[i * 4 + 3];
     const float den = S + T + 1.f, num = 2.f * st + 1.f;
     const float gb = g_bce[i] / (float)P, gd = g_dice[i];
-    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    const int p_end = min(P, (int)(blockIdx.y + 1) * chunk);
+    for (int p = blockIdx.y * chunk + threadIdx.x; p < p_end; p += blockDim.x) {
         const float* c = coords + ((int64_t)i * P + p) * 2;
         float cx = __ldg(c), cy = __ldg(c + 1);
         Bilin tp = bilin_setup(cx, cy, H, W);
@@ -489,27 +503,44 @@ extern "C" int pdb_lsap_batched(const float* cost, const int32_t* tgt_offset, in
     return launched("lsap_batched");
 }
 
+// splits > 1: the P points of every pair are cut into `splits` chunks handled by different CTAs (few pairs: B = 2); `partial`
+// (Nm * splits * 4 floats) receives their sums and a second launch adds them in order.  splits <= 1: one CTA per pair.
 extern "C" int pdb_point_loss_forward(const float* pred, const int64_t* pred_index, const void* gt,
-                                      const int64_t* gt_index, const float* coords, float* sums, int Nm, int P, int H,
-                                      int W, int Hg, int Wg, int gt_bits, void* stream) {
+                                      const int64_t* gt_index, const float* coords, float* sums, float* partial, int splits,
+                                      int Nm, int P, int H, int W, int Hg, int Wg, int gt_bits, void* stream) {
     PDB_REQUIRE(pred && pred_index && gt && gt_index && coords && sums, "point_loss_forward: null pointer");
     PDB_REQUIRE(Nm >= 0 && P > 0 && H > 0 && W > 0 && Hg > 0 && Wg > 0, "point_loss_forward: bad shape");
+    PDB_REQUIRE(splits <= 1 || partial, "point_loss_forward: splits > 1 needs the partial-sum buffer");
     if (Nm == 0) return PDB_OK;
-    point_loss_fwd<<<(unsigned)Nm, 1024, 0, as_stream(stream)>>>(pred, pred_index, gt, gt_index, coords, sums, P, H, W,
-                                                                Hg, Wg, gt_bits);
-    return launched("point_loss_forward");
+    if (splits <= 1) {
+        point_loss_fwd<<<(unsigned)Nm, 1024, 0, as_stream(stream)>>>(pred, pred_index, gt, gt_index, coords, sums, P, H, W,
+                                                                    Hg, Wg, gt_bits, P);
+        return launched("point_loss_forward");
+    }
+    const int chunk = (P + splits - 1) / splits;
+    point_loss_fwd<<<dim3((unsigned)Nm, (unsigned)splits), 256, 0, as_stream(stream)>>>(pred, pred_index, gt, gt_index, coords,
+                                                                                       partial, P, H, W, Hg, Wg, gt_bits, chunk);
+    PDB_TRY(launched("point_loss_forward(partial)"));
+    point_loss_fwd_final<<<(unsigned)((Nm * 4 + 127) / 128), 128, 0, as_stream(stream)>>>(partial, sums, Nm * 4, splits);
+    return launched("point_loss_forward(final)");
 }
 
 extern "C" int pdb_point_loss_backward(const float* pred, const int64_t* pred_index, const void* gt,
                                        const int64_t* gt_index, const float* coords, const float* sums,
-                                       const float* g_bce, const float* g_dice, float* grad_pred, int Nm, int P, int H,
-                                       int W, int Hg, int Wg, int gt_bits, void* stream) {
+                                       const float* g_bce, const float* g_dice, float* grad_pred, int splits, int Nm, int P,
+                                       int H, int W, int Hg, int Wg, int gt_bits, void* stream) {
     PDB_REQUIRE(pred && pred_index && gt && gt_index && coords && sums && g_bce && g_dice && grad_pred,
                 "point_loss_backward: null pointer");
     PDB_REQUIRE(Nm >= 0 && P > 0 && H > 0 && W > 0 && Hg > 0 && Wg > 0, "point_loss_backward: bad shape");
     if (Nm == 0) return PDB_OK;
-    point_loss_bwd<<<(unsigned)Nm, 1024, 0, as_stream(stream)>>>(pred, pred_index, gt, gt_index, coords, sums, g_bce,
-                                                                g_dice, grad_pred, P, H, W, Hg, Wg, gt_bits);
+    if (splits <= 1) {
+        point_loss_bwd<<<(unsigned)Nm, 1024, 0, as_stream(stream)>>>(pred, pred_index, gt, gt_index, coords, sums, g_bce,
+                                                                    g_dice, grad_pred, P, H, W, Hg, Wg, gt_bits, P);
+    } else {
+        point_loss_bwd<<<dim3((unsigned)Nm, (unsigned)splits), 256, 0, as_stream(stream)>>>(
+            pred, pred_index, gt, gt_index, coords, sums, g_bce, g_dice, grad_pred, P, H, W, Hg, Wg, gt_bits,
+            (P + splits - 1) / splits);
+    }
     return launched("point_loss_backward");
 }
 

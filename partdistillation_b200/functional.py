@@ -459,9 +459,15 @@ class PointLossFunction(Function):
             Wg *= 32
         Nm, P = coords.shape[0], coords.shape[1]
         sums = torch.empty((Nm, 4), dtype=torch.float32, device=pred.device)
+        # few pairs (B = 2: a dozen per decoder output): the points of a pair are split over several CTAs as well
+        splits = 1 if Nm >= 148 or Nm == 0 else max(1, min((P + 255) // 256, (2 * 148 + Nm - 1) // Nm))
+        ctx.splits = splits
         if Nm:      # no matched pair (a batch without targets): the losses are empty sums, as in the reference
+            partial = torch.empty((Nm, splits, 4), dtype=torch.float32, device=pred.device) if splits > 1 else None
             rc = _lib.load().pdb_point_loss_forward(pred.data_ptr(), pred_index.data_ptr(), gt.data_ptr(), gt_index.data_ptr(),
-                                                    coords.data_ptr(), sums.data_ptr(), Nm, P, H, W, Hg, Wg, bits, _stream())
+                                                    coords.data_ptr(), sums.data_ptr(),
+                                                    partial.data_ptr() if partial is not None else None, splits,
+                                                    Nm, P, H, W, Hg, Wg, bits, _stream())
             _lib.check(rc, "pdb_point_loss_forward")
         ctx.save_for_backward(pred, pred_index, gt, gt_index, coords, sums)
         bce = sums[:, 0] / P
@@ -483,7 +489,7 @@ class PointLossFunction(Function):
         if Nm:
             rc = _lib.load().pdb_point_loss_backward(pred.data_ptr(), pred_index.data_ptr(), gt.data_ptr(), gt_index.data_ptr(),
                                                      coords.data_ptr(), sums.data_ptr(), g_bce.data_ptr(), g_dice.data_ptr(),
-                                                     gp.data_ptr(), Nm, P, H, W, Hg, Wg, bits, _stream())
+                                                     gp.data_ptr(), ctx.splits, Nm, P, H, W, Hg, Wg, bits, _stream())
             _lib.check(rc, "pdb_point_loss_backward")
         return gp, None, None, None, None
 

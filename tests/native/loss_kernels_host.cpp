@@ -49,19 +49,35 @@ extern "C" int host_lsap_batched(const float* cost, const int32_t* tgt_offset, i
 }
 
 extern "C" int host_point_loss_forward(const float* pred, const int64_t* pred_index, const void* gt, const int64_t* gt_index,
-                                       const float* coords, float* sums, int Nm, int P, int H, int W, int Hg, int Wg, int gt_bits) {
+                                       const float* coords, float* sums, float* partial, int splits, int Nm, int P, int H, int W,
+                                       int Hg, int Wg, int gt_bits) {
     if (Nm == 0) return 0;
-    launch(dim3((unsigned)Nm), dim3(1024), [&] { point_loss_fwd(pred, pred_index, gt, gt_index, coords, sums, P, H, W, Hg, Wg, gt_bits); });
+    if (splits <= 1) {
+        launch(dim3((unsigned)Nm), dim3(1024),
+               [&] { point_loss_fwd(pred, pred_index, gt, gt_index, coords, sums, P, H, W, Hg, Wg, gt_bits, P); });
+        return 0;
+    }
+    const int chunk = (P + splits - 1) / splits;
+    launch(dim3((unsigned)Nm, (unsigned)splits), dim3(256),
+           [&] { point_loss_fwd(pred, pred_index, gt, gt_index, coords, partial, P, H, W, Hg, Wg, gt_bits, chunk); });
+    launch(dim3((unsigned)((Nm * 4 + 127) / 128)), dim3(128), [&] { point_loss_fwd_final(partial, sums, Nm * 4, splits); });
     return 0;
 }
 
 extern "C" int host_point_loss_backward(const float* pred, const int64_t* pred_index, const void* gt,
                                         const int64_t* gt_index, const float* coords, const float* sums, const float* g_bce,
-                                        const float* g_dice, float* grad_pred, int Nm, int P, int H, int W, int Hg, int Wg,
-                                        int gt_bits) {
+                                        const float* g_dice, float* grad_pred, int splits, int Nm, int P, int H, int W, int Hg,
+                                        int Wg, int gt_bits) {
     if (Nm == 0) return 0;
-    launch(dim3((unsigned)Nm), dim3(1024),
-           [&] { point_loss_bwd(pred, pred_index, gt, gt_index, coords, sums, g_bce, g_dice, grad_pred, P, H, W, Hg, Wg, gt_bits); });
+    if (splits <= 1)
+        launch(dim3((unsigned)Nm), dim3(1024), [&] {
+            point_loss_bwd(pred, pred_index, gt, gt_index, coords, sums, g_bce, g_dice, grad_pred, P, H, W, Hg, Wg, gt_bits, P);
+        });
+    else
+        launch(dim3((unsigned)Nm, (unsigned)splits), dim3(256), [&] {
+            point_loss_bwd(pred, pred_index, gt, gt_index, coords, sums, g_bce, g_dice, grad_pred, P, H, W, Hg, Wg, gt_bits,
+                           (P + splits - 1) / splits);
+        });
     return 0;
 }
 
