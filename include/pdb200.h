@@ -366,6 +366,17 @@ PDB_API int pdb_layer_norm_forward_scaled(const float* x, const float* residual,
                                   int64_t rows, int C, float eps, int y_bf16, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * FPN top-down step of the pixel decoder (msdeformattn.py:352-356): out = lateral + F.interpolate(x, size=(H, W),
+ * mode="bilinear", align_corners=False) on channels-last maps, and the gradient with respect to x as a gather (deterministic).
+ *   x (B, h, w, C) f32 pixel-major, batch stride x_batch_stride elements; lateral (B, H, W, C) or NULL; out / grad_out
+ *   (B, H, W, C); grad_x (B, h, w, C) overwritten.  C % 4 == 0, 16-byte aligned.  Source index and weights as ATen's
+ *   upsample_bilinear2d (scale = in / out, negative source clamped to 0, upper neighbour clamped to the border).
+ * ---------------------------------------------------------------------------------------------- */
+PDB_API int pdb_upsample_add_forward(const float* x, const float* lateral, float* out, int B, int h, int w, int H, int W, int C,
+                             int64_t x_batch_stride, void* stream);
+PDB_API int pdb_upsample_backward(const float* grad_out, float* grad_x, int B, int h, int w, int H, int W, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * GroupNorm (+ ReLU) over channels-last maps — replaces nn.GroupNorm(32, C) and the F.relu behind it on the pixel decoder's
  * input_proj / lateral / output convolutions (msdeformattn.py:249-287 via detectron2 Conv2d(norm=get_norm("GN", C),
  * activation=F.relu)).  ATen's kernel wants NCHW; the convolutions here produce pixel-major maps.

@@ -34,6 +34,8 @@ SIGNATURES = {
     "pdb_col_sum": (_i, [_p, _p, _i, _i, _i, _p]),
     "pdb_col_sum_bf16": (_i, [_p, _p, _i, _i, _i, _p]),
     "pdb_set_xattn_passes": (_i, [_i]),
+    "pdb_upsample_add_forward": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _l, _p]),
+    "pdb_upsample_backward": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "pdb_gemm_small_tf32x3": (_i, [_p, _p, _p, _p, _i, _i, _i, _l, _l, _l, _i, _i, _i, _p]),
     "pdb_gemm_taps_tf32x3": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _l, _l, _l, _l, _i, _hp32, _i, _p]),
     "pdb_split_lo": (_i, [_p, _p, _l, _p]),

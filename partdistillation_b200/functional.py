@@ -1512,6 +1512,53 @@ def layer_norm(x, weight, bias, eps=1e-5, residual=None, return_sum=False, resid
 
 
 # --------------------------------------------------------------------------------------------------
+# FPN top-down step: lateral + bilinear up-sampling  (msdeformattn.py:352-356)  — csrc/upsample.cu
+# --------------------------------------------------------------------------------------------------
+class UpsampleAddFunction(Function):
+    """lateral + F.interpolate(x, size=lateral.shape[-2:], mode="bilinear", align_corners=False) on channels-last maps: one
+    forward pass, gather backward (deterministic); the gradient of ``lateral`` is the incoming gradient itself."""
+
+    @staticmethod
+    def forward(ctx, x, lateral):
+        _need_cuda(x, lateral)
+        B, C, h, w = x.shape
+        H, W = lateral.shape[-2:]
+        xp = x.permute(0, 2, 3, 1)                        # pixel-major view; rows of a batch item must be dense
+        if not (xp.stride(3) == 1 and xp.stride(2) == C and xp.stride(1) == w * C and xp.stride(0) % 4 == 0
+                and xp.data_ptr() % 16 == 0):
+            xp = xp.contiguous()
+        lp = _c(lateral.permute(0, 2, 3, 1))
+        out = torch.empty((B, H, W, C), dtype=torch.float32, device=x.device)
+        rc = _lib.load().pdb_upsample_add_forward(xp.data_ptr(), lp.data_ptr(), out.data_ptr(), B, h, w, H, W, C, xp.stride(0),
+                                                  _stream())
+        _lib.check(rc, "pdb_upsample_add_forward")
+        ctx.geom = (B, C, h, w, H, W)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        B, C, h, w, H, W = ctx.geom
+        gp = _c(gy.permute(0, 2, 3, 1))                   # no copy when gy is channels-last
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gxp = torch.empty((B, h, w, C), dtype=torch.float32, device=gy.device)
+            rc = _lib.load().pdb_upsample_backward(gp.data_ptr(), gxp.data_ptr(), B, h, w, H, W, C, _stream())
+            _lib.check(rc, "pdb_upsample_backward")
+            gx = gxp.permute(0, 3, 1, 2)
+        return gx, (gy if ctx.needs_input_grad[1] else None)
+
+
+def upsample_add(x, lateral):
+    """lateral + bilinear up-sampling of x to lateral's size (align_corners=False), fp32 CUDA maps with C % 4 == 0 on the
+    library kernel; anything else through F.interpolate."""
+    if (x.is_cuda and x.dtype == torch.float32 and lateral.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0
+            and x.shape[:2] == lateral.shape[:2] and getattr(_lib.load(), "pdb_upsample_add_forward", None) is not None):
+        return UpsampleAddFunction.apply(x, lateral)
+    return lateral + torch.nn.functional.interpolate(x, size=lateral.shape[-2:], mode="bilinear", align_corners=False)
+
+
+# --------------------------------------------------------------------------------------------------
 # GroupNorm (+ ReLU) on channels-last maps  (msdeformattn.py:249-287: Conv2d(norm=get_norm("GN", C), activation=F.relu))
 # --------------------------------------------------------------------------------------------------
 class GroupNormFunction(Function):

@@ -229,8 +229,7 @@ class MSDeformAttnPixelDecoder(nn.Module):
                 out.append(y[:, starts[i]:end].transpose(1, 2).reshape(bs, -1, h, w))
             for idx, f in enumerate(self.in_features[:self.num_fpn_levels][::-1]):
                 cur = self._lateral(self.lateral_convs[idx], features[f].float())
-                up = F.interpolate(out[-1], size=cur.shape[-2:], mode="bilinear", align_corners=False)
-                out.append(self._output_conv(self.output_convs[idx], cur + up))
+                out.append(self._output_conv(self.output_convs[idx], PF.upsample_add(out[-1], cur)))
             multi_scale = out[:self.maskformer_num_feature_levels]
             return self._mask_features_pixel_major(out[-1]), out[0], multi_scale
 

@@ -1053,3 +1053,22 @@ def test_ffn_fused_node_matches_two_linears(fn, rows, C, Fd):
             assert _rel(a_.double().cpu(), r_) < 2e-5
     # the gate is exact: gradient entries behind inactive units are exactly zero in both paths' dh, hence identical dx patterns
     assert torch.equal(res[0][1] == 0, res[1][1] == 0)
+
+
+@pytest.mark.parametrize("B,C,h,w,H,W", [(2, 256, 32, 32, 64, 64), (1, 64, 20, 20, 40, 40), (2, 32, 7, 9, 13, 20), (1, 8, 5, 5, 5, 5),
+                                         (2, 16, 12, 10, 6, 5)])
+def test_upsample_add_matches_interpolate(fn, B, C, h, w, H, W):
+    """lateral + bilinear up-sampling (align_corners=False) in one kernel and its gather backward against F.interpolate + add and
+    autograd: exact 2x, odd ratios, identity and down-sampling sizes; x given as the strided channels-last view the pixel decoder
+    produces (rows of a longer token sequence)."""
+    g = torch.Generator().manual_seed(70)
+    tokens = torch.randn(B, h * w + 17, C, generator=g).cuda()                       # a level inside the flattened pyramid
+    x = tokens[:, 5:5 + h * w].transpose(1, 2).reshape(B, C, h, w).requires_grad_()
+    lat = torch.randn(B, H, W, C, generator=g).cuda().permute(0, 3, 1, 2).requires_grad_()
+    go = torch.randn(B, H, W, C, generator=g).cuda().permute(0, 3, 1, 2)
+    y = fn.upsample_add(x, lat)
+    ref = lat + F.interpolate(x, size=(H, W), mode="bilinear", align_corners=False)
+    assert torch.allclose(y, ref, rtol=1e-6, atol=1e-6)
+    gx, gl = torch.autograd.grad(y, (x, lat), go)
+    rx, rl = torch.autograd.grad(ref, (x, lat), go)
+    assert torch.allclose(gx, rx, rtol=1e-5, atol=1e-5) and torch.equal(gl, rl)
