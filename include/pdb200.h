@@ -156,6 +156,11 @@ PDB_API int pdb_gemm_small_tf32x3(const float* A, const float* B, float* C, cons
 PDB_API int pdb_gemm_taps_tf32x3(const float* A, const float* B, const float* B_lo, float* C, const float* bias, int M, int N,
                          int Ck, int batch, int a_rows, int64_t lda, int64_t ldc, int64_t sa, int64_t sc, int taps,
                          const int32_t* tap_off, int relu, void* stream);
+/* Same, with a store that drops the garbage columns of the padded-width grid: row m = y * wp + x of the product goes to row
+ * y * w + x of C when x < w — C is the (H, w, N) map itself (sc = H * w * N), no crop pass afterwards.  N > 112, M % wp == 0. */
+PDB_API int pdb_gemm_taps_cropped_tf32x3(const float* A, const float* B, const float* B_lo, float* C, const float* bias, int M, int N,
+                                 int Ck, int batch, int a_rows, int64_t lda, int64_t ldc, int64_t sa, int64_t sc, int taps,
+                                 const int32_t* tap_off, int relu, int wp, int w, void* stream);
 /* lo[i] = x[i] - trunc_tf32(x[i]) (x with its low 13 mantissa bits cleared); n % 4 == 0, 16-byte aligned. */
 PDB_API int pdb_split_lo(const float* x, float* lo, int64_t n, void* stream);
 

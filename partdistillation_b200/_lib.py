@@ -38,6 +38,7 @@ SIGNATURES = {
     "pdb_upsample_backward": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "pdb_gemm_small_tf32x3": (_i, [_p, _p, _p, _p, _i, _i, _i, _l, _l, _l, _i, _i, _i, _p]),
     "pdb_gemm_taps_tf32x3": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _l, _l, _l, _l, _i, _hp32, _i, _p]),
+    "pdb_gemm_taps_cropped_tf32x3": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _l, _l, _l, _l, _i, _hp32, _i, _i, _i, _p]),
     "pdb_split_lo": (_i, [_p, _p, _l, _p]),
     "pdb_attn_mask_build": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "pdb_attn_mask_reset_rows": (_i, [_p, _p, _i, _l, _p]),

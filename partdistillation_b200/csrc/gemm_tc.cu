@@ -67,6 +67,8 @@ struct GemmParams {
     int b_box_rows;                   // rows of the K-major B box (BN, or the 16-multiple covering N when N < BN)
     long long* trace;                 // debug timeline of CTA 0 (pdb_debug_set_trace), normally NULL
     int stages, stage_bytes;          // raw ring: depth and bytes per stage (A raw/hi | B raw/hi | B lo)
+    int crop_wp, crop_w;              // CROP kernels (3x3 convolution on the padded-width pixel grid): row m = y * crop_wp + x is stored
+                                      // at row y * crop_w + x when x < crop_w and dropped otherwise (the two garbage columns)
     const float* gate;                // ReLU backward fused into the store: C[m][n] = gate[m][n] > 0 ? value : 0 (same layout as C;
                                       // row-major stores only) — the input gradient of the layer behind a ReLU
 };
@@ -199,7 +201,7 @@ __device__ __forceinline__ void b_layout(const GemmParams& p, int bn_eff, int& b
 // ALO: the A_lo k-blocks live in tensor memory instead of shared memory: the split warps write them with tcgen05.st (thread =
 // one row = one TMEM lane) and the correction MMA takes its A operand from TMEM, which removes 16 KB of shared-memory writes and
 // 16 KB of operand reads per k-block.  K-major A only, and the accumulators must leave 64 columns (see GemmSmem).
-template <int BN, bool A_MN, bool B_MN, bool ALO, bool GATE = false>
+template <int BN, bool A_MN, bool B_MN, bool ALO, bool GATE = false, bool CROP = false>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const __grid_constant__ CUtensorMap tm_blo, const GemmParams p) {
@@ -575,7 +577,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                             float4 x = *reinterpret_cast<const float4*>(tile_s + r * 36 + sub_c);
                             x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
                             if (p.relu) { x.x = epi_act(x.x, p.relu); x.y = epi_act(x.y, p.relu); x.z = epi_act(x.z, p.relu); x.w = epi_act(x.w, p.relu); }
-                            if (n_ok && mrow0 + r < p.M) {
+                            if (CROP) {
+                                const int m = mrow0 + r, y = m / p.crop_wp, xc = m - y * p.crop_wp;
+                                if (n_ok && m < p.M && xc < p.crop_w)
+                                    *reinterpret_cast<float4*>(Cb + ((int64_t)y * p.crop_w + xc) * p.ldc + n) = x;
+                            } else if (n_ok && mrow0 + r < p.M) {
                                 if (GATE) {
                                     const float4 h = hg[GATE ? i : 0];
                                     x.x = h.x > 0.f ? x.x : 0.f; x.y = h.y > 0.f ? x.y : 0.f;
@@ -593,7 +599,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                         float* dst = Cb + (int64_t)mrow0 * p.ldc + n;
 #pragma unroll 4
                         for (int r = 0; r < 32; ++r) {
-                            if (mrow0 + r < p.M && n_ok) {
+                            if (CROP) {
+                                const int m = mrow0 + r, y = m / p.crop_wp, xc = m - y * p.crop_wp;
+                                if (m < p.M && n_ok && xc < p.crop_w)
+                                    Cb[((int64_t)y * p.crop_w + xc) * p.ldc + n] = epi_act(tile_s[r * 36 + lane] + bv, p.relu);
+                            } else if (mrow0 + r < p.M && n_ok) {
                                 float x = tile_s[r * 36 + lane] + bv;
                                 x = epi_act(x, p.relu);
                                 if (GATE && !(__ldg(p.gate + (dst - p.C)) > 0.f)) x = 0.f;
@@ -715,6 +725,27 @@ static int launch_gemm_gated(const CUtensorMap& ta, const CUtensorMap& tb, const
     return launched("gemm_tf32x3(gated)");
 }
 
+// The cropping store of the 3x3 convolutions (K-major A and B, 128-wide tiles), its own instantiation like the gated one.
+static int launch_gemm_crop(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbl, const GemmParams& p, cudaStream_t st) {
+    using S = GemmSmem<128>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<128, false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) return fail(PDB_ERR_LAUNCH, "gemm_tf32x3: smem attribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    GemmParams q = p;
+    q.trace = g_trace_ptr;
+    q.stages = G_RS;
+    q.stage_bytes = S::RAW_STAGE;
+    q.mt = (p.M + G_BM - 1) / G_BM;
+    q.nt = (p.N + 127) / 128;
+    q.total_tiles = q.mt * q.nt * p.batch * p.ksplit;
+    const unsigned grid = (unsigned)std::min(q.total_tiles, kNumSMs);
+    gemm_tf32x3_kernel<128, false, false, false, false, true><<<grid, G_THREADS, S::TOTAL, st>>>(ta, tb, tbl, q);
+    return launched("gemm_tf32x3(crop)");
+}
+
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbl, const GemmParams& p, cudaStream_t st) {
     // A_lo in tensor memory: K-major A only (the split warps own whole rows), and the accumulators must leave 64 columns
@@ -735,7 +766,7 @@ static int dispatch_layout(const CUtensorMap& ta, const CUtensorMap& tb, const C
 static int gemm_impl(const float* A, const float* B, const float* B_lo, float* C, const float* bias, int M, int N, int K, int batch,
                      int64_t lda, int64_t ldb, int64_t ldc, int64_t sa, int64_t sb, int64_t sc, int a_mn, int b_mn,
                      int c_trans, int relu, int accumulate, int ksplit, int taps, const int32_t* tap_off, int a_rows,
-                     cudaStream_t st, const float* gate = nullptr) {
+                     cudaStream_t st, const float* gate = nullptr, int crop_wp = 0, int crop_w = 0) {
     PDB_REQUIRE(A && B && C, "gemm_tf32x3: null pointer");
     PDB_REQUIRE(!gate || (!c_trans && ksplit == 1 && !accumulate && (reinterpret_cast<uintptr_t>(gate) & 15) == 0),
                 "gemm_tf32x3: the ReLU gate needs a plain row-major store (no transpose, split-K or accumulation), 16-byte aligned");
@@ -747,6 +778,7 @@ static int gemm_impl(const float* A, const float* B, const float* B_lo, float* C
     GemmParams p;
     p.C = C; p.bias = bias; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.sc = sc; p.batch = batch;
     p.gate = gate;
+    p.crop_wp = crop_wp; p.crop_w = crop_w;
     int kb_total = (K + G_BK - 1) / G_BK;
     if (ksplit > kb_total) ksplit = kb_total;
     p.ksplit = ksplit;
@@ -775,6 +807,13 @@ static int gemm_impl(const float* A, const float* B, const float* B_lo, float* C
     PDB_TRY(make_operand_map(&tb, B, b_mn != 0, N, K, batch, ldb, sb, p.b_box_rows));
     tbl = tb;
     if (B_lo) PDB_TRY(make_operand_map(&tbl, B_lo, b_mn != 0, N, K, batch, ldb, sb, p.b_box_rows));
+    if (crop_wp > 0) {
+        PDB_REQUIRE(BN == 128 && !a_mn && !b_mn && N > 112 && !c_trans && !accumulate && ksplit == 1 && crop_w > 0 &&
+                        crop_w <= crop_wp && M % crop_wp == 0,
+                    "gemm_tf32x3: the cropping store needs 128-wide tiles (N > 112), K-major operands, a plain store and M a "
+                    "multiple of the padded width");
+        return launch_gemm_crop(ta, tb, tbl, p, st);
+    }
     if (gate) {
         PDB_REQUIRE(BN == 128 && !a_mn && b_mn && N > 112 && N % 4 == 0,
                     "gemm_tf32x3: the gated store needs 128-wide tiles (many rows, N > 112, N %% 4 == 0), K-major A and MN-major B");
@@ -804,6 +843,19 @@ extern "C" int pdb_gemm_taps_tf32x3(const float* A, const float* B, const float*
     for (int t = 0; t < taps; ++t) PDB_REQUIRE(tap_off[t] >= 0, "gemm_taps: negative row offset");
     return gemm_impl(A, B, B_lo, C, bias, M, N, taps * Ck, batch, lda, (int64_t)taps * Ck, ldc, sa, 0, sc, 0, 0, 0, relu, 0, 1,
                      taps, tap_off, a_rows, as_stream(stream));
+}
+
+// pdb_gemm_taps_tf32x3 whose store drops the garbage columns of the padded-width pixel grid: row m = y * wp + x of the product is
+// written to row y * w + x of C (x < w) — C is the (H, W, N) map itself (batch stride sc = H * w * N), no crop pass afterwards.
+extern "C" int pdb_gemm_taps_cropped_tf32x3(const float* A, const float* B, const float* B_lo, float* C, const float* bias, int M,
+                                            int N, int Ck, int batch, int a_rows, int64_t lda, int64_t ldc, int64_t sa, int64_t sc,
+                                            int taps, const int32_t* tap_off, int relu, int wp, int w, void* stream) {
+    PDB_REQUIRE(taps >= 1 && taps <= 9 && tap_off, "gemm_taps: 1 <= taps <= 9");
+    PDB_REQUIRE(Ck > 0 && Ck % G_BK == 0, "gemm_taps: channels per tap (%d) must be a multiple of %d", Ck, G_BK);
+    PDB_REQUIRE(wp > 0 && w > 0, "gemm_taps_cropped: widths");
+    for (int t = 0; t < taps; ++t) PDB_REQUIRE(tap_off[t] >= 0, "gemm_taps: negative row offset");
+    return gemm_impl(A, B, B_lo, C, bias, M, N, taps * Ck, batch, lda, (int64_t)taps * Ck, ldc, sa, 0, sc, 0, 0, 0, relu, 0, 1,
+                     taps, tap_off, a_rows, as_stream(stream), nullptr, wp, w);
 }
 
 extern "C" int pdb_gemm_tf32x3(const float* A, const float* B, const float* B_lo, float* C, const float* bias, int M, int N, int K, int batch,

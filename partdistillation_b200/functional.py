@@ -931,6 +931,26 @@ def _gemm_taps(A, Bw, C, M, N, Ck, batch, a_rows, tap_off, bias=None, relu=False
     return C
 
 
+def _conv_taps(xp, w9, B, H, W, Cin, Cout, bias=None):
+    """The 9-tap GEMM of a 3x3 convolution on the zero-padded (B, H + 3, W + 2, Cin) image -> (B, H, W, Cout).  With the
+    cropping store (pdb_gemm_taps_cropped_tf32x3) the result is written at the true width; otherwise on the padded-width grid
+    and cropped by a copy."""
+    Wp = W + 2
+    taps = [ky * Wp + kx for ky in range(3) for kx in range(3)]
+    lo = split_lo(w9)
+    f = getattr(_lib.load(), "pdb_gemm_taps_cropped_tf32x3", None)        # absent only in the CPU-tier host builds of the tests
+    if f is not None and Cout > 112 and Cout % 4 == 0:
+        out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=xp.device)
+        rc = f(xp.data_ptr(), w9.data_ptr(), lo.data_ptr(), out.data_ptr(), bias.data_ptr() if bias is not None else None,
+               H * Wp, Cout, Cin, B, (H + 3) * Wp, Cin, Cout, (H + 3) * Wp * Cin, H * W * Cout, 9, _lib.host_i32(taps), 0, Wp, W,
+               _stream())
+        _lib.check(rc, "pdb_gemm_taps_cropped_tf32x3")
+        return out
+    full = torch.empty((B, H * Wp, Cout), dtype=torch.float32, device=xp.device)
+    _gemm_taps(xp, w9, full, H * Wp, Cout, Cin, B, (H + 3) * Wp, taps, bias=bias, B_lo=lo)
+    return full.view(B, H, Wp, Cout)[:, :, :W].contiguous()
+
+
 def _pad_nhwc(x_nhwc):
     """(B, H, W, C) -> zero-padded (B, H + 3, W + 2, C): one row above, one column left / right, two rows below (the
     second one only keeps the shifted reads of the padded-width grid inside the image's own buffer)."""
@@ -951,16 +971,13 @@ class Conv3x3Function(Function):
         _need_cuda(x, weight, bias)
         B, C, H, W = x.shape
         O = weight.shape[0]
-        Wp = W + 2
-        taps = [ky * Wp + kx for ky in range(3) for kx in range(3)]
         xp = _pad_nhwc(x.permute(0, 2, 3, 1))
         w9 = weight.permute(0, 2, 3, 1).reshape(O, 9 * C).contiguous()
-        full = torch.empty((B, H * Wp, O), dtype=torch.float32, device=x.device)
-        _gemm_taps(xp, w9, full, H * Wp, O, C, B, (H + 3) * Wp, taps, bias=bias, B_lo=split_lo(w9))
+        out = _conv_taps(xp, w9, B, H, W, C, O, bias)
         ctx.save_for_backward(xp, weight)
         ctx.dims = (B, C, H, W, O)
         ctx.has_bias = bias is not None
-        return full.view(B, H, Wp, O)[:, :, :W].contiguous().permute(0, 3, 1, 2)
+        return out.permute(0, 3, 1, 2)
 
     @staticmethod
     @once_differentiable
@@ -971,22 +988,28 @@ class Conv3x3Function(Function):
         taps = [ky * Wp + kx for ky in range(3) for kx in range(3)]
         gy_nhwc = _c(gy.permute(0, 2, 3, 1))
         gx = gw = gb = None
+        gyp = None
         if ctx.needs_input_grad[0]:
             gyp = _pad_nhwc(gy_nhwc)
             w9t = weight.flip(2, 3).permute(1, 2, 3, 0).reshape(C, 9 * O).contiguous()
-            full = torch.empty((B, H * Wp, C), dtype=torch.float32, device=gy.device)
-            _gemm_taps(gyp, w9t, full, H * Wp, C, O, B, (H + 3) * Wp, taps, B_lo=split_lo(w9t))
-            gx = full.view(B, H, Wp, C)[:, :, :W].contiguous().permute(0, 3, 1, 2)
+            gx = _conv_taps(gyp, w9t, B, H, W, O, C).permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
-            gyf = torch.nn.functional.pad(gy_nhwc, (0, 0, 0, 2))              # zero garbage columns of the padded-width grid
-            gw9 = torch.zeros((O, 9 * C), dtype=torch.float32, device=gy.device)
             rows, K = (H + 3) * Wp, H * Wp
+            if gyp is not None:
+                # gy on the padded-width grid with zero garbage columns is the padded image read Wp + 1 pixels in:
+                # gyp[(y + 1) * Wp + x + 1] = gy[y][x], and x = W, W + 1 land on its zero right / left border columns
+                gyf = gyp.view(B, rows * O)[:, (Wp + 1) * O:]
+                sa = rows * O
+            else:
+                gyf = torch.nn.functional.pad(gy_nhwc, (0, 0, 0, 2))          # zero garbage columns of the padded-width grid
+                sa = K * O
+            gw9 = torch.zeros((O, 9 * C), dtype=torch.float32, device=gy.device)
             xflat = xp.view(B, rows * C)
             ks = _split_k(O, C, K)
             for t, off in enumerate(taps):
                 # gw9[o, t*C + i] = sum_{b,q} gyf[b, q, o] * xp[b, q + off, i]
                 gemm_tf32x3(gyf, xflat[:, off * C:], gw9[:, t * C:], O, C, K, batch=B, lda=O, ldb=C, ldc=9 * C,
-                            sa=K * O, sb=rows * C, sc=0, a_mn=True, b_mn=True, accumulate=True, ksplit=ks)
+                            sa=sa, sb=rows * C, sc=0, a_mn=True, b_mn=True, accumulate=True, ksplit=ks)
             gw = gw9.view(O, 3, 3, C).permute(0, 3, 1, 2)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = col_sum(gy_nhwc.reshape(-1, gy_nhwc.shape[-1]))

@@ -41,9 +41,9 @@ def test_tensor_core_kernels_are_tcgen05_tma_sass():
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "UTCBAR", "SYNCS"):
         assert mnemonic in sass, mnemonic
     assert " HMMA." not in sass and "LDGSTS" not in sass
-    # one kernel per (BN, A layout, B layout), the ALO variants of the K-major-A ones, and the one gated-store instantiation
+    # one kernel per (BN, A layout, B layout), the ALO variants of the K-major-A ones, and the gated-store and cropping-store instantiations
     kernels = set(re.findall(r"Function : (\w*gemm_tf32x3_kernel\w*)", sass))
-    assert len(kernels) == 19, sorted(kernels)
+    assert len(kernels) == 20, sorted(kernels)
 
 
 def test_cabi_rejects_bad_arguments_without_gpu():

@@ -308,7 +308,7 @@ def test_conv1x1(fn, channels_last):
     assert _rel(gb.double(), rb.double()) < 1e-5
 
 
-@pytest.mark.parametrize("B,C,O,H,W", [(2, 64, 32, 9, 14), (1, 32, 64, 16, 16)])
+@pytest.mark.parametrize("B,C,O,H,W", [(2, 64, 32, 9, 14), (1, 32, 64, 16, 16), (2, 128, 256, 20, 13), (1, 256, 128, 33, 40)])
 def test_conv3x3(fn, B, C, O, H, W):
     """3x3 convolution as one tap-shifted tensor-core GEMM on the padded-width grid (forward, input gradient with the
     flipped kernel, weight gradient as 9 split-K GEMMs) vs float64 F.conv2d."""
