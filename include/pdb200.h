@@ -380,6 +380,10 @@ PDB_API int pdb_layer_norm_forward_scaled(const float* x, const float* residual,
 PDB_API int pdb_upsample_add_forward(const float* x, const float* lateral, float* out, int B, int h, int w, int H, int W, int C,
                              int64_t x_batch_stride, void* stream);
 PDB_API int pdb_upsample_backward(const float* grad_out, float* grad_x, int B, int h, int w, int H, int W, int C, void* stream);
+/* Zero-padded copy of a channels-last map, (B, H, W, C) -> (B, top + H + bottom, left + W + right, C), borders written in the same
+ * pass: the A operand of the tap-shifted 3x3 convolution GEMM (top 1, bottom 2, left 1, right 1).  C % 4 == 0. */
+PDB_API int pdb_pad_nhwc(const float* x, float* out, int B, int H, int W, int C, int top, int bottom, int left, int right,
+                 void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm (+ ReLU) over channels-last maps — replaces nn.GroupNorm(32, C) and the F.relu behind it on the pixel decoder's

@@ -36,6 +36,7 @@ SIGNATURES = {
     "pdb_set_xattn_passes": (_i, [_i]),
     "pdb_upsample_add_forward": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _l, _p]),
     "pdb_upsample_backward": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "pdb_pad_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "pdb_gemm_small_tf32x3": (_i, [_p, _p, _p, _p, _i, _i, _i, _l, _l, _l, _i, _i, _i, _p]),
     "pdb_gemm_taps_tf32x3": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _l, _l, _l, _l, _i, _hp32, _i, _p]),
     "pdb_gemm_taps_cropped_tf32x3": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _l, _l, _l, _l, _i, _hp32, _i, _i, _i, _p]),

@@ -127,3 +127,36 @@ extern "C" int pdb_upsample_backward(const float* grad_out, float* grad_x, int B
         (float)w / (float)W, (float)H / (float)h, (float)W / (float)w);
     return launched("upsample_backward");
 }
+
+// Zero-padded copy of a channels-last map for the tap-shifted 3x3 convolution GEMM (functional._pad_nhwc): (B, H, W, C) ->
+// (B, H + top + bottom, W + left + right, C), borders written as zeros in the same pass (ATen: a fill pass plus a strided copy
+// at 1.4 TB/s).
+namespace pdb {
+__global__ void __launch_bounds__(256)
+pad_nhwc_kernel(const float4* __restrict__ x, float4* __restrict__ out, int64_t total, int H, int W, int C4, int Hp, int Wp, int top,
+                int left) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % C4);
+    int64_t p = idx / C4;
+    const int xx = (int)(p % Wp) - left;
+    p /= Wp;
+    const int yy = (int)(p % Hp) - top, b = (int)(p / Hp);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (xx >= 0 && xx < W && yy >= 0 && yy < H) v = __ldg(x + (((int64_t)b * H + yy) * W + xx) * C4 + c);
+    out[idx] = v;
+}
+}  // namespace pdb
+
+extern "C" int pdb_pad_nhwc(const float* x, float* out, int B, int H, int W, int C, int top, int bottom, int left, int right,
+                            void* stream) {
+    PDB_REQUIRE(x && out, "pad_nhwc: null pointer");
+    PDB_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && top >= 0 && bottom >= 0 && left >= 0 && right >= 0, "pad_nhwc: bad shape");
+    PDB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "pad_nhwc: buffers must be 16-byte aligned");
+    const int Hp = H + top + bottom, Wp = W + left + right, C4 = C / 4;
+    const int64_t total = (int64_t)B * Hp * Wp * C4;
+    PDB_REQUIRE((total + 255) / 256 < (1ll << 31), "pad_nhwc: too large");
+    pdb::pad_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(out), total, H, W, C4, Hp, Wp, top, left);
+    return launched("pad_nhwc");
+}

@@ -1072,3 +1072,12 @@ def test_upsample_add_matches_interpolate(fn, B, C, h, w, H, W):
     gx, gl = torch.autograd.grad(y, (x, lat), go)
     rx, rl = torch.autograd.grad(ref, (x, lat), go)
     assert torch.allclose(gx, rx, rtol=1e-5, atol=1e-5) and torch.equal(gl, rl)
+
+
+def test_pad_nhwc_kernel(fn):
+    g = torch.Generator().manual_seed(71)
+    x = torch.randn(2, 9, 14, 32, generator=g).cuda()
+    ref = F.pad(x, (0, 0, 1, 1, 1, 2))
+    assert torch.equal(fn._pad_nhwc(x), ref)
+    xs = torch.randn(2, 32, 9, 14, generator=g).cuda().permute(0, 2, 3, 1)         # non-contiguous pixel-major view
+    assert torch.equal(fn._pad_nhwc(xs), F.pad(xs, (0, 0, 1, 1, 1, 2)))
