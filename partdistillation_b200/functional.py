@@ -1431,7 +1431,7 @@ def swin_window_attention(qkv, qkv_bias, bias, heads, window_size, shift, scale,
 # --------------------------------------------------------------------------------------------------
 class LayerNormFunction(Function):
     """y = LayerNorm(x (+ residual)); optionally also returns the sum.  Forward is one pass of the warp-per-row kernel;
-    backward is ATen's native_layer_norm_backward on the saved mean / rstd (the sum is recomputed there)."""
+    backward is ATen's native_layer_norm_backward on the saved mean / rstd and the saved sum."""
 
     @staticmethod
     def forward(ctx, x, residual, weight, bias, eps, want_sum):
@@ -1441,16 +1441,19 @@ class LayerNormFunction(Function):
         r2 = _c(residual).view(-1, C) if residual is not None else None
         rows = x2.shape[0]
         y = torch.empty_like(x2)
-        z = torch.empty_like(x2) if (want_sum and r2 is not None) else None
+        # with a residual the kernel also writes the sum whenever a backward will follow: the LayerNorm gradient needs it, and one
+        # extra write here is cheaper than re-adding x + residual there (a 3-pass ATen add per LayerNorm of the encoder)
+        z = torch.empty_like(x2) if (r2 is not None and (want_sum or any(ctx.needs_input_grad[:4]))) else None
         mean = torch.empty((rows,), dtype=torch.float32, device=x.device)
         rstd = torch.empty((rows,), dtype=torch.float32, device=x.device)
         rc = _lib.load().pdb_layer_norm_forward(x2.data_ptr(), r2.data_ptr() if r2 is not None else None, weight.data_ptr(),
                                                 bias.data_ptr(), y.data_ptr(), z.data_ptr() if z is not None else None,
                                                 mean.data_ptr(), rstd.data_ptr(), rows, C, float(eps), _stream())
         _lib.check(rc, "pdb_layer_norm_forward")
-        ctx.save_for_backward(x2, r2, weight, bias, mean, rstd, z)
+        ctx.save_for_backward(x2 if z is None else None, weight, bias, mean, rstd, z)
         ctx.shape = x.shape
         ctx.want_sum = want_sum
+        ctx.has_residual = r2 is not None
         if want_sum:
             return y.view(x.shape), (z if z is not None else x2).view(x.shape)
         return y.view(x.shape), None
@@ -1458,10 +1461,11 @@ class LayerNormFunction(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, gy, gz):
-        x2, r2, weight, bias, mean, rstd, z = ctx.saved_tensors
-        C = x2.shape[-1]
-        zin = z if z is not None else (x2 + r2 if r2 is not None else x2)
-        mask = [ctx.needs_input_grad[0] or (r2 is not None and ctx.needs_input_grad[1]), ctx.needs_input_grad[2],
+        x2, weight, bias, mean, rstd, z = ctx.saved_tensors
+        zin = z if z is not None else x2                # no residual: the input itself
+        C = zin.shape[-1]
+        has_res = ctx.has_residual
+        mask = [ctx.needs_input_grad[0] or (has_res and ctx.needs_input_grad[1]), ctx.needs_input_grad[2],
                 ctx.needs_input_grad[3]]
         gin, gw, gb = torch.ops.aten.native_layer_norm_backward(_c(gy).view(-1, C), zin, [C], mean.view(-1, 1), rstd.view(-1, 1),
                                                                 weight, bias, mask)
@@ -1471,7 +1475,7 @@ class LayerNormFunction(Function):
             gin = gin.view(ctx.shape)
         elif gz is not None:
             gin = gz
-        return (gin if ctx.needs_input_grad[0] else None, gin if (r2 is not None and ctx.needs_input_grad[1]) else None,
+        return (gin if ctx.needs_input_grad[0] else None, gin if (has_res and ctx.needs_input_grad[1]) else None,
                 gw, gb, None, None)
 
 
